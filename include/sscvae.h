@@ -1,0 +1,201 @@
+/* sscvae.h — C ABI of libsscvae_b200.so: the B200-native (sm_100a) implementation of the
+ * Style-SeqCVAE `var_updown` sequential-decoder hot path.
+ *
+ * This is the drop-in boundary. The reference has no FFI of its own — its hot path
+ * is PyTorch eager code — so each entry point replaces a *Python* interface of the reference; the
+ * reference-side binding (a ctypes stub inside the reference's UpDownCaptioner) is shown in
+ * INTEGRATION.md. Paths below are relative to the reference root.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless it says "host".
+ *   - the caller (PyTorch) owns all memory: inputs, outputs, packed weights and workspace. The
+ *     library never allocates or frees caller-visible device memory and keeps no pointer after
+ *     a call returns. The opaque handle holds host-side shape bookkeeping only.
+ *   - every call enqueues work on `stream` (a cudaStream_t passed as void*) and returns
+ *     immediately; 0 = success, <0 = SSCVAE_ERR_*, >0 = cudaError_t. No exception crosses the ABI;
+ *     sscvae_last_error() returns the message of the last failure on the calling thread.
+ *   - float tensors are fp32 row-major contiguous; token ids are int64 as in the reference.
+ *   - not re-entrant on one handle; one handle per device.
+ */
+#ifndef SSCVAE_H_
+#define SSCVAE_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SSCVAE_ABI_VERSION 1
+
+#define SSCVAE_ERR_BAD_ARG (-1)
+#define SSCVAE_ERR_WORKSPACE (-2)
+#define SSCVAE_ERR_UNSUPPORTED (-3)
+#define SSCVAE_ERR_DRIVER (-4)
+
+/* Model dimensions and switches = the ctor arguments of the reference captioner
+ * (var_updown/var_updown/models/updown_captioner.py:21-41) that shape the hot path. */
+typedef struct SscvaeDims {
+  int32_t image_feature_size;        /* F */
+  int32_t embedding_size;            /* E */
+  int32_t hidden_size;               /* H */
+  int32_t attention_projection_size; /* A */
+  int32_t z_space;                   /* Z */
+  int32_t vocab_size;                /* V */
+  int32_t max_caption_length;        /* L; teacher-forced steps T = L + 1 */
+  int32_t sentiment_vae;             /* 0 | 1   (2 = attribute-grounded prior: unsupported) */
+  int32_t simple_vae;                /* 0 | 1 */
+  int32_t tied_embedding;            /* 1: frozen embedding tied to the output layer + tanh projection (E in {300,600}) */
+  int32_t pad_index;                 /* "@@UNKNOWN@@"  */
+  int32_t boundary_index;            /* "@@BOUNDARY@@" */
+  float prior_std;
+  float senti_prior_multip;
+} SscvaeDims;
+
+/* Order of the weight / gradient pointer arrays = the reference state_dict. */
+enum SscvaeWeight {
+  SSCVAE_W_EMBEDDING = 0,        /* _embedding_layer.weight                     (V,E)            */
+  SSCVAE_W_ATT_IH,               /* _updown_cell._attention_lstm_cell.weight_ih (4H,E+F+2H)      */
+  SSCVAE_W_ATT_HH,               /*                                  .weight_hh (4H,H)           */
+  SSCVAE_W_ATT_BIH,              /*                                  .bias_ih   (4H)             */
+  SSCVAE_W_ATT_BHH,              /*                                  .bias_hh   (4H)             */
+  SSCVAE_W_QUERY_PROJ,           /* _butd_attention._query_vector_projection_layer.weight   (A,H) */
+  SSCVAE_W_IMAGE_PROJ,           /* _butd_attention._image_features_projection_layer.weight (A,F) */
+  SSCVAE_W_ATT_VEC,              /* _butd_attention._attention_layer.weight     (1,A)            */
+  SSCVAE_W_ENC_IH,               /* _language_lstm_cell_encoder.weight_ih       (4H,F+2H+s)      */
+  SSCVAE_W_ENC_HH,
+  SSCVAE_W_ENC_BIH,
+  SSCVAE_W_ENC_BHH,
+  SSCVAE_W_DEC_IH,               /* _language_lstm_cell_decoder.weight_ih       (4H,F+2H+s+Z)    */
+  SSCVAE_W_DEC_HH,
+  SSCVAE_W_DEC_BIH,
+  SSCVAE_W_DEC_BHH,
+  SSCVAE_W_FC_MEAN_W,            /* fc_mean.weight (Z,H) */
+  SSCVAE_W_FC_MEAN_B,
+  SSCVAE_W_FC_LOGVAR_W,
+  SSCVAE_W_FC_LOGVAR_B,
+  SSCVAE_W_OUT_PROJ_W,           /* tied: _output_projection.0.weight (E,H)   | untied: _output_layer.weight (V,H) */
+  SSCVAE_W_OUT_PROJ_B,           /* tied: _output_projection.0.bias   (E)     | untied: _output_layer.bias   (V)   */
+  SSCVAE_W_COUNT
+};
+
+typedef struct SscvaeHandle SscvaeHandle;
+
+int sscvae_abi_version(void);
+const char* sscvae_last_error(void);
+/* number of CUDA kernels this library has launched since it was loaded (bench.py `gpu_launches`) */
+uint64_t sscvae_launch_count(void);
+
+/* Replaces UpDownCaptioner.__init__ shape bookkeeping (updown_captioner.py:21-139). */
+int sscvae_create(const SscvaeDims* dims, SscvaeHandle** out);
+void sscvae_destroy(SscvaeHandle* h);
+
+/* Packed bf16 operand copies of the weights (K-padded, recurrent blocks folded, transposed twins for
+ * backward). Re-run after every optimizer step. `weights_f32` = host array of SSCVAE_W_COUNT device
+ * pointers in reference layout. */
+size_t sscvae_packed_bytes(const SscvaeHandle* h);
+int sscvae_pack_weights(SscvaeHandle* h, const void* const* weights_f32, void* packed, size_t packed_bytes,
+                        void* stream);
+
+/* ---- training: replaces UpDownCaptioner.forward, training branch (updown_captioner.py:263-323),
+ * i.e. _decode_step x T (:371-455), UpDownCell.forward (var_updown/var_updown/modules/updown_cell.py:86-231),
+ * BottomUpTopDownAttention.forward (updown-baseline/updown/modules/attention.py:36-97), the KL terms
+ * (:295-303) and _get_loss (:457-466). */
+size_t sscvae_train_workspace_bytes(const SscvaeHandle* h, int batch, int num_boxes);
+int sscvae_train_forward(SscvaeHandle* h, int batch, int num_boxes,
+                         const void* packed,
+                         const void* const* weights_f32,  /* host array; biases / w_a are read in fp32 */
+                         const float* image_features,     /* (B,N,F) zero rows = padding boxes */
+                         const int64_t* caption_tokens,   /* (B,L) pad = pad_index */
+                         const float* sentiment,          /* (B,1) or NULL when sentiment_vae == 0 */
+                         const float* eps,                /* (T,B,Z) N(0,1) draws, or NULL -> Philox(seed) */
+                         uint64_t seed,
+                         void* workspace, size_t workspace_bytes,
+                         float* loss,                     /* out (B) */
+                         float* kld,                      /* out (B) */
+                         void* stream);
+/* ---- replaces the autograd BPTT of `loss.backward()` (var_updown/scripts/train.py:172).
+ * Must follow sscvae_train_forward on the same workspace. `grads_f32` = host array of
+ * SSCVAE_W_COUNT device pointers in reference layout; NULL entries are skipped (frozen parameters:
+ * the tied embedding always, the decoder LSTM under the freeze schedule of train.py:156-161).
+ * Gradients are OVERWRITTEN, not accumulated. `group_events` = optional host array of
+ * SSCVAE_GRAD_GROUPS cudaEvent_t recorded on `stream` as soon as a group's gradients are final,
+ * so a data-parallel wrapper can start all-reducing that bucket while the rest still computes. */
+#define SSCVAE_GRAD_GROUPS 5   /* 0 head, 1 decoder LSTM, 2 encoder LSTM + fc, 3 attention LSTM, 4 attention */
+int sscvae_train_backward(SscvaeHandle* h, int batch, int num_boxes,
+                          const void* packed, const void* const* weights_f32,
+                          void* workspace, size_t workspace_bytes,
+                          const float* grad_loss,         /* (B) dObjective/dloss_b */
+                          const float* grad_kld,          /* (B) dObjective/dkld_b  */
+                          void* const* grads_f32,
+                          void* const* group_events,
+                          void* stream);
+/* Named view into the training workspace for tests ("logits", "alpha", "mean", "logvar", "kl", ...).
+ * Returns 0 and fills offset/bytes, or SSCVAE_ERR_BAD_ARG for an unknown name. */
+int sscvae_train_region(const SscvaeHandle* h, int batch, int num_boxes, const char* name, size_t* offset,
+                        size_t* bytes);
+
+/* ---- search: replaces ConstrainedBeamSearch.search (updown-baseline/updown/modules/cbs.py:59-277),
+ * allennlp BeamSearch.search (in-tree text: var_updown/var_updown/modules/beam_search.py:592-766;
+ * = the S=1, fsm==NULL case) and select_best_beam[_with_constraints]
+ * (updown-baseline/updown/utils/decoding.py:10-138, cbs_simple). Declared in the search section below. */
+
+/* One search step on given log-probabilities (replay / unit-test entry point, and the kernel the
+ * full decode uses). Row r = (b*S + s)*K + k.
+ *   first step : logp (B,V)      -> tokens/scores (B,S,K); backptr untouched
+ *   later steps: logp (B*S*K,V)  -> tokens, backptr (index into the image's S*K rows), scores
+ * fsm_bits: (B,S,V) uint32, bit i of fsm_bits[b,s,w] = reference fsm[b,s,i,w]; NULL = all allowed (plain beam).
+ * normalized = 1: `logp` already holds log-softmax values; 0: raw logits, log-softmax is fused. */
+int sscvae_fsm_pack(const uint8_t* fsm /*(B,S,S,V)*/, int batch, int states, int vocab, uint32_t* fsm_bits, void* stream);
+int sscvae_search_first_step(const float* logp, int batch, int states, int beam, int vocab, const uint32_t* fsm_bits,
+                             int normalized, int32_t* tokens, float* scores, void* stream);
+int sscvae_search_step(const float* logp, int batch, int states, int beam, int per_node, int vocab,
+                       const uint32_t* fsm_bits, int normalized, int end_index, const int32_t* last_tokens,
+                       const float* last_scores, void* scratch, size_t scratch_bytes, int32_t* tokens,
+                       int32_t* backptr, float* scores, void* stream);
+size_t sscvae_search_scratch_bytes(int batch, int states, int beam, int per_node);
+/* Back-trace (cbs.py:252-277) + early-exit step count (cbs.py:167) + best-beam selection.
+ * tokens_hist / backptr_hist / scores_hist: (steps_run, B, S*K) as produced step by step [backptr entry 0 unused].
+ * predictions (B,S,K,steps_run) int64 (entries >= n_steps are filled with end_index); final_scores (B,S,K) = the
+ * scores at the reference's exit step; best (B,steps_run) int64; n_steps: device int32 = the number of steps the
+ * reference would have produced (its early exit); num_constraints NULL -> plain beam rule (state 0, beam 0). */
+int sscvae_search_finish(const int32_t* tokens_hist, const int32_t* backptr_hist, const float* scores_hist, int steps_run,
+                         int batch, int states, int beam, int end_index, const int64_t* num_constraints,
+                         int min_constraints_to_satisfy, int64_t* predictions, float* final_scores, int64_t* best,
+                         int32_t* n_steps, void* stream);
+
+/* ---- decode: replaces UpDownCaptioner.forward, eval branch (updown_captioner.py:324-366): runs the
+ * whole search on the device. R = B*S*K rows, rows of one image share its region features.
+ * eps: (max_steps, R, Z) external normals (parity) or NULL -> Philox(seed). Step 0 uses eps[0, b*S*K]
+ * for image b (the reference draws a (B,Z) tensor there). */
+size_t sscvae_decode_workspace_bytes(const SscvaeHandle* h, int batch, int num_boxes, int states, int beam);
+int sscvae_decode(SscvaeHandle* h, int batch, int num_boxes, int states, int beam, int per_node,
+                  const void* packed, const void* const* weights_f32,
+                  const float* image_features, const float* sentiment,
+                  const uint8_t* fsm,                 /* (B,S,S,V) uint8 as the reference passes it, or NULL */
+                  const int64_t* num_constraints,     /* (B) or NULL */
+                  int min_constraints_to_satisfy,
+                  const float* eps, uint64_t seed,
+                  void* workspace, size_t workspace_bytes,
+                  int64_t* predictions,               /* out (B,S,K,L) */
+                  float* log_probs,                   /* out (B,S,K) */
+                  int64_t* best,                      /* out (B,L) */
+                  int32_t* n_steps,                   /* out device int32: valid leading steps */
+                  void* stream);
+
+/* ---- training-step tail: clip_grad_norm_ + SGD(momentum, weight decay) fused over
+ * a flat parameter buffer; replaces var_updown/scripts/train.py:173-176. */
+int sscvae_grad_sqnorm(const float* grads, size_t n, float* partial /*>= 1024 floats*/, float* sqnorm_out, void* stream);
+int sscvae_sgd_step(float* params, const float* grads, float* momentum_buf, size_t n, const float* sqnorm,
+                    float max_norm, float lr, float momentum, float weight_decay, int first_step, void* stream);
+
+/* generic bf16 TN GEMM exposed for unit tests of the tcgen05 kernel:
+ * C32[M,N] = A[M,K] (bf16, lda) * B[N,K]^T (bf16, ldb) */
+int sscvae_test_gemm(const void* A, int lda, const void* B, int ldb, int M, int N, int K, float* C32, int ldc,
+                     const float* bias, int act_tanh, int accumulate, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SSCVAE_H_ */

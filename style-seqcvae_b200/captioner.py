@@ -1,0 +1,378 @@
+"""Drop-in `UpDownCaptioner` for the reference's var_updown model, running on libsscvae_b200.so.
+
+Mirrors var_updown/var_updown/models/updown_captioner.py:20-466 of visinf/style-seqcvae: same ctor and
+`from_config` arguments, same `forward` signature and outputs (training: {"loss": (B,), "kld": (B,)};
+otherwise {"predictions": (B, steps)} int64), same `state_dict` keys and shapes, so reference
+checkpoints load and `train.py` / `inference.py` work unchanged.
+
+The nn.Module below owns nothing but parameters: the torch sub-modules are parameter containers whose
+`forward` is never called. All arithmetic of the hot path (the T-step UpDown cell, latent nets, KL/CE,
+BPTT, beam/CBS search) happens in hand-written sm_100a kernels behind the C ABI; there is no eager /
+CPU fallback — without a CUDA device and the built library this module raises.
+"""
+import ctypes as C
+from typing import Dict, Optional
+
+import torch
+from torch import nn
+
+from . import _lib
+
+
+class _ButdAttentionParams(nn.Module):
+    """Parameter container with the reference's names (updown-baseline/updown/modules/attention.py:27-34)."""
+
+    def __init__(self, query_size, image_feature_size, projection_size):
+        super().__init__()
+        self._query_vector_projection_layer = nn.Linear(query_size, projection_size, bias=False)
+        self._image_features_projection_layer = nn.Linear(image_feature_size, projection_size, bias=False)
+        self._attention_layer = nn.Linear(projection_size, 1, bias=False)
+
+
+class _UpDownCellParams(nn.Module):
+    """Parameter container with the reference's names and shapes
+    (var_updown/var_updown/modules/updown_cell.py:34-84)."""
+
+    def __init__(self, F, E, H, A, Z, cond):
+        super().__init__()
+        self._attention_lstm_cell = nn.LSTMCell(E + F + 2 * H, H)
+        self._butd_attention = _ButdAttentionParams(H, F, A)
+        self._language_lstm_cell_encoder = nn.LSTMCell(cond + F + 2 * H, H)
+        self._language_lstm_cell_decoder = nn.LSTMCell(cond + F + 2 * H + Z, H)
+        self.fc_mean = nn.Linear(H, Z)
+        self.fc_log_var = nn.Linear(H, Z)
+
+
+class _TrainStep(torch.autograd.Function):
+    """forward = sscvae_train_forward, backward = sscvae_train_backward (BPTT kernels)."""
+
+    @staticmethod
+    def forward(ctx, module, image_features, caption_tokens, sentiment, eps, seed, *params):
+        L = _lib.lib()
+        B, N, _ = image_features.shape
+        packed = module._packed_weights()
+        ws = module._train_workspace(B, N)
+        loss = torch.empty(B, dtype=torch.float32, device=image_features.device)
+        kld = torch.empty_like(loss)
+        stream = C.c_void_p(torch.cuda.current_stream(image_features.device).cuda_stream)
+        wptr = _lib.ptr_array(module._weight_tensors())
+        _lib.check(L.sscvae_train_forward(
+            module._handle, B, N, _lib.ptr(packed), wptr, _lib.ptr(image_features), _lib.ptr(caption_tokens),
+            _lib.ptr(sentiment), _lib.ptr(eps), C.c_uint64(seed), _lib.ptr(ws), ws.numel(), _lib.ptr(loss),
+            _lib.ptr(kld), stream))
+        module._ws_generation += 1
+        ctx.module, ctx.B, ctx.N, ctx.generation = module, B, N, module._ws_generation
+        ctx.keep = (image_features, caption_tokens, sentiment, eps)
+        return loss, kld
+
+    @staticmethod
+    def backward(ctx, grad_loss, grad_kld):
+        module = ctx.module
+        if ctx.generation != module._ws_generation:
+            raise RuntimeError("sscvae: backward() after a newer forward() reused the training workspace; "
+                               "call backward before the next forward")
+        L = _lib.lib()
+        params = module._weight_tensors()
+        needs = ctx.needs_input_grad[6:]
+        grads = [torch.empty_like(p) if (need and p.requires_grad) else None for p, need in zip(params, needs)]
+        dev = grad_loss.device
+        gl = (grad_loss if grad_loss is not None else torch.zeros(ctx.B, device=dev)).contiguous().float()
+        gk = (grad_kld if grad_kld is not None else torch.zeros(ctx.B, device=dev)).contiguous().float()
+        ws = module._train_workspace(ctx.B, ctx.N)
+        stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        events = module._group_events
+        ev = None
+        if events is not None:
+            ev = (C.c_void_p * _lib.GRAD_GROUPS)(*[e.cuda_event for e in events])
+        _lib.check(L.sscvae_train_backward(
+            module._handle, ctx.B, ctx.N, _lib.ptr(module._packed_weights()), _lib.ptr_array(params), _lib.ptr(ws),
+            ws.numel(), _lib.ptr(gl), _lib.ptr(gk), _lib.ptr_array(grads), ev, stream))
+        return (None, None, None, None, None, None) + tuple(grads)
+
+
+class UpDownCaptioner(nn.Module):
+    def __init__(
+        self,
+        vocabulary,
+        image_feature_size,
+        embedding_size,
+        hidden_size,
+        attention_projection_size,
+        max_caption_length=20,
+        beam_size=1,
+        use_cbs=False,
+        min_constraints_to_satisfy=2,
+        z_space=150,
+        prior_std=None,
+        simple_vae=False,
+        latent_embedding=None,
+        latent_embedding_multip=1,
+        sentiment_vae=False,
+        senti_prior_multip=1,
+        cbs_simple=False,
+        device=None,
+        glove_vectors: Optional[torch.Tensor] = None,
+    ):
+        super().__init__()
+        self._vocabulary = vocabulary
+        self.image_feature_size = image_feature_size
+        self.embedding_size = embedding_size
+        self.hidden_size = hidden_size
+        self.attention_projection_size = attention_projection_size
+        self._max_caption_length = max_caption_length
+        self._use_cbs = use_cbs
+        self._min_constraints_to_satisfy = min_constraints_to_satisfy
+        self.z_space = z_space
+        _vocab_size = vocabulary.get_vocab_size()
+        self._vocab_size = _vocab_size
+        self._pad_index = vocabulary.get_token_index("@@UNKNOWN@@")
+        self._boundary_index = vocabulary.get_token_index("@@BOUNDARY@@")
+        self.prior_std = 1.0 if prior_std is None else prior_std
+        self.sentiment_vae = int(sentiment_vae)
+        self.senti_prior_multip = senti_prior_multip
+        self.simple_vae = bool(simple_vae)
+        self.latent_embedding = latent_embedding
+        self.latent_embedding_multip = latent_embedding_multip
+        self.beam_size = beam_size
+        self.per_node_beam_size = (beam_size // 2) or beam_size     # updown_captioner.py:134, cbs.py:57
+        self.device = device
+        self.cbs_simple = cbs_simple
+        if self.sentiment_vae not in (0, 1):
+            raise NotImplementedError("SENTIMENT_VAE=2 (attribute-grounded prior) is not on this path yet (SURVEY §8(f)-4)")
+        if latent_embedding not in ("glove", "senti_word_net"):
+            raise NotImplementedError()                              # updown_cell.py:169-174
+        if use_cbs and not cbs_simple:
+            raise NotImplementedError("only cbs_simple best-beam selection is implemented (SURVEY §8(f)-2)")
+
+        self._tied = embedding_size in (300, 600)                    # updown_captioner.py:75
+        if self._tied:
+            if glove_vectors is None:
+                # the reference's rule for words without a pre-trained vector (updown_captioner.py:197,209,215)
+                glove_vectors = 2 * torch.randn(_vocab_size, embedding_size) - 1
+                glove_vectors[self._pad_index] = 0
+            self._embedding_layer = nn.Embedding.from_pretrained(glove_vectors, freeze=True, padding_idx=self._pad_index)
+        else:
+            self._embedding_layer = nn.Embedding(_vocab_size, embedding_size, padding_idx=self._pad_index)
+            assert not use_cbs, "CBS is not supported without Frozen GloVe embeddings (300d / 600d)"
+
+        cond = 0 if (self.simple_vae or self.sentiment_vae == 0) else 1
+        self._updown_cell = _UpDownCellParams(image_feature_size, embedding_size, hidden_size,
+                                              attention_projection_size, z_space, cond)
+        if self._tied:
+            self._output_projection = nn.Sequential(nn.Linear(hidden_size, embedding_size), nn.Tanh())
+            self._output_layer = nn.Linear(embedding_size, _vocab_size, bias=False)
+            self._output_layer.weight = self._embedding_layer.weight
+        else:
+            self._output_projection = nn.Identity()
+            self._output_layer = nn.Linear(hidden_size, _vocab_size)
+
+        # ---- native state (not part of state_dict)
+        dims = _lib.SscvaeDims(
+            image_feature_size, embedding_size, hidden_size, attention_projection_size, z_space, _vocab_size,
+            max_caption_length, self.sentiment_vae, int(self.simple_vae), int(self._tied), self._pad_index,
+            self._boundary_index, float(self.prior_std), float(senti_prior_multip))
+        self._dims = dims
+        self._handle = C.c_void_p()
+        _lib.check(_lib.lib().sscvae_create(C.byref(dims), C.byref(self._handle)))
+        self._packed = None
+        self._packed_key = None
+        self._ws_cache: Dict[tuple, torch.Tensor] = {}
+        self._ws_generation = 0
+        self._group_events = None          # set by the data-parallel wrapper
+        self.rng_mode = "philox"           # "reference": draw eps from the CPU generator like updown_cell.py:206
+        self._eps_override = None          # tests: explicit eps tensor
+        self._call_counter = 0
+        self.last_search = None
+
+    def __del__(self):
+        try:
+            if getattr(self, "_handle", None):
+                _lib.lib().sscvae_destroy(self._handle)
+                self._handle = None
+        except Exception:
+            pass
+
+    @classmethod
+    def from_config(cls, config, **kwargs):
+        _C = config
+        vocabulary = kwargs.pop("vocabulary")
+        return cls(
+            vocabulary=vocabulary,
+            image_feature_size=_C.MODEL.IMAGE_FEATURE_SIZE,
+            embedding_size=_C.MODEL.EMBEDDING_SIZE,
+            hidden_size=_C.MODEL.HIDDEN_SIZE,
+            attention_projection_size=_C.MODEL.ATTENTION_PROJECTION_SIZE,
+            beam_size=_C.MODEL.BEAM_SIZE,
+            max_caption_length=_C.DATA.MAX_CAPTION_LENGTH,
+            use_cbs=_C.MODEL.USE_CBS,
+            min_constraints_to_satisfy=_C.MODEL.MIN_CONSTRAINTS_TO_SATISFY,
+            z_space=_C.MODEL.Z_SPACE,
+            prior_std=_C.MODEL.PRIOR_STD,
+            simple_vae=_C.MODEL.SIMPLE_VAE,
+            latent_embedding=_C.MODEL.LATENT_EMBEDDING,
+            sentiment_vae=_C.MODEL.SENTIMENT_VAE,
+            senti_prior_multip=_C.MODEL.SENTI_PRIOR_MULTIP,
+            latent_embedding_multip=_C.MODEL.LATENT_EMBEDDING_MULTIP,
+            cbs_simple=_C.MODEL.CBS_SIMPLE,
+            device=kwargs["device"],
+        )
+
+    # ------------------------------------------------------------------------------------------
+    def _weight_tensors(self):
+        """Parameters in SSCVAE_W_* order (include/sscvae.h)."""
+        c = self._updown_cell
+        out = [self._embedding_layer.weight]
+        for cell in (c._attention_lstm_cell,):
+            out += [cell.weight_ih, cell.weight_hh, cell.bias_ih, cell.bias_hh]
+        a = c._butd_attention
+        out += [a._query_vector_projection_layer.weight, a._image_features_projection_layer.weight, a._attention_layer.weight]
+        for cell in (c._language_lstm_cell_encoder, c._language_lstm_cell_decoder):
+            out += [cell.weight_ih, cell.weight_hh, cell.bias_ih, cell.bias_hh]
+        out += [c.fc_mean.weight, c.fc_mean.bias, c.fc_log_var.weight, c.fc_log_var.bias]
+        if self._tied:
+            out += [self._output_projection[0].weight, self._output_projection[0].bias]
+        else:
+            out += [self._output_layer.weight, self._output_layer.bias]
+        return out
+
+    def _require_cuda(self, t: torch.Tensor):
+        if not t.is_cuda:
+            raise RuntimeError("sscvae UpDownCaptioner runs only on a CUDA (sm_100a) device: move the module and its "
+                               "inputs to cuda; there is no CPU fallback")
+        for p in self._weight_tensors():
+            if p.device != t.device or p.dtype != torch.float32 or not p.is_contiguous():
+                raise RuntimeError("sscvae: parameters must be contiguous fp32 tensors on the input's device")
+
+    def _packed_weights(self) -> torch.Tensor:
+        ws = self._weight_tensors()
+        key = tuple((p.data_ptr(), p._version) for p in ws)
+        if self._packed is None or key != self._packed_key or self._packed.device != ws[0].device:
+            L = _lib.lib()
+            nbytes = L.sscvae_packed_bytes(self._handle)
+            if self._packed is None or self._packed.numel() != nbytes or self._packed.device != ws[0].device:
+                self._packed = torch.empty(nbytes, dtype=torch.uint8, device=ws[0].device)
+            stream = C.c_void_p(torch.cuda.current_stream(ws[0].device).cuda_stream)
+            _lib.check(L.sscvae_pack_weights(self._handle, _lib.ptr_array(ws), _lib.ptr(self._packed), nbytes, stream))
+            self._packed_key = key
+        return self._packed
+
+    def _train_workspace(self, B, N) -> torch.Tensor:
+        dev = self._embedding_layer.weight.device
+        key = ("train", B, N, dev)
+        ws = self._ws_cache.get(key)
+        if ws is None:
+            nbytes = _lib.lib().sscvae_train_workspace_bytes(self._handle, B, N)
+            self._ws_cache = {k: v for k, v in self._ws_cache.items() if k[0] != "train"}
+            ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+            self._ws_cache[key] = ws
+        return ws
+
+    def train_region(self, B, N, name, dtype, shape):
+        """Typed view of a named region of the training workspace (tests / debugging)."""
+        off, nb = C.c_size_t(), C.c_size_t()
+        _lib.check(_lib.lib().sscvae_train_region(self._handle, B, N, name.encode(), C.byref(off), C.byref(nb)))
+        ws = self._train_workspace(B, N)
+        n = 1
+        for s in shape:
+            n *= s
+        itemsize = torch.empty(0, dtype=dtype).element_size()
+        assert n * itemsize <= nb.value, (name, n * itemsize, nb.value)
+        return ws[off.value: off.value + n * itemsize].view(dtype).view(*shape)
+
+    def _next_seed(self) -> int:
+        self._call_counter += 1
+        return (int(torch.initial_seed()) * 1000003 + self._call_counter) & 0xFFFFFFFFFFFFFFFF
+
+    # ------------------------------------------------------------------------------------------
+    def forward(
+        self,
+        image_features: torch.Tensor,
+        obj_atts=None,
+        image_attributes=None,
+        caption_tokens=None,
+        sentiment=None,
+        fsm: torch.Tensor = None,
+        num_constraints: torch.Tensor = None,
+        constraints=None,
+        constraint2states=None,
+    ):
+        self._require_cuda(image_features)
+        image_features = image_features.contiguous().float()
+        B, N, F = image_features.shape
+        if F != self.image_feature_size:
+            raise ValueError(f"image_features last dim {F} != image_feature_size {self.image_feature_size}")
+        cond = self.sentiment_vae == 1
+        if cond:
+            if sentiment is None:
+                raise ValueError("sentiment is required when sentiment_vae == 1")
+            sentiment = sentiment.to(image_features.device).contiguous().float().view(B, 1)
+        else:
+            sentiment = None
+
+        if self.training and caption_tokens is not None:
+            caption_tokens = caption_tokens.to(image_features.device).contiguous().long()
+            if caption_tokens.shape != (B, self._max_caption_length):
+                raise ValueError(f"caption_tokens must be (B, {self._max_caption_length}), got {tuple(caption_tokens.shape)}")
+            T = self._max_caption_length + 1
+            eps = self._eps_override
+            if eps is None and self.rng_mode == "reference":
+                # one (B,Z) CPU draw per step, in step order, exactly like updown_cell.py:206
+                eps = torch.stack([torch.randn(B, self.z_space) for _ in range(T)]).to(image_features.device)
+            if eps is not None:
+                eps = eps.to(image_features.device).contiguous().float()
+                assert eps.shape == (T, B, self.z_space)
+            loss, kld = _TrainStep.apply(self, image_features, caption_tokens, sentiment, eps, self._next_seed(),
+                                         *self._weight_tensors())
+            return {"loss": loss, "kld": kld}
+
+        return {"predictions": self._decode(image_features, sentiment, fsm, num_constraints)}
+
+    @torch.no_grad()
+    def _decode(self, image_features, sentiment, fsm, num_constraints):
+        L = _lib.lib()
+        dev = image_features.device
+        B, N, _ = image_features.shape
+        K, P, steps = self.beam_size, self.per_node_beam_size, self._max_caption_length
+        if self._use_cbs:
+            if fsm is None:
+                raise ValueError("fsm is required when use_cbs=True")
+            fsm = fsm.to(dev).to(torch.uint8).contiguous()
+            S = fsm.shape[1]
+            if fsm.shape != (B, S, S, self._vocab_size):
+                raise ValueError(f"fsm must be (B,S,S,V), got {tuple(fsm.shape)}")
+            nc = None if num_constraints is None else num_constraints.to(dev).long().contiguous()
+            if nc is None:
+                nc = torch.zeros(B, dtype=torch.long, device=dev)
+        else:
+            S, fsm, nc = 1, None, None
+        R = B * S * K
+        eps = self._eps_override
+        if eps is None and self.rng_mode == "reference":
+            e = torch.zeros(steps, R, self.z_space)
+            e[0, ::S * K] = torch.randn(B, self.z_space)            # first step: one row per image (cbs.py:127)
+            for t in range(1, steps):
+                e[t] = torch.randn(R, self.z_space)
+            eps = e
+        if eps is not None:
+            eps = eps.to(dev).contiguous().float()
+            assert eps.shape == (steps, R, self.z_space)
+        nbytes = L.sscvae_decode_workspace_bytes(self._handle, B, N, S, K)
+        key = ("decode", B, N, S, K, dev)
+        ws = self._ws_cache.get(key)
+        if ws is None:
+            self._ws_cache = {k: v for k, v in self._ws_cache.items() if k[0] != "decode"}
+            ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+            self._ws_cache[key] = ws
+        preds = torch.empty(B, S, K, steps, dtype=torch.long, device=dev)
+        scores = torch.empty(B, S, K, dtype=torch.float32, device=dev)
+        best = torch.empty(B, steps, dtype=torch.long, device=dev)
+        n_steps = torch.zeros(1, dtype=torch.int32, device=dev)
+        stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        _lib.check(L.sscvae_decode(
+            self._handle, B, N, S, K, P, _lib.ptr(self._packed_weights()), _lib.ptr_array(self._weight_tensors()),
+            _lib.ptr(image_features), _lib.ptr(sentiment), _lib.ptr(fsm), _lib.ptr(nc),
+            int(self._min_constraints_to_satisfy), _lib.ptr(eps), C.c_uint64(self._next_seed()), _lib.ptr(ws), nbytes,
+            _lib.ptr(preds), _lib.ptr(scores), _lib.ptr(best), _lib.ptr(n_steps), stream))
+        n = int(n_steps.item())                                     # the reference's data-dependent early exit (cbs.py:167)
+        self.last_search = {"predictions": preds[..., :n], "log_probs": scores, "n_steps": n}
+        return best[:, :n]

@@ -1,0 +1,267 @@
+// C ABI: eval-mode decode (greedy / beam / constrained beam search) entirely on the device, plus the
+// stand-alone search entry points used by the replay parity tests (include/sscvae.h).
+//
+// Rows r = (b*S + s)*K + k share image b's region features, projected features and mean-feature gate
+// block through a row->image map; nothing image-sized is replicated per beam (the reference
+// re-materialises (B*S*K, N, F) and re-projects it every step, updown_captioner.py:405-416).
+#include "api_internal.cuh"
+#include "search.cuh"
+
+namespace sscvae {
+
+static void plan_decode(const Dims& d, int B, int N, int S, int K, Plan& p) {
+  const size_t b = sizeof(bf16), f = 4;
+  const size_t R = (size_t)B * S * K, BN = (size_t)B * N;
+  const int Pmax = K;
+  p.add("featsb", BN * d.Fp * b);
+  p.add("mask", BN * f);
+  p.add("avgb", (size_t)B * d.Fp * b);
+  p.add("projb", BN * d.Ap * b);
+  p.add("gavg", (size_t)B * d.G * f);
+  p.add("pm_row", B * f);
+  p.add("sent", B * f);
+  p.add("rowmap", R * 4);
+  p.add("rowmap0", (size_t)B * 4);
+  p.add("start_tok", (size_t)B * 4);
+  p.add("XA0", R * 2 * d.Hp * b);
+  p.add("XA1", R * 2 * d.Hp * b);
+  p.add("c1a", R * d.H * f);
+  p.add("c1b", R * d.H * f);
+  p.add("cda", R * d.H * f);
+  p.add("cdb", R * d.H * f);
+  p.add("XE", R * (d.Fp + d.Hp) * b);
+  p.add("embb_r", R * d.Ep * b);
+  p.add("ZB", R * d.Zp * b);
+  p.add("acc", R * d.G * f);
+  p.add("q", R * d.A * f);
+  p.add("alpha", R * N * f);
+  if (d.tied) p.add("ob", R * d.Ep * b);
+  p.add("logits", R * d.V * f);
+  p.add("fsm_bits", (size_t)B * S * d.V * 4);
+  p.add("cand_val", R * S * Pmax * f);
+  p.add("cand_tok", R * S * Pmax * 4);
+  p.add("tok_hist", (size_t)d.L * R * 4);
+  p.add("bp_hist", (size_t)d.L * R * 4);
+  p.add("score_hist", (size_t)d.L * R * f);
+}
+
+const Plan& Handle::decode_plan(int B, int N, int S, int K) {
+  if (dp_B != B || dp_N != N || dp_S != S || dp_K != K) {
+    dp = Plan();
+    plan_decode(d, B, N, S, K, dp);
+    dp_B = B; dp_N = N; dp_S = S; dp_K = K;
+  }
+  return dp;
+}
+
+static inline GemmSeg seg(const bf16* A, int lda, const bf16* B, int ldb, int K) {
+  GemmSeg s; s.A = A; s.lda = lda; s.B = B; s.ldb = ldb; s.K = K; return s;
+}
+
+static int decode_impl(Handle* h, int B, int N, int S, int K, int P, const char* pk, const void* const* wv,
+                       const float* feats, const float* sent, const uint8_t* fsm, const long long* num_constraints,
+                       int min_sat, const float* eps, unsigned long long seed, char* ws, size_t ws_bytes,
+                       long long* predictions, float* log_probs, long long* best, int32_t* n_steps, cudaStream_t s) {
+  const Dims& d = h->d;
+  REQUIRE(B > 0 && N > 0 && S >= 1 && S <= 32 && K >= 1 && K <= 8 && P >= 1 && P <= K, "bad decode shape B=%d N=%d S=%d K=%d P=%d", B, N, S, K, P);
+  REQUIRE(d.cond == 0 || sent != nullptr, "sentiment is required when sentiment_vae == 1");
+  REQUIRE(S == 1 || fsm != nullptr, "an FSM is required for more than one state");
+  const Plan& dp = h->decode_plan(B, N, S, K);
+  if (ws_bytes < dp.total) { set_error("workspace too small: %zu < %zu", ws_bytes, dp.total); return SSCVAE_ERR_WORKSPACE; }
+  REQUIRE((reinterpret_cast<uintptr_t>(ws) & 255) == 0 && (reinterpret_cast<uintptr_t>(pk) & 255) == 0,
+          "workspace and packed weights must be 256-byte aligned");
+  const Plan& pp = h->pp;
+  auto W = [&](int i) { return reinterpret_cast<const float*>(wv[i]); };
+  auto Pb = [&](const char* n) { return reinterpret_cast<const bf16*>(pk + pp.find(n)->off); };
+  auto Pf = [&](const char* n) { return reinterpret_cast<const float*>(pk + pp.find(n)->off); };
+  auto Wb = [&](const char* n) { return reinterpret_cast<bf16*>(ws + dp.find(n)->off); };
+  auto Wf = [&](const char* n) { return reinterpret_cast<float*>(ws + dp.find(n)->off); };
+  auto Wi = [&](const char* n) { return reinterpret_cast<int*>(ws + dp.find(n)->off); };
+  auto zero = [&](const char* n) { return cudaMemsetAsync(ws + dp.find(n)->off, 0, dp.find(n)->bytes, s); };
+  const int SK = S * K, R = B * SK, G = d.G, H = d.H, Hp = d.Hp, Fp = d.Fp, KXe = d.Fp + d.Hp, KX = d.KX, L = d.L;
+
+  CUDA_TRY(zero("XA0")); CUDA_TRY(zero("XA1")); CUDA_TRY(zero("XE")); CUDA_TRY(zero("projb")); CUDA_TRY(zero("bp_hist"));
+  if (d.tied) CUDA_TRY(zero("ob"));
+  TRY(image_prep(s, feats, B, N, d.F, Wb("featsb"), Fp, Wf("mask"), Wb("avgb")));
+  TRY(scale_rows_f32(s, d.cond ? sent : nullptr, d.mult, Wf("pm_row"), B));
+  TRY(scale_rows_f32(s, d.cond ? sent : nullptr, 1.0f, Wf("sent"), B));
+  TRY(iota_div_i32(s, Wi("rowmap"), R, SK));
+  TRY(iota_div_i32(s, Wi("rowmap0"), B, 1));
+  TRY(fill_i32(s, Wi("start_tok"), d.boundary, B));                       // updown_captioner.py:326
+  const uint32_t* fsm_bits = nullptr;
+  if (fsm) { TRY(fsm_pack(s, fsm, B, S, d.V, reinterpret_cast<uint32_t*>(Wi("fsm_bits")))); fsm_bits = reinterpret_cast<uint32_t*>(Wi("fsm_bits")); }
+  {  // once per image (the reference recomputes both every step in decode)
+    GemmSeg sg = seg(Wb("featsb"), Fp, Pb("wv"), Fp, d.F);
+    GemmEpi e; e.C16 = Wb("projb"); e.ldc16 = d.Ap;
+    TRY(gemm_bf16_tn(s, B * N, d.A, 1, &sg, e));
+    GemmSeg sa = seg(Wb("avgb"), Fp, Pb("w_att_f"), Fp, d.F);
+    GemmEpi ea; ea.C32 = Wf("gavg"); ea.ldc32 = G; ea.bias = Pf("b_att");
+    TRY(gemm_bf16_tn(s, B, G, 1, &sa, ea));
+  }
+  int* tok_hist = Wi("tok_hist"); int* bp_hist = Wi("bp_hist"); float* score_hist = Wf("score_hist");
+  bf16* XA[2] = {Wb("XA0"), Wb("XA1")};
+  float* c1[2] = {Wf("c1a"), Wf("c1b")};
+  float* cd[2] = {Wf("cda"), Wf("cdb")};
+
+  auto cell = [&](int rows, const int* tokens, const int* rowmap, bool first, const float* eps_t, int eps_stride,
+                  int step) -> int {
+    // in = index 0, out = index 1
+    TRY(embed_gather_rows(s, tokens, rows, Pb("embb"), d.Ep, Wb("embb_r")));
+    {
+      GemmSeg sg[2] = {seg(Wb("embb_r"), d.Ep, Pb("w_att_e"), d.Ep, d.E), seg(XA[0], 2 * Hp, Pb("w_att_rec"), 2 * Hp, 2 * Hp)};
+      GemmEpi e; e.C32 = Wf("acc"); e.ldc32 = G;
+      TRY(gemm_bf16_tn(s, rows, G, first ? 1 : 2, sg, e));
+      LstmFwdArgs l = {};
+      l.R = rows; l.H = H; l.acc = Wf("acc"); l.ld_acc = G; l.add2 = Wf("gavg"); l.ld2 = G; l.rowmap = rowmap;
+      l.c_prev = first ? nullptr : c1[0]; l.c_out = c1[1];
+      l.h1_dst = Wb("XE") + Fp; l.ld_h1 = KXe; l.h2_dst = XA[1]; l.ld_h2 = 2 * Hp;
+      TRY(lstm_forward(s, l));
+    }
+    {
+      GemmSeg sg = seg(Wb("XE") + Fp, KXe, Pb("wq"), Hp, Hp);
+      GemmEpi e; e.C32 = Wf("q"); e.ldc32 = d.A;
+      TRY(gemm_bf16_tn(s, rows, d.A, 1, &sg, e));
+      AttnArgs aa; aa.R = rows; aa.N = N; aa.A = d.A; aa.Ap = d.Ap; aa.F = d.F; aa.Fp = Fp; aa.rowmap = rowmap;
+      aa.q = Wf("q"); aa.ld_q = d.A; aa.proj = Wb("projb"); aa.feats = Wb("featsb"); aa.mask = Wf("mask");
+      aa.w_a = W(SSCVAE_W_ATT_VEC);
+      TRY(attention_forward(s, aa, Wf("alpha"), Wb("XE"), KXe));
+    }
+    {  // eval: z ~ N(prior_mean, prior_var) (updown_cell.py:200-208); no encoder LSTM
+      LatentArgs la; la.R = rows; la.Z = d.Z; la.Zp = d.Zp; la.sentiment_vae = d.sv; la.prior_var = d.prior_std * d.prior_std;
+      la.prior_mean_row = Wf("pm_row"); la.rowmap = rowmap;
+      TRY(latent_forward_eval(s, la, eps_t, eps_stride, seed, (unsigned long long)step, Wb("ZB"), d.Zp));
+    }
+    {
+      GemmSeg sg[3] = {seg(Wb("XE"), KXe, Pb("w_dec_x"), KX, KXe),
+                       seg(Wb("ZB"), d.Zp, Pb("w_dec_z"), d.Zp, d.Zp),
+                       seg(XA[0] + Hp, 2 * Hp, Pb("w_dec_x") + KXe, KX, Hp)};
+      GemmEpi e; e.C32 = Wf("acc"); e.ldc32 = G;
+      TRY(gemm_bf16_tn(s, rows, G, first ? 2 : 3, sg, e));
+      LstmFwdArgs l = {};
+      l.R = rows; l.H = H; l.acc = Wf("acc"); l.ld_acc = G; l.bias = Pf("b_dec"); l.rowmap = rowmap;
+      if (d.cond) { l.sent = Wf("sent"); l.scol = Pf("scol_dec"); }
+      l.c_prev = first ? nullptr : cd[0]; l.c_out = cd[1];
+      l.h1_dst = XA[1] + Hp; l.ld_h1 = 2 * Hp;
+      TRY(lstm_forward(s, l));
+    }
+    if (d.tied) {
+      GemmSeg sg = seg(XA[1] + Hp, 2 * Hp, Pb("w_out"), Hp, Hp);
+      GemmEpi e; e.bias = W(SSCVAE_W_OUT_PROJ_B); e.act = 1; e.C16 = Wb("ob"); e.ldc16 = d.Ep;
+      TRY(gemm_bf16_tn(s, rows, d.E, 1, &sg, e));
+      GemmSeg sv = seg(Wb("ob"), d.Ep, Pb("embb"), d.Ep, d.E);
+      GemmEpi ev; ev.C32 = Wf("logits"); ev.ldc32 = d.V;
+      TRY(gemm_bf16_tn(s, rows, d.V, 1, &sv, ev));
+    } else {
+      GemmSeg sg = seg(XA[1] + Hp, 2 * Hp, Pb("w_out"), Hp, Hp);
+      GemmEpi e; e.bias = W(SSCVAE_W_OUT_PROJ_B); e.C32 = Wf("logits"); e.ldc32 = d.V;
+      TRY(gemm_bf16_tn(s, rows, d.V, 1, &sg, e));
+    }
+    return 0;
+  };
+
+  // ---- step 0: one row per image, zero states (cbs.py:127-155)
+  TRY(cell(B, Wi("start_tok"), Wi("rowmap0"), true, eps, SK, 0));
+  {
+    SearchRowsArgs a = {};
+    a.logp = Wf("logits"); a.ld = d.V; a.V = d.V; a.normalized = 0; a.fsm_bits = fsm_bits; a.R = B; a.S = S; a.K = K;
+    a.rows_per_image = 1; a.P = K; a.end_index = d.boundary; a.neg_value = -INFINITY;
+    a.cand_val = score_hist; a.cand_tok = tok_hist;
+    TRY(search_rows(s, a));
+  }
+  TRY(gather_rows_bf16(s, XA[1], Wi("rowmap"), R, 2 * Hp, 2 * Hp, XA[0]));
+  TRY(gather_rows_f32(s, c1[1], Wi("rowmap"), R, H, c1[0]));
+  TRY(gather_rows_f32(s, cd[1], Wi("rowmap"), R, H, cd[0]));
+  // ---- steps 1..L-1 on all R rows (cbs.py:161-250); the early exit is resolved at the end
+  for (int t = 1; t < L; ++t) {
+    TRY(cell(R, tok_hist + (size_t)(t - 1) * R, Wi("rowmap"), false, eps ? eps + (size_t)t * R * d.Z : nullptr, 1, t));
+    SearchRowsArgs a = {};
+    a.logp = Wf("logits"); a.ld = d.V; a.V = d.V; a.normalized = 0; a.fsm_bits = fsm_bits; a.R = R; a.S = S; a.K = K;
+    a.rows_per_image = SK; a.P = P; a.end_index = d.boundary; a.neg_value = -1e20f;
+    a.last_tokens = tok_hist + (size_t)(t - 1) * R; a.last_scores = score_hist + (size_t)(t - 1) * R;
+    a.cand_val = Wf("cand_val"); a.cand_tok = Wi("cand_tok");
+    TRY(search_rows(s, a));
+    TRY(search_merge(s, Wf("cand_val"), Wi("cand_tok"), B, S, K, P, tok_hist + (size_t)t * R, bp_hist + (size_t)t * R,
+                     score_hist + (size_t)t * R));
+    TRY(state_gather(s, bp_hist + (size_t)t * R, R, SK, XA[1], XA[0], 2 * Hp, c1[1], c1[0], cd[1], cd[0], H));
+  }
+  TRY(search_finish(s, tok_hist, bp_hist, score_hist, L, B, S, K, d.boundary, num_constraints, min_sat, predictions,
+                    log_probs, best, n_steps));
+  return 0;
+}
+
+}  // namespace sscvae
+
+using namespace sscvae;
+
+extern "C" {
+
+int sscvae_fsm_pack(const uint8_t* fsm, int batch, int states, int vocab, uint32_t* fsm_bits, void* stream) {
+  REQUIRE(fsm && fsm_bits && batch > 0 && vocab > 0, "bad argument");
+  return fsm_pack(reinterpret_cast<cudaStream_t>(stream), fsm, batch, states, vocab, fsm_bits);
+}
+
+int sscvae_search_first_step(const float* logp, int batch, int states, int beam, int vocab, const uint32_t* fsm_bits,
+                             int normalized, int32_t* tokens, float* scores, void* stream) {
+  REQUIRE(logp && tokens && scores, "NULL argument");
+  SearchRowsArgs a = {};
+  a.logp = logp; a.ld = vocab; a.V = vocab; a.normalized = normalized; a.fsm_bits = fsm_bits; a.R = batch; a.S = states;
+  a.K = beam; a.rows_per_image = 1; a.P = beam; a.end_index = -1; a.neg_value = -INFINITY;
+  a.cand_val = scores; a.cand_tok = tokens;
+  return search_rows(reinterpret_cast<cudaStream_t>(stream), a);
+}
+
+size_t sscvae_search_scratch_bytes(int batch, int states, int beam, int per_node) {
+  return (size_t)batch * states * beam * states * per_node * 8 + 1024;
+}
+
+int sscvae_search_step(const float* logp, int batch, int states, int beam, int per_node, int vocab,
+                       const uint32_t* fsm_bits, int normalized, int end_index, const int32_t* last_tokens,
+                       const float* last_scores, void* scratch, size_t scratch_bytes, int32_t* tokens, int32_t* backptr,
+                       float* scores, void* stream) {
+  REQUIRE(logp && last_tokens && last_scores && scratch && tokens && backptr && scores, "NULL argument");
+  const int R = batch * states * beam;
+  const size_t n = (size_t)R * states * per_node;
+  if (scratch_bytes < n * 8) { set_error("search scratch too small"); return SSCVAE_ERR_WORKSPACE; }
+  float* cand_val = reinterpret_cast<float*>(scratch);
+  int32_t* cand_tok = reinterpret_cast<int32_t*>(cand_val + n);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  SearchRowsArgs a = {};
+  a.logp = logp; a.ld = vocab; a.V = vocab; a.normalized = normalized; a.fsm_bits = fsm_bits; a.R = R; a.S = states;
+  a.K = beam; a.rows_per_image = states * beam; a.P = per_node; a.end_index = end_index; a.neg_value = -1e20f;
+  a.last_tokens = last_tokens; a.last_scores = last_scores; a.cand_val = cand_val; a.cand_tok = cand_tok;
+  TRY(search_rows(st, a));
+  return search_merge(st, cand_val, cand_tok, batch, states, beam, per_node, tokens, backptr, scores);
+}
+
+int sscvae_search_finish(const int32_t* tokens_hist, const int32_t* backptr_hist, const float* scores_hist, int steps_run,
+                         int batch, int states, int beam, int end_index, const int64_t* num_constraints,
+                         int min_constraints_to_satisfy, int64_t* predictions, float* final_scores, int64_t* best,
+                         int32_t* n_steps, void* stream) {
+  REQUIRE(tokens_hist && backptr_hist && scores_hist && predictions && final_scores && best && n_steps, "NULL argument");
+  return search_finish(reinterpret_cast<cudaStream_t>(stream), tokens_hist, backptr_hist, scores_hist, steps_run, batch,
+                       states, beam, end_index, reinterpret_cast<const long long*>(num_constraints),
+                       min_constraints_to_satisfy, reinterpret_cast<long long*>(predictions), final_scores,
+                       reinterpret_cast<long long*>(best), n_steps);
+}
+
+size_t sscvae_decode_workspace_bytes(const SscvaeHandle* hh, int batch, int num_boxes, int states, int beam) {
+  Handle* h = const_cast<Handle*>(reinterpret_cast<const Handle*>(hh));
+  if (!h || batch <= 0 || num_boxes <= 0 || states <= 0 || beam <= 0) return 0;
+  return h->decode_plan(batch, num_boxes, states, beam).total;
+}
+
+int sscvae_decode(SscvaeHandle* hh, int batch, int num_boxes, int states, int beam, int per_node, const void* packed,
+                  const void* const* weights, const float* image_features, const float* sentiment, const uint8_t* fsm,
+                  const int64_t* num_constraints, int min_constraints_to_satisfy, const float* eps, uint64_t seed,
+                  void* workspace, size_t workspace_bytes, int64_t* predictions, float* log_probs, int64_t* best,
+                  int32_t* n_steps, void* stream) {
+  Handle* h = reinterpret_cast<Handle*>(hh);
+  REQUIRE(h && packed && weights && image_features && workspace && predictions && log_probs && best && n_steps, "NULL argument");
+  return decode_impl(h, batch, num_boxes, states, beam, per_node, reinterpret_cast<const char*>(packed), weights,
+                     image_features, sentiment, fsm, reinterpret_cast<const long long*>(num_constraints),
+                     min_constraints_to_satisfy, eps, seed, reinterpret_cast<char*>(workspace), workspace_bytes,
+                     reinterpret_cast<long long*>(predictions), log_probs, reinterpret_cast<long long*>(best), n_steps,
+                     reinterpret_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

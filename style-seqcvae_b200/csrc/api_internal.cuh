@@ -1,0 +1,39 @@
+// Internal declarations shared by the C-ABI translation units.
+#pragma once
+#include <algorithm>
+#include <cstring>
+#include <initializer_list>
+#include <vector>
+#include "../../include/sscvae.h"
+#include "common.cuh"
+#include "gemm.cuh"
+#include "kernels.cuh"
+
+namespace sscvae {
+
+struct Dims {
+  int F, E, H, A, Z, V, L, T;
+  int sv, simple, tied, pad, boundary, cond;
+  float prior_std, mult;
+  int Fp, Ep, Hp, Ap, Zp, Vp, G, Gp, Z2, Z2p, KX;
+};
+int init_dims(const SscvaeDims* in, Dims& d);
+
+struct Region { const char* name; size_t off, bytes; };
+struct Plan {
+  std::vector<Region> regs;
+  size_t total = 0;
+  void add(const char* name, size_t bytes);
+  const Region* find(const char* name) const;
+};
+
+struct Handle {
+  Dims d;
+  Plan pp;                 // packed weights
+  Plan tp; int tp_B = -1, tp_N = -1;   // training workspace for the last (B,N)
+  Plan dp; int dp_B = -1, dp_N = -1, dp_S = -1, dp_K = -1;   // decode workspace
+  const Plan& train_plan(int B, int N);
+  const Plan& decode_plan(int B, int N, int S, int K);
+};
+
+}  // namespace sscvae

@@ -1,0 +1,721 @@
+// C ABI: handle, weight packing, training forward and backward-through-time (include/sscvae.h).
+//
+// Data layout in HBM (all time-stacked buffers are time-major, row r = t*B + b):
+//   XA  ((T+1)B, 2Hp) bf16  [h1_{t-1} | h_dec_{t-1}]            operand of the attention-LSTM recurrence
+//   XE  (TB, Fp+2Hp)  bf16  [xhat_t | h1_t | h_dec_{t-1}]       operand of the encoder / decoder LSTMs
+//   HE  ((T+1)B, Hp)  bf16  h_enc_{t-1}                         encoder hidden operand / fc input
+//   ZB  (TB, Zp)      bf16  z_t
+// Hidden states exist only as bf16 GEMM operands (written once by the LSTM pointwise kernel into
+// every buffer that consumes them); cell states, gate activations, softmax/KL/CE stay fp32.
+// "p" suffixes are sizes rounded up to 8 elements so every row stride is a multiple of 16 bytes (TMA).
+#include "api_internal.cuh"
+
+namespace sscvae {
+
+// ---- error string ------------------------------------------------------------------------------
+static thread_local char g_err[1024] = "";
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+const char* get_error() { return g_err; }
+
+// ---- dims --------------------------------------------------------------------------------------
+int init_dims(const SscvaeDims* in, Dims& d) {
+  REQUIRE(in != nullptr, "dims is NULL");
+  d.F = in->image_feature_size; d.E = in->embedding_size; d.H = in->hidden_size;
+  d.A = in->attention_projection_size; d.Z = in->z_space; d.V = in->vocab_size; d.L = in->max_caption_length;
+  d.sv = in->sentiment_vae; d.simple = in->simple_vae; d.tied = in->tied_embedding;
+  d.pad = in->pad_index; d.boundary = in->boundary_index; d.prior_std = in->prior_std; d.mult = in->senti_prior_multip;
+  REQUIRE(d.F > 0 && d.E > 0 && d.H > 0 && d.A > 0 && d.Z > 0 && d.V > 1 && d.L > 0, "non-positive dimension");
+  if (d.sv != 0 && d.sv != 1) {
+    set_error("sentiment_vae=%d unsupported (only 0 and 1; 2 is SURVEY §8(f)-4)", d.sv);
+    return SSCVAE_ERR_UNSUPPORTED;
+  }
+  REQUIRE(d.pad >= 0 && d.pad < d.V && d.boundary >= 0 && d.boundary < d.V, "pad/boundary index out of range");
+  REQUIRE(d.prior_std > 0.f, "prior_std must be positive");
+  d.T = d.L + 1;
+  d.cond = (d.simple || d.sv == 0) ? 0 : 1;
+  d.Fp = round_up(d.F, 8); d.Ep = round_up(d.E, 8); d.Hp = round_up(d.H, 8); d.Ap = round_up(d.A, 8);
+  d.Zp = round_up(d.Z, 8); d.Vp = round_up(d.V, 8);
+  d.G = 4 * d.H; d.Gp = round_up(d.G, 8); d.Z2 = 2 * d.Z; d.Z2p = round_up(d.Z2, 8);
+  d.KX = d.Fp + 2 * d.Hp;
+  return 0;
+}
+
+// ---- region planner ----------------------------------------------------------------------------
+void Plan::add(const char* name, size_t bytes) {
+  Region r; r.name = name; r.off = total; r.bytes = bytes;
+  regs.push_back(r);
+  total += round_up_sz(bytes, 1024);
+}
+const Region* Plan::find(const char* name) const {
+  for (const Region& r : regs)
+    if (strcmp(r.name, name) == 0) return &r;
+  return nullptr;
+}
+
+static void plan_packed(const Dims& d, Plan& p) {
+  const size_t b = sizeof(bf16);
+  p.add("embb", (size_t)d.V * d.Ep * b);
+  if (d.tied) p.add("embT", (size_t)d.E * d.Vp * b);
+  p.add("w_att_e", (size_t)d.G * d.Ep * b);
+  p.add("w_att_eT", (size_t)d.Ep * d.Gp * b);
+  p.add("w_att_f", (size_t)d.G * d.Fp * b);
+  p.add("w_att_rec", (size_t)d.G * 2 * d.Hp * b);
+  p.add("w_att_recT", (size_t)2 * d.Hp * d.Gp * b);
+  p.add("wq", (size_t)d.A * d.Hp * b);
+  p.add("wqT", (size_t)d.Hp * d.Ap * b);
+  p.add("wv", (size_t)d.A * d.Fp * b);
+  p.add("w_enc_x", (size_t)d.G * d.KX * b);
+  p.add("w_enc_xT", (size_t)d.KX * d.Gp * b);
+  p.add("w_enc_hh", (size_t)d.G * d.Hp * b);
+  p.add("w_enc_hhT", (size_t)d.Hp * d.Gp * b);
+  p.add("w_dec_x", (size_t)d.G * d.KX * b);
+  p.add("w_dec_xT", (size_t)d.KX * d.Gp * b);
+  p.add("w_dec_z", (size_t)d.G * d.Zp * b);
+  p.add("w_dec_zT", (size_t)d.Zp * d.Gp * b);
+  p.add("w_fc", (size_t)d.Z2 * d.Hp * b);
+  p.add("w_fcT", (size_t)d.Hp * d.Z2p * b);
+  const int NO = d.tied ? d.E : d.V, NOp = d.tied ? d.Ep : d.Vp;
+  p.add("w_out", (size_t)NO * d.Hp * b);
+  p.add("w_outT", (size_t)d.Hp * NOp * b);
+  p.add("b_att", (size_t)d.G * 4);
+  p.add("b_enc", (size_t)d.G * 4);
+  p.add("b_dec", (size_t)d.G * 4);
+  p.add("scol_enc", (size_t)d.G * 4);
+  p.add("scol_dec", (size_t)d.G * 4);
+  p.add("b_fc", (size_t)d.Z2 * 4);
+}
+
+static void plan_train(const Dims& d, int B, int N, Plan& p) {
+  const size_t b = sizeof(bf16), f = 4;
+  const size_t T = d.T, TB = T * B, TBp = round_up((int)TB, 8), BN = (size_t)B * N, BNp = round_up((int)BN, 8);
+  const size_t Bp = round_up(B, 8);
+  // ---- forward, kept for backward
+  p.add("tok", (size_t)B * (d.L + 2) * 4);
+  p.add("tmask", TB * f);
+  p.add("lengths", B * f);
+  p.add("pm_row", B * f);
+  p.add("sent", B * f);
+  p.add("featsb", BN * d.Fp * b);
+  p.add("mask", BN * f);
+  p.add("avgb", (size_t)B * d.Fp * b);
+  p.add("projb", BN * d.Ap * b);
+  p.add("embb_t", TB * d.Ep * b);
+  p.add("gx_att", TB * d.G * f);
+  p.add("gavg", (size_t)B * d.G * f);
+  p.add("XA", (T + 1) * B * 2 * d.Hp * b);
+  p.add("XE", TB * d.KX * b);
+  p.add("HE", (T + 1) * B * d.Hp * b);
+  p.add("ZB", TB * d.Zp * b);
+  p.add("acc", (size_t)B * d.G * f);
+  p.add("gates_att", TB * d.G * f);
+  p.add("gates_enc", TB * d.G * f);
+  p.add("gates_dec", TB * d.G * f);
+  p.add("c1", TB * d.H * f);
+  p.add("c_enc", TB * d.H * f);
+  p.add("c_dec", TB * d.H * f);
+  p.add("q", TB * d.A * f);
+  p.add("alpha", TB * N * f);
+  p.add("ml", (size_t)B * d.Z2 * f);
+  p.add("mean", TB * d.Z * f);
+  p.add("logvar", TB * d.Z * f);
+  p.add("eps", TB * d.Z * f);
+  p.add("kl", TB * f);
+  if (d.tied) {
+    p.add("ob", TB * d.Ep * b);
+    p.add("o32", TB * d.E * f);
+  }
+  p.add("logits", TB * d.V * f);
+  p.add("lse", TB * f);
+  p.add("nll", TB * f);
+  // ---- backward
+  p.add("dlogits", TB * d.Vp * b);
+  if (d.tied) p.add("dpreo", TB * d.Ep * b);
+  p.add("dhead", TB * d.H * f);
+  p.add("dG_att", TB * d.Gp * b);
+  p.add("dG_enc", TB * d.Gp * b);
+  p.add("dG_dec", TB * d.Gp * b);
+  p.add("dml", TB * d.Z2p * b);
+  p.add("dqb", TB * d.Ap * b);
+  p.add("dXE0", (size_t)B * d.KX * f);
+  p.add("dXE1", (size_t)B * d.KX * f);
+  p.add("dXA0", (size_t)B * 2 * d.Hp * f);
+  p.add("dXA1", (size_t)B * 2 * d.Hp * f);
+  p.add("dhenc_fc", (size_t)B * d.H * f);
+  p.add("dhenc_hh0", (size_t)B * d.H * f);
+  p.add("dhenc_hh1", (size_t)B * d.H * f);
+  p.add("dh1_q", (size_t)B * d.H * f);
+  p.add("dz", (size_t)B * d.Z * f);
+  p.add("dc1", (size_t)B * d.H * f);
+  p.add("dc_enc", (size_t)B * d.H * f);
+  p.add("dc_dec", (size_t)B * d.H * f);
+  p.add("dproj_acc", BN * d.A * f);
+  p.add("dwa_acc", (size_t)B * d.A * f);
+  // ---- transposed operands of the batched-over-time weight-gradient GEMMs
+  p.add("dGT", (size_t)d.G * TBp * b);
+  p.add("XAT", (size_t)2 * d.Hp * TBp * b);
+  p.add("XET", (size_t)d.KX * TBp * b);
+  p.add("HETp", (size_t)d.Hp * TBp * b);
+  p.add("HETc", (size_t)d.Hp * TBp * b);
+  p.add("hdecTc", (size_t)d.Hp * TBp * b);
+  p.add("ZBT", (size_t)d.Zp * TBp * b);
+  p.add("embT_t", (size_t)d.Ep * TBp * b);
+  p.add("dmlT", (size_t)d.Z2p * TBp * b);
+  p.add("dqT", (size_t)d.Ap * TBp * b);
+  if (d.tied) p.add("dpreoT", (size_t)d.Ep * TBp * b);
+  else {
+    p.add("dlogitsT", (size_t)d.V * TBp * b);
+    p.add("dxemb", TB * d.E * f);
+  }
+  p.add("dGsum", (size_t)B * d.Gp * b);
+  p.add("dGsumT", (size_t)d.G * Bp * b);
+  p.add("avgT", (size_t)d.Fp * Bp * b);
+  p.add("dPT", (size_t)d.A * BNp * b);
+  p.add("featsT", (size_t)d.Fp * BNp * b);
+  p.add("biasg", (size_t)std::max(d.G, std::max(d.V, d.E)) * f);
+}
+
+const Plan& Handle::train_plan(int B, int N) {
+  if (tp_B != B || tp_N != N) {
+    tp = Plan();
+    plan_train(d, B, N, tp);
+    tp_B = B; tp_N = N;
+  }
+  return tp;
+}
+
+// ---- weight packing ----------------------------------------------------------------------------
+static int pack_weights_impl(Handle* h, const void* const* wv, char* pk, cudaStream_t s) {
+  const Dims& d = h->d;
+  const Plan& pp = h->pp;
+  auto W = [&](int i) { return reinterpret_cast<const float*>(wv[i]); };
+  auto Pb = [&](const char* n) { return reinterpret_cast<bf16*>(pk + pp.find(n)->off); };
+  auto Pf = [&](const char* n) { return reinterpret_cast<float*>(pk + pp.find(n)->off); };
+  for (int i = 0; i < SSCVAE_W_COUNT; ++i) REQUIRE(wv[i] != nullptr, "weight pointer %d is NULL", i);
+  CUDA_TRY(cudaMemsetAsync(pk, 0, pp.total, s));
+  const int E = d.E, F = d.F, H = d.H, A = d.A, Z = d.Z, V = d.V, G = d.G, c = d.cond;
+  // embedding (gather source and, tied, the vocabulary GEMM operand)
+  TRY(pack_block(s, Pb("embb"), d.Ep, 0, W(SSCVAE_W_EMBEDDING), E, V, E, nullptr, 0));
+  if (d.tied) TRY(pack_block(s, Pb("embT"), d.Vp, 1, W(SSCVAE_W_EMBEDDING), E, V, E, nullptr, 0));
+  // attention LSTM: W_ih columns [emb E | avg F | h1 H | h_dec H] (updown_cell.py:143-145); W_hh folded onto h1
+  const int ldi = E + F + 2 * H;
+  const float* wih = W(SSCVAE_W_ATT_IH);
+  TRY(pack_block(s, Pb("w_att_e"), d.Ep, 0, wih, ldi, G, E, nullptr, 0));
+  TRY(pack_block(s, Pb("w_att_eT"), d.Gp, 1, wih, ldi, G, E, nullptr, 0));
+  TRY(pack_block(s, Pb("w_att_f"), d.Fp, 0, wih + E, ldi, G, F, nullptr, 0));
+  TRY(pack_block(s, Pb("w_att_rec"), 2 * d.Hp, 0, wih + E + F, ldi, G, H, W(SSCVAE_W_ATT_HH), H));
+  TRY(pack_block(s, Pb("w_att_rec") + d.Hp, 2 * d.Hp, 0, wih + E + F + H, ldi, G, H, nullptr, 0));
+  TRY(pack_block(s, Pb("w_att_recT"), d.Gp, 1, wih + E + F, ldi, G, H, W(SSCVAE_W_ATT_HH), H));
+  TRY(pack_block(s, Pb("w_att_recT") + (size_t)d.Hp * d.Gp, d.Gp, 1, wih + E + F + H, ldi, G, H, nullptr, 0));
+  TRY(vec_add_f32(s, W(SSCVAE_W_ATT_BIH), W(SSCVAE_W_ATT_BHH), Pf("b_att"), G));
+  // attention
+  TRY(pack_block(s, Pb("wq"), d.Hp, 0, W(SSCVAE_W_QUERY_PROJ), H, A, H, nullptr, 0));
+  TRY(pack_block(s, Pb("wqT"), d.Ap, 1, W(SSCVAE_W_QUERY_PROJ), H, A, H, nullptr, 0));
+  TRY(pack_block(s, Pb("wv"), d.Fp, 0, W(SSCVAE_W_IMAGE_PROJ), F, A, F, nullptr, 0));
+  // encoder LSTM: W_ih columns [xhat F | h1 H | h_dec H | cond c] (updown_cell.py:178-190)
+  const int lde = F + 2 * H + c;
+  const float* we = W(SSCVAE_W_ENC_IH);
+  bf16* wex = Pb("w_enc_x"); bf16* wexT = Pb("w_enc_xT");
+  const int offs_src[3] = {0, F, F + H};
+  const int offs_dst[3] = {0, d.Fp, d.Fp + d.Hp};
+  const int widths[3] = {F, H, H};
+  for (int k = 0; k < 3; ++k) {
+    TRY(pack_block(s, wex + offs_dst[k], d.KX, 0, we + offs_src[k], lde, G, widths[k], nullptr, 0));
+    TRY(pack_block(s, wexT + (size_t)offs_dst[k] * d.Gp, d.Gp, 1, we + offs_src[k], lde, G, widths[k], nullptr, 0));
+  }
+  TRY(pack_block(s, Pb("w_enc_hh"), d.Hp, 0, W(SSCVAE_W_ENC_HH), H, G, H, nullptr, 0));
+  TRY(pack_block(s, Pb("w_enc_hhT"), d.Gp, 1, W(SSCVAE_W_ENC_HH), H, G, H, nullptr, 0));
+  TRY(vec_add_f32(s, W(SSCVAE_W_ENC_BIH), W(SSCVAE_W_ENC_BHH), Pf("b_enc"), G));
+  if (c) TRY(copy_block_f32(s, we + F + 2 * H, lde, Pf("scol_enc"), 1, G, 1));
+  // decoder LSTM: W_ih columns [xhat F | h1 H | h_dec H | cond c | z Z] (updown_cell.py:211-224); W_hh folded onto h_dec
+  const int ldd = F + 2 * H + c + Z;
+  const float* wd = W(SSCVAE_W_DEC_IH);
+  bf16* wdx = Pb("w_dec_x"); bf16* wdxT = Pb("w_dec_xT");
+  for (int k = 0; k < 3; ++k) {
+    const float* fold = (k == 2) ? W(SSCVAE_W_DEC_HH) : nullptr;
+    TRY(pack_block(s, wdx + offs_dst[k], d.KX, 0, wd + offs_src[k], ldd, G, widths[k], fold, H));
+    TRY(pack_block(s, wdxT + (size_t)offs_dst[k] * d.Gp, d.Gp, 1, wd + offs_src[k], ldd, G, widths[k], fold, H));
+  }
+  TRY(pack_block(s, Pb("w_dec_z"), d.Zp, 0, wd + F + 2 * H + c, ldd, G, Z, nullptr, 0));
+  TRY(pack_block(s, Pb("w_dec_zT"), d.Gp, 1, wd + F + 2 * H + c, ldd, G, Z, nullptr, 0));
+  TRY(vec_add_f32(s, W(SSCVAE_W_DEC_BIH), W(SSCVAE_W_DEC_BHH), Pf("b_dec"), G));
+  if (c) TRY(copy_block_f32(s, wd + F + 2 * H, ldd, Pf("scol_dec"), 1, G, 1));
+  // latent heads stacked [fc_mean ; fc_log_var]
+  TRY(pack_block(s, Pb("w_fc"), d.Hp, 0, W(SSCVAE_W_FC_MEAN_W), H, Z, H, nullptr, 0));
+  TRY(pack_block(s, Pb("w_fc") + (size_t)Z * d.Hp, d.Hp, 0, W(SSCVAE_W_FC_LOGVAR_W), H, Z, H, nullptr, 0));
+  TRY(pack_block(s, Pb("w_fcT"), d.Z2p, 1, W(SSCVAE_W_FC_MEAN_W), H, Z, H, nullptr, 0));
+  TRY(pack_block(s, Pb("w_fcT") + Z, d.Z2p, 1, W(SSCVAE_W_FC_LOGVAR_W), H, Z, H, nullptr, 0));
+  TRY(copy_block_f32(s, W(SSCVAE_W_FC_MEAN_B), 1, Pf("b_fc"), 1, Z, 1));
+  TRY(copy_block_f32(s, W(SSCVAE_W_FC_LOGVAR_B), 1, Pf("b_fc") + Z, 1, Z, 1));
+  // output head
+  const int NO = d.tied ? E : V, NOp = d.tied ? d.Ep : d.Vp;
+  TRY(pack_block(s, Pb("w_out"), d.Hp, 0, W(SSCVAE_W_OUT_PROJ_W), H, NO, H, nullptr, 0));
+  TRY(pack_block(s, Pb("w_outT"), NOp, 1, W(SSCVAE_W_OUT_PROJ_W), H, NO, H, nullptr, 0));
+  return 0;
+}
+
+// ---- small helpers -----------------------------------------------------------------------------
+static inline GemmSeg seg(const bf16* A, int lda, const bf16* B, int ldb, int K) {
+  GemmSeg s; s.A = A; s.lda = lda; s.B = B; s.ldb = ldb; s.K = K; return s;
+}
+
+// ---- training forward --------------------------------------------------------------------------
+static int train_forward_impl(Handle* h, int B, int N, const char* pk, const void* const* wv, const float* feats,
+                              const long long* cap, const float* sent, const float* eps, unsigned long long seed,
+                              char* ws, size_t ws_bytes, float* loss, float* kld, cudaStream_t s) {
+  const Dims& d = h->d;
+  REQUIRE(B > 0 && N > 0, "batch/num_boxes must be positive");
+  REQUIRE(d.cond == 0 || sent != nullptr, "sentiment is required when sentiment_vae == 1");
+  const Plan& tp = h->train_plan(B, N);
+  if (ws_bytes < tp.total) { set_error("workspace too small: %zu < %zu", ws_bytes, tp.total); return SSCVAE_ERR_WORKSPACE; }
+  REQUIRE((reinterpret_cast<uintptr_t>(ws) & 255) == 0 && (reinterpret_cast<uintptr_t>(pk) & 255) == 0,
+          "workspace and packed weights must be 256-byte aligned");
+  const Plan& pp = h->pp;
+  auto W = [&](int i) { return reinterpret_cast<const float*>(wv[i]); };
+  auto Pb = [&](const char* n) { return reinterpret_cast<const bf16*>(pk + pp.find(n)->off); };
+  auto Pf = [&](const char* n) { return reinterpret_cast<const float*>(pk + pp.find(n)->off); };
+  auto Wb = [&](const char* n) { return reinterpret_cast<bf16*>(ws + tp.find(n)->off); };
+  auto Wf = [&](const char* n) { return reinterpret_cast<float*>(ws + tp.find(n)->off); };
+  auto Wi = [&](const char* n) { return reinterpret_cast<int*>(ws + tp.find(n)->off); };
+  auto zero = [&](const char* n) { return cudaMemsetAsync(ws + tp.find(n)->off, 0, tp.find(n)->bytes, s); };
+  const int T = d.T, TB = T * B, G = d.G, H = d.H, Hp = d.Hp, KX = d.KX, Fp = d.Fp;
+
+  // operand buffers carry zero padding columns and the zero initial states (updown_cell.py:131-140)
+  CUDA_TRY(zero("XA")); CUDA_TRY(zero("XE")); CUDA_TRY(zero("HE")); CUDA_TRY(zero("projb"));
+  if (d.tied) CUDA_TRY(zero("ob"));
+
+  int* tok = Wi("tok");
+  float* tmask = Wf("tmask");
+  TRY(boundary_tokens(s, cap, B, d.L, d.pad, d.boundary, tok, tmask, Wf("lengths")));
+  TRY(image_prep(s, feats, B, N, d.F, Wb("featsb"), Fp, Wf("mask"), Wb("avgb")));
+  TRY(scale_rows_f32(s, d.cond ? sent : nullptr, d.mult, Wf("pm_row"), B));    // prior mean (updown_captioner.py:253)
+  TRY(scale_rows_f32(s, d.cond ? sent : nullptr, 1.0f, Wf("sent"), B));
+  {  // P = W_v x  (attention.py:125), once per image, kept in bf16
+    GemmSeg sg = seg(Wb("featsb"), Fp, Pb("wv"), Fp, d.F);
+    GemmEpi e; e.C16 = Wb("projb"); e.ldc16 = d.Ap;
+    TRY(gemm_bf16_tn(s, B * N, d.A, 1, &sg, e));
+  }
+  TRY(embed_gather_train(s, tok, B, d.L, Pb("embb"), d.Ep, Wb("embb_t")));
+  {  // teacher-forced embedding block of the attention-LSTM gates for all T at once
+    GemmSeg sg = seg(Wb("embb_t"), d.Ep, Pb("w_att_e"), d.Ep, d.E);
+    GemmEpi e; e.C32 = Wf("gx_att"); e.ldc32 = G;
+    TRY(gemm_bf16_tn(s, TB, G, 1, &sg, e));
+  }
+  {  // time-invariant mean-feature block + both biases
+    GemmSeg sg = seg(Wb("avgb"), Fp, Pb("w_att_f"), Fp, d.F);
+    GemmEpi e; e.C32 = Wf("gavg"); e.ldc32 = G; e.bias = Pf("b_att");
+    TRY(gemm_bf16_tn(s, B, G, 1, &sg, e));
+  }
+  LatentArgs la; la.R = B; la.Z = d.Z; la.Zp = d.Zp; la.sentiment_vae = d.sv; la.prior_var = d.prior_std * d.prior_std;
+  la.prior_mean_row = Wf("pm_row"); la.rowmap = nullptr;
+  AttnArgs aa; aa.R = B; aa.N = N; aa.A = d.A; aa.Ap = d.Ap; aa.F = d.F; aa.Fp = Fp; aa.rowmap = nullptr;
+  aa.proj = Wb("projb"); aa.feats = Wb("featsb"); aa.mask = Wf("mask"); aa.w_a = W(SSCVAE_W_ATT_VEC); aa.ld_q = d.A;
+  float* acc = Wf("acc");
+  for (int t = 0; t < T; ++t) {
+    bf16* XA_t = Wb("XA") + (size_t)t * B * 2 * Hp;
+    bf16* XA_n = XA_t + (size_t)B * 2 * Hp;
+    bf16* XE_t = Wb("XE") + (size_t)t * B * KX;
+    bf16* XE_n = (t + 1 < T) ? XE_t + (size_t)B * KX : nullptr;
+    bf16* HE_t = Wb("HE") + (size_t)t * B * Hp;
+    bf16* HE_n = HE_t + (size_t)B * Hp;
+    bf16* ZB_t = Wb("ZB") + (size_t)t * B * d.Zp;
+    const size_t rG = (size_t)t * B * G, rH = (size_t)t * B * H;
+    {  // attention LSTM (updown_cell.py:143-148)
+      GemmSeg sg = seg(XA_t, 2 * Hp, Pb("w_att_rec"), 2 * Hp, 2 * Hp);
+      GemmEpi e; e.C32 = acc; e.ldc32 = G;
+      TRY(gemm_bf16_tn(s, B, G, 1, &sg, e));
+      LstmFwdArgs l = {};
+      l.R = B; l.H = H; l.acc = acc; l.ld_acc = G; l.add1 = Wf("gx_att") + rG; l.ld1 = G; l.add2 = Wf("gavg"); l.ld2 = G;
+      l.c_prev = t ? Wf("c1") + rH - (size_t)B * H : nullptr; l.c_out = Wf("c1") + rH; l.gates_out = Wf("gates_att") + rG;
+      l.h1_dst = XE_t + Fp; l.ld_h1 = KX; l.h2_dst = XA_n; l.ld_h2 = 2 * Hp;
+      TRY(lstm_forward(s, l));
+    }
+    {  // query projection + fused region attention (attention.py:69-93, updown_cell.py:156)
+      GemmSeg sg = seg(XE_t + Fp, KX, Pb("wq"), Hp, Hp);
+      GemmEpi e; e.C32 = Wf("q") + (size_t)t * B * d.A; e.ldc32 = d.A;
+      TRY(gemm_bf16_tn(s, B, d.A, 1, &sg, e));
+      aa.q = Wf("q") + (size_t)t * B * d.A;
+      TRY(attention_forward(s, aa, Wf("alpha") + (size_t)t * B * N, XE_t, KX));
+    }
+    {  // posterior (encoder) LSTM + latent heads + reparameterised sample (updown_cell.py:176-208)
+      GemmSeg sg[2] = {seg(XE_t, KX, Pb("w_enc_x"), KX, KX), seg(HE_t, Hp, Pb("w_enc_hh"), Hp, Hp)};
+      GemmEpi e; e.C32 = acc; e.ldc32 = G;
+      TRY(gemm_bf16_tn(s, B, G, 2, sg, e));
+      LstmFwdArgs l = {};
+      l.R = B; l.H = H; l.acc = acc; l.ld_acc = G; l.bias = Pf("b_enc");
+      if (d.cond) { l.sent = sent; l.scol = Pf("scol_enc"); }
+      l.c_prev = t ? Wf("c_enc") + rH - (size_t)B * H : nullptr; l.c_out = Wf("c_enc") + rH;
+      l.gates_out = Wf("gates_enc") + rG; l.h1_dst = HE_n; l.ld_h1 = Hp;
+      TRY(lstm_forward(s, l));
+      GemmSeg sf = seg(HE_n, Hp, Pb("w_fc"), Hp, Hp);
+      GemmEpi ef; ef.C32 = Wf("ml"); ef.ldc32 = d.Z2;
+      TRY(gemm_bf16_tn(s, B, d.Z2, 1, &sf, ef));
+      const size_t rZ = (size_t)t * B * d.Z;
+      TRY(latent_forward_train(s, la, Wf("ml"), d.Z2, Pf("b_fc"), eps ? eps + rZ : nullptr, seed, (unsigned long long)t,
+                               Wf("mean") + rZ, Wf("logvar") + rZ, Wf("eps") + rZ, ZB_t, d.Zp, Wf("kl") + (size_t)t * B));
+    }
+    {  // language (decoder) LSTM (updown_cell.py:211-229)
+      GemmSeg sg[2] = {seg(XE_t, KX, Pb("w_dec_x"), KX, KX), seg(ZB_t, d.Zp, Pb("w_dec_z"), d.Zp, d.Zp)};
+      GemmEpi e; e.C32 = acc; e.ldc32 = G;
+      TRY(gemm_bf16_tn(s, B, G, 2, sg, e));
+      LstmFwdArgs l = {};
+      l.R = B; l.H = H; l.acc = acc; l.ld_acc = G; l.bias = Pf("b_dec");
+      if (d.cond) { l.sent = sent; l.scol = Pf("scol_dec"); }
+      l.c_prev = t ? Wf("c_dec") + rH - (size_t)B * H : nullptr; l.c_out = Wf("c_dec") + rH;
+      l.gates_out = Wf("gates_dec") + rG; l.h1_dst = XA_n + Hp; l.ld_h1 = 2 * Hp;
+      if (XE_n) { l.h2_dst = XE_n + Fp + Hp; l.ld_h2 = KX; }
+      TRY(lstm_forward(s, l));
+    }
+  }
+  // output head over all T*B rows at once (updown_captioner.py:444-445)
+  const bf16* hdec_all = Wb("XA") + (size_t)B * 2 * Hp + Hp;
+  if (d.tied) {
+    GemmSeg sg = seg(hdec_all, 2 * Hp, Pb("w_out"), Hp, Hp);
+    GemmEpi e; e.bias = W(SSCVAE_W_OUT_PROJ_B); e.act = 1; e.C32 = Wf("o32"); e.ldc32 = d.E; e.C16 = Wb("ob"); e.ldc16 = d.Ep;
+    TRY(gemm_bf16_tn(s, TB, d.E, 1, &sg, e));
+    GemmSeg sv = seg(Wb("ob"), d.Ep, Pb("embb"), d.Ep, d.E);
+    GemmEpi ev; ev.C32 = Wf("logits"); ev.ldc32 = d.V;
+    TRY(gemm_bf16_tn(s, TB, d.V, 1, &sv, ev));
+  } else {
+    GemmSeg sg = seg(hdec_all, 2 * Hp, Pb("w_out"), Hp, Hp);
+    GemmEpi e; e.bias = W(SSCVAE_W_OUT_PROJ_B); e.C32 = Wf("logits"); e.ldc32 = d.V;
+    TRY(gemm_bf16_tn(s, TB, d.V, 1, &sg, e));
+  }
+  // masked cross entropy and KL sums (updown_captioner.py:315-322, 457-466)
+  TRY(ce_forward(s, Wf("logits"), d.V, TB, d.V, tok, B, d.L, tmask, Wf("lse"), Wf("nll")));
+  TRY(loss_reduce(s, Wf("nll"), Wf("kl"), tmask, Wf("lengths"), T, B, loss, kld));
+  return 0;
+}
+
+// ---- training backward (BPTT) ------------------------------------------------------------------
+static int train_backward_impl(Handle* h, int B, int N, const char* pk, const void* const* wv, char* ws, size_t ws_bytes,
+                               const float* gloss, const float* gkld, void* const* gv, void* const* events,
+                               cudaStream_t s) {
+  const Dims& d = h->d;
+  const Plan& tp = h->train_plan(B, N);
+  if (ws_bytes < tp.total) { set_error("workspace too small: %zu < %zu", ws_bytes, tp.total); return SSCVAE_ERR_WORKSPACE; }
+  const Plan& pp = h->pp;
+  auto W = [&](int i) { return reinterpret_cast<const float*>(wv[i]); };
+  auto Gr = [&](int i) { return reinterpret_cast<float*>(gv[i]); };
+  auto Pb = [&](const char* n) { return reinterpret_cast<const bf16*>(pk + pp.find(n)->off); };
+  auto Wb = [&](const char* n) { return reinterpret_cast<bf16*>(ws + tp.find(n)->off); };
+  auto Wf = [&](const char* n) { return reinterpret_cast<float*>(ws + tp.find(n)->off); };
+  auto Wi = [&](const char* n) { return reinterpret_cast<int*>(ws + tp.find(n)->off); };
+  auto zero = [&](const char* n) { return cudaMemsetAsync(ws + tp.find(n)->off, 0, tp.find(n)->bytes, s); };
+  auto event = [&](int g) -> int {
+    if (events && events[g]) CUDA_TRY(cudaEventRecord(reinterpret_cast<cudaEvent_t>(events[g]), s));
+    return 0;
+  };
+  const int T = d.T, TB = T * B, TBp = round_up(TB, 8), G = d.G, Gp = d.Gp, H = d.H, Hp = d.Hp, KX = d.KX, Fp = d.Fp;
+  const int E = d.E, F = d.F, A = d.A, Z = d.Z, V = d.V, c = d.cond, Bp = round_up(B, 8), BN = B * N, BNp = round_up(BN, 8);
+  const int* tok = Wi("tok");
+  const float* tmask = Wf("tmask");
+
+  const char* zl[] = {"dproj_acc", "dwa_acc", "dc1", "dc_enc", "dc_dec", "dXE0", "dXE1", "dXA0", "dXA1",
+                      "dhenc_hh0", "dhenc_hh1", "dG_att", "dG_enc", "dG_dec", "dqb"};
+  for (const char* n : zl) CUDA_TRY(zero(n));
+  if (d.tied) CUDA_TRY(zero("dpreo"));
+
+  // ---- head: d logits, d h_dec from the vocabulary projection
+  TRY(ce_backward(s, Wf("logits"), V, TB, V, tok, B, d.L, tmask, Wf("lengths"), Wf("lse"), gloss, Wb("dlogits"), d.Vp));
+  const bf16* hdec_all = Wb("XA") + (size_t)B * 2 * Hp + Hp;     // h_dec_t, t = 0..T-1, ld 2Hp
+  if (d.tied) {
+    GemmSeg sg = seg(Wb("dlogits"), d.Vp, Pb("embT"), d.Vp, V);
+    GemmEpi e; e.dtanh = Wf("o32"); e.ldd = E; e.C16 = Wb("dpreo"); e.ldc16 = d.Ep;
+    TRY(gemm_bf16_tn(s, TB, E, 1, &sg, e));
+    GemmSeg s2 = seg(Wb("dpreo"), d.Ep, Pb("w_outT"), d.Ep, E);
+    GemmEpi e2; e2.C32 = Wf("dhead"); e2.ldc32 = H;
+    TRY(gemm_bf16_tn(s, TB, H, 1, &s2, e2));
+  } else {
+    GemmSeg sg = seg(Wb("dlogits"), d.Vp, Pb("w_outT"), d.Vp, V);
+    GemmEpi e; e.C32 = Wf("dhead"); e.ldc32 = H;
+    TRY(gemm_bf16_tn(s, TB, H, 1, &sg, e));
+  }
+  // head weight gradients are final before the time loop starts
+  TRY(transpose_bf16(s, hdec_all, TB, H, 2 * Hp, Wb("hdecTc"), TBp));
+  if (d.tied) {
+    if (Gr(SSCVAE_W_OUT_PROJ_W) || Gr(SSCVAE_W_OUT_PROJ_B)) TRY(transpose_bf16(s, Wb("dpreo"), TB, E, d.Ep, Wb("dpreoT"), TBp));
+    if (Gr(SSCVAE_W_OUT_PROJ_W)) {
+      GemmSeg sg = seg(Wb("dpreoT"), TBp, Wb("hdecTc"), TBp, TB);
+      GemmEpi e; e.C32 = Gr(SSCVAE_W_OUT_PROJ_W); e.ldc32 = H;
+      TRY(gemm_bf16_tn(s, E, H, 1, &sg, e));
+    }
+    if (Gr(SSCVAE_W_OUT_PROJ_B)) TRY(rowsum_bf16(s, Wb("dpreoT"), E, TB, TBp, Gr(SSCVAE_W_OUT_PROJ_B), 0));
+  } else {
+    if (Gr(SSCVAE_W_OUT_PROJ_W) || Gr(SSCVAE_W_OUT_PROJ_B)) TRY(transpose_bf16(s, Wb("dlogits"), TB, V, d.Vp, Wb("dlogitsT"), TBp));
+    if (Gr(SSCVAE_W_OUT_PROJ_W)) {
+      GemmSeg sg = seg(Wb("dlogitsT"), TBp, Wb("hdecTc"), TBp, TB);
+      GemmEpi e; e.C32 = Gr(SSCVAE_W_OUT_PROJ_W); e.ldc32 = H;
+      TRY(gemm_bf16_tn(s, V, H, 1, &sg, e));
+    }
+    if (Gr(SSCVAE_W_OUT_PROJ_B)) TRY(rowsum_bf16(s, Wb("dlogitsT"), V, TB, TBp, Gr(SSCVAE_W_OUT_PROJ_B), 0));
+  }
+  TRY(event(0));
+
+  // ---- reverse time loop
+  LatentArgs la; la.R = B; la.Z = Z; la.Zp = d.Zp; la.sentiment_vae = d.sv; la.prior_var = d.prior_std * d.prior_std;
+  la.prior_mean_row = Wf("pm_row"); la.rowmap = nullptr;
+  AttnArgs aa; aa.R = B; aa.N = N; aa.A = A; aa.Ap = d.Ap; aa.F = F; aa.Fp = Fp; aa.rowmap = nullptr;
+  aa.proj = Wb("projb"); aa.feats = Wb("featsb"); aa.mask = Wf("mask"); aa.w_a = W(SSCVAE_W_ATT_VEC); aa.ld_q = A;
+  float* dXE[2] = {Wf("dXE0"), Wf("dXE1")};
+  float* dXA[2] = {Wf("dXA0"), Wf("dXA1")};
+  float* dhh[2] = {Wf("dhenc_hh0"), Wf("dhenc_hh1")};
+  for (int t = T - 1; t >= 0; --t) {
+    const int cur = t & 1, nxt = cur ^ 1;
+    const size_t rG = (size_t)t * B * G, rH = (size_t)t * B * H, rGp = (size_t)t * B * Gp, rZ = (size_t)t * B * Z;
+    bf16* dGd = Wb("dG_dec") + rGp; bf16* dGe = Wb("dG_enc") + rGp; bf16* dGa = Wb("dG_att") + rGp;
+    {  // decoder LSTM: d h_dec_t = head + enc/dec inputs of step t+1 + attention-LSTM input of step t+1
+      LstmBwdArgs l = {};
+      l.R = B; l.H = H;
+      l.dh[0] = Wf("dhead") + rH; l.ld_dh[0] = H;
+      l.dh[1] = dXE[nxt] + Fp + Hp; l.ld_dh[1] = KX;
+      l.dh[2] = dXA[nxt] + Hp; l.ld_dh[2] = 2 * Hp;
+      l.dc_in = Wf("dc_dec"); l.dc_prev = Wf("dc_dec");
+      l.gates = Wf("gates_dec") + rG; l.c = Wf("c_dec") + rH; l.c_prev = t ? Wf("c_dec") + rH - (size_t)B * H : nullptr;
+      l.dgates = dGd; l.ld_dg = Gp;
+      TRY(lstm_backward(s, l));
+    }
+    {  // d z -> d mean, d log_var (+ KL gradient) -> d h_enc
+      GemmSeg sg = seg(dGd, Gp, Pb("w_dec_zT"), Gp, G);
+      GemmEpi e; e.C32 = Wf("dz"); e.ldc32 = Z;
+      TRY(gemm_bf16_tn(s, B, Z, 1, &sg, e));
+      bf16* dml_t = Wb("dml") + (size_t)t * B * d.Z2p;
+      TRY(latent_backward(s, la, Wf("dz"), Z, Wf("eps") + rZ, Wf("mean") + rZ, Wf("logvar") + rZ, gkld,
+                          tmask + (size_t)t * B, dml_t, d.Z2p));
+      GemmSeg s2 = seg(dml_t, d.Z2p, Pb("w_fcT"), d.Z2p, d.Z2);
+      GemmEpi e2; e2.C32 = Wf("dhenc_fc"); e2.ldc32 = H;
+      TRY(gemm_bf16_tn(s, B, H, 1, &s2, e2));
+    }
+    {  // encoder LSTM
+      LstmBwdArgs l = {};
+      l.R = B; l.H = H;
+      l.dh[0] = Wf("dhenc_fc"); l.ld_dh[0] = H;
+      l.dh[1] = dhh[nxt]; l.ld_dh[1] = H;
+      l.dc_in = Wf("dc_enc"); l.dc_prev = Wf("dc_enc");
+      l.gates = Wf("gates_enc") + rG; l.c = Wf("c_enc") + rH; l.c_prev = t ? Wf("c_enc") + rH - (size_t)B * H : nullptr;
+      l.dgates = dGe; l.ld_dg = Gp;
+      TRY(lstm_backward(s, l));
+    }
+    {  // d [xhat | h1 | h_dec_{t-1}] from both language LSTMs, d h_enc_{t-1}
+      GemmSeg sg[2] = {seg(dGe, Gp, Pb("w_enc_xT"), Gp, G), seg(dGd, Gp, Pb("w_dec_xT"), Gp, G)};
+      GemmEpi e; e.C32 = dXE[cur]; e.ldc32 = KX;
+      TRY(gemm_bf16_tn(s, B, KX, 2, sg, e));
+      GemmSeg s2 = seg(dGe, Gp, Pb("w_enc_hhT"), Gp, G);
+      GemmEpi e2; e2.C32 = dhh[cur]; e2.ldc32 = H;
+      TRY(gemm_bf16_tn(s, B, H, 1, &s2, e2));
+    }
+    {  // fused attention backward, then d h1 through the query projection
+      aa.q = Wf("q") + (size_t)t * B * A;
+      bf16* dq_t = Wb("dqb") + (size_t)t * B * d.Ap;
+      TRY(attention_backward(s, aa, Wf("alpha") + (size_t)t * B * N, dXE[cur], KX, dq_t, d.Ap, Wf("dproj_acc"), Wf("dwa_acc")));
+      GemmSeg sg = seg(dq_t, d.Ap, Pb("wqT"), d.Ap, A);
+      GemmEpi e; e.C32 = Wf("dh1_q"); e.ldc32 = H;
+      TRY(gemm_bf16_tn(s, B, H, 1, &sg, e));
+    }
+    {  // attention LSTM
+      LstmBwdArgs l = {};
+      l.R = B; l.H = H;
+      l.dh[0] = dXE[cur] + Fp; l.ld_dh[0] = KX;
+      l.dh[1] = Wf("dh1_q"); l.ld_dh[1] = H;
+      l.dh[2] = dXA[nxt]; l.ld_dh[2] = 2 * Hp;
+      l.dc_in = Wf("dc1"); l.dc_prev = Wf("dc1");
+      l.gates = Wf("gates_att") + rG; l.c = Wf("c1") + rH; l.c_prev = t ? Wf("c1") + rH - (size_t)B * H : nullptr;
+      l.dgates = dGa; l.ld_dg = Gp;
+      TRY(lstm_backward(s, l));
+      GemmSeg sg = seg(dGa, Gp, Pb("w_att_recT"), Gp, G);
+      GemmEpi e; e.C32 = dXA[cur]; e.ldc32 = 2 * Hp;
+      TRY(gemm_bf16_tn(s, B, 2 * Hp, 1, &sg, e));
+    }
+  }
+
+  // ---- weight gradients: one GEMM per weight block over all T*B rows (K = T*B)
+  auto wgrad = [&](const bf16* AT, int M, const bf16* BT, int Ncols, int K, int ldk, float* C, int ldc) -> int {
+    if (!C) return 0;
+    GemmSeg sg = seg(AT, ldk, BT, ldk, K);
+    GemmEpi e; e.C32 = C; e.ldc32 = ldc;
+    return gemm_bf16_tn(s, M, Ncols, 1, &sg, e);
+  };
+  auto any = [&](std::initializer_list<int> ids) { for (int i : ids) if (gv[i]) return true; return false; };
+  bf16* dGT = Wb("dGT");
+  TRY(transpose_bf16(s, Wb("XE"), TB, KX, KX, Wb("XET"), TBp));                   // xhat_t, h1_t, h_dec_{t-1}
+  const bf16* xhatT = Wb("XET");
+  const bf16* h1T = Wb("XET") + (size_t)Fp * TBp;
+  const bf16* hdecpT = Wb("XET") + (size_t)(Fp + Hp) * TBp;
+  const float* sentv = Wf("sent");
+  const int ldE = F + 2 * H + c, ldD = F + 2 * H + c + Z, ldA = E + F + 2 * H;
+
+  // group 1: decoder LSTM. W_ih column blocks [xhat | h1 | h_dec | cond | z]; W_hh shares the h_dec operand.
+  if (any({SSCVAE_W_DEC_IH, SSCVAE_W_DEC_HH, SSCVAE_W_DEC_BIH, SSCVAE_W_DEC_BHH})) {
+    TRY(transpose_bf16(s, Wb("dG_dec"), TB, G, Gp, dGT, TBp));
+    float* g = Gr(SSCVAE_W_DEC_IH);
+    if (g) {
+      TRY(transpose_bf16(s, Wb("ZB"), TB, d.Zp, d.Zp, Wb("ZBT"), TBp));
+      TRY(wgrad(dGT, G, xhatT, F, TB, TBp, g, ldD));
+      TRY(wgrad(dGT, G, h1T, H, TB, TBp, g + F, ldD));
+      TRY(wgrad(dGT, G, hdecpT, H, TB, TBp, g + F + H, ldD));
+      TRY(wgrad(dGT, G, Wb("ZBT"), Z, TB, TBp, g + F + 2 * H + c, ldD));
+      if (c) TRY(rowdot_bf16(s, dGT, G, TB, TBp, sentv, B, g + F + 2 * H, ldD));
+    }
+    TRY(wgrad(dGT, G, hdecpT, H, TB, TBp, Gr(SSCVAE_W_DEC_HH), H));
+    if (Gr(SSCVAE_W_DEC_BIH)) TRY(rowsum_bf16(s, dGT, G, TB, TBp, Gr(SSCVAE_W_DEC_BIH), 0));
+    if (Gr(SSCVAE_W_DEC_BHH)) TRY(rowsum_bf16(s, dGT, G, TB, TBp, Gr(SSCVAE_W_DEC_BHH), 0));
+  }
+  TRY(event(1));
+
+  // group 2: encoder LSTM + latent heads
+  if (any({SSCVAE_W_ENC_IH, SSCVAE_W_ENC_HH, SSCVAE_W_ENC_BIH, SSCVAE_W_ENC_BHH})) {
+    TRY(transpose_bf16(s, Wb("dG_enc"), TB, G, Gp, dGT, TBp));
+    float* g = Gr(SSCVAE_W_ENC_IH);
+    if (g) {
+      TRY(wgrad(dGT, G, xhatT, F, TB, TBp, g, ldE));
+      TRY(wgrad(dGT, G, h1T, H, TB, TBp, g + F, ldE));
+      TRY(wgrad(dGT, G, hdecpT, H, TB, TBp, g + F + H, ldE));
+      if (c) TRY(rowdot_bf16(s, dGT, G, TB, TBp, sentv, B, g + F + 2 * H, ldE));
+    }
+    if (Gr(SSCVAE_W_ENC_HH)) {
+      TRY(transpose_bf16(s, Wb("HE"), TB, Hp, Hp, Wb("HETp"), TBp));               // h_enc_{t-1}
+      TRY(wgrad(dGT, G, Wb("HETp"), H, TB, TBp, Gr(SSCVAE_W_ENC_HH), H));
+    }
+    if (Gr(SSCVAE_W_ENC_BIH)) TRY(rowsum_bf16(s, dGT, G, TB, TBp, Gr(SSCVAE_W_ENC_BIH), 0));
+    if (Gr(SSCVAE_W_ENC_BHH)) TRY(rowsum_bf16(s, dGT, G, TB, TBp, Gr(SSCVAE_W_ENC_BHH), 0));
+  }
+  if (any({SSCVAE_W_FC_MEAN_W, SSCVAE_W_FC_MEAN_B, SSCVAE_W_FC_LOGVAR_W, SSCVAE_W_FC_LOGVAR_B})) {
+    TRY(transpose_bf16(s, Wb("dml"), TB, d.Z2p, d.Z2p, Wb("dmlT"), TBp));
+    TRY(transpose_bf16(s, Wb("HE") + (size_t)B * Hp, TB, Hp, Hp, Wb("HETc"), TBp));   // h_enc_t
+    const bf16* dmT = Wb("dmlT");
+    const bf16* dlT = Wb("dmlT") + (size_t)Z * TBp;
+    TRY(wgrad(dmT, Z, Wb("HETc"), H, TB, TBp, Gr(SSCVAE_W_FC_MEAN_W), H));
+    TRY(wgrad(dlT, Z, Wb("HETc"), H, TB, TBp, Gr(SSCVAE_W_FC_LOGVAR_W), H));
+    if (Gr(SSCVAE_W_FC_MEAN_B)) TRY(rowsum_bf16(s, dmT, Z, TB, TBp, Gr(SSCVAE_W_FC_MEAN_B), 0));
+    if (Gr(SSCVAE_W_FC_LOGVAR_B)) TRY(rowsum_bf16(s, dlT, Z, TB, TBp, Gr(SSCVAE_W_FC_LOGVAR_B), 0));
+  }
+  TRY(event(2));
+
+  // group 3: attention LSTM. W_ih column blocks [emb | avg | h1 | h_dec]; W_hh shares the h1 operand.
+  const bool need_demb = !d.tied && Gr(SSCVAE_W_EMBEDDING);
+  if (need_demb || any({SSCVAE_W_ATT_IH, SSCVAE_W_ATT_HH, SSCVAE_W_ATT_BIH, SSCVAE_W_ATT_BHH})) {
+    TRY(transpose_bf16(s, Wb("dG_att"), TB, G, Gp, dGT, TBp));
+    TRY(transpose_bf16(s, Wb("XA"), TB, 2 * Hp, 2 * Hp, Wb("XAT"), TBp));           // h1_{t-1}, h_dec_{t-1}
+    const bf16* h1pT = Wb("XAT");
+    const bf16* hdecp2T = Wb("XAT") + (size_t)Hp * TBp;
+    float* g = Gr(SSCVAE_W_ATT_IH);
+    if (g) {
+      TRY(transpose_bf16(s, Wb("embb_t"), TB, d.Ep, d.Ep, Wb("embT_t"), TBp));
+      TRY(wgrad(dGT, G, Wb("embT_t"), E, TB, TBp, g, ldA));
+      // mean-feature block: the operand is constant over time, so sum the gate gradients over t first
+      TRY(timesum_bf16(s, Wb("dG_att"), T, B, G, Gp, Wb("dGsum"), Gp));
+      TRY(transpose_bf16(s, Wb("dGsum"), B, G, Gp, Wb("dGsumT"), Bp));
+      TRY(transpose_bf16(s, Wb("avgb"), B, Fp, Fp, Wb("avgT"), Bp));
+      TRY(wgrad(Wb("dGsumT"), G, Wb("avgT"), F, B, Bp, g + E, ldA));
+      TRY(wgrad(dGT, G, h1pT, H, TB, TBp, g + E + F, ldA));
+      TRY(wgrad(dGT, G, hdecp2T, H, TB, TBp, g + E + F + H, ldA));
+    }
+    TRY(wgrad(dGT, G, h1pT, H, TB, TBp, Gr(SSCVAE_W_ATT_HH), H));
+    if (Gr(SSCVAE_W_ATT_BIH)) TRY(rowsum_bf16(s, dGT, G, TB, TBp, Gr(SSCVAE_W_ATT_BIH), 0));
+    if (Gr(SSCVAE_W_ATT_BHH)) TRY(rowsum_bf16(s, dGT, G, TB, TBp, Gr(SSCVAE_W_ATT_BHH), 0));
+    if (need_demb) {  // learned embedding (untied): d emb rows = dG_att W_att_ih[:, :E], scattered by token id
+      GemmSeg sg = seg(Wb("dG_att"), Gp, Pb("w_att_eT"), Gp, G);
+      GemmEpi e; e.C32 = Wf("dxemb"); e.ldc32 = E;
+      TRY(gemm_bf16_tn(s, TB, E, 1, &sg, e));
+      CUDA_TRY(cudaMemsetAsync(Gr(SSCVAE_W_EMBEDDING), 0, (size_t)V * E * sizeof(float), s));
+      TRY(embed_scatter_add(s, tok, B, d.L, d.pad, Wf("dxemb"), E, E, Gr(SSCVAE_W_EMBEDDING)));
+    }
+  }
+  TRY(event(3));
+
+  // group 4: attention module
+  if (Gr(SSCVAE_W_QUERY_PROJ)) {
+    TRY(transpose_bf16(s, Wb("dqb"), TB, d.Ap, d.Ap, Wb("dqT"), TBp));
+    TRY(wgrad(Wb("dqT"), A, h1T, H, TB, TBp, Gr(SSCVAE_W_QUERY_PROJ), H));
+  }
+  if (Gr(SSCVAE_W_IMAGE_PROJ)) {
+    TRY(transpose_f32_to_bf16(s, Wf("dproj_acc"), BN, A, A, Wb("dPT"), BNp));
+    TRY(transpose_bf16(s, Wb("featsb"), BN, Fp, Fp, Wb("featsT"), BNp));
+    TRY(wgrad(Wb("dPT"), A, Wb("featsT"), F, BN, BNp, Gr(SSCVAE_W_IMAGE_PROJ), F));
+  }
+  if (Gr(SSCVAE_W_ATT_VEC)) TRY(colsum_f32(s, Wf("dwa_acc"), B, A, A, Gr(SSCVAE_W_ATT_VEC)));
+  TRY(event(4));
+  return 0;
+}
+
+// ---- exported C ABI ----------------------------------------------------------------------------
+}  // namespace sscvae
+
+using namespace sscvae;
+
+extern "C" {
+
+int sscvae_abi_version(void) { return SSCVAE_ABI_VERSION; }
+const char* sscvae_last_error(void) { return get_error(); }
+uint64_t sscvae_launch_count(void) { return g_launch_count + g_launch_count_pw; }
+
+int sscvae_create(const SscvaeDims* dims, SscvaeHandle** out) {
+  REQUIRE(out != nullptr, "out is NULL");
+  Handle* h = new Handle();
+  int r = init_dims(dims, h->d);
+  if (r) { delete h; return r; }
+  plan_packed(h->d, h->pp);
+  *out = reinterpret_cast<SscvaeHandle*>(h);
+  return 0;
+}
+void sscvae_destroy(SscvaeHandle* h) { delete reinterpret_cast<Handle*>(h); }
+
+size_t sscvae_packed_bytes(const SscvaeHandle* h) { return reinterpret_cast<const Handle*>(h)->pp.total; }
+
+int sscvae_pack_weights(SscvaeHandle* hh, const void* const* weights, void* packed, size_t packed_bytes, void* stream) {
+  Handle* h = reinterpret_cast<Handle*>(hh);
+  REQUIRE(h && weights && packed, "NULL argument");
+  if (packed_bytes < h->pp.total) { set_error("packed buffer too small: %zu < %zu", packed_bytes, h->pp.total); return SSCVAE_ERR_WORKSPACE; }
+  REQUIRE((reinterpret_cast<uintptr_t>(packed) & 255) == 0, "packed buffer must be 256-byte aligned");
+  return pack_weights_impl(h, weights, reinterpret_cast<char*>(packed), reinterpret_cast<cudaStream_t>(stream));
+}
+
+size_t sscvae_train_workspace_bytes(const SscvaeHandle* hh, int batch, int num_boxes) {
+  Handle* h = const_cast<Handle*>(reinterpret_cast<const Handle*>(hh));
+  if (!h || batch <= 0 || num_boxes <= 0) return 0;
+  return h->train_plan(batch, num_boxes).total;
+}
+
+int sscvae_train_region(const SscvaeHandle* hh, int batch, int num_boxes, const char* name, size_t* offset, size_t* bytes) {
+  Handle* h = const_cast<Handle*>(reinterpret_cast<const Handle*>(hh));
+  REQUIRE(h && name && offset && bytes, "NULL argument");
+  const Region* r = h->train_plan(batch, num_boxes).find(name);
+  REQUIRE(r != nullptr, "unknown workspace region '%s'", name);
+  *offset = r->off; *bytes = r->bytes;
+  return 0;
+}
+
+int sscvae_train_forward(SscvaeHandle* hh, int batch, int num_boxes, const void* packed, const void* const* weights,
+                         const float* image_features, const int64_t* caption_tokens, const float* sentiment,
+                         const float* eps, uint64_t seed, void* workspace, size_t workspace_bytes, float* loss, float* kld,
+                         void* stream) {
+  Handle* h = reinterpret_cast<Handle*>(hh);
+  REQUIRE(h && packed && weights && image_features && caption_tokens && workspace && loss && kld, "NULL argument");
+  return train_forward_impl(h, batch, num_boxes, reinterpret_cast<const char*>(packed), weights, image_features,
+                            reinterpret_cast<const long long*>(caption_tokens), sentiment, eps, seed,
+                            reinterpret_cast<char*>(workspace), workspace_bytes, loss, kld,
+                            reinterpret_cast<cudaStream_t>(stream));
+}
+
+int sscvae_train_backward(SscvaeHandle* hh, int batch, int num_boxes, const void* packed, const void* const* weights,
+                          void* workspace, size_t workspace_bytes, const float* grad_loss, const float* grad_kld,
+                          void* const* grads, void* const* group_events, void* stream) {
+  Handle* h = reinterpret_cast<Handle*>(hh);
+  REQUIRE(h && packed && weights && workspace && grad_loss && grad_kld && grads, "NULL argument");
+  return train_backward_impl(h, batch, num_boxes, reinterpret_cast<const char*>(packed), weights,
+                             reinterpret_cast<char*>(workspace), workspace_bytes, grad_loss, grad_kld, grads, group_events,
+                             reinterpret_cast<cudaStream_t>(stream));
+}
+
+int sscvae_test_gemm(const void* A, int lda, const void* B, int ldb, int M, int N, int K, float* C32, int ldc,
+                     const float* bias, int act_tanh, int accumulate, void* stream) {
+  GemmSeg sg; sg.A = reinterpret_cast<const bf16*>(A); sg.lda = lda; sg.B = reinterpret_cast<const bf16*>(B); sg.ldb = ldb; sg.K = K;
+  GemmEpi e; e.C32 = C32; e.ldc32 = ldc; e.bias = bias; e.act = act_tanh; e.accumulate = accumulate;
+  return gemm_bf16_tn(reinterpret_cast<cudaStream_t>(stream), M, N, 1, &sg, e);
+}
+
+}  // extern "C"

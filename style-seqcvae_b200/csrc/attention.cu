@@ -1,0 +1,214 @@
+// Fused bottom-up/top-down region attention (north_star kernel #2), forward and backward.
+//
+// forward, per row r (a caption in training, an (image,state,beam) row in decode):
+//   u_n   = w_a . tanh(q_r + P[img(r), n, :])             (attention.py:69-88)
+//   alpha = masked_softmax(u, mask[img(r)])                (allennlp: softmax(u*m)*m / (sum + 1e-13))
+//   xhat  = sum_n alpha_n * x[img(r), n, :]                (updown_cell.py:156-158)
+// One CTA per row; projection, tanh, score, softmax and the weighted sum never leave the SM.
+// HBM/L2 traffic per row: N*Ap + N*Fp bf16 elements read once (16-byte coalesced vectors), F written.
+#include "kernels.cuh"
+
+namespace sscvae {
+
+#define LAUNCHED() do { CUDA_TRY(cudaGetLastError()); ++g_launch_count_pw; } while (0)
+
+__device__ __forceinline__ float tanh_approx(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+static constexpr int ATT_THREADS = 256;
+
+// scores u_n for all boxes of this row: warp per box, lanes over the projection axis
+__device__ __forceinline__ void attn_scores(const AttnArgs& a, const bf16* __restrict__ proj_img,
+                                            const float* __restrict__ mask_img, const float* q_s, const float* wa_s,
+                                            float* u_s) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
+  const int nvec = a.Ap >> 3;
+  for (int n = warp; n < a.N; n += nwarp) {
+    float s = 0.f;
+    if (mask_img[n] != 0.f) {                      // masked boxes enter the softmax as u*m = 0
+      const bf16x8* p = reinterpret_cast<const bf16x8*>(proj_img + (size_t)n * a.Ap);
+      for (int i = lane; i < nvec; i += 32) {
+        const bf16x8 v = p[i];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float2 f = __bfloat1622float2(v.v[k]);
+          const int idx = i * 8 + 2 * k;
+          s += wa_s[idx] * tanh_approx(q_s[idx] + f.x) + wa_s[idx + 1] * tanh_approx(q_s[idx + 1] + f.y);
+        }
+      }
+      s = warp_sum(s);
+    }
+    if (lane == 0) u_s[n] = s;
+  }
+}
+
+// masked softmax by warp 0. On exit: s_s[n] = softmax(u*m)[n], al_s[n] = alpha[n]; returns R = sum r + 1e-13
+__device__ __forceinline__ float attn_softmax(int N, const float* mask_img, const float* u_s, float* s_s, float* al_s) {
+  const int lane = threadIdx.x & 31;
+  float mx = -INFINITY;
+  for (int n = lane; n < N; n += 32) mx = fmaxf(mx, u_s[n] * mask_img[n]);
+  mx = warp_max(mx);
+  float se = 0.f;
+  for (int n = lane; n < N; n += 32) { const float e = __expf(u_s[n] * mask_img[n] - mx); s_s[n] = e; se += e; }
+  se = warp_sum(se);
+  float sr = 0.f;
+  for (int n = lane; n < N; n += 32) { const float sv = s_s[n] / se; s_s[n] = sv; sr += sv * mask_img[n]; }
+  sr = warp_sum(sr);
+  const float Rn = sr + 1e-13f;
+  for (int n = lane; n < N; n += 32) al_s[n] = s_s[n] * mask_img[n] / Rn;
+  return Rn;
+}
+
+__global__ void __launch_bounds__(ATT_THREADS) attention_fwd_kernel(AttnArgs a, float* __restrict__ alpha,
+                                                                   bf16* __restrict__ xhat, int ld_x) {
+  extern __shared__ float sm[];
+  float* q_s = sm;                      // Ap
+  float* wa_s = q_s + a.Ap;             // Ap
+  float* u_s = wa_s + a.Ap;             // N
+  float* s_s = u_s + a.N;               // N
+  float* al_s = s_s + a.N;              // N
+  const int r = blockIdx.x;
+  const int img = a.rowmap ? a.rowmap[r] : r;
+  const bf16* proj_img = a.proj + (size_t)img * a.N * a.Ap;
+  const bf16* feat_img = a.feats + (size_t)img * a.N * a.Fp;
+  const float* mask_img = a.mask + (size_t)img * a.N;
+  for (int i = threadIdx.x; i < a.Ap; i += blockDim.x) {
+    q_s[i] = (i < a.A) ? a.q[(size_t)r * a.ld_q + i] : 0.f;
+    wa_s[i] = (i < a.A) ? a.w_a[i] : 0.f;
+  }
+  __syncthreads();
+  attn_scores(a, proj_img, mask_img, q_s, wa_s, u_s);
+  __syncthreads();
+  if (threadIdx.x < 32) attn_softmax(a.N, mask_img, u_s, s_s, al_s);
+  __syncthreads();
+  for (int n = threadIdx.x; n < a.N; n += blockDim.x) alpha[(size_t)r * a.N + n] = al_s[n];
+  // weighted sum: each thread owns 8 consecutive features
+  const int nvec = a.Fp >> 3;
+  for (int i = threadIdx.x; i < nvec; i += blockDim.x) {
+    float acc[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+    const bf16x8* col = reinterpret_cast<const bf16x8*>(feat_img) + i;
+#pragma unroll 4
+    for (int n = 0; n < a.N; ++n) {
+      const float w = al_s[n];
+      if (w != 0.f) {
+        const bf16x8 v = col[(size_t)n * nvec];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float2 f = __bfloat1622float2(v.v[k]);
+          acc[2 * k] += w * f.x; acc[2 * k + 1] += w * f.y;
+        }
+      }
+    }
+    bf16x8 o;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) o.v[k] = __floats2bfloat162_rn(acc[2 * k], acc[2 * k + 1]);
+    st_bf16x8(xhat + (size_t)r * ld_x + i * 8, o);
+  }
+}
+
+int attention_forward(cudaStream_t s, const AttnArgs& a, float* alpha, bf16* xhat, int ld_x) {
+  const size_t smem = (size_t)(2 * a.Ap + 3 * a.N) * sizeof(float);
+  attention_fwd_kernel<<<a.R, ATT_THREADS, smem, s>>>(a, alpha, xhat, ld_x);
+  LAUNCHED();
+  return 0;
+}
+
+// backward of the same three fused ops. dproj_acc (images,N,A) and dwa_acc (R,A) are accumulated
+// across timesteps by the owning CTA (row r == image r in training), so no atomics are needed.
+__global__ void __launch_bounds__(ATT_THREADS) attention_bwd_kernel(AttnArgs a, const float* __restrict__ alpha_in,
+                                                                   const float* __restrict__ dxhat, int ld_dx,
+                                                                   bf16* __restrict__ dq, int ld_dq,
+                                                                   float* __restrict__ dproj_acc,
+                                                                   float* __restrict__ dwa_acc) {
+  extern __shared__ float sm[];
+  float* q_s = sm;                      // Ap
+  float* wa_s = q_s + a.Ap;             // Ap
+  float* dx_s = wa_s + a.Ap;            // Fp
+  float* u_s = dx_s + a.Fp;             // N
+  float* s_s = u_s + a.N;               // N
+  float* al_s = s_s + a.N;              // N
+  float* da_s = al_s + a.N;             // N  (d alpha, then d u)
+  const int r = blockIdx.x;
+  const int img = a.rowmap ? a.rowmap[r] : r;
+  const bf16* proj_img = a.proj + (size_t)img * a.N * a.Ap;
+  const bf16* feat_img = a.feats + (size_t)img * a.N * a.Fp;
+  const float* mask_img = a.mask + (size_t)img * a.N;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
+  for (int i = threadIdx.x; i < a.Ap; i += blockDim.x) {
+    q_s[i] = (i < a.A) ? a.q[(size_t)r * a.ld_q + i] : 0.f;
+    wa_s[i] = (i < a.A) ? a.w_a[i] : 0.f;
+  }
+  for (int i = threadIdx.x; i < a.Fp; i += blockDim.x) dx_s[i] = (i < a.F) ? dxhat[(size_t)r * ld_dx + i] : 0.f;
+  __syncthreads();
+  // d alpha_n = dxhat . x_n
+  const int fvec = a.Fp >> 3;
+  for (int n = warp; n < a.N; n += nwarp) {
+    float s = 0.f;
+    if (mask_img[n] != 0.f) {
+      const bf16x8* p = reinterpret_cast<const bf16x8*>(feat_img + (size_t)n * a.Fp);
+      for (int i = lane; i < fvec; i += 32) {
+        const bf16x8 v = p[i];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float2 f = __bfloat1622float2(v.v[k]);
+          s += dx_s[i * 8 + 2 * k] * f.x + dx_s[i * 8 + 2 * k + 1] * f.y;
+        }
+      }
+      s = warp_sum(s);
+    }
+    if (lane == 0) da_s[n] = s;
+  }
+  attn_scores(a, proj_img, mask_img, q_s, wa_s, u_s);
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    const float Rn = attn_softmax(a.N, mask_img, u_s, s_s, al_s);
+    // alpha = r / R with r = s*m :  dr = (dalpha - sum_k dalpha_k alpha_k) / R ; ds = dr*m
+    float dot = 0.f;
+    for (int n = lane; n < a.N; n += 32) dot += da_s[n] * al_s[n];
+    dot = warp_sum(dot);
+    float dss = 0.f;
+    for (int n = lane; n < a.N; n += 32) {
+      const float ds = (da_s[n] - dot) / Rn * mask_img[n];
+      da_s[n] = ds;
+      dss += ds * s_s[n];
+    }
+    dss = warp_sum(dss);
+    // softmax backward on x = u*m, then du = dx * m
+    for (int n = lane; n < a.N; n += 32) da_s[n] = s_s[n] * (da_s[n] - dss) * mask_img[n];
+  }
+  __syncthreads();
+  // per projection column a: dq_a = sum_n du_n w_a (1 - th^2), dP_na += du_n w_a (1 - th^2), dw_a += du_n th
+  for (int i = threadIdx.x; i < ld_dq; i += blockDim.x) {
+    float dqa = 0.f, dwa = 0.f;
+    if (i < a.A) {
+      const float qa = q_s[i], wa = wa_s[i];
+      for (int n = 0; n < a.N; ++n) {
+        const float du = da_s[n];
+        if (du != 0.f) {
+          const float th = tanh_approx(qa + __bfloat162float(proj_img[(size_t)n * a.Ap + i]));
+          const float g = du * wa * (1.f - th * th);
+          dqa += g;
+          dwa += du * th;
+          dproj_acc[((size_t)img * a.N + n) * a.A + i] += g;
+        }
+      }
+      dwa_acc[(size_t)r * a.A + i] += dwa;
+    }
+    dq[(size_t)r * ld_dq + i] = __float2bfloat16_rn(dqa);
+  }
+}
+
+int attention_backward(cudaStream_t s, const AttnArgs& a, const float* alpha, const float* dxhat, int ld_dx, bf16* dq,
+                       int ld_dq, float* dproj_acc, float* dwa_acc) {
+  const size_t smem = (size_t)(2 * a.Ap + a.Fp + 4 * a.N) * sizeof(float);
+  attention_bwd_kernel<<<a.R, ATT_THREADS, smem, s>>>(a, alpha, dxhat, ld_dx, dq, ld_dq, dproj_acc, dwa_acc);
+  LAUNCHED();
+  return 0;
+}
+
+}  // namespace sscvae

@@ -1,0 +1,33 @@
+// bf16 x bf16 -> fp32 "TN" GEMM for sm_100a:  C[M,N] = epilogue( sum_seg A_seg[M,K_seg] * B_seg[N,K_seg]^T )
+// Both operands are K-major (row-major with K contiguous), i.e. activations (rows, features) and
+// PyTorch-layout weights (out, in). Up to three K-segments accumulate into one TMEM accumulator, so
+// a gate pre-activation like  [x_hat|h1|h_dec] W_x^T + z W_z^T  is one launch without concatenating.
+#pragma once
+#include "common.cuh"
+
+namespace sscvae {
+
+struct GemmSeg {
+  const bf16* A; int lda;   // (M, K) row-major, lda in elements (multiple of 8, base 16B aligned)
+  const bf16* B; int ldb;   // (N, K) row-major
+  int K;
+};
+
+struct GemmEpi {
+  float alpha = 1.0f;                                  // v = alpha * acc
+  const float* bias = nullptr;                         // v += bias[n]
+  const float* add1 = nullptr; int ld1 = 0;            // v += add1[m, n]
+  const float* add2 = nullptr; int ld2 = 0;            // v += add2[m, n]
+  int act = 0;                                         // 1: v = tanh(v)
+  const float* dtanh = nullptr; int ldd = 0;           // v *= 1 - dtanh[m,n]^2
+  float* C32 = nullptr; int ldc32 = 0; int accumulate = 0;   // C32[m,n] (+)= v
+  bf16* C16 = nullptr; int ldc16 = 0;                  // C16[m,n] = bf16(v)
+};
+
+// Launches on `stream`; returns 0 or an error code (message via get_error()).
+int gemm_bf16_tn(cudaStream_t stream, int M, int N, int nseg, const GemmSeg* segs, const GemmEpi& epi);
+
+// number of kernels launched by this translation unit since load (bench.py's gpu_launches)
+extern unsigned long long g_launch_count;
+
+}  // namespace sscvae

@@ -1,0 +1,123 @@
+// Launch wrappers of the non-GEMM kernels of the var_updown decoder path. All pointers are device
+// pointers; every function enqueues on `stream` and returns 0 / error code. Row index of every
+// time-stacked buffer is r = t * B + b (time-major).
+#pragma once
+#include "common.cuh"
+
+namespace sscvae {
+
+// ---- pre-loop -----------------------------------------------------------------------------------
+// a6 (updown_cell.py:233-270): mask = sum_f |x| > 0 ; avg = masked mean ; bf16 copy of the features.
+int image_prep(cudaStream_t s, const float* feats, int B, int N, int F, bf16* featsb, int Fp, float* mask,
+               bf16* avgb);
+// a16 (allennlp add_sentence_boundary_token_ids) + mask/lengths of the targets (updown_captioner.py:265-278)
+int boundary_tokens(cudaStream_t s, const long long* caption_tokens, int B, int L, int pad, int boundary,
+                    int* tok /*(B,L+2)*/, float* tmask /*(T,B)*/, float* lengths /*(B)*/);
+// a4: embb[t*B+b, :] = Embb[tok[b, t], :]  (bf16 rows of Ep elements)
+int embed_gather_train(cudaStream_t s, const int* tok, int B, int L, const bf16* embb, int Ep, bf16* out);
+int embed_gather_rows(cudaStream_t s, const int* tokens, int R, const bf16* embb, int Ep, bf16* out);
+
+// ---- LSTM pointwise (torch.nn.LSTMCell semantics, gate order i,f,g,o) ----------------------------
+struct LstmFwdArgs {
+  int R, H;
+  const float* acc; int ld_acc;        // (R,4H) GEMM result
+  const float* add1; int ld1;          // optional (R,4H)
+  const float* add2; int ld2;          // optional (rows2,4H) indexed by rowmap (or row)
+  const int* rowmap;                   // optional row -> add2/sent row
+  const float* bias;                   // optional (4H)  (b_ih + b_hh)
+  const float* sent; const float* scol;  // optional rank-1 term sent[row] * scol[4H]
+  const float* c_prev;                 // (R,H) or null (zeros)
+  float* c_out;                        // (R,H)
+  float* gates_out;                    // optional (R,4H) activated gates, saved for BPTT
+  bf16* h1_dst; int ld_h1;             // bf16 h -> up to two operand buffers
+  bf16* h2_dst; int ld_h2;
+};
+int lstm_forward(cudaStream_t s, const LstmFwdArgs& a);
+
+struct LstmBwdArgs {
+  int R, H;
+  const float* dh[3]; int ld_dh[3];    // up to three fp32 sources summed (null = skip)
+  const float* dc_in;                  // (R,H) or null
+  const float* gates;                  // (R,4H) saved activations
+  const float* c_prev;                 // (R,H) or null (zeros)
+  const float* c;                      // (R,H)
+  bf16* dgates; int ld_dg;             // (R,4H) bf16 pre-activation grads (GEMM operand)
+  float* dc_prev;                      // (R,H)
+};
+int lstm_backward(cudaStream_t s, const LstmBwdArgs& a);
+
+// ---- latent: reparameterised z, per-step KL (updown_cell.py:196-208, updown_captioner.py:295-303) ----
+struct LatentArgs {
+  int R, Z, Zp;
+  int sentiment_vae;                   // 0: KL against N(0,1) ignoring the prior; else prior form
+  float prior_var;                     // prior_std^2
+  const float* prior_mean_row;         // (R) per-row prior mean value (broadcast over Z) or null (0)
+  const int* rowmap;                   // optional row -> prior_mean_row index
+};
+// training: ml (R,2Z) = [mean|log_var] pre-bias GEMM output
+int latent_forward_train(cudaStream_t s, const LatentArgs& a, const float* ml, int ld_ml, const float* bias_ml,
+                         const float* eps_in /*(R,Z) or null*/, unsigned long long seed, unsigned long long step,
+                         float* mean_out, float* logvar_out, float* eps_out, bf16* zb, int ld_z, float* kl_out);
+// eval: z = eps * prior_std + prior_mean
+// eps row r is read at eps_in[r * eps_row_stride, :]
+int latent_forward_eval(cudaStream_t s, const LatentArgs& a, const float* eps_in, int eps_row_stride,
+                        unsigned long long seed, unsigned long long step, bf16* zb, int ld_z);
+int fill_i32(cudaStream_t s, int* dst, int value, int n);
+int iota_div_i32(cudaStream_t s, int* dst, int n, int div);   // dst[i] = i / div
+int latent_backward(cudaStream_t s, const LatentArgs& a, const float* dz, int ld_dz, const float* eps,
+                    const float* mean, const float* logvar, const float* gkld /*(B)*/, const float* tmask_t /*(B)*/,
+                    bf16* dml /*(R, ld) [dmean | dlogvar]*/, int ld_dml);
+
+// ---- vocabulary cross-entropy (updown_captioner.py:457-466 + allennlp sequence_cross_entropy_with_logits) ----
+int ce_forward(cudaStream_t s, const float* logits, int ld, int TB, int V, const int* tok, int B, int L,
+               const float* tmask, float* lse, float* nll);
+int loss_reduce(cudaStream_t s, const float* nll, const float* kl, const float* tmask, const float* lengths, int T,
+                int B, float* loss, float* kld);
+int ce_backward(cudaStream_t s, const float* logits, int ld, int TB, int V, const int* tok, int B, int L,
+                const float* tmask, const float* lengths, const float* lse, const float* gloss, bf16* dlogits,
+                int ld_d);
+
+// ---- layout helpers -------------------------------------------------------------------------------
+int transpose_bf16(cudaStream_t s, const bf16* in, int rows, int cols, int ld_in, bf16* out, int ld_out);
+int transpose_f32_to_bf16(cudaStream_t s, const float* in, int rows, int cols, int ld_in, bf16* out, int ld_out);
+// out[r] = sum_c in[r, c]  (bf16 in, fp32 accumulate; one warp per row; deterministic)
+int rowsum_bf16(cudaStream_t s, const bf16* in, int rows, int cols, int ld, float* out, int accumulate);
+int rowsum_f32(cudaStream_t s, const float* in, int rows, int cols, int ld, float* out, int accumulate);
+// out (rows, cols) bf16 with ld  <- fp32 in (rows, cols) with ld_in ; pad columns [cols, ld) zeroed
+int convert_f32_to_bf16(cudaStream_t s, const float* in, int rows, int cols, int ld_in, bf16* out, int ld_out);
+// sum over T of time-stacked (T, B, n) bf16 -> (B, n) bf16
+int timesum_bf16(cudaStream_t s, const bf16* in, int T, int B, int n, int ld, bf16* out, int ld_out);
+int add_f32(cudaStream_t s, float* dst, const float* src, size_t n);
+// out[c] = sum_r in[r, c]   (thread per column, deterministic)
+int colsum_f32(cudaStream_t s, const float* in, int rows, int cols, int ld, float* out);
+// out[r * out_stride] = sum_c in[r, c] * vec[c % period]   (bf16 matrix row . periodic fp32 vector)
+int rowdot_bf16(cudaStream_t s, const bf16* in, int rows, int cols, int ld, const float* vec, int period, float* out,
+                int out_stride);
+// strided fp32 block copy: dst[r*ld_dst + c] = src[r*ld_src + c]
+int copy_block_f32(cudaStream_t s, const float* src, int ld_src, float* dst, int ld_dst, int rows, int cols);
+// weight packing: dst (bf16) <- src (+ src2) fp32, optionally transposed
+int pack_block(cudaStream_t s, bf16* dst, int ld_dst, int transposed, const float* src, int ld_src, int rows, int cols,
+               const float* src2, int ld_src2);
+int vec_add_f32(cudaStream_t s, const float* a, const float* b, float* out, int n);
+int scale_rows_f32(cudaStream_t s, const float* in, float scale, float* out, int n);
+// dEmb[tok[b,t], :] += dx[(t*B+b), :] skipping the padding index (nn.Embedding padding_idx)
+int embed_scatter_add(cudaStream_t s, const int* tok, int B, int L, int pad, const float* dx, int ld_dx, int E, float* demb);
+int gather_rows_f32(cudaStream_t s, const float* src, const int* idx, int R, int n, float* dst);
+int gather_rows_bf16(cudaStream_t s, const bf16* src, const int* idx, int R, int n, int ld, bf16* dst);
+
+// ---- region attention (attention.py:36-97, updown_cell.py:156-158) -----------------------------
+struct AttnArgs {
+  int R, N, A, Ap, F, Fp;
+  const int* rowmap;                   // row -> image (null = identity)
+  const float* q; int ld_q;            // (R,A) projected query
+  const bf16* proj;                    // (images, N, Ap) projected region features
+  const bf16* feats;                   // (images, N, Fp)
+  const float* mask;                   // (images, N)
+  const float* w_a;                    // (A)
+};
+int attention_forward(cudaStream_t s, const AttnArgs& a, float* alpha /*(R,N)*/, bf16* xhat, int ld_x);
+int attention_backward(cudaStream_t s, const AttnArgs& a, const float* alpha, const float* dxhat, int ld_dx,
+                       bf16* dq /*(R,Ap)*/, int ld_dq, float* dproj_acc /*(images,N,A) +=*/, float* dwa_acc /*(R,A) +=*/);
+
+extern unsigned long long g_launch_count_pw;   // launches from the non-GEMM kernels
+}  // namespace sscvae

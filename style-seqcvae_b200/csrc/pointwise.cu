@@ -1,0 +1,658 @@
+// Pointwise / reduction kernels of the var_updown decoder path (everything that is not a GEMM, the
+// region attention or the search). All are HBM- or latency-bound: coalesced along the feature axis,
+// 16-byte vector accesses where the layout allows, warp-shuffle reductions.
+#include "kernels.cuh"
+#include <curand_kernel.h>
+
+namespace sscvae {
+
+unsigned long long g_launch_count_pw = 0;
+#define LAUNCHED() do { CUDA_TRY(cudaGetLastError()); ++g_launch_count_pw; } while (0)
+
+// ---------------------------------------------------------------------------------------------
+// image_prep: one CTA per image. Pass 1: bf16 copy + per-box |x| sum -> mask. Pass 2: masked mean.
+// ---------------------------------------------------------------------------------------------
+__global__ void image_prep_kernel(const float* __restrict__ feats, int N, int F, bf16* __restrict__ featsb, int Fp,
+                                  float* __restrict__ mask, bf16* __restrict__ avgb) {
+  extern __shared__ float s_mask[];                 // N
+  const int b = blockIdx.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
+  const float* x = feats + (size_t)b * N * F;
+  bf16* xb = featsb + (size_t)b * N * Fp;
+  for (int n = warp; n < N; n += nwarp) {
+    float s = 0.f;
+    for (int f = lane; f < Fp; f += 32) {
+      float v = (f < F) ? x[(size_t)n * F + f] : 0.f;
+      s += fabsf(v);
+      xb[(size_t)n * Fp + f] = __float2bfloat16_rn(v);
+    }
+    s = warp_sum(s);
+    if (lane == 0) { float m = s > 0.f ? 1.f : 0.f; s_mask[n] = m; mask[(size_t)b * N + n] = m; }
+  }
+  __syncthreads();
+  float cnt = 0.f;
+  for (int n = 0; n < N; ++n) cnt += s_mask[n];
+  const float inv = 1.0f / fmaxf(cnt, 1e-8f);
+  for (int f = threadIdx.x; f < Fp; f += blockDim.x) {
+    float s = 0.f;
+    if (f < F)
+      for (int n = 0; n < N; ++n)
+        if (s_mask[n] != 0.f) s += __bfloat162float(xb[(size_t)n * Fp + f]);
+    avgb[(size_t)b * Fp + f] = __float2bfloat16_rn(s * inv);
+  }
+}
+
+int image_prep(cudaStream_t s, const float* feats, int B, int N, int F, bf16* featsb, int Fp, float* mask, bf16* avgb) {
+  image_prep_kernel<<<B, 256, N * sizeof(float), s>>>(feats, N, F, featsb, Fp, mask, avgb);
+  LAUNCHED();
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// tokens
+// ---------------------------------------------------------------------------------------------
+__global__ void boundary_tokens_kernel(const long long* __restrict__ cap, int B, int L, int pad, int boundary,
+                                       int* __restrict__ tok, float* __restrict__ tmask, float* __restrict__ lengths) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  int len = 0;
+  for (int l = 0; l < L; ++l) len += (cap[(size_t)b * L + l] != pad) ? 1 : 0;
+  int* row = tok + (size_t)b * (L + 2);
+  row[0] = boundary;
+  for (int l = 0; l < L; ++l) row[l + 1] = (int)cap[(size_t)b * L + l];
+  row[L + 1] = 0;
+  row[len + 1] = boundary;
+  float cnt = 0.f;
+  for (int t = 0; t < L + 1; ++t) {              // targets are tok[:, 1:]
+    float m = (row[t + 1] != pad) ? 1.f : 0.f;
+    tmask[(size_t)t * B + b] = m;
+    cnt += m;
+  }
+  lengths[b] = cnt;
+}
+
+int boundary_tokens(cudaStream_t s, const long long* cap, int B, int L, int pad, int boundary, int* tok, float* tmask,
+                    float* lengths) {
+  boundary_tokens_kernel<<<ceil_div(B, 128), 128, 0, s>>>(cap, B, L, pad, boundary, tok, tmask, lengths);
+  LAUNCHED();
+  return 0;
+}
+
+__global__ void embed_gather_kernel(const int* __restrict__ tok, int tok_stride_b, int tok_stride_t, int B, int rows,
+                                    const bf16* __restrict__ embb, int Ep, bf16* __restrict__ out) {
+  // one warp per output row, 16-byte vectors
+  const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (r >= rows) return;
+  const int lane = threadIdx.x & 31;
+  const int t = r / B, b = r % B;
+  const int id = tok[(size_t)b * tok_stride_b + (size_t)t * tok_stride_t];
+  const bf16x8* src = reinterpret_cast<const bf16x8*>(embb + (size_t)id * Ep);
+  bf16x8* dst = reinterpret_cast<bf16x8*>(out + (size_t)r * Ep);
+  for (int i = lane; i < Ep / 8; i += 32) dst[i] = src[i];
+}
+
+int embed_gather_train(cudaStream_t s, const int* tok, int B, int L, const bf16* embb, int Ep, bf16* out) {
+  const int rows = (L + 1) * B;
+  embed_gather_kernel<<<ceil_div(rows, 8), 256, 0, s>>>(tok, L + 2, 1, B, rows, embb, Ep, out);
+  LAUNCHED();
+  return 0;
+}
+int embed_gather_rows(cudaStream_t s, const int* tokens, int R, const bf16* embb, int Ep, bf16* out) {
+  embed_gather_kernel<<<ceil_div(R, 8), 256, 0, s>>>(tokens, 1, 0, R, R, embb, Ep, out);
+  LAUNCHED();
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// LSTM pointwise forward / backward: one thread per (row, hidden unit)
+// ---------------------------------------------------------------------------------------------
+__global__ void lstm_fwd_kernel(LstmFwdArgs a) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  const int r = blockIdx.y;
+  if (j >= a.H) return;
+  const int H = a.H;
+  const int r2 = a.rowmap ? a.rowmap[r] : r;
+  float g[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int n = k * H + j;
+    float v = a.acc[(size_t)r * a.ld_acc + n];
+    if (a.add1) v += a.add1[(size_t)r * a.ld1 + n];
+    if (a.add2) v += a.add2[(size_t)r2 * a.ld2 + n];
+    if (a.bias) v += a.bias[n];
+    if (a.sent) v += a.sent[r2] * a.scol[n];
+    g[k] = v;
+  }
+  const float i = sigmoidf_(g[0]), f = sigmoidf_(g[1]), gg = tanhf(g[2]), o = sigmoidf_(g[3]);
+  const float cp = a.c_prev ? a.c_prev[(size_t)r * H + j] : 0.f;
+  const float c = f * cp + i * gg;
+  const float h = o * tanhf(c);
+  a.c_out[(size_t)r * H + j] = c;
+  if (a.gates_out) {
+    float* go = a.gates_out + (size_t)r * 4 * H;
+    go[j] = i; go[H + j] = f; go[2 * H + j] = gg; go[3 * H + j] = o;
+  }
+  const bf16 hb = __float2bfloat16_rn(h);
+  if (a.h1_dst) a.h1_dst[(size_t)r * a.ld_h1 + j] = hb;
+  if (a.h2_dst) a.h2_dst[(size_t)r * a.ld_h2 + j] = hb;
+}
+
+int lstm_forward(cudaStream_t s, const LstmFwdArgs& a) {
+  dim3 grid(ceil_div(a.H, 128), a.R);
+  lstm_fwd_kernel<<<grid, 128, 0, s>>>(a);
+  LAUNCHED();
+  return 0;
+}
+
+__global__ void lstm_bwd_kernel(LstmBwdArgs a) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  const int r = blockIdx.y;
+  const int H = a.H;
+  if (j >= H) return;
+  float dh = 0.f;
+#pragma unroll
+  for (int k = 0; k < 3; ++k)
+    if (a.dh[k]) dh += a.dh[k][(size_t)r * a.ld_dh[k] + j];
+  const float* g = a.gates + (size_t)r * 4 * H;
+  const float i = g[j], f = g[H + j], gg = g[2 * H + j], o = g[3 * H + j];
+  const float c = a.c[(size_t)r * H + j];
+  const float cp = a.c_prev ? a.c_prev[(size_t)r * H + j] : 0.f;
+  const float tc = tanhf(c);
+  float dc = dh * o * (1.f - tc * tc);
+  if (a.dc_in) dc += a.dc_in[(size_t)r * H + j];
+  const float d_o = dh * tc;
+  bf16* dg = a.dgates + (size_t)r * a.ld_dg;
+  dg[j] = __float2bfloat16_rn(dc * gg * i * (1.f - i));
+  dg[H + j] = __float2bfloat16_rn(dc * cp * f * (1.f - f));
+  dg[2 * H + j] = __float2bfloat16_rn(dc * i * (1.f - gg * gg));
+  dg[3 * H + j] = __float2bfloat16_rn(d_o * o * (1.f - o));
+  a.dc_prev[(size_t)r * H + j] = dc * f;
+}
+
+int lstm_backward(cudaStream_t s, const LstmBwdArgs& a) {
+  dim3 grid(ceil_div(a.H, 128), a.R);
+  lstm_bwd_kernel<<<grid, 128, 0, s>>>(a);
+  LAUNCHED();
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// latent
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float philox_normal(unsigned long long seed, unsigned long long step, int r, int z, int Z) {
+  curandStatePhilox4_32_10_t st;
+  curand_init(seed, (unsigned long long)r * Z + z, step, &st);
+  return curand_normal(&st);
+}
+
+__global__ void latent_fwd_train_kernel(LatentArgs a, const float* __restrict__ ml, int ld_ml,
+                                        const float* __restrict__ bias_ml, const float* __restrict__ eps_in,
+                                        unsigned long long seed, unsigned long long step, float* __restrict__ mean_out,
+                                        float* __restrict__ logvar_out, float* __restrict__ eps_out, bf16* __restrict__ zb,
+                                        int ld_z, float* __restrict__ kl_out) {
+  __shared__ float red[32];
+  const int r = blockIdx.x;
+  const int Z = a.Z;
+  const float pm = a.prior_mean_row ? a.prior_mean_row[a.rowmap ? a.rowmap[r] : r] : 0.f;
+  const float log_pv = logf(a.prior_var);
+  float part = 0.f;
+  for (int z = threadIdx.x; z < a.Zp; z += blockDim.x) {
+    if (z < Z) {
+      const float mu = ml[(size_t)r * ld_ml + z] + bias_ml[z];
+      const float lv = ml[(size_t)r * ld_ml + Z + z] + bias_ml[Z + z];
+      const float var = __expf(lv);
+      const float e = eps_in ? eps_in[(size_t)r * Z + z] : philox_normal(seed, step, r, z, Z);
+      const float zz = e * sqrtf(var) + mu;
+      mean_out[(size_t)r * Z + z] = mu;
+      logvar_out[(size_t)r * Z + z] = lv;
+      eps_out[(size_t)r * Z + z] = e;
+      zb[(size_t)r * ld_z + z] = __float2bfloat16_rn(zz);
+      if (a.sentiment_vae == 0) part += 1.f + lv - mu * mu - var;
+      else part += 1.f + lv - log_pv - ((mu - pm) * (mu - pm) + var) / (a.prior_var + 0.00001f);
+    } else {
+      zb[(size_t)r * ld_z + z] = __float2bfloat16_rn(0.f);
+    }
+  }
+  part = warp_sum(part);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = part;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float v = (threadIdx.x < (blockDim.x >> 5)) ? red[threadIdx.x] : 0.f;
+    v = warp_sum(v);
+    if (threadIdx.x == 0) kl_out[r] = -0.5f * v;
+  }
+}
+
+int latent_forward_train(cudaStream_t s, const LatentArgs& a, const float* ml, int ld_ml, const float* bias_ml,
+                         const float* eps_in, unsigned long long seed, unsigned long long step, float* mean_out,
+                         float* logvar_out, float* eps_out, bf16* zb, int ld_z, float* kl_out) {
+  const int threads = min(256, round_up(a.Zp, 32));
+  latent_fwd_train_kernel<<<a.R, threads, 0, s>>>(a, ml, ld_ml, bias_ml, eps_in, seed, step, mean_out, logvar_out,
+                                                 eps_out, zb, ld_z, kl_out);
+  LAUNCHED();
+  return 0;
+}
+
+__global__ void latent_fwd_eval_kernel(LatentArgs a, const float* __restrict__ eps_in, int eps_row_stride,
+                                       unsigned long long seed, unsigned long long step, bf16* __restrict__ zb,
+                                       int ld_z) {
+  const int r = blockIdx.x;
+  const float pm = a.prior_mean_row ? a.prior_mean_row[a.rowmap ? a.rowmap[r] : r] : 0.f;
+  const float sd = sqrtf(a.prior_var);
+  for (int z = threadIdx.x; z < a.Zp; z += blockDim.x) {
+    float v = 0.f;
+    if (z < a.Z) {
+      const float e = eps_in ? eps_in[(size_t)r * eps_row_stride * a.Z + z] : philox_normal(seed, step, r, z, a.Z);
+      v = e * sd + pm;
+    }
+    zb[(size_t)r * ld_z + z] = __float2bfloat16_rn(v);
+  }
+}
+
+int latent_forward_eval(cudaStream_t s, const LatentArgs& a, const float* eps_in, int eps_row_stride,
+                        unsigned long long seed, unsigned long long step, bf16* zb, int ld_z) {
+  const int threads = min(256, round_up(a.Zp, 32));
+  latent_fwd_eval_kernel<<<a.R, threads, 0, s>>>(a, eps_in, eps_row_stride, seed, step, zb, ld_z);
+  LAUNCHED();
+  return 0;
+}
+
+__global__ void latent_bwd_kernel(LatentArgs a, const float* __restrict__ dz, int ld_dz, const float* __restrict__ eps,
+                                  const float* __restrict__ mean, const float* __restrict__ logvar,
+                                  const float* __restrict__ gkld, const float* __restrict__ tmask_t,
+                                  bf16* __restrict__ dml, int ld_dml) {
+  const int r = blockIdx.x;
+  const int Z = a.Z;
+  const float pm = a.prior_mean_row ? a.prior_mean_row[a.rowmap ? a.rowmap[r] : r] : 0.f;
+  const float w = gkld[r] * tmask_t[r];
+  const float inv_pv = 1.0f / (a.prior_var + 0.00001f);
+  for (int z = threadIdx.x; z < ld_dml; z += blockDim.x) {
+    float out = 0.f;
+    if (z < 2 * Z) {
+      const int zi = (z < Z) ? z : z - Z;
+      const float mu = mean[(size_t)r * Z + zi], lv = logvar[(size_t)r * Z + zi];
+      const float var = __expf(lv);
+      const float g = dz[(size_t)r * ld_dz + zi];
+      if (z < Z) {
+        const float dkl = (a.sentiment_vae == 0) ? mu : (mu - pm) * inv_pv;
+        out = g + w * dkl;
+      } else {
+        const float dkl = (a.sentiment_vae == 0) ? -0.5f * (1.f - var) : -0.5f * (1.f - var * inv_pv);
+        out = g * eps[(size_t)r * Z + zi] * 0.5f * sqrtf(var) + w * dkl;
+      }
+    }
+    dml[(size_t)r * ld_dml + z] = __float2bfloat16_rn(out);
+  }
+}
+
+int latent_backward(cudaStream_t s, const LatentArgs& a, const float* dz, int ld_dz, const float* eps, const float* mean,
+                    const float* logvar, const float* gkld, const float* tmask_t, bf16* dml, int ld_dml) {
+  latent_bwd_kernel<<<a.R, min(256, round_up(ld_dml, 32)), 0, s>>>(a, dz, ld_dz, eps, mean, logvar, gkld, tmask_t, dml,
+                                                                 ld_dml);
+  LAUNCHED();
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// cross entropy over the vocabulary: one CTA per (t,b) row, skipped when the target is padding
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float block_reduce(float v, float* red, bool is_max) {
+  v = is_max ? warp_max(v) : warp_sum(v);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float x = (threadIdx.x < (blockDim.x >> 5)) ? red[threadIdx.x] : (is_max ? -INFINITY : 0.f);
+  if (threadIdx.x < 32) {
+    x = is_max ? warp_max(x) : warp_sum(x);
+    if (threadIdx.x == 0) red[0] = x;
+  }
+  __syncthreads();
+  const float out = red[0];
+  __syncthreads();
+  return out;
+}
+
+__global__ void ce_fwd_kernel(const float* __restrict__ logits, int ld, int V, const int* __restrict__ tok, int B, int L,
+                              const float* __restrict__ tmask, float* __restrict__ lse, float* __restrict__ nll) {
+  __shared__ float red[32];
+  const int r = blockIdx.x;
+  if (tmask[r] == 0.f) { if (threadIdx.x == 0) { lse[r] = 0.f; nll[r] = 0.f; } return; }
+  const int t = r / B, b = r % B;
+  const float* x = logits + (size_t)r * ld;
+  float m = -INFINITY;
+  for (int v = threadIdx.x; v < V; v += blockDim.x) m = fmaxf(m, x[v]);
+  m = block_reduce(m, red, true);
+  float sum = 0.f;
+  for (int v = threadIdx.x; v < V; v += blockDim.x) sum += __expf(x[v] - m);
+  sum = block_reduce(sum, red, false);
+  if (threadIdx.x == 0) {
+    const float l = m + logf(sum);
+    const int target = tok[(size_t)b * (L + 2) + t + 1];
+    lse[r] = l;
+    nll[r] = l - x[target];
+  }
+}
+
+int ce_forward(cudaStream_t s, const float* logits, int ld, int TB, int V, const int* tok, int B, int L,
+               const float* tmask, float* lse, float* nll) {
+  ce_fwd_kernel<<<TB, 256, 0, s>>>(logits, ld, V, tok, B, L, tmask, lse, nll);
+  LAUNCHED();
+  return 0;
+}
+
+__global__ void loss_reduce_kernel(const float* __restrict__ nll, const float* __restrict__ kl,
+                                   const float* __restrict__ tmask, const float* __restrict__ lengths, int T, int B,
+                                   float* __restrict__ loss, float* __restrict__ kld) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  float sn = 0.f, sk = 0.f;
+  for (int t = 0; t < T; ++t) {
+    const float m = tmask[(size_t)t * B + b];
+    sn += nll[(size_t)t * B + b] * m;
+    sk += kl[(size_t)t * B + b] * m;
+  }
+  const float len = lengths[b];
+  loss[b] = len * (sn / (len + 1e-13f));
+  kld[b] = sk;
+}
+
+int loss_reduce(cudaStream_t s, const float* nll, const float* kl, const float* tmask, const float* lengths, int T, int B,
+                float* loss, float* kld) {
+  loss_reduce_kernel<<<ceil_div(B, 128), 128, 0, s>>>(nll, kl, tmask, lengths, T, B, loss, kld);
+  LAUNCHED();
+  return 0;
+}
+
+__global__ void ce_bwd_kernel(const float* __restrict__ logits, int ld, int V, const int* __restrict__ tok, int B, int L,
+                              const float* __restrict__ tmask, const float* __restrict__ lengths,
+                              const float* __restrict__ lse, const float* __restrict__ gloss, bf16* __restrict__ dlogits,
+                              int ld_d) {
+  const int r = blockIdx.x;
+  const int t = r / B, b = r % B;
+  bf16* d = dlogits + (size_t)r * ld_d;
+  if (tmask[r] == 0.f) {
+    for (int v = threadIdx.x; v < ld_d; v += blockDim.x) d[v] = __float2bfloat16_rn(0.f);
+    return;
+  }
+  const float len = lengths[b];
+  const float g = gloss[b] * (len / (len + 1e-13f));
+  const float l = lse[r];
+  const int target = tok[(size_t)b * (L + 2) + t + 1];
+  const float* x = logits + (size_t)r * ld;
+  for (int v = threadIdx.x; v < ld_d; v += blockDim.x) {
+    float o = 0.f;
+    if (v < V) o = g * (__expf(x[v] - l) - (v == target ? 1.f : 0.f));
+    d[v] = __float2bfloat16_rn(o);
+  }
+}
+
+int ce_backward(cudaStream_t s, const float* logits, int ld, int TB, int V, const int* tok, int B, int L,
+                const float* tmask, const float* lengths, const float* lse, const float* gloss, bf16* dlogits, int ld_d) {
+  ce_bwd_kernel<<<TB, 256, 0, s>>>(logits, ld, V, tok, B, L, tmask, lengths, lse, gloss, dlogits, ld_d);
+  LAUNCHED();
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// layout helpers
+// ---------------------------------------------------------------------------------------------
+template <typename TIn>
+__device__ __forceinline__ float to_f(TIn v);
+template <> __device__ __forceinline__ float to_f<float>(float v) { return v; }
+template <> __device__ __forceinline__ float to_f<bf16>(bf16 v) { return __bfloat162float(v); }
+
+// out[c, r] = in[r, c]; columns of `out` in [rows, ld_out) are zero-filled so it can be a GEMM operand
+template <typename TIn>
+__global__ void transpose_kernel(const TIn* __restrict__ in, int rows, int cols, int ld_in, bf16* __restrict__ out,
+                                 int ld_out) {
+  __shared__ float tile[32][33];
+  const int r0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int r = r0 + i, c = c0 + threadIdx.x;
+    tile[i][threadIdx.x] = (r < rows && c < cols) ? to_f<TIn>(in[(size_t)r * ld_in + c]) : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int c = c0 + i, r = r0 + threadIdx.x;
+    if (c < cols && r < ld_out) out[(size_t)c * ld_out + r] = __float2bfloat16_rn(tile[threadIdx.x][i]);
+  }
+}
+
+int transpose_bf16(cudaStream_t s, const bf16* in, int rows, int cols, int ld_in, bf16* out, int ld_out) {
+  dim3 grid(ceil_div(ld_out, 32), ceil_div(cols, 32));
+  transpose_kernel<bf16><<<grid, dim3(32, 8), 0, s>>>(in, rows, cols, ld_in, out, ld_out);
+  LAUNCHED();
+  return 0;
+}
+int transpose_f32_to_bf16(cudaStream_t s, const float* in, int rows, int cols, int ld_in, bf16* out, int ld_out) {
+  dim3 grid(ceil_div(ld_out, 32), ceil_div(cols, 32));
+  transpose_kernel<float><<<grid, dim3(32, 8), 0, s>>>(in, rows, cols, ld_in, out, ld_out);
+  LAUNCHED();
+  return 0;
+}
+
+template <typename TIn>
+__global__ void rowsum_kernel(const TIn* __restrict__ in, int rows, int cols, int ld, float* __restrict__ out,
+                              int accumulate) {
+  const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (r >= rows) return;
+  const int lane = threadIdx.x & 31;
+  float s = 0.f;
+  for (int c = lane; c < cols; c += 32) s += to_f<TIn>(in[(size_t)r * ld + c]);
+  s = warp_sum(s);
+  if (lane == 0) out[r] = accumulate ? out[r] + s : s;
+}
+int rowsum_bf16(cudaStream_t s, const bf16* in, int rows, int cols, int ld, float* out, int accumulate) {
+  rowsum_kernel<bf16><<<ceil_div(rows, 8), 256, 0, s>>>(in, rows, cols, ld, out, accumulate);
+  LAUNCHED();
+  return 0;
+}
+int rowsum_f32(cudaStream_t s, const float* in, int rows, int cols, int ld, float* out, int accumulate) {
+  rowsum_kernel<float><<<ceil_div(rows, 8), 256, 0, s>>>(in, rows, cols, ld, out, accumulate);
+  LAUNCHED();
+  return 0;
+}
+
+__global__ void convert_kernel(const float* __restrict__ in, int rows, int cols, int ld_in, bf16* __restrict__ out,
+                               int ld_out) {
+  const int r = blockIdx.y;
+  for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < ld_out; c += gridDim.x * blockDim.x)
+    out[(size_t)r * ld_out + c] = __float2bfloat16_rn(c < cols ? in[(size_t)r * ld_in + c] : 0.f);
+}
+int convert_f32_to_bf16(cudaStream_t s, const float* in, int rows, int cols, int ld_in, bf16* out, int ld_out) {
+  dim3 grid(min(8, ceil_div(ld_out, 256)), rows);
+  convert_kernel<<<grid, 256, 0, s>>>(in, rows, cols, ld_in, out, ld_out);
+  LAUNCHED();
+  return 0;
+}
+
+__global__ void timesum_kernel(const bf16* __restrict__ in, int T, int B, int n, int ld, bf16* __restrict__ out,
+                               int ld_out) {
+  const int b = blockIdx.y;
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= ld_out) return;
+  float s = 0.f;
+  if (c < n)
+    for (int t = 0; t < T; ++t) s += __bfloat162float(in[((size_t)t * B + b) * ld + c]);
+  out[(size_t)b * ld_out + c] = __float2bfloat16_rn(s);
+}
+int timesum_bf16(cudaStream_t s, const bf16* in, int T, int B, int n, int ld, bf16* out, int ld_out) {
+  dim3 grid(ceil_div(ld_out, 256), B);
+  timesum_kernel<<<grid, 256, 0, s>>>(in, T, B, n, ld, out, ld_out);
+  LAUNCHED();
+  return 0;
+}
+
+__global__ void add_kernel(float* __restrict__ dst, const float* __restrict__ src, size_t n) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    dst[i] += src[i];
+}
+int add_f32(cudaStream_t s, float* dst, const float* src, size_t n) {
+  add_kernel<<<(int)min((size_t)1184, (n + 255) / 256), 256, 0, s>>>(dst, src, n);
+  LAUNCHED();
+  return 0;
+}
+
+__global__ void gather_rows_f32_kernel(const float* __restrict__ src, const int* __restrict__ idx, int n,
+                                       float* __restrict__ dst) {
+  const int r = blockIdx.x;
+  const float* s = src + (size_t)idx[r] * n;
+  for (int c = threadIdx.x; c < n; c += blockDim.x) dst[(size_t)r * n + c] = s[c];
+}
+int gather_rows_f32(cudaStream_t s, const float* src, const int* idx, int R, int n, float* dst) {
+  gather_rows_f32_kernel<<<R, 256, 0, s>>>(src, idx, n, dst);
+  LAUNCHED();
+  return 0;
+}
+__global__ void gather_rows_bf16_kernel(const bf16* __restrict__ src, const int* __restrict__ idx, int n, int ld,
+                                        bf16* __restrict__ dst) {
+  const int r = blockIdx.x;
+  const bf16* s = src + (size_t)idx[r] * ld;
+  for (int c = threadIdx.x; c < n; c += blockDim.x) dst[(size_t)r * ld + c] = s[c];
+}
+int gather_rows_bf16(cudaStream_t s, const bf16* src, const int* idx, int R, int n, int ld, bf16* dst) {
+  gather_rows_bf16_kernel<<<R, 256, 0, s>>>(src, idx, n, ld, dst);
+  LAUNCHED();
+  return 0;
+}
+
+}  // namespace sscvae
+
+namespace sscvae {
+
+__global__ void colsum_kernel(const float* __restrict__ in, int rows, int cols, int ld, float* __restrict__ out) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= cols) return;
+  float s = 0.f;
+  for (int r = 0; r < rows; ++r) s += in[(size_t)r * ld + c];
+  out[c] = s;
+}
+int colsum_f32(cudaStream_t s, const float* in, int rows, int cols, int ld, float* out) {
+  colsum_kernel<<<ceil_div(cols, 128), 128, 0, s>>>(in, rows, cols, ld, out);
+  LAUNCHED();
+  return 0;
+}
+
+__global__ void rowdot_kernel(const bf16* __restrict__ in, int rows, int cols, int ld, const float* __restrict__ vec,
+                              int period, float* __restrict__ out, int out_stride) {
+  const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (r >= rows) return;
+  const int lane = threadIdx.x & 31;
+  float s = 0.f;
+  for (int c = lane; c < cols; c += 32) s += __bfloat162float(in[(size_t)r * ld + c]) * vec[c % period];
+  s = warp_sum(s);
+  if (lane == 0) out[(size_t)r * out_stride] = s;
+}
+int rowdot_bf16(cudaStream_t s, const bf16* in, int rows, int cols, int ld, const float* vec, int period, float* out,
+                int out_stride) {
+  rowdot_kernel<<<ceil_div(rows, 8), 256, 0, s>>>(in, rows, cols, ld, vec, period, out, out_stride);
+  LAUNCHED();
+  return 0;
+}
+
+__global__ void copy_block_kernel(const float* __restrict__ src, int ld_src, float* __restrict__ dst, int ld_dst,
+                                  int cols) {
+  const int r = blockIdx.y;
+  for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < cols; c += gridDim.x * blockDim.x)
+    dst[(size_t)r * ld_dst + c] = src[(size_t)r * ld_src + c];
+}
+int copy_block_f32(cudaStream_t s, const float* src, int ld_src, float* dst, int ld_dst, int rows, int cols) {
+  dim3 grid(min(8, ceil_div(cols, 256)), rows);
+  copy_block_kernel<<<grid, 256, 0, s>>>(src, ld_src, dst, ld_dst, cols);
+  LAUNCHED();
+  return 0;
+}
+
+__global__ void pack_block_kernel(bf16* __restrict__ dst, int ld_dst, const float* __restrict__ src, int ld_src,
+                                  int rows, int cols, const float* __restrict__ src2, int ld_src2) {
+  const int r = blockIdx.y;
+  for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < cols; c += gridDim.x * blockDim.x) {
+    float v = src[(size_t)r * ld_src + c];
+    if (src2) v += src2[(size_t)r * ld_src2 + c];
+    dst[(size_t)r * ld_dst + c] = __float2bfloat16_rn(v);
+  }
+}
+// transposed variant through a shared-memory tile: dst[c, r] = src[r, c] (+ src2[r, c])
+__global__ void pack_block_t_kernel(bf16* __restrict__ dst, int ld_dst, const float* __restrict__ src, int ld_src,
+                                    int rows, int cols, const float* __restrict__ src2, int ld_src2) {
+  __shared__ float tile[32][33];
+  const int r0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int r = r0 + i, c = c0 + threadIdx.x;
+    float v = 0.f;
+    if (r < rows && c < cols) {
+      v = src[(size_t)r * ld_src + c];
+      if (src2) v += src2[(size_t)r * ld_src2 + c];
+    }
+    tile[i][threadIdx.x] = v;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int c = c0 + i, r = r0 + threadIdx.x;
+    if (c < cols && r < rows) dst[(size_t)c * ld_dst + r] = __float2bfloat16_rn(tile[threadIdx.x][i]);
+  }
+}
+int pack_block(cudaStream_t s, bf16* dst, int ld_dst, int transposed, const float* src, int ld_src, int rows, int cols,
+               const float* src2, int ld_src2) {
+  if (!transposed) {
+    dim3 grid(min(16, ceil_div(cols, 256)), rows);
+    pack_block_kernel<<<grid, 256, 0, s>>>(dst, ld_dst, src, ld_src, rows, cols, src2, ld_src2);
+  } else {
+    dim3 grid(ceil_div(rows, 32), ceil_div(cols, 32));
+    pack_block_t_kernel<<<grid, dim3(32, 8), 0, s>>>(dst, ld_dst, src, ld_src, rows, cols, src2, ld_src2);
+  }
+  LAUNCHED();
+  return 0;
+}
+
+__global__ void vec_add_kernel(const float* a, const float* b, float* out, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = a[i] + (b ? b[i] : 0.f);
+}
+int vec_add_f32(cudaStream_t s, const float* a, const float* b, float* out, int n) {
+  vec_add_kernel<<<ceil_div(n, 256), 256, 0, s>>>(a, b, out, n);
+  LAUNCHED();
+  return 0;
+}
+__global__ void scale_kernel(const float* in, float scale, float* out, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = in ? in[i] * scale : 0.f;
+}
+int scale_rows_f32(cudaStream_t s, const float* in, float scale, float* out, int n) {
+  scale_kernel<<<ceil_div(n, 256), 256, 0, s>>>(in, scale, out, n);
+  LAUNCHED();
+  return 0;
+}
+
+__global__ void embed_scatter_kernel(const int* __restrict__ tok, int B, int L, int pad, const float* __restrict__ dx,
+                                     int ld_dx, int E, float* __restrict__ demb) {
+  const int r = blockIdx.x;
+  const int t = r / B, b = r % B;
+  const int id = tok[(size_t)b * (L + 2) + t];
+  if (id == pad) return;
+  for (int e = threadIdx.x; e < E; e += blockDim.x) atomicAdd(&demb[(size_t)id * E + e], dx[(size_t)r * ld_dx + e]);
+}
+int embed_scatter_add(cudaStream_t s, const int* tok, int B, int L, int pad, const float* dx, int ld_dx, int E,
+                      float* demb) {
+  embed_scatter_kernel<<<(L + 1) * B, 128, 0, s>>>(tok, B, L, pad, dx, ld_dx, E, demb);
+  LAUNCHED();
+  return 0;
+}
+
+}  // namespace sscvae
+
+namespace sscvae {
+__global__ void fill_i32_kernel(int* dst, int value, int n, int div) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = div ? i / div : value;
+}
+int fill_i32(cudaStream_t s, int* dst, int value, int n) {
+  fill_i32_kernel<<<ceil_div(n, 256), 256, 0, s>>>(dst, value, n, 0);
+  LAUNCHED();
+  return 0;
+}
+int iota_div_i32(cudaStream_t s, int* dst, int n, int div) {
+  fill_i32_kernel<<<ceil_div(n, 256), 256, 0, s>>>(dst, 0, n, div);
+  LAUNCHED();
+  return 0;
+}
+}  // namespace sscvae

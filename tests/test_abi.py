@@ -1,0 +1,71 @@
+"""CPU: the C-ABI shared library loads and exports every symbol include/sscvae.h declares (no compute)."""
+import ctypes
+import os
+import re
+
+import pytest
+
+import sscvae
+from sscvae import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    text = open(os.path.join(ROOT, "include", "sscvae.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(sscvae_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    L = ctypes.CDLL(_lib.LIB_PATH)
+    names = declared_symbols()
+    assert len(names) >= 20
+    for n in names:
+        assert hasattr(L, n), f"{n} declared in include/sscvae.h but not exported"
+    assert sorted(_lib.SYMBOLS) == names
+
+
+def test_abi_version_and_error_string():
+    L = _lib.lib()
+    assert L.sscvae_abi_version() == 1
+    h = ctypes.c_void_p()
+    bad = _lib.SscvaeDims(64, 600, 32, 24, 16, 100, 20, 2, 0, 1, 0, 1, 1.0, 0.5)   # sentiment_vae=2 unsupported
+    rc = L.sscvae_create(ctypes.byref(bad), ctypes.byref(h))
+    assert rc == -3
+    assert b"sentiment_vae" in L.sscvae_last_error()
+    with pytest.raises(RuntimeError):
+        _lib.check(rc)
+
+
+def test_workspace_sizes_are_host_side_queries():
+    L = _lib.lib()
+    h = ctypes.c_void_p()
+    d = _lib.SscvaeDims(2048, 600, 900, 768, 150, 10000, 20, 1, 0, 1, 0, 1, 1.0, 0.5)
+    _lib.check(L.sscvae_create(ctypes.byref(d), ctypes.byref(h)))
+    packed = L.sscvae_packed_bytes(h)
+    ws = L.sscvae_train_workspace_bytes(h, 256, 36)
+    dws = L.sscvae_decode_workspace_bytes(h, 64, 36, 8, 5)
+    assert 100e6 < packed < 400e6, packed
+    assert 0.5e9 < ws < 4e9, ws
+    assert 50e6 < dws < 2e9, dws
+    off, nb = ctypes.c_size_t(), ctypes.c_size_t()
+    _lib.check(L.sscvae_train_region(h, 256, 36, b"logits", ctypes.byref(off), ctypes.byref(nb)))
+    assert nb.value == 21 * 256 * 10000 * 4
+    assert L.sscvae_train_region(h, 256, 36, b"nope", ctypes.byref(off), ctypes.byref(nb)) != 0
+    L.sscvae_destroy(h)
+
+
+def test_module_has_reference_state_dict_and_refuses_cpu():
+    import torch
+    from helpers import StubVocabulary
+    from oracle import updown_oracle as uo
+    for E in (600, 48):
+        m = sscvae.UpDownCaptioner(StubVocabulary(90), 64, E, 32, 24, z_space=16, prior_std=1.0,
+                                   latent_embedding="glove", sentiment_vae=1, senti_prior_multip=0.5, cbs_simple=True,
+                                   use_cbs=(E == 600), device=torch.device("cpu"))
+        cfg = uo.OracleConfig(vocab_size=90, image_feature_size=64, embedding_size=E, hidden_size=32,
+                              attention_projection_size=24, z_space=16)
+        assert {k: tuple(v.shape) for k, v in m.state_dict().items()} == uo.param_shapes(cfg)
+        with pytest.raises(RuntimeError, match="no CPU fallback"):
+            m(torch.rand(2, 3, 64), caption_tokens=torch.zeros(2, 20, dtype=torch.long), sentiment=torch.zeros(2, 1))
