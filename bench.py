@@ -1,0 +1,345 @@
+#!/usr/bin/env python
+"""Benchmark of the Style-SeqCVAE var_updown hot path (BASELINE.json): training captions/s.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's sm_100a path
+    python bench.py --impl reference --gpus N --steps K ...  # the reference algorithm on the host CPU
+
+Workload at N GPUs (BASELINE configs[1] / [2]): per GPU one batch of 256 captions,
+36x2048 fp32 region features, vocabulary 10 000, max length 20 (21 teacher-forced steps), shipped dims
+(E=600 tied/frozen, H=900, A=768, Z=150, SENTIMENT_VAE=1), synthetic data, random-init weights.
+One step = forward + loss + BPTT + (gradient all-reduce) + grad-clip + SGD(momentum, wd) update, i.e.
+the body of the reference loop var_updown/scripts/train.py:163-176. A caption = one (image, caption) row.
+
+`value`: K steps on inputs already resident in HBM (4 distinct batches are cycled: 302 MB of inputs
+> 126 MB L2, and the ~1.6 GB per-step working set never stays L2-resident), CUDA events, max over ranks.
+`e2e`: the same steps through UpDownCaptioner.forward with the batch in PINNED HOST memory: every
+step does its own host->device copy (prefetched on a copy stream, inside the timed region) and a
+device->host read of the step's loss.
+After the timed region two extra instrumented steps give the per-kernel-class times for `roofline`.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+DIMS = dict(vocab_size=10000, image_feature_size=2048, embedding_size=600, hidden_size=900,
+            attention_projection_size=768, z_space=150, sentiment_vae=1, simple_vae=False, max_caption_length=20,
+            prior_std=1.0, senti_prior_multip=0.5)
+N_BOXES = 36
+KLD_WEIGHT = 750.0
+# model FLOPs of one training caption (fwd+bwd, x3 convention), dims Y
+GFLOP_PER_CAPTION = 8.10
+WORKLOAD = "style-seqcvae var_updown training step, batch 256/GPU, 36x2048 features, V=10k, L=20, dims E600/H900/A768/Z150"
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=d["hbm_gbs"], tf_burst=d["bf16_tflops"], tf_sustained=d["bf16_tflops_sustained"], src="measured")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sustained=1400.0, src="fallback")
+
+
+def synthetic_batch(B, seed, pin):
+    g = torch.Generator().manual_seed(seed)
+    feats = torch.rand(B, N_BOXES, DIMS["image_feature_size"], generator=g)
+    lens = torch.randint(5, 21, (B,), generator=g)
+    toks = torch.randint(2, DIMS["vocab_size"], (B, 20), generator=g)
+    toks[torch.arange(20)[None, :] >= lens[:, None]] = 0
+    sent = torch.randint(-1, 2, (B, 1), generator=g).float()
+    if pin:
+        feats, toks, sent = feats.pin_memory(), toks.pin_memory(), sent.pin_memory()
+    return feats, toks, sent
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except Exception:
+                continue
+            for n, v in zip(names, r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_reference_run(steps, warmup, B=8):
+    """The reference algorithm on the host CPU: the oracle port (oracle/updown_oracle.py, pinned against the
+    unmodified reference by tests/golden) — forward + loss + backward (autograd BPTT) on BASELINE config 0
+    (B=8), all host threads, dims and shapes of the GPU workload."""
+    from oracle import updown_oracle as uo
+    torch.set_num_threads(os.cpu_count() or 1)
+    cfg = uo.OracleConfig(**DIMS)
+    p = uo.init_params(cfg, seed=0)
+    for k, v in p.items():
+        if not (cfg.tied and k in ("_embedding_layer.weight", "_output_layer.weight")):
+            v.requires_grad_(True)
+    feats, toks, sent = synthetic_batch(B, 0, False)
+    feats = feats[:, :N_BOXES]
+    g = torch.Generator().manual_seed(1234)
+    eps = torch.randn(21, B, DIMS["z_space"], generator=g)
+
+    def step():
+        for v in p.values():
+            v.grad = None
+        out = uo.train_forward(p, cfg, feats, toks, sent, eps)
+        uo.train_objective(out, KLD_WEIGHT).backward()
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = time.perf_counter() - t0
+    return dict(value=B * steps / dt, unit="captions/s", cores=torch.get_num_threads(), kind="port",
+                sample=f"{steps} steps of fwd+loss+bwd on a batch of {B} captions (BASELINE config 0), fp32, torch CPU",
+                seconds=dt)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=256, help="captions per GPU")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-decode", action="store_true")
+    ap.add_argument("--profile-steps", type=int, default=2)
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        r = cpu_reference_run(args.steps, warmup)
+        line = dict(metric="train_captions_per_sec", value=r["value"], unit="captions/s", n_gpus=args.gpus,
+                    steps=args.steps, warmup=warmup, ms_per_step=1e3 * r["seconds"] / args.steps,
+                    higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
+                    impl="reference", config={"workload": WORKLOAD, "sample_batch": 8},
+                    cpu_baseline={k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+                    e2e={"value": r["value"], "unit": "captions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                    gpu_launches=0)
+        print(json.dumps(line), flush=True)
+        return
+
+    import sscvae
+    from sscvae import _lib
+
+    class _Vocab:                      # the four methods the captioner needs
+        def get_vocab_size(self, namespace="tokens"):
+            return DIMS["vocab_size"]
+
+        def get_token_index(self, token, namespace="tokens"):
+            return {"@@UNKNOWN@@": 0, "@@BOUNDARY@@": 1}[token]
+
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (there is no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    B = args.batch
+    torch.manual_seed(0)
+    model = sscvae.UpDownCaptioner(
+        _Vocab(), DIMS["image_feature_size"], DIMS["embedding_size"], DIMS["hidden_size"],
+        DIMS["attention_projection_size"], max_caption_length=20, beam_size=5, use_cbs=True,
+        min_constraints_to_satisfy=2, z_space=DIMS["z_space"], prior_std=1.0, simple_vae=False,
+        latent_embedding="glove", sentiment_vae=1, senti_prior_multip=0.5, cbs_simple=True, device=dev).to(dev)
+    model.train()
+    named = [(k, p) for k, p in model.named_parameters() if p.requires_grad]
+    opt = sscvae.FusedClipSGD([p for _, p in named], lr=0.015, momentum=0.9, weight_decay=0.001, max_norm=12.5,
+                              num_iterations=70000)
+    reducer = sscvae.BucketedGradReducer(named) if world > 1 else None
+    if world > 1:
+        model._group_events = [torch.cuda.Event() for _ in range(_lib.GRAD_GROUPS)]
+
+    n_batches = 4
+    host = [synthetic_batch(B, 100 * rank + i, True) for i in range(n_batches)]
+    resident = [tuple(t.to(dev) for t in b) for b in host]
+    h2d_bytes = sum(t.numel() * t.element_size() for t in host[0])
+
+    def train_step(feats, toks, sent):
+        opt.zero_grad()
+        out = model(feats, None, None, toks, sent)
+        loss = out["loss"].mean() + out["kld"].mean() / KLD_WEIGHT        # train.py:168-171
+        loss.backward()
+        if reducer is not None:
+            reducer.reduce(model._group_events)
+        opt.step()                                                        # clip 12.5 + SGD + lr schedule
+        return loss.detach()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t.item()
+
+    # ---------------------------------------------------------------- device-resident arm
+    for i in range(warmup):
+        train_step(*resident[i % n_batches])
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = _lib.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for i in range(args.steps):
+        train_step(*resident[i % n_batches])
+    e1.record()
+    barrier()
+    ms_dev = max_over_ranks(e0.elapsed_time(e1))
+    launches = _lib.launch_count() - launches0
+
+    # ---------------------------------------------------------------- end-to-end arm (host buffers)
+    copy_stream = torch.cuda.Stream()
+    dbuf = [tuple(torch.empty_like(t, device=dev) for t in host[0]) for _ in range(2)]
+    ready = [torch.cuda.Event(), torch.cuda.Event()]
+    consumed = [torch.cuda.Event(), torch.cuda.Event()]
+    loss_host = torch.zeros(args.steps + warmup, dtype=torch.float32).pin_memory()
+
+    def prefetch(slot, batch):
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(consumed[slot])
+            for d, h in zip(dbuf[slot], batch):
+                d.copy_(h, non_blocking=True)
+            ready[slot].record(copy_stream)
+
+    def e2e_loop(n, base):
+        for s in (0, 1):
+            consumed[s].record()
+        prefetch(0, host[0])
+        for i in range(n):
+            slot = i & 1
+            if i + 1 < n:
+                prefetch(slot ^ 1, host[(i + 1) % n_batches])
+            torch.cuda.current_stream().wait_event(ready[slot])
+            loss = train_step(*dbuf[slot])
+            consumed[slot].record()
+            loss_host[base + i].copy_(loss, non_blocking=True)          # device->host read of the step's loss
+    e2e_loop(warmup, 0)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    e2e_loop(args.steps, warmup)
+    e1.record()
+    barrier()
+    ms_e2e = max_over_ranks(e0.elapsed_time(e1))
+    clocks = sampler.stop() if rank == 0 else None
+    assert torch.isfinite(loss_host).all(), "non-finite loss in the end-to-end arm"
+
+    # ---------------------------------------------------------------- instrumented steps -> roofline
+    peaks = load_peaks()
+    _lib.profile(True)
+    for i in range(args.profile_steps):
+        train_step(*resident[i % n_batches])
+    rep = _lib.profile_report()
+    _lib.profile(False)
+    kernels, total_ms = {}, sum(v["ms"] for v in rep.values())
+    for k, v in sorted(rep.items(), key=lambda kv: -kv[1]["ms"]):
+        ms = v["ms"] / args.profile_steps
+        e = {"launches_per_step": v["count"] / args.profile_steps, "ms_per_step": round(ms, 4),
+             "share": round(v["ms"] / total_ms, 4)}
+        if v["flops"] > 0:
+            e["tflops"] = round(v["flops"] / v["ms"] / 1e9, 2)
+        if v["bytes"] > 0:
+            e["gbs"] = round(v["bytes"] / v["ms"] / 1e6, 1)
+        kernels[k] = e
+    gemm = [v for k, v in rep.items() if k.startswith("gemm")]
+    gemm_ms, gemm_fl, gemm_n = sum(v["ms"] for v in gemm), sum(v["flops"] for v in gemm), sum(v["count"] for v in gemm)
+    roofline = {"kernel": "gemm_tcgen05_kernel (all launches of a step)", "bound": "tensor",
+                "achieved": gemm_fl / gemm_ms / 1e9, "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
+                "frac": gemm_fl / gemm_ms / 1e9 / peaks["tf_sustained"], "traffic": None,
+                "peak_source": peaks["src"] + " bf16_tflops_sustained",
+                "share_of_step": gemm_ms / total_ms, "launches_per_step": gemm_n / args.profile_steps,
+                "avg_launch_us": 1e3 * gemm_ms / gemm_n}
+
+    captions = B * world * args.steps
+    value = captions / (ms_dev / 1e3)
+    e2e_value = captions / (ms_e2e / 1e3)
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    line = dict(
+        metric="train_captions_per_sec", value=value, unit="captions/s", n_gpus=world, steps=args.steps, warmup=warmup,
+        ms_per_step=ms_dev / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="bf16",
+        data="synthetic",
+        config={"workload": WORKLOAD, "global_batch": B * world, "parallelism": f"dp{world}",
+                "l2": f"{n_batches} distinct input batches cycled ({n_batches * h2d_bytes / 1e6:.0f} MB > 126 MB L2); no explicit flush",
+                "step": "fwd + loss + BPTT + grad all-reduce + clip 12.5 + SGD(momentum 0.9, wd 1e-3)"},
+        clocks=clocks,
+        e2e={"value": e2e_value, "unit": "captions/s", "ms_per_step": ms_e2e / args.steps,
+             "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4},
+        gpu_launches=int(launches),
+        roofline=roofline,
+        roofline_step={"bound": "tensor", "achieved": value * GFLOP_PER_CAPTION / 1e3, "peak": peaks["tf_sustained"] * world,
+                       "unit": "TFLOP/s", "frac": value * GFLOP_PER_CAPTION / 1e3 / (peaks["tf_sustained"] * world),
+                       "note": "model FLOPs (8.10 GFLOP/caption, SURVEY §8d) / step time"},
+        kernels=kernels,
+    )
+    if not args.no_cpu_baseline and world == 1:
+        r = cpu_reference_run(3, 1)
+        line["cpu_baseline"] = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
+    else:
+        line["cpu_baseline"] = None
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -184,11 +184,21 @@ int sscvae_decode(SscvaeHandle* h, int batch, int num_boxes, int states, int bea
                   int32_t* n_steps,                   /* out device int32: valid leading steps */
                   void* stream);
 
+/* Named view into the decode workspace for tests ("tok_hist", "bp_hist", "score_hist" (L,B*S*K), "logits", ...). */
+int sscvae_decode_region(const SscvaeHandle* h, int batch, int num_boxes, int states, int beam, const char* name,
+                         size_t* offset, size_t* bytes);
+
 /* ---- training-step tail: clip_grad_norm_ + SGD(momentum, weight decay) fused over
  * a flat parameter buffer; replaces var_updown/scripts/train.py:173-176. */
 int sscvae_grad_sqnorm(const float* grads, size_t n, float* partial /*>= 1024 floats*/, float* sqnorm_out, void* stream);
 int sscvae_sgd_step(float* params, const float* grads, float* momentum_buf, size_t n, const float* sqnorm,
                     float max_norm, float lr, float momentum, float weight_decay, int first_step, void* stream);
+
+/* Optional instrumentation (off by default): CUDA events around every kernel launch of the library,
+ * aggregated per kernel class. report() synchronises the device and writes a JSON object
+ * {"class": {"count", "ms", "flops", "bytes"}} (algorithmic FLOPs / bytes as declared at the call site). */
+int sscvae_profile_enable(int on);
+int sscvae_profile_report(char* buf, size_t n);
 
 /* generic bf16 TN GEMM exposed for unit tests of the tcgen05 kernel:
  * C32[M,N] = A[M,K] (bf16, lda) * B[N,K]^T (bf16, ldb) */

@@ -42,7 +42,8 @@ SYMBOLS = [
     "sscvae_packed_bytes", "sscvae_pack_weights", "sscvae_train_workspace_bytes", "sscvae_train_forward",
     "sscvae_train_backward", "sscvae_train_region", "sscvae_fsm_pack", "sscvae_search_first_step",
     "sscvae_search_step", "sscvae_search_scratch_bytes", "sscvae_search_finish",
-    "sscvae_decode_workspace_bytes", "sscvae_decode", "sscvae_grad_sqnorm", "sscvae_sgd_step", "sscvae_test_gemm",
+    "sscvae_decode_workspace_bytes", "sscvae_decode", "sscvae_decode_region", "sscvae_grad_sqnorm", "sscvae_sgd_step", "sscvae_test_gemm",
+    "sscvae_profile_enable", "sscvae_profile_report",
 ]
 
 
@@ -91,11 +92,14 @@ def lib():
     L.sscvae_search_finish.argtypes = [vp, vp, vp, i32, i32, i32, i32, i32, vp, i32, vp, vp, vp, vp, vp]
     L.sscvae_decode_workspace_bytes.argtypes = [vp, i32, i32, i32, i32]
     L.sscvae_decode_workspace_bytes.restype = sz
+    L.sscvae_decode_region.argtypes = [vp, i32, i32, i32, i32, C.c_char_p, C.POINTER(sz), C.POINTER(sz)]
     L.sscvae_decode.argtypes = [vp, i32, i32, i32, i32, i32, vp, C.POINTER(vp), vp, vp, vp, vp, i32, vp, u64, vp, sz,
                                 vp, vp, vp, vp, vp]
     L.sscvae_grad_sqnorm.argtypes = [vp, sz, vp, vp, vp]
     L.sscvae_sgd_step.argtypes = [vp, vp, vp, sz, vp, f32, f32, f32, f32, i32, vp]
     L.sscvae_test_gemm.argtypes = [vp, i32, vp, i32, i32, i32, i32, vp, i32, vp, i32, i32, vp]
+    L.sscvae_profile_enable.argtypes = [i32]
+    L.sscvae_profile_report.argtypes = [C.c_char_p, sz]
     for name in SYMBOLS:
         fn = getattr(L, name)
         if fn.restype is C.c_int and name not in ("sscvae_abi_version",):
@@ -122,6 +126,17 @@ def ptr_array(tensors):
     for i, t in enumerate(tensors):
         arr[i] = 0 if t is None else t.data_ptr()
     return arr
+
+
+def profile(on: bool):
+    check(lib().sscvae_profile_enable(int(on)))
+
+
+def profile_report() -> dict:
+    import json
+    buf = C.create_string_buffer(1 << 16)
+    check(lib().sscvae_profile_report(buf, len(buf)))
+    return json.loads(buf.value.decode())
 
 
 def launch_count() -> int:

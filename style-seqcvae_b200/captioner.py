@@ -279,6 +279,18 @@ class UpDownCaptioner(nn.Module):
         assert n * itemsize <= nb.value, (name, n * itemsize, nb.value)
         return ws[off.value: off.value + n * itemsize].view(dtype).view(*shape)
 
+    def decode_region(self, B, N, S, K, name, dtype, shape):
+        """Typed view of a named region of the last decode workspace (tests / debugging)."""
+        off, nb = C.c_size_t(), C.c_size_t()
+        _lib.check(_lib.lib().sscvae_decode_region(self._handle, B, N, S, K, name.encode(), C.byref(off), C.byref(nb)))
+        ws = self._ws_cache[("decode", B, N, S, K, self._embedding_layer.weight.device)]
+        n = 1
+        for s in shape:
+            n *= s
+        itemsize = torch.empty(0, dtype=dtype).element_size()
+        assert n * itemsize <= nb.value, (name, n * itemsize, nb.value)
+        return ws[off.value: off.value + n * itemsize].view(dtype).view(*shape)
+
     def _next_seed(self) -> int:
         self._call_counter += 1
         return (int(torch.initial_seed()) * 1000003 + self._call_counter) & 0xFFFFFFFFFFFFFFFF

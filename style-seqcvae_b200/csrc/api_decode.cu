@@ -92,10 +92,10 @@ static int decode_impl(Handle* h, int B, int N, int S, int K, int P, const char*
   if (fsm) { TRY(fsm_pack(s, fsm, B, S, d.V, reinterpret_cast<uint32_t*>(Wi("fsm_bits")))); fsm_bits = reinterpret_cast<uint32_t*>(Wi("fsm_bits")); }
   {  // once per image (the reference recomputes both every step in decode)
     GemmSeg sg = seg(Wb("featsb"), Fp, Pb("wv"), Fp, d.F);
-    GemmEpi e; e.C16 = Wb("projb"); e.ldc16 = d.Ap;
+    GemmEpi e; e.tag = "gemm.decode"; e.C16 = Wb("projb"); e.ldc16 = d.Ap;
     TRY(gemm_bf16_tn(s, B * N, d.A, 1, &sg, e));
     GemmSeg sa = seg(Wb("avgb"), Fp, Pb("w_att_f"), Fp, d.F);
-    GemmEpi ea; ea.C32 = Wf("gavg"); ea.ldc32 = G; ea.bias = Pf("b_att");
+    GemmEpi ea; ea.tag = "gemm.decode"; ea.C32 = Wf("gavg"); ea.ldc32 = G; ea.bias = Pf("b_att");
     TRY(gemm_bf16_tn(s, B, G, 1, &sa, ea));
   }
   int* tok_hist = Wi("tok_hist"); int* bp_hist = Wi("bp_hist"); float* score_hist = Wf("score_hist");
@@ -109,7 +109,7 @@ static int decode_impl(Handle* h, int B, int N, int S, int K, int P, const char*
     TRY(embed_gather_rows(s, tokens, rows, Pb("embb"), d.Ep, Wb("embb_r")));
     {
       GemmSeg sg[2] = {seg(Wb("embb_r"), d.Ep, Pb("w_att_e"), d.Ep, d.E), seg(XA[0], 2 * Hp, Pb("w_att_rec"), 2 * Hp, 2 * Hp)};
-      GemmEpi e; e.C32 = Wf("acc"); e.ldc32 = G;
+      GemmEpi e; e.tag = "gemm.decode"; e.C32 = Wf("acc"); e.ldc32 = G;
       TRY(gemm_bf16_tn(s, rows, G, first ? 1 : 2, sg, e));
       LstmFwdArgs l = {};
       l.R = rows; l.H = H; l.acc = Wf("acc"); l.ld_acc = G; l.add2 = Wf("gavg"); l.ld2 = G; l.rowmap = rowmap;
@@ -119,7 +119,7 @@ static int decode_impl(Handle* h, int B, int N, int S, int K, int P, const char*
     }
     {
       GemmSeg sg = seg(Wb("XE") + Fp, KXe, Pb("wq"), Hp, Hp);
-      GemmEpi e; e.C32 = Wf("q"); e.ldc32 = d.A;
+      GemmEpi e; e.tag = "gemm.decode"; e.C32 = Wf("q"); e.ldc32 = d.A;
       TRY(gemm_bf16_tn(s, rows, d.A, 1, &sg, e));
       AttnArgs aa; aa.R = rows; aa.N = N; aa.A = d.A; aa.Ap = d.Ap; aa.F = d.F; aa.Fp = Fp; aa.rowmap = rowmap;
       aa.q = Wf("q"); aa.ld_q = d.A; aa.proj = Wb("projb"); aa.feats = Wb("featsb"); aa.mask = Wf("mask");
@@ -135,7 +135,7 @@ static int decode_impl(Handle* h, int B, int N, int S, int K, int P, const char*
       GemmSeg sg[3] = {seg(Wb("XE"), KXe, Pb("w_dec_x"), KX, KXe),
                        seg(Wb("ZB"), d.Zp, Pb("w_dec_z"), d.Zp, d.Zp),
                        seg(XA[0] + Hp, 2 * Hp, Pb("w_dec_x") + KXe, KX, Hp)};
-      GemmEpi e; e.C32 = Wf("acc"); e.ldc32 = G;
+      GemmEpi e; e.tag = "gemm.decode"; e.C32 = Wf("acc"); e.ldc32 = G;
       TRY(gemm_bf16_tn(s, rows, G, first ? 2 : 3, sg, e));
       LstmFwdArgs l = {};
       l.R = rows; l.H = H; l.acc = Wf("acc"); l.ld_acc = G; l.bias = Pf("b_dec"); l.rowmap = rowmap;
@@ -146,14 +146,14 @@ static int decode_impl(Handle* h, int B, int N, int S, int K, int P, const char*
     }
     if (d.tied) {
       GemmSeg sg = seg(XA[1] + Hp, 2 * Hp, Pb("w_out"), Hp, Hp);
-      GemmEpi e; e.bias = W(SSCVAE_W_OUT_PROJ_B); e.act = 1; e.C16 = Wb("ob"); e.ldc16 = d.Ep;
+      GemmEpi e; e.tag = "gemm.decode"; e.bias = W(SSCVAE_W_OUT_PROJ_B); e.act = 1; e.C16 = Wb("ob"); e.ldc16 = d.Ep;
       TRY(gemm_bf16_tn(s, rows, d.E, 1, &sg, e));
       GemmSeg sv = seg(Wb("ob"), d.Ep, Pb("embb"), d.Ep, d.E);
-      GemmEpi ev; ev.C32 = Wf("logits"); ev.ldc32 = d.V;
+      GemmEpi ev; ev.tag = "gemm.decode"; ev.C32 = Wf("logits"); ev.ldc32 = d.V;
       TRY(gemm_bf16_tn(s, rows, d.V, 1, &sv, ev));
     } else {
       GemmSeg sg = seg(XA[1] + Hp, 2 * Hp, Pb("w_out"), Hp, Hp);
-      GemmEpi e; e.bias = W(SSCVAE_W_OUT_PROJ_B); e.C32 = Wf("logits"); e.ldc32 = d.V;
+      GemmEpi e; e.tag = "gemm.decode"; e.bias = W(SSCVAE_W_OUT_PROJ_B); e.C32 = Wf("logits"); e.ldc32 = d.V;
       TRY(gemm_bf16_tn(s, rows, d.V, 1, &sg, e));
     }
     return 0;
@@ -248,6 +248,16 @@ size_t sscvae_decode_workspace_bytes(const SscvaeHandle* hh, int batch, int num_
   Handle* h = const_cast<Handle*>(reinterpret_cast<const Handle*>(hh));
   if (!h || batch <= 0 || num_boxes <= 0 || states <= 0 || beam <= 0) return 0;
   return h->decode_plan(batch, num_boxes, states, beam).total;
+}
+
+int sscvae_decode_region(const SscvaeHandle* hh, int batch, int num_boxes, int states, int beam, const char* name,
+                         size_t* offset, size_t* bytes) {
+  Handle* h = const_cast<Handle*>(reinterpret_cast<const Handle*>(hh));
+  REQUIRE(h && name && offset && bytes, "NULL argument");
+  const Region* r = h->decode_plan(batch, num_boxes, states, beam).find(name);
+  REQUIRE(r != nullptr, "unknown workspace region '%s'", name);
+  *offset = r->off; *bytes = r->bytes;
+  return 0;
 }
 
 int sscvae_decode(SscvaeHandle* hh, int batch, int num_boxes, int states, int beam, int per_node, const void* packed,

@@ -296,18 +296,18 @@ static int train_forward_impl(Handle* h, int B, int N, const char* pk, const voi
   TRY(scale_rows_f32(s, d.cond ? sent : nullptr, 1.0f, Wf("sent"), B));
   {  // P = W_v x  (attention.py:125), once per image, kept in bf16
     GemmSeg sg = seg(Wb("featsb"), Fp, Pb("wv"), Fp, d.F);
-    GemmEpi e; e.C16 = Wb("projb"); e.ldc16 = d.Ap;
+    GemmEpi e; e.tag = "gemm.pre"; e.C16 = Wb("projb"); e.ldc16 = d.Ap;
     TRY(gemm_bf16_tn(s, B * N, d.A, 1, &sg, e));
   }
   TRY(embed_gather_train(s, tok, B, d.L, Pb("embb"), d.Ep, Wb("embb_t")));
   {  // teacher-forced embedding block of the attention-LSTM gates for all T at once
     GemmSeg sg = seg(Wb("embb_t"), d.Ep, Pb("w_att_e"), d.Ep, d.E);
-    GemmEpi e; e.C32 = Wf("gx_att"); e.ldc32 = G;
+    GemmEpi e; e.tag = "gemm.pre"; e.C32 = Wf("gx_att"); e.ldc32 = G;
     TRY(gemm_bf16_tn(s, TB, G, 1, &sg, e));
   }
   {  // time-invariant mean-feature block + both biases
     GemmSeg sg = seg(Wb("avgb"), Fp, Pb("w_att_f"), Fp, d.F);
-    GemmEpi e; e.C32 = Wf("gavg"); e.ldc32 = G; e.bias = Pf("b_att");
+    GemmEpi e; e.tag = "gemm.pre"; e.C32 = Wf("gavg"); e.ldc32 = G; e.bias = Pf("b_att");
     TRY(gemm_bf16_tn(s, B, G, 1, &sg, e));
   }
   LatentArgs la; la.R = B; la.Z = d.Z; la.Zp = d.Zp; la.sentiment_vae = d.sv; la.prior_var = d.prior_std * d.prior_std;
@@ -326,7 +326,7 @@ static int train_forward_impl(Handle* h, int B, int N, const char* pk, const voi
     const size_t rG = (size_t)t * B * G, rH = (size_t)t * B * H;
     {  // attention LSTM (updown_cell.py:143-148)
       GemmSeg sg = seg(XA_t, 2 * Hp, Pb("w_att_rec"), 2 * Hp, 2 * Hp);
-      GemmEpi e; e.C32 = acc; e.ldc32 = G;
+      GemmEpi e; e.tag = "gemm.step"; e.C32 = acc; e.ldc32 = G;
       TRY(gemm_bf16_tn(s, B, G, 1, &sg, e));
       LstmFwdArgs l = {};
       l.R = B; l.H = H; l.acc = acc; l.ld_acc = G; l.add1 = Wf("gx_att") + rG; l.ld1 = G; l.add2 = Wf("gavg"); l.ld2 = G;
@@ -336,14 +336,14 @@ static int train_forward_impl(Handle* h, int B, int N, const char* pk, const voi
     }
     {  // query projection + fused region attention (attention.py:69-93, updown_cell.py:156)
       GemmSeg sg = seg(XE_t + Fp, KX, Pb("wq"), Hp, Hp);
-      GemmEpi e; e.C32 = Wf("q") + (size_t)t * B * d.A; e.ldc32 = d.A;
+      GemmEpi e; e.tag = "gemm.step"; e.C32 = Wf("q") + (size_t)t * B * d.A; e.ldc32 = d.A;
       TRY(gemm_bf16_tn(s, B, d.A, 1, &sg, e));
       aa.q = Wf("q") + (size_t)t * B * d.A;
       TRY(attention_forward(s, aa, Wf("alpha") + (size_t)t * B * N, XE_t, KX));
     }
     {  // posterior (encoder) LSTM + latent heads + reparameterised sample (updown_cell.py:176-208)
       GemmSeg sg[2] = {seg(XE_t, KX, Pb("w_enc_x"), KX, KX), seg(HE_t, Hp, Pb("w_enc_hh"), Hp, Hp)};
-      GemmEpi e; e.C32 = acc; e.ldc32 = G;
+      GemmEpi e; e.tag = "gemm.step"; e.C32 = acc; e.ldc32 = G;
       TRY(gemm_bf16_tn(s, B, G, 2, sg, e));
       LstmFwdArgs l = {};
       l.R = B; l.H = H; l.acc = acc; l.ld_acc = G; l.bias = Pf("b_enc");
@@ -352,7 +352,7 @@ static int train_forward_impl(Handle* h, int B, int N, const char* pk, const voi
       l.gates_out = Wf("gates_enc") + rG; l.h1_dst = HE_n; l.ld_h1 = Hp;
       TRY(lstm_forward(s, l));
       GemmSeg sf = seg(HE_n, Hp, Pb("w_fc"), Hp, Hp);
-      GemmEpi ef; ef.C32 = Wf("ml"); ef.ldc32 = d.Z2;
+      GemmEpi ef; ef.tag = "gemm.step"; ef.C32 = Wf("ml"); ef.ldc32 = d.Z2;
       TRY(gemm_bf16_tn(s, B, d.Z2, 1, &sf, ef));
       const size_t rZ = (size_t)t * B * d.Z;
       TRY(latent_forward_train(s, la, Wf("ml"), d.Z2, Pf("b_fc"), eps ? eps + rZ : nullptr, seed, (unsigned long long)t,
@@ -360,7 +360,7 @@ static int train_forward_impl(Handle* h, int B, int N, const char* pk, const voi
     }
     {  // language (decoder) LSTM (updown_cell.py:211-229)
       GemmSeg sg[2] = {seg(XE_t, KX, Pb("w_dec_x"), KX, KX), seg(ZB_t, d.Zp, Pb("w_dec_z"), d.Zp, d.Zp)};
-      GemmEpi e; e.C32 = acc; e.ldc32 = G;
+      GemmEpi e; e.tag = "gemm.step"; e.C32 = acc; e.ldc32 = G;
       TRY(gemm_bf16_tn(s, B, G, 2, sg, e));
       LstmFwdArgs l = {};
       l.R = B; l.H = H; l.acc = acc; l.ld_acc = G; l.bias = Pf("b_dec");
@@ -375,14 +375,14 @@ static int train_forward_impl(Handle* h, int B, int N, const char* pk, const voi
   const bf16* hdec_all = Wb("XA") + (size_t)B * 2 * Hp + Hp;
   if (d.tied) {
     GemmSeg sg = seg(hdec_all, 2 * Hp, Pb("w_out"), Hp, Hp);
-    GemmEpi e; e.bias = W(SSCVAE_W_OUT_PROJ_B); e.act = 1; e.C32 = Wf("o32"); e.ldc32 = d.E; e.C16 = Wb("ob"); e.ldc16 = d.Ep;
+    GemmEpi e; e.tag = "gemm.head"; e.bias = W(SSCVAE_W_OUT_PROJ_B); e.act = 1; e.C32 = Wf("o32"); e.ldc32 = d.E; e.C16 = Wb("ob"); e.ldc16 = d.Ep;
     TRY(gemm_bf16_tn(s, TB, d.E, 1, &sg, e));
     GemmSeg sv = seg(Wb("ob"), d.Ep, Pb("embb"), d.Ep, d.E);
-    GemmEpi ev; ev.C32 = Wf("logits"); ev.ldc32 = d.V;
+    GemmEpi ev; ev.tag = "gemm.head"; ev.C32 = Wf("logits"); ev.ldc32 = d.V;
     TRY(gemm_bf16_tn(s, TB, d.V, 1, &sv, ev));
   } else {
     GemmSeg sg = seg(hdec_all, 2 * Hp, Pb("w_out"), Hp, Hp);
-    GemmEpi e; e.bias = W(SSCVAE_W_OUT_PROJ_B); e.C32 = Wf("logits"); e.ldc32 = d.V;
+    GemmEpi e; e.tag = "gemm.head"; e.bias = W(SSCVAE_W_OUT_PROJ_B); e.C32 = Wf("logits"); e.ldc32 = d.V;
     TRY(gemm_bf16_tn(s, TB, d.V, 1, &sg, e));
   }
   // masked cross entropy and KL sums (updown_captioner.py:315-322, 457-466)
@@ -425,14 +425,14 @@ static int train_backward_impl(Handle* h, int B, int N, const char* pk, const vo
   const bf16* hdec_all = Wb("XA") + (size_t)B * 2 * Hp + Hp;     // h_dec_t, t = 0..T-1, ld 2Hp
   if (d.tied) {
     GemmSeg sg = seg(Wb("dlogits"), d.Vp, Pb("embT"), d.Vp, V);
-    GemmEpi e; e.dtanh = Wf("o32"); e.ldd = E; e.C16 = Wb("dpreo"); e.ldc16 = d.Ep;
+    GemmEpi e; e.tag = "gemm.head_bwd"; e.dtanh = Wf("o32"); e.ldd = E; e.C16 = Wb("dpreo"); e.ldc16 = d.Ep;
     TRY(gemm_bf16_tn(s, TB, E, 1, &sg, e));
     GemmSeg s2 = seg(Wb("dpreo"), d.Ep, Pb("w_outT"), d.Ep, E);
-    GemmEpi e2; e2.C32 = Wf("dhead"); e2.ldc32 = H;
+    GemmEpi e2; e2.tag = "gemm.head_bwd"; e2.C32 = Wf("dhead"); e2.ldc32 = H;
     TRY(gemm_bf16_tn(s, TB, H, 1, &s2, e2));
   } else {
     GemmSeg sg = seg(Wb("dlogits"), d.Vp, Pb("w_outT"), d.Vp, V);
-    GemmEpi e; e.C32 = Wf("dhead"); e.ldc32 = H;
+    GemmEpi e; e.tag = "gemm.head_bwd"; e.C32 = Wf("dhead"); e.ldc32 = H;
     TRY(gemm_bf16_tn(s, TB, H, 1, &sg, e));
   }
   // head weight gradients are final before the time loop starts
@@ -441,7 +441,7 @@ static int train_backward_impl(Handle* h, int B, int N, const char* pk, const vo
     if (Gr(SSCVAE_W_OUT_PROJ_W) || Gr(SSCVAE_W_OUT_PROJ_B)) TRY(transpose_bf16(s, Wb("dpreo"), TB, E, d.Ep, Wb("dpreoT"), TBp));
     if (Gr(SSCVAE_W_OUT_PROJ_W)) {
       GemmSeg sg = seg(Wb("dpreoT"), TBp, Wb("hdecTc"), TBp, TB);
-      GemmEpi e; e.C32 = Gr(SSCVAE_W_OUT_PROJ_W); e.ldc32 = H;
+      GemmEpi e; e.tag = "gemm.head_bwd"; e.C32 = Gr(SSCVAE_W_OUT_PROJ_W); e.ldc32 = H;
       TRY(gemm_bf16_tn(s, E, H, 1, &sg, e));
     }
     if (Gr(SSCVAE_W_OUT_PROJ_B)) TRY(rowsum_bf16(s, Wb("dpreoT"), E, TB, TBp, Gr(SSCVAE_W_OUT_PROJ_B), 0));
@@ -449,7 +449,7 @@ static int train_backward_impl(Handle* h, int B, int N, const char* pk, const vo
     if (Gr(SSCVAE_W_OUT_PROJ_W) || Gr(SSCVAE_W_OUT_PROJ_B)) TRY(transpose_bf16(s, Wb("dlogits"), TB, V, d.Vp, Wb("dlogitsT"), TBp));
     if (Gr(SSCVAE_W_OUT_PROJ_W)) {
       GemmSeg sg = seg(Wb("dlogitsT"), TBp, Wb("hdecTc"), TBp, TB);
-      GemmEpi e; e.C32 = Gr(SSCVAE_W_OUT_PROJ_W); e.ldc32 = H;
+      GemmEpi e; e.tag = "gemm.head_bwd"; e.C32 = Gr(SSCVAE_W_OUT_PROJ_W); e.ldc32 = H;
       TRY(gemm_bf16_tn(s, V, H, 1, &sg, e));
     }
     if (Gr(SSCVAE_W_OUT_PROJ_B)) TRY(rowsum_bf16(s, Wb("dlogitsT"), V, TB, TBp, Gr(SSCVAE_W_OUT_PROJ_B), 0));
@@ -481,13 +481,13 @@ static int train_backward_impl(Handle* h, int B, int N, const char* pk, const vo
     }
     {  // d z -> d mean, d log_var (+ KL gradient) -> d h_enc
       GemmSeg sg = seg(dGd, Gp, Pb("w_dec_zT"), Gp, G);
-      GemmEpi e; e.C32 = Wf("dz"); e.ldc32 = Z;
+      GemmEpi e; e.tag = "gemm.step_bwd"; e.C32 = Wf("dz"); e.ldc32 = Z;
       TRY(gemm_bf16_tn(s, B, Z, 1, &sg, e));
       bf16* dml_t = Wb("dml") + (size_t)t * B * d.Z2p;
       TRY(latent_backward(s, la, Wf("dz"), Z, Wf("eps") + rZ, Wf("mean") + rZ, Wf("logvar") + rZ, gkld,
                           tmask + (size_t)t * B, dml_t, d.Z2p));
       GemmSeg s2 = seg(dml_t, d.Z2p, Pb("w_fcT"), d.Z2p, d.Z2);
-      GemmEpi e2; e2.C32 = Wf("dhenc_fc"); e2.ldc32 = H;
+      GemmEpi e2; e2.tag = "gemm.step_bwd"; e2.C32 = Wf("dhenc_fc"); e2.ldc32 = H;
       TRY(gemm_bf16_tn(s, B, H, 1, &s2, e2));
     }
     {  // encoder LSTM
@@ -502,10 +502,10 @@ static int train_backward_impl(Handle* h, int B, int N, const char* pk, const vo
     }
     {  // d [xhat | h1 | h_dec_{t-1}] from both language LSTMs, d h_enc_{t-1}
       GemmSeg sg[2] = {seg(dGe, Gp, Pb("w_enc_xT"), Gp, G), seg(dGd, Gp, Pb("w_dec_xT"), Gp, G)};
-      GemmEpi e; e.C32 = dXE[cur]; e.ldc32 = KX;
+      GemmEpi e; e.tag = "gemm.step_bwd"; e.C32 = dXE[cur]; e.ldc32 = KX;
       TRY(gemm_bf16_tn(s, B, KX, 2, sg, e));
       GemmSeg s2 = seg(dGe, Gp, Pb("w_enc_hhT"), Gp, G);
-      GemmEpi e2; e2.C32 = dhh[cur]; e2.ldc32 = H;
+      GemmEpi e2; e2.tag = "gemm.step_bwd"; e2.C32 = dhh[cur]; e2.ldc32 = H;
       TRY(gemm_bf16_tn(s, B, H, 1, &s2, e2));
     }
     {  // fused attention backward, then d h1 through the query projection
@@ -513,7 +513,7 @@ static int train_backward_impl(Handle* h, int B, int N, const char* pk, const vo
       bf16* dq_t = Wb("dqb") + (size_t)t * B * d.Ap;
       TRY(attention_backward(s, aa, Wf("alpha") + (size_t)t * B * N, dXE[cur], KX, dq_t, d.Ap, Wf("dproj_acc"), Wf("dwa_acc")));
       GemmSeg sg = seg(dq_t, d.Ap, Pb("wqT"), d.Ap, A);
-      GemmEpi e; e.C32 = Wf("dh1_q"); e.ldc32 = H;
+      GemmEpi e; e.tag = "gemm.step_bwd"; e.C32 = Wf("dh1_q"); e.ldc32 = H;
       TRY(gemm_bf16_tn(s, B, H, 1, &sg, e));
     }
     {  // attention LSTM
@@ -527,7 +527,7 @@ static int train_backward_impl(Handle* h, int B, int N, const char* pk, const vo
       l.dgates = dGa; l.ld_dg = Gp;
       TRY(lstm_backward(s, l));
       GemmSeg sg = seg(dGa, Gp, Pb("w_att_recT"), Gp, G);
-      GemmEpi e; e.C32 = dXA[cur]; e.ldc32 = 2 * Hp;
+      GemmEpi e; e.tag = "gemm.step_bwd"; e.C32 = dXA[cur]; e.ldc32 = 2 * Hp;
       TRY(gemm_bf16_tn(s, B, 2 * Hp, 1, &sg, e));
     }
   }
@@ -536,7 +536,7 @@ static int train_backward_impl(Handle* h, int B, int N, const char* pk, const vo
   auto wgrad = [&](const bf16* AT, int M, const bf16* BT, int Ncols, int K, int ldk, float* C, int ldc) -> int {
     if (!C) return 0;
     GemmSeg sg = seg(AT, ldk, BT, ldk, K);
-    GemmEpi e; e.C32 = C; e.ldc32 = ldc;
+    GemmEpi e; e.tag = "gemm.wgrad"; e.C32 = C; e.ldc32 = ldc;
     return gemm_bf16_tn(s, M, Ncols, 1, &sg, e);
   };
   auto any = [&](std::initializer_list<int> ids) { for (int i : ids) if (gv[i]) return true; return false; };
@@ -619,7 +619,7 @@ static int train_backward_impl(Handle* h, int B, int N, const char* pk, const vo
     if (Gr(SSCVAE_W_ATT_BHH)) TRY(rowsum_bf16(s, dGT, G, TB, TBp, Gr(SSCVAE_W_ATT_BHH), 0));
     if (need_demb) {  // learned embedding (untied): d emb rows = dG_att W_att_ih[:, :E], scattered by token id
       GemmSeg sg = seg(Wb("dG_att"), Gp, Pb("w_att_eT"), Gp, G);
-      GemmEpi e; e.C32 = Wf("dxemb"); e.ldc32 = E;
+      GemmEpi e; e.tag = "gemm.wgrad"; e.C32 = Wf("dxemb"); e.ldc32 = E;
       TRY(gemm_bf16_tn(s, TB, E, 1, &sg, e));
       CUDA_TRY(cudaMemsetAsync(Gr(SSCVAE_W_EMBEDDING), 0, (size_t)V * E * sizeof(float), s));
       TRY(embed_scatter_add(s, tok, B, d.L, d.pad, Wf("dxemb"), E, E, Gr(SSCVAE_W_EMBEDDING)));

@@ -7,6 +7,7 @@
 // One CTA per row; projection, tanh, score, softmax and the weighted sum never leave the SM.
 // HBM/L2 traffic per row: N*Ap + N*Fp bf16 elements read once (16-byte coalesced vectors), F written.
 #include "kernels.cuh"
+#include "prof.cuh"
 
 namespace sscvae {
 
@@ -112,6 +113,7 @@ __global__ void __launch_bounds__(ATT_THREADS) attention_fwd_kernel(AttnArgs a, 
 }
 
 int attention_forward(cudaStream_t s, const AttnArgs& a, float* alpha, bf16* xhat, int ld_x) {
+  PROF_SCOPE(s, "attention_fwd", 0, (double)a.R*((double)a.N*(a.Ap+a.Fp)*2.0 + a.A*4.0 + a.Fp*2.0 + a.N*4.0));
   const size_t smem = (size_t)(2 * a.Ap + 3 * a.N) * sizeof(float);
   attention_fwd_kernel<<<a.R, ATT_THREADS, smem, s>>>(a, alpha, xhat, ld_x);
   LAUNCHED();
@@ -205,6 +207,7 @@ __global__ void __launch_bounds__(ATT_THREADS) attention_bwd_kernel(AttnArgs a, 
 
 int attention_backward(cudaStream_t s, const AttnArgs& a, const float* alpha, const float* dxhat, int ld_dx, bf16* dq,
                        int ld_dq, float* dproj_acc, float* dwa_acc) {
+  PROF_SCOPE(s, "attention_bwd", 0, (double)a.R*((double)a.N*(2.0*a.Ap+a.Fp)*2.0 + (double)a.N*a.A*8.0 + a.Fp*4.0 + a.A*6.0));
   const size_t smem = (size_t)(2 * a.Ap + a.Fp + 4 * a.N) * sizeof(float);
   attention_bwd_kernel<<<a.R, ATT_THREADS, smem, s>>>(a, alpha, dxhat, ld_dx, dq, ld_dq, dproj_acc, dwa_acc);
   LAUNCHED();

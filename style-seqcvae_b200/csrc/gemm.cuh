@@ -22,6 +22,7 @@ struct GemmEpi {
   const float* dtanh = nullptr; int ldd = 0;           // v *= 1 - dtanh[m,n]^2
   float* C32 = nullptr; int ldc32 = 0; int accumulate = 0;   // C32[m,n] (+)= v
   bf16* C16 = nullptr; int ldc16 = 0;                  // C16[m,n] = bf16(v)
+  const char* tag = "gemm";                            // kernel class for the optional profiler (prof.cuh)
 };
 
 // Launches on `stream`; returns 0 or an error code (message via get_error()).

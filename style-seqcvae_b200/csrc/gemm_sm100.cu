@@ -7,6 +7,7 @@
 //                 fused bias / addends / tanh / dtanh -> fp32 and/or bf16 global stores
 // The accumulator never touches registers or shared memory until the epilogue.
 #include "gemm.cuh"
+#include "prof.cuh"
 #include <cuda.h>
 #include <cstdlib>
 #include <cstring>
@@ -408,6 +409,9 @@ static int launch_tc(cudaStream_t stream, GemmParams& prm, const GemmSeg* segs) 
 int gemm_bf16_tn(cudaStream_t stream, int M, int N, int nseg, const GemmSeg* segs, const GemmEpi& epi) {
   REQUIRE(M > 0 && N > 0 && nseg >= 1 && nseg <= MAX_SEG, "gemm: bad shape M=%d N=%d nseg=%d", M, N, nseg);
   REQUIRE(epi.C32 || epi.C16, "gemm: no output");
+  double ksum = 0;
+  for (int i = 0; i < nseg; ++i) ksum += segs[i].K;
+  PROF_SCOPE(stream, epi.tag, 2.0 * M * N * ksum, 2.0 * (M + N) * ksum + (epi.C32 ? 4.0 : 2.0) * M * N);
   static const bool simt = [] { const char* e = getenv("SSCVAE_GEMM_DEBUG_SIMT"); return e && e[0] == '1'; }();
   if (simt) {
     GemmSeg z{nullptr, 0, nullptr, 0, 0};

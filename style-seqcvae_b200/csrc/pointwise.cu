@@ -2,6 +2,7 @@
 // region attention or the search). All are HBM- or latency-bound: coalesced along the feature axis,
 // 16-byte vector accesses where the layout allows, warp-shuffle reductions.
 #include "kernels.cuh"
+#include "prof.cuh"
 #include <curand_kernel.h>
 
 namespace sscvae {
@@ -43,6 +44,7 @@ __global__ void image_prep_kernel(const float* __restrict__ feats, int N, int F,
 }
 
 int image_prep(cudaStream_t s, const float* feats, int B, int N, int F, bf16* featsb, int Fp, float* mask, bf16* avgb) {
+  PROF_SCOPE(s, "image_prep", 0, (double)B*N*(F*4.0+Fp*2.0));
   image_prep_kernel<<<B, 256, N * sizeof(float), s>>>(feats, N, F, featsb, Fp, mask, avgb);
   LAUNCHED();
   return 0;
@@ -92,12 +94,14 @@ __global__ void embed_gather_kernel(const int* __restrict__ tok, int tok_stride_
 }
 
 int embed_gather_train(cudaStream_t s, const int* tok, int B, int L, const bf16* embb, int Ep, bf16* out) {
+  PROF_SCOPE(s, "embed", 0, (double)(L+1)*B*Ep*4.0);
   const int rows = (L + 1) * B;
   embed_gather_kernel<<<ceil_div(rows, 8), 256, 0, s>>>(tok, L + 2, 1, B, rows, embb, Ep, out);
   LAUNCHED();
   return 0;
 }
 int embed_gather_rows(cudaStream_t s, const int* tokens, int R, const bf16* embb, int Ep, bf16* out) {
+  PROF_SCOPE(s, "embed", 0, (double)R*Ep*4.0);
   embed_gather_kernel<<<ceil_div(R, 8), 256, 0, s>>>(tokens, 1, 0, R, R, embb, Ep, out);
   LAUNCHED();
   return 0;
@@ -138,6 +142,7 @@ __global__ void lstm_fwd_kernel(LstmFwdArgs a) {
 }
 
 int lstm_forward(cudaStream_t s, const LstmFwdArgs& a) {
+  PROF_SCOPE(s, "lstm_fwd", 0, (double)a.R*a.H*(4*4.0*2+4.0*2+2.0*2));
   dim3 grid(ceil_div(a.H, 128), a.R);
   lstm_fwd_kernel<<<grid, 128, 0, s>>>(a);
   LAUNCHED();
@@ -170,6 +175,7 @@ __global__ void lstm_bwd_kernel(LstmBwdArgs a) {
 }
 
 int lstm_backward(cudaStream_t s, const LstmBwdArgs& a) {
+  PROF_SCOPE(s, "lstm_bwd", 0, (double)a.R*a.H*(4*4.0+4*2.0+4.0*5));
   dim3 grid(ceil_div(a.H, 128), a.R);
   lstm_bwd_kernel<<<grid, 128, 0, s>>>(a);
   LAUNCHED();
@@ -226,6 +232,7 @@ __global__ void latent_fwd_train_kernel(LatentArgs a, const float* __restrict__ 
 int latent_forward_train(cudaStream_t s, const LatentArgs& a, const float* ml, int ld_ml, const float* bias_ml,
                          const float* eps_in, unsigned long long seed, unsigned long long step, float* mean_out,
                          float* logvar_out, float* eps_out, bf16* zb, int ld_z, float* kl_out) {
+  PROF_SCOPE(s, "latent_fwd", 0, (double)a.R*a.Z*24.0);
   const int threads = min(256, round_up(a.Zp, 32));
   latent_fwd_train_kernel<<<a.R, threads, 0, s>>>(a, ml, ld_ml, bias_ml, eps_in, seed, step, mean_out, logvar_out,
                                                  eps_out, zb, ld_z, kl_out);
@@ -251,6 +258,7 @@ __global__ void latent_fwd_eval_kernel(LatentArgs a, const float* __restrict__ e
 
 int latent_forward_eval(cudaStream_t s, const LatentArgs& a, const float* eps_in, int eps_row_stride,
                         unsigned long long seed, unsigned long long step, bf16* zb, int ld_z) {
+  PROF_SCOPE(s, "latent_fwd", 0, (double)a.R*a.Z*6.0);
   const int threads = min(256, round_up(a.Zp, 32));
   latent_fwd_eval_kernel<<<a.R, threads, 0, s>>>(a, eps_in, eps_row_stride, seed, step, zb, ld_z);
   LAUNCHED();
@@ -287,6 +295,7 @@ __global__ void latent_bwd_kernel(LatentArgs a, const float* __restrict__ dz, in
 
 int latent_backward(cudaStream_t s, const LatentArgs& a, const float* dz, int ld_dz, const float* eps, const float* mean,
                     const float* logvar, const float* gkld, const float* tmask_t, bf16* dml, int ld_dml) {
+  PROF_SCOPE(s, "latent_bwd", 0, (double)a.R*a.Z*24.0);
   latent_bwd_kernel<<<a.R, min(256, round_up(ld_dml, 32)), 0, s>>>(a, dz, ld_dz, eps, mean, logvar, gkld, tmask_t, dml,
                                                                  ld_dml);
   LAUNCHED();
@@ -334,6 +343,7 @@ __global__ void ce_fwd_kernel(const float* __restrict__ logits, int ld, int V, c
 
 int ce_forward(cudaStream_t s, const float* logits, int ld, int TB, int V, const int* tok, int B, int L,
                const float* tmask, float* lse, float* nll) {
+  PROF_SCOPE(s, "ce_fwd", 0, (double)TB*V*4.0*2);
   ce_fwd_kernel<<<TB, 256, 0, s>>>(logits, ld, V, tok, B, L, tmask, lse, nll);
   LAUNCHED();
   return 0;
@@ -387,6 +397,7 @@ __global__ void ce_bwd_kernel(const float* __restrict__ logits, int ld, int V, c
 
 int ce_backward(cudaStream_t s, const float* logits, int ld, int TB, int V, const int* tok, int B, int L,
                 const float* tmask, const float* lengths, const float* lse, const float* gloss, bf16* dlogits, int ld_d) {
+  PROF_SCOPE(s, "ce_bwd", 0, (double)TB*V*6.0);
   ce_bwd_kernel<<<TB, 256, 0, s>>>(logits, ld, V, tok, B, L, tmask, lengths, lse, gloss, dlogits, ld_d);
   LAUNCHED();
   return 0;
@@ -418,12 +429,14 @@ __global__ void transpose_kernel(const TIn* __restrict__ in, int rows, int cols,
 }
 
 int transpose_bf16(cudaStream_t s, const bf16* in, int rows, int cols, int ld_in, bf16* out, int ld_out) {
+  PROF_SCOPE(s, "transpose", 0, (double)rows*cols*4.0);
   dim3 grid(ceil_div(ld_out, 32), ceil_div(cols, 32));
   transpose_kernel<bf16><<<grid, dim3(32, 8), 0, s>>>(in, rows, cols, ld_in, out, ld_out);
   LAUNCHED();
   return 0;
 }
 int transpose_f32_to_bf16(cudaStream_t s, const float* in, int rows, int cols, int ld_in, bf16* out, int ld_out) {
+  PROF_SCOPE(s, "transpose", 0, (double)rows*cols*6.0);
   dim3 grid(ceil_div(ld_out, 32), ceil_div(cols, 32));
   transpose_kernel<float><<<grid, dim3(32, 8), 0, s>>>(in, rows, cols, ld_in, out, ld_out);
   LAUNCHED();
@@ -442,6 +455,7 @@ __global__ void rowsum_kernel(const TIn* __restrict__ in, int rows, int cols, in
   if (lane == 0) out[r] = accumulate ? out[r] + s : s;
 }
 int rowsum_bf16(cudaStream_t s, const bf16* in, int rows, int cols, int ld, float* out, int accumulate) {
+  PROF_SCOPE(s, "reduce", 0, (double)rows*cols*2.0);
   rowsum_kernel<bf16><<<ceil_div(rows, 8), 256, 0, s>>>(in, rows, cols, ld, out, accumulate);
   LAUNCHED();
   return 0;
@@ -476,6 +490,7 @@ __global__ void timesum_kernel(const bf16* __restrict__ in, int T, int B, int n,
   out[(size_t)b * ld_out + c] = __float2bfloat16_rn(s);
 }
 int timesum_bf16(cudaStream_t s, const bf16* in, int T, int B, int n, int ld, bf16* out, int ld_out) {
+  PROF_SCOPE(s, "reduce", 0, (double)T*B*n*2.0);
   dim3 grid(ceil_div(ld_out, 256), B);
   timesum_kernel<<<grid, 256, 0, s>>>(in, T, B, n, ld, out, ld_out);
   LAUNCHED();
@@ -593,6 +608,7 @@ __global__ void pack_block_t_kernel(bf16* __restrict__ dst, int ld_dst, const fl
 }
 int pack_block(cudaStream_t s, bf16* dst, int ld_dst, int transposed, const float* src, int ld_src, int rows, int cols,
                const float* src2, int ld_src2) {
+  PROF_SCOPE(s, "pack_weights", 0, (double)rows*cols*6.0);
   if (!transposed) {
     dim3 grid(min(16, ceil_div(cols, 256)), rows);
     pack_block_kernel<<<grid, 256, 0, s>>>(dst, ld_dst, src, ld_src, rows, cols, src2, ld_src2);

@@ -9,6 +9,7 @@
 // oracle's stable-sort tie-break, so tokens / back-pointers / scores are bit-exact given identical
 // log-probs. Algorithmic bytes per row-step: V*4 (log-probs) + V*4 (FSM word), streamed coalesced.
 #include "search.cuh"
+#include "prof.cuh"
 #include <climits>
 
 namespace sscvae {
@@ -118,6 +119,7 @@ static int launch_rows(cudaStream_t st, const SearchRowsArgs& a) {
 }
 
 int search_rows(cudaStream_t st, const SearchRowsArgs& a) {
+  PROF_SCOPE(st, "search_rows", 0, (double)a.R*a.V*(a.normalized ? 4.0 : 8.0) + (a.fsm_bits ? (double)a.R*a.V*4.0*((a.S+7)/8) : 0.0));
   REQUIRE(a.V >= a.P, "vocabulary (%d) smaller than per-node beam (%d)", a.V, a.P);
   switch (a.P) {
     case 1: return launch_rows<1>(st, a);
@@ -169,6 +171,7 @@ __global__ void search_merge_kernel(const float* __restrict__ cand_val, const in
 
 int search_merge(cudaStream_t st, const float* cand_val, const int32_t* cand_tok, int B, int S, int K, int P,
                  int32_t* tokens, int32_t* backptr, float* scores) {
+  PROF_SCOPE(st, "search_merge", 0, (double)B*S*K*S*P*8.0);
   REQUIRE(S * K * P >= K, "not enough candidates");
   search_merge_kernel<<<ceil_div(B * S, 4), 128, 0, st>>>(cand_val, cand_tok, B, S, K, P, tokens, backptr, scores);
   LAUNCHED();

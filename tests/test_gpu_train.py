@@ -143,10 +143,14 @@ def test_full_size_properties():
     m._eps_override = eps.cuda()
     out = m(feats.cuda(), None, None, toks.cuda(), sent.cuda())
     loss = out["loss"]
-    # random init: NLL per token ~ ln(V) (SURVEY §8c observed 130.2 for ~14 tokens)
-    per_tok = (loss / (lens.cuda() + 1)).mean().item()
-    assert 8.0 < per_tok < 11.5, per_tok
-    assert torch.isfinite(out["kld"]).all() and (out["kld"] >= 0).all()
+    assert torch.isfinite(loss).all() and torch.isfinite(out["kld"]).all() and (out["kld"] >= 0).all()
+    # rows are independent captions: the first 3 rows must match the oracle run on just those rows
+    ocfg = uo.OracleConfig(**cfg)
+    params = {k: v.detach().cpu() for k, v in m.state_dict().items()}
+    o = uo.train_forward(oracle_params(params, ocfg), ocfg, feats[:3], toks[:3], sent[:3], eps[:, :3].contiguous(),
+                         q=uo.Rounding("bf16"))
+    assert ((loss[:3].cpu() - o["loss"]).abs() / o["loss"].abs().clamp(min=1)).max() < 1e-2
+    assert ((out["kld"][:3].cpu() - o["kld"]).abs() / o["kld"].abs().clamp(min=1)).max() < 1e-2
     (out["loss"].mean() + out["kld"].mean() / 750.0).backward()
     grads = {k: p.grad.clone() for k, p in m.named_parameters() if p.grad is not None}
     assert all(torch.isfinite(v).all() for v in grads.values())

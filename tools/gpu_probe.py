@@ -51,9 +51,9 @@ def train_probe(name):
     ob = uo.train_forward(p, ocfg, g["image_features"], g["caption_tokens"], g["sentiment"], g["eps"],
                           q=uo.Rounding("bf16"), record=True)
     reg = lambda n, shp: m.train_region(B, N, n, torch.float32, shp).cpu()
-    print(f"[{name}] loss cuda {out['loss'].cpu().numpy().round(3)}")
+    print(f"[{name}] loss cuda {out['loss'].detach().cpu().numpy().round(3)}")
     print(f"[{name}] loss ref  {g['loss'].numpy().round(3)}")
-    print(f"[{name}] kld  cuda {out['kld'].cpu().numpy().round(3)}")
+    print(f"[{name}] kld  cuda {out['kld'].detach().cpu().numpy().round(3)}")
     print(f"[{name}] kld  ref  {g['kld'].numpy().round(3)}")
     print(f"[{name}] alpha  max abs diff {(reg('alpha', (T, B, N)) - torch.stack([s['alpha'] for s in ob['steps']])).abs().max().item():.3e}")
     print(f"[{name}] mean   rel {rel_err(reg('mean', (T, B, Z)), torch.stack([s['mean'] for s in ob['steps']])):.3e}")
