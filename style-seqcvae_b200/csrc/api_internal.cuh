@@ -18,6 +18,7 @@ struct Dims {
   int Fp, Ep, Hp, Ap, Zp, Vp, G, Gp, Z2, Z2p, KX;
 };
 int init_dims(const SscvaeDims* in, Dims& d);
+int set_l2_window(cudaStream_t s, const void* base, size_t bytes);
 
 struct Region { const char* name; size_t off, bytes; };
 struct Plan {

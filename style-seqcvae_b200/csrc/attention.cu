@@ -31,6 +31,7 @@ __device__ __forceinline__ void attn_scores(const AttnArgs& a, const bf16* __res
     float s = 0.f;
     if (mask_img[n] != 0.f) {                      // masked boxes enter the softmax as u*m = 0
       const bf16x8* p = reinterpret_cast<const bf16x8*>(proj_img + (size_t)n * a.Ap);
+#pragma unroll 4
       for (int i = lane; i < nvec; i += 32) {
         const bf16x8 v = p[i];
 #pragma unroll
@@ -93,14 +94,20 @@ __global__ void __launch_bounds__(ATT_THREADS) attention_fwd_kernel(AttnArgs a, 
 #pragma unroll
     for (int k = 0; k < 8; ++k) acc[k] = 0.f;
     const bf16x8* col = reinterpret_cast<const bf16x8*>(feat_img) + i;
-#pragma unroll 4
-    for (int n = 0; n < a.N; ++n) {
-      const float w = al_s[n];
-      if (w != 0.f) {
-        const bf16x8 v = col[(size_t)n * nvec];
+    constexpr int NB = 6;                       // 6 independent 16-byte loads in flight per thread
+    for (int n0 = 0; n0 < a.N; n0 += NB) {
+      bf16x8 v[NB];
+#pragma unroll
+      for (int j = 0; j < NB; ++j) {
+        const int n = min(n0 + j, a.N - 1);
+        v[j] = col[(size_t)n * nvec];
+      }
+#pragma unroll
+      for (int j = 0; j < NB; ++j) {
+        const float w = (n0 + j < a.N) ? al_s[n0 + j] : 0.f;
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-          const float2 f = __bfloat1622float2(v.v[k]);
+          const float2 f = __bfloat1622float2(v[j].v[k]);
           acc[2 * k] += w * f.x; acc[2 * k + 1] += w * f.y;
         }
       }
@@ -153,6 +160,7 @@ __global__ void __launch_bounds__(ATT_THREADS) attention_bwd_kernel(AttnArgs a, 
     float s = 0.f;
     if (mask_img[n] != 0.f) {
       const bf16x8* p = reinterpret_cast<const bf16x8*>(feat_img + (size_t)n * a.Fp);
+#pragma unroll 8
       for (int i = lane; i < fvec; i += 32) {
         const bf16x8 v = p[i];
 #pragma unroll
@@ -185,18 +193,35 @@ __global__ void __launch_bounds__(ATT_THREADS) attention_bwd_kernel(AttnArgs a, 
   }
   __syncthreads();
   // per projection column a: dq_a = sum_n du_n w_a (1 - th^2), dP_na += du_n w_a (1 - th^2), dw_a += du_n th
+  // Boxes are processed NB at a time with all loads issued before any use, so every thread keeps
+  // 2*NB independent global loads in flight (the serial one-box-at-a-time form was latency-bound).
+  constexpr int NB = 6;
   for (int i = threadIdx.x; i < ld_dq; i += blockDim.x) {
     float dqa = 0.f, dwa = 0.f;
     if (i < a.A) {
       const float qa = q_s[i], wa = wa_s[i];
-      for (int n = 0; n < a.N; ++n) {
-        const float du = da_s[n];
-        if (du != 0.f) {
-          const float th = tanh_approx(qa + __bfloat162float(proj_img[(size_t)n * a.Ap + i]));
-          const float g = du * wa * (1.f - th * th);
-          dqa += g;
-          dwa += du * th;
-          dproj_acc[((size_t)img * a.N + n) * a.A + i] += g;
+      float* acc = dproj_acc + (size_t)img * a.N * a.A + i;
+      const bf16* pj = proj_img + i;
+      for (int n0 = 0; n0 < a.N; n0 += NB) {
+        float pv[NB], av[NB];
+#pragma unroll
+        for (int k = 0; k < NB; ++k) {
+          const int n = n0 + k;
+          const bool ok = n < a.N;
+          pv[k] = ok ? __bfloat162float(pj[(size_t)n * a.Ap]) : 0.f;
+          av[k] = ok ? acc[(size_t)n * a.A] : 0.f;
+        }
+#pragma unroll
+        for (int k = 0; k < NB; ++k) {
+          const int n = n0 + k;
+          if (n < a.N) {
+            const float du = da_s[n];
+            const float th = tanh_approx(qa + pv[k]);
+            const float g = du * wa * (1.f - th * th);
+            dqa += g;
+            dwa += du * th;
+            acc[(size_t)n * a.A] = av[k] + g;
+          }
         }
       }
       dwa_acc[(size_t)r * a.A + i] += dwa;

@@ -16,7 +16,8 @@ struct GemmSeg {
 struct GemmEpi {
   float alpha = 1.0f;                                  // v = alpha * acc
   const float* bias = nullptr;                         // v += bias[n]
-  const float* add1 = nullptr; int ld1 = 0;            // v += add1[m, n]
+  const float* add1 = nullptr; int ld1 = 0;            // v += add1[m, n]   (only for n < add1_cols)
+  int add1_cols = 0x7fffffff;
   const float* add2 = nullptr; int ld2 = 0;            // v += add2[m, n]
   int act = 0;                                         // 1: v = tanh(v)
   const float* dtanh = nullptr; int ldd = 0;           // v *= 1 - dtanh[m,n]^2

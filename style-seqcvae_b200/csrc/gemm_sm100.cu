@@ -139,12 +139,15 @@ __device__ __forceinline__ float tanh_fast(float x) {
   return tanhf(x);
 }
 
-__device__ __forceinline__ void epilogue_row32(const GemmEpi& e, int vec, int M, int N, int row, int col0,
+__device__ __forceinline__ void epilogue_row32(const GemmEpi& e, int vec, int M, int N, int row, int col0, int ncols,
                                                const uint32_t (&acc)[32]) {
   float v[32];
 #pragma unroll
   for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[j]) * e.alpha;
-  const bool full = (col0 + 32 <= N);
+  // `ncols` < 32 only for the narrow (BN=16) tiles; add1 may cover just the first add1_cols columns
+  const bool add1_all = e.add1 && (col0 + 32 <= e.add1_cols);
+  const bool add1_none = !e.add1 || (col0 >= e.add1_cols);
+  const bool full = (ncols == 32) && (col0 + 32 <= N) && (add1_all || add1_none);
   if (vec && full) {
     if (e.bias) {
 #pragma unroll
@@ -153,7 +156,7 @@ __device__ __forceinline__ void epilogue_row32(const GemmEpi& e, int vec, int M,
         v[4 * j] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
       }
     }
-    if (e.add1) {
+    if (add1_all) {
       const float* p = e.add1 + (size_t)row * e.ld1 + col0;
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
@@ -211,10 +214,10 @@ __device__ __forceinline__ void epilogue_row32(const GemmEpi& e, int vec, int M,
 #pragma unroll
   for (int j = 0; j < 32; ++j) {
     const int n = col0 + j;
-    if (n < N) {
+    if (n < N && j < ncols) {
       float x = v[j];
       if (e.bias) x += e.bias[n];
-      if (e.add1) x += e.add1[(size_t)row * e.ld1 + n];
+      if (e.add1 && n < e.add1_cols) x += e.add1[(size_t)row * e.ld1 + n];
       if (e.add2) x += e.add2[(size_t)row * e.ld2 + n];
       if (e.act == 1) x = tanh_fast(x);
       if (e.dtanh) { float t = e.dtanh[(size_t)row * e.ldd + n]; x *= 1.0f - t * t; }
@@ -231,9 +234,10 @@ __device__ __forceinline__ void epilogue_row32(const GemmEpi& e, int vec, int M,
 // the kernel
 // ---------------------------------------------------------------------------------------------
 template <int BN, int STAGES>
-__global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
+__global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
   constexpr int B_STAGE_BYTES = BN * BK * 2;
   constexpr uint32_t IDESC = make_idesc(BM, BN);
+  constexpr int TMEM_COLS = BN < 32 ? 32 : BN;          // allocation granularity: power of two >= 32
   extern __shared__ uint8_t smem_raw[];
   // 128B swizzle needs 1024-byte aligned tiles
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -259,7 +263,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
     mbar_init(accum_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 1) tmem_alloc<BN>(tmem_slot);
+  if (warp == 1) tmem_alloc<TMEM_COLS>(tmem_slot);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -310,14 +314,14 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
       uint32_t acc[32];
       tmem_ld_32x32(tmem_acc + (static_cast<uint32_t>(q * 32) << 16) + c0, acc);
       tmem_ld_wait();
-      if (row < p.M) epilogue_row32(p.epi, p.vec, p.M, p.N, row, n0 + c0, acc);
+      if (row < p.M) epilogue_row32(p.epi, p.vec, p.M, p.N, row, n0 + c0, BN - c0 < 32 ? BN - c0 : 32, acc);
     }
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc<BN>(tmem_acc);
+    tmem_dealloc<TMEM_COLS>(tmem_acc);
   }
 }
 
@@ -437,10 +441,15 @@ int gemm_bf16_tn(cudaStream_t stream, int M, int N, int nseg, const GemmSeg* seg
   if (epi.C32) vec &= aligned16(epi.C32) && (epi.ldc32 % 4 == 0);
   if (epi.C16) vec &= aligned16(epi.C16) && (epi.ldc16 % 8 == 0);
   prm.vec = vec ? 1 : 0;
-  // wide tiles once they fill the 148 SMs, narrow ones for the small-M recurrent GEMMs
-  const long tiles128 = (long)ceil_div(M, BM) * ceil_div(N, 128);
-  if (tiles128 >= 120) return launch_tc<128, 4>(stream, prm, segs);
-  return launch_tc<64, 6>(stream, prm, segs);
+  // The recurrent GEMMs have M = batch (two 128-row tiles) and stream their weights once: they are bound by
+  // bytes in flight per SM, not by the tensor pipe. So: the widest N tile that still yields >= ~100 CTAs,
+  // ~100 KB of TMA stages per CTA and two CTAs resident per SM (no wave-quantisation tail at 149..296 CTAs,
+  // one CTA's epilogue overlaps the other's main loop).
+  const long mt = ceil_div(M, BM);
+  if (mt * ceil_div(N, 128) >= 96) return launch_tc<128, 3>(stream, prm, segs);
+  if (mt * ceil_div(N, 64) >= 96) return launch_tc<64, 4>(stream, prm, segs);
+  if (mt * ceil_div(N, 32) >= 96) return launch_tc<32, 5>(stream, prm, segs);
+  return launch_tc<16, 6>(stream, prm, segs);
 }
 
 }  // namespace sscvae
