@@ -59,25 +59,30 @@ const Region* Plan::find(const char* name) const {
 
 static void plan_packed(const Dims& d, Plan& p) {
   const size_t b = sizeof(bf16);
+  const int NO = d.tied ? d.E : d.V, NOp = d.tied ? d.Ep : d.Vp;
+  // --- weights streamed at every forward timestep, contiguous so one L2 access-policy window covers them
+  p.add("w_att_rec", (size_t)d.G * 2 * d.Hp * b);
+  p.add("wq", (size_t)d.A * d.Hp * b);
+  p.add("w_enc_x", (size_t)d.G * d.KX * b);
+  p.add("w_enc_hh", (size_t)d.G * d.Hp * b);
+  p.add("w_fc", (size_t)d.Z2 * d.Hp * b);
+  p.add("w_dec_x", (size_t)d.G * d.KX * b);
+  p.add("w_dec_z", (size_t)d.G * d.Zp * b);
+  p.add("fwd_end", 0);
+  // --- transposed twins streamed at every backward timestep
+  p.add("w_dec_xzT", (size_t)(d.KX + d.Zp) * d.Gp * b);   // rows [0,KX): W_dec_x^T ; rows [KX,KX+Zp): W_dec_z^T
+  p.add("w_fcT", (size_t)d.Hp * d.Z2p * b);
+  p.add("w_enc_xhT", (size_t)(d.KX + d.Hp) * d.Gp * b);   // rows [0,KX): W_enc_x^T ; rows [KX,KX+Hp): W_enc_hh^T
+  p.add("wqT", (size_t)d.Hp * d.Ap * b);
+  p.add("w_att_recT", (size_t)2 * d.Hp * d.Gp * b);
+  p.add("bwd_end", 0);
+  // --- used once per sequence
   p.add("embb", (size_t)d.V * d.Ep * b);
   if (d.tied) p.add("embT", (size_t)d.E * d.Vp * b);
   p.add("w_att_e", (size_t)d.G * d.Ep * b);
   p.add("w_att_eT", (size_t)d.Ep * d.Gp * b);
   p.add("w_att_f", (size_t)d.G * d.Fp * b);
-  p.add("w_att_rec", (size_t)d.G * 2 * d.Hp * b);
-  p.add("w_att_recT", (size_t)2 * d.Hp * d.Gp * b);
-  p.add("wq", (size_t)d.A * d.Hp * b);
-  p.add("wqT", (size_t)d.Hp * d.Ap * b);
   p.add("wv", (size_t)d.A * d.Fp * b);
-  p.add("w_enc_x", (size_t)d.G * d.KX * b);
-  p.add("w_enc_xhT", (size_t)(d.KX + d.Hp) * d.Gp * b);   // rows [0,KX): W_enc_x^T ; rows [KX,KX+Hp): W_enc_hh^T
-  p.add("w_enc_hh", (size_t)d.G * d.Hp * b);
-  p.add("w_dec_x", (size_t)d.G * d.KX * b);
-  p.add("w_dec_xzT", (size_t)(d.KX + d.Zp) * d.Gp * b);   // rows [0,KX): W_dec_x^T ; rows [KX,KX+Zp): W_dec_z^T
-  p.add("w_dec_z", (size_t)d.G * d.Zp * b);
-  p.add("w_fc", (size_t)d.Z2 * d.Hp * b);
-  p.add("w_fcT", (size_t)d.Hp * d.Z2p * b);
-  const int NO = d.tied ? d.E : d.V, NOp = d.tied ? d.Ep : d.Vp;
   p.add("w_out", (size_t)NO * d.Hp * b);
   p.add("w_outT", (size_t)d.Hp * NOp * b);
   p.add("b_att", (size_t)d.G * 4);
@@ -309,10 +314,8 @@ static int train_forward_impl(Handle* h, int B, int N, const char* pk, const voi
   auto zero = [&](const char* n) { return cudaMemsetAsync(ws + tp.find(n)->off, 0, tp.find(n)->bytes, s); };
   const int T = d.T, TB = T * B, G = d.G, H = d.H, Hp = d.Hp, KX = d.KX, Fp = d.Fp;
 
-  {
-    const Region* r0 = tp.find("featsb"); const Region* r1 = tp.find("projb");
-    TRY(set_l2_window(s, ws + r0->off, r1->off + r1->bytes - r0->off));
-  }
+  // keep the per-timestep weights L2-resident across the 21 steps (they are re-read every step)
+  TRY(set_l2_window(s, pk + pp.find("w_att_rec")->off, pp.find("fwd_end")->off - pp.find("w_att_rec")->off));
   // operand buffers carry zero padding columns and the zero initial states (updown_cell.py:131-140)
   CUDA_TRY(zero("XA")); CUDA_TRY(zero("XE")); CUDA_TRY(zero("HE")); CUDA_TRY(zero("projb"));
   if (d.tied) CUDA_TRY(zero("ob"));
@@ -445,10 +448,7 @@ static int train_backward_impl(Handle* h, int B, int N, const char* pk, const vo
   const int* tok = Wi("tok");
   const float* tmask = Wf("tmask");
 
-  {
-    const Region* r0 = tp.find("featsb"); const Region* r1 = tp.find("projb");
-    TRY(set_l2_window(s, ws + r0->off, r1->off + r1->bytes - r0->off));
-  }
+  TRY(set_l2_window(s, pk + pp.find("w_dec_xzT")->off, pp.find("bwd_end")->off - pp.find("w_dec_xzT")->off));
   const char* zl[] = {"dproj_acc", "dwa_acc", "dc1", "dc_enc", "dc_dec", "dXEH0", "dXEH1", "dXA0", "dXA1",
                       "dG_att", "dG_enc", "dG_dec", "dqb"};
   for (const char* n : zl) CUDA_TRY(zero(n));

@@ -4,10 +4,14 @@
 //   u_n   = w_a . tanh(q_r + P[img(r), n, :])             (attention.py:69-88)
 //   alpha = masked_softmax(u, mask[img(r)])                (allennlp: softmax(u*m)*m / (sum + 1e-13))
 //   xhat  = sum_n alpha_n * x[img(r), n, :]                (updown_cell.py:156-158)
-// One CTA per row; projection, tanh, score, softmax and the weighted sum never leave the SM.
+// One 4-CTA thread-block cluster per row (boxes / feature slices / projection columns split across the CTAs,
+// the N scores exchanged through distributed shared memory); nothing intermediate goes to global memory.
 // HBM/L2 traffic per row: N*Ap + N*Fp bf16 elements read once (16-byte coalesced vectors), F written.
 #include "kernels.cuh"
 #include "prof.cuh"
+#include <cooperative_groups.h>
+
+namespace cg = cooperative_groups;
 
 namespace sscvae {
 
@@ -20,14 +24,15 @@ __device__ __forceinline__ float tanh_approx(float x) {
 }
 
 static constexpr int ATT_THREADS = 256;
+static constexpr int CL = 4;      // CTAs per row: a thread-block cluster splits boxes, features and projection columns
 
-// scores u_n for all boxes of this row: warp per box, lanes over the projection axis
+// scores u_n for boxes [n_lo, n_hi) of this row: warp per box, lanes over the projection axis
 __device__ __forceinline__ void attn_scores(const AttnArgs& a, const bf16* __restrict__ proj_img,
                                             const float* __restrict__ mask_img, const float* q_s, const float* wa_s,
-                                            float* u_s) {
+                                            float* u_s, int n_lo, int n_hi) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
   const int nvec = a.Ap >> 3;
-  for (int n = warp; n < a.N; n += nwarp) {
+  for (int n = n_lo + warp; n < n_hi; n += nwarp) {
     float s = 0.f;
     if (mask_img[n] != 0.f) {                      // masked boxes enter the softmax as u*m = 0
       const bf16x8* p = reinterpret_cast<const bf16x8*>(proj_img + (size_t)n * a.Ap);
@@ -44,6 +49,15 @@ __device__ __forceinline__ void attn_scores(const AttnArgs& a, const bf16* __res
       s = warp_sum(s);
     }
     if (lane == 0) u_s[n] = s;
+  }
+}
+
+// After every CTA of the cluster has filled its slice [rank*nper, ...) of a per-box array in its own shared
+// memory, copy the other slices over distributed shared memory so each CTA holds all N values.
+__device__ __forceinline__ void cluster_gather(cg::cluster_group& cluster, float* arr, int N, int nper, int rank) {
+  for (int n = threadIdx.x; n < N; n += blockDim.x) {
+    const int owner = n / nper;
+    if (owner != rank) arr[n] = *cluster.map_shared_rank(arr + n, owner);
   }
 }
 
@@ -64,76 +78,72 @@ __device__ __forceinline__ float attn_softmax(int N, const float* mask_img, cons
   return Rn;
 }
 
-__global__ void __launch_bounds__(ATT_THREADS) attention_fwd_kernel(AttnArgs a, float* __restrict__ alpha,
-                                                                   bf16* __restrict__ xhat, int ld_x) {
+__global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(ATT_THREADS)
+attention_fwd_kernel(AttnArgs a, float* __restrict__ alpha, bf16* __restrict__ xhat, int ld_x) {
   extern __shared__ float sm[];
   float* q_s = sm;                      // Ap
   float* wa_s = q_s + a.Ap;             // Ap
   float* u_s = wa_s + a.Ap;             // N
   float* s_s = u_s + a.N;               // N
   float* al_s = s_s + a.N;              // N
-  const int r = blockIdx.x;
+  cg::cluster_group cluster = cg::this_cluster();
+  const int rank = (int)cluster.block_rank();
+  const int r = blockIdx.x / CL;
   const int img = a.rowmap ? a.rowmap[r] : r;
   const bf16* proj_img = a.proj + (size_t)img * a.N * a.Ap;
   const bf16* feat_img = a.feats + (size_t)img * a.N * a.Fp;
   const float* mask_img = a.mask + (size_t)img * a.N;
+  const int nper = (a.N + CL - 1) / CL;
   for (int i = threadIdx.x; i < a.Ap; i += blockDim.x) {
     q_s[i] = (i < a.A) ? a.q[(size_t)r * a.ld_q + i] : 0.f;
     wa_s[i] = (i < a.A) ? a.w_a[i] : 0.f;
   }
   __syncthreads();
-  attn_scores(a, proj_img, mask_img, q_s, wa_s, u_s);
-  __syncthreads();
+  attn_scores(a, proj_img, mask_img, q_s, wa_s, u_s, rank * nper, min(a.N, (rank + 1) * nper));
+  cluster.sync();
+  cluster_gather(cluster, u_s, a.N, nper, rank);
+  cluster.sync();                       // nobody's shared memory is read remotely after this point
   if (threadIdx.x < 32) attn_softmax(a.N, mask_img, u_s, s_s, al_s);
   __syncthreads();
-  for (int n = threadIdx.x; n < a.N; n += blockDim.x) alpha[(size_t)r * a.N + n] = al_s[n];
-  // weighted sum: each thread owns 8 consecutive features
-  const int nvec = a.Fp >> 3;
-  for (int i = threadIdx.x; i < nvec; i += blockDim.x) {
-    float acc[8];
-#pragma unroll
-    for (int k = 0; k < 8; ++k) acc[k] = 0.f;
-    const bf16x8* col = reinterpret_cast<const bf16x8*>(feat_img) + i;
-    constexpr int NB = 6;                       // 6 independent 16-byte loads in flight per thread
+  if (rank == 0)
+    for (int n = threadIdx.x; n < a.N; n += blockDim.x) alpha[(size_t)r * a.N + n] = al_s[n];
+  // weighted sum over this CTA's quarter of the feature axis; a thread owns 2 consecutive features (a warp
+  // reads 128 contiguous bytes per box), NB independent loads in flight
+  const int npair = a.Fp >> 1;
+  const int pper = (npair + CL - 1) / CL;
+  const int p_hi = min(npair, (rank + 1) * pper);
+  constexpr int NB = 12;
+  for (int i = rank * pper + threadIdx.x; i < p_hi; i += blockDim.x) {
+    float acc0 = 0.f, acc1 = 0.f;
+    const __nv_bfloat162* col = reinterpret_cast<const __nv_bfloat162*>(feat_img) + i;
     for (int n0 = 0; n0 < a.N; n0 += NB) {
-      bf16x8 v[NB];
+      __nv_bfloat162 v[NB];
 #pragma unroll
-      for (int j = 0; j < NB; ++j) {
-        const int n = min(n0 + j, a.N - 1);
-        v[j] = col[(size_t)n * nvec];
-      }
+      for (int j = 0; j < NB; ++j) v[j] = col[(size_t)min(n0 + j, a.N - 1) * npair];
 #pragma unroll
       for (int j = 0; j < NB; ++j) {
         const float w = (n0 + j < a.N) ? al_s[n0 + j] : 0.f;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const float2 f = __bfloat1622float2(v[j].v[k]);
-          acc[2 * k] += w * f.x; acc[2 * k + 1] += w * f.y;
-        }
+        const float2 f = __bfloat1622float2(v[j]);
+        acc0 += w * f.x; acc1 += w * f.y;
       }
     }
-    bf16x8 o;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) o.v[k] = __floats2bfloat162_rn(acc[2 * k], acc[2 * k + 1]);
-    st_bf16x8(xhat + (size_t)r * ld_x + i * 8, o);
+    *reinterpret_cast<__nv_bfloat162*>(xhat + (size_t)r * ld_x + 2 * i) = __floats2bfloat162_rn(acc0, acc1);
   }
 }
 
 int attention_forward(cudaStream_t s, const AttnArgs& a, float* alpha, bf16* xhat, int ld_x) {
   PROF_SCOPE(s, "attention_fwd", 0, (double)a.R*((double)a.N*(a.Ap+a.Fp)*2.0 + a.A*4.0 + a.Fp*2.0 + a.N*4.0));
   const size_t smem = (size_t)(2 * a.Ap + 3 * a.N) * sizeof(float);
-  attention_fwd_kernel<<<a.R, ATT_THREADS, smem, s>>>(a, alpha, xhat, ld_x);
+  attention_fwd_kernel<<<a.R * CL, ATT_THREADS, smem, s>>>(a, alpha, xhat, ld_x);
   LAUNCHED();
   return 0;
 }
 
 // backward of the same three fused ops. dproj_acc (images,N,A) and dwa_acc (R,A) are accumulated
 // across timesteps by the owning CTA (row r == image r in training), so no atomics are needed.
-__global__ void __launch_bounds__(ATT_THREADS) attention_bwd_kernel(AttnArgs a, const float* __restrict__ alpha_in,
-                                                                   const float* __restrict__ dxhat, int ld_dx,
-                                                                   bf16* __restrict__ dq, int ld_dq,
-                                                                   float* __restrict__ dproj_acc,
-                                                                   float* __restrict__ dwa_acc) {
+__global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(ATT_THREADS)
+attention_bwd_kernel(AttnArgs a, const float* __restrict__ alpha_in, const float* __restrict__ dxhat, int ld_dx,
+                     bf16* __restrict__ dq, int ld_dq, float* __restrict__ dproj_acc, float* __restrict__ dwa_acc) {
   extern __shared__ float sm[];
   float* q_s = sm;                      // Ap
   float* wa_s = q_s + a.Ap;             // Ap
@@ -142,21 +152,25 @@ __global__ void __launch_bounds__(ATT_THREADS) attention_bwd_kernel(AttnArgs a, 
   float* s_s = u_s + a.N;               // N
   float* al_s = s_s + a.N;              // N
   float* da_s = al_s + a.N;             // N  (d alpha, then d u)
-  const int r = blockIdx.x;
+  cg::cluster_group cluster = cg::this_cluster();
+  const int rank = (int)cluster.block_rank();
+  const int r = blockIdx.x / CL;
   const int img = a.rowmap ? a.rowmap[r] : r;
   const bf16* proj_img = a.proj + (size_t)img * a.N * a.Ap;
   const bf16* feat_img = a.feats + (size_t)img * a.N * a.Fp;
   const float* mask_img = a.mask + (size_t)img * a.N;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
+  const int nper = (a.N + CL - 1) / CL;
+  const int n_lo = rank * nper, n_hi = min(a.N, (rank + 1) * nper);
   for (int i = threadIdx.x; i < a.Ap; i += blockDim.x) {
     q_s[i] = (i < a.A) ? a.q[(size_t)r * a.ld_q + i] : 0.f;
     wa_s[i] = (i < a.A) ? a.w_a[i] : 0.f;
   }
   for (int i = threadIdx.x; i < a.Fp; i += blockDim.x) dx_s[i] = (i < a.F) ? dxhat[(size_t)r * ld_dx + i] : 0.f;
   __syncthreads();
-  // d alpha_n = dxhat . x_n
+  // d alpha_n = dxhat . x_n for this CTA's boxes
   const int fvec = a.Fp >> 3;
-  for (int n = warp; n < a.N; n += nwarp) {
+  for (int n = n_lo + warp; n < n_hi; n += nwarp) {
     float s = 0.f;
     if (mask_img[n] != 0.f) {
       const bf16x8* p = reinterpret_cast<const bf16x8*>(feat_img + (size_t)n * a.Fp);
@@ -173,8 +187,11 @@ __global__ void __launch_bounds__(ATT_THREADS) attention_bwd_kernel(AttnArgs a, 
     }
     if (lane == 0) da_s[n] = s;
   }
-  attn_scores(a, proj_img, mask_img, q_s, wa_s, u_s);
-  __syncthreads();
+  attn_scores(a, proj_img, mask_img, q_s, wa_s, u_s, n_lo, n_hi);
+  cluster.sync();
+  cluster_gather(cluster, u_s, a.N, nper, rank);
+  cluster_gather(cluster, da_s, a.N, nper, rank);
+  cluster.sync();
   if (threadIdx.x < 32) {
     const float Rn = attn_softmax(a.N, mask_img, u_s, s_s, al_s);
     // alpha = r / R with r = s*m :  dr = (dalpha - sum_k dalpha_k alpha_k) / R ; ds = dr*m
@@ -192,11 +209,12 @@ __global__ void __launch_bounds__(ATT_THREADS) attention_bwd_kernel(AttnArgs a, 
     for (int n = lane; n < a.N; n += 32) da_s[n] = s_s[n] * (da_s[n] - dss) * mask_img[n];
   }
   __syncthreads();
-  // per projection column a: dq_a = sum_n du_n w_a (1 - th^2), dP_na += du_n w_a (1 - th^2), dw_a += du_n th
-  // Boxes are processed NB at a time with all loads issued before any use, so every thread keeps
-  // 2*NB independent global loads in flight (the serial one-box-at-a-time form was latency-bound).
+  // this CTA's quarter of the projection columns: dq_a = sum_n du_n w_a (1 - th^2), dP_na += du_n w_a (1 - th^2),
+  // dw_a += du_n th. Boxes are processed NB at a time with all loads issued before any use.
   constexpr int NB = 6;
-  for (int i = threadIdx.x; i < ld_dq; i += blockDim.x) {
+  const int cper = (ld_dq + CL - 1) / CL;
+  const int c_hi = min(ld_dq, (rank + 1) * cper);
+  for (int i = rank * cper + threadIdx.x; i < c_hi; i += blockDim.x) {
     float dqa = 0.f, dwa = 0.f;
     if (i < a.A) {
       const float qa = q_s[i], wa = wa_s[i];
@@ -234,7 +252,7 @@ int attention_backward(cudaStream_t s, const AttnArgs& a, const float* alpha, co
                        int ld_dq, float* dproj_acc, float* dwa_acc) {
   PROF_SCOPE(s, "attention_bwd", 0, (double)a.R*((double)a.N*(2.0*a.Ap+a.Fp)*2.0 + (double)a.N*a.A*8.0 + a.Fp*4.0 + a.A*6.0));
   const size_t smem = (size_t)(2 * a.Ap + a.Fp + 4 * a.N) * sizeof(float);
-  attention_bwd_kernel<<<a.R, ATT_THREADS, smem, s>>>(a, alpha, dxhat, ld_dx, dq, ld_dq, dproj_acc, dwa_acc);
+  attention_bwd_kernel<<<a.R * CL, ATT_THREADS, smem, s>>>(a, alpha, dxhat, ld_dx, dq, ld_dq, dproj_acc, dwa_acc);
   LAUNCHED();
   return 0;
 }

@@ -139,76 +139,74 @@ __device__ __forceinline__ float tanh_fast(float x) {
   return tanhf(x);
 }
 
-__device__ __forceinline__ void epilogue_row32(const GemmEpi& e, int vec, int M, int N, int row, int col0, int ncols,
-                                               const uint32_t (&acc)[32]) {
-  float v[32];
-#pragma unroll
-  for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[j]) * e.alpha;
+__device__ __forceinline__ void epilogue_row32(const GemmEpi& e, int vec, int M, int N, int row0, int col0, int ncols,
+                                               const uint32_t (&acc)[32], float* stage) {
+  const int lane = threadIdx.x & 31;
+  const int row = row0 + lane;           // TMEM lane == output row of this thread's 32 accumulator columns
   // `ncols` < 32 only for the narrow (BN=16) tiles; add1 may cover just the first add1_cols columns
   const bool add1_all = e.add1 && (col0 + 32 <= e.add1_cols);
   const bool add1_none = !e.add1 || (col0 >= e.add1_cols);
   const bool full = (ncols == 32) && (col0 + 32 <= N) && (add1_all || add1_none);
   if (vec && full) {
-    if (e.bias) {
+    // Transpose the warp's 32x32 fp32 block through shared memory (the pipeline's stage buffers are free by
+    // now) so that global traffic is coalesced: afterwards 8 consecutive lanes own 32 consecutive columns of
+    // ONE row (128 contiguous bytes), 4 rows per instruction, for the addend loads and for the stores.
+    constexpr int PITCH = 36;            // floats; keeps float4 alignment
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        float4 b = *reinterpret_cast<const float4*>(e.bias + col0 + 4 * j);
-        v[4 * j] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
-      }
-    }
-    if (add1_all) {
-      const float* p = e.add1 + (size_t)row * e.ld1 + col0;
+    for (int j = 0; j < 8; ++j)
+      *reinterpret_cast<float4*>(stage + lane * PITCH + 4 * j) =
+          make_float4(__uint_as_float(acc[4 * j]), __uint_as_float(acc[4 * j + 1]), __uint_as_float(acc[4 * j + 2]),
+                      __uint_as_float(acc[4 * j + 3]));
+    __syncwarp();
+    const int c4 = (lane & 7) * 4;
+    const int n = col0 + c4;
+    float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (e.bias) bias4 = *reinterpret_cast<const float4*>(e.bias + n);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        float4 b = *reinterpret_cast<const float4*>(p + 4 * j);
-        v[4 * j] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
-      }
-    }
-    if (e.add2) {
-      const float* p = e.add2 + (size_t)row * e.ld2 + col0;
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        float4 b = *reinterpret_cast<const float4*>(p + 4 * j);
-        v[4 * j] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
-      }
-    }
-    if (e.act == 1) {
-#pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] = tanh_fast(v[j]);
-    }
-    if (e.dtanh) {
-      const float* p = e.dtanh + (size_t)row * e.ldd + col0;
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        float4 t = *reinterpret_cast<const float4*>(p + 4 * j);
-        v[4 * j] *= 1.0f - t.x * t.x; v[4 * j + 1] *= 1.0f - t.y * t.y;
-        v[4 * j + 2] *= 1.0f - t.z * t.z; v[4 * j + 3] *= 1.0f - t.w * t.w;
-      }
-    }
-    if (e.C32) {
-      float* p = e.C32 + (size_t)row * e.ldc32 + col0;
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        float4 o = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-        if (e.accumulate) {
-          float4 c = *reinterpret_cast<const float4*>(p + 4 * j);
-          o.x += c.x; o.y += c.y; o.z += c.z; o.w += c.w;
+    for (int k = 0; k < 8; ++k) {
+      const int rr = k * 4 + (lane >> 3);
+      const int r = row0 + rr;
+      if (r < M) {
+        float4 v = *reinterpret_cast<const float4*>(stage + rr * PITCH + c4);
+        v.x = v.x * e.alpha + bias4.x; v.y = v.y * e.alpha + bias4.y;
+        v.z = v.z * e.alpha + bias4.z; v.w = v.w * e.alpha + bias4.w;
+        if (add1_all) {
+          const float4 b = *reinterpret_cast<const float4*>(e.add1 + (size_t)r * e.ld1 + n);
+          v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
         }
-        *reinterpret_cast<float4*>(p + 4 * j) = o;
+        if (e.add2) {
+          const float4 b = *reinterpret_cast<const float4*>(e.add2 + (size_t)r * e.ld2 + n);
+          v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+        }
+        if (e.act == 1) { v.x = tanh_fast(v.x); v.y = tanh_fast(v.y); v.z = tanh_fast(v.z); v.w = tanh_fast(v.w); }
+        if (e.dtanh) {
+          const float4 t = *reinterpret_cast<const float4*>(e.dtanh + (size_t)r * e.ldd + n);
+          v.x *= 1.0f - t.x * t.x; v.y *= 1.0f - t.y * t.y; v.z *= 1.0f - t.z * t.z; v.w *= 1.0f - t.w * t.w;
+        }
+        if (e.C32) {
+          float* p = e.C32 + (size_t)r * e.ldc32 + n;
+          if (e.accumulate) {
+            const float4 c = *reinterpret_cast<const float4*>(p);
+            v.x += c.x; v.y += c.y; v.z += c.z; v.w += c.w;
+          }
+          *reinterpret_cast<float4*>(p) = v;
+        }
+        if (e.C16) {
+          __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+          uint2 o;
+          o.x = *reinterpret_cast<uint32_t*>(&lo);
+          o.y = *reinterpret_cast<uint32_t*>(&hi);
+          *reinterpret_cast<uint2*>(e.C16 + (size_t)r * e.ldc16 + n) = o;
+        }
       }
     }
-    if (e.C16) {
-      bf16* p = e.C16 + (size_t)row * e.ldc16 + col0;
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        bf16x8 o;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) o.v[k] = __floats2bfloat162_rn(v[8 * j + 2 * k], v[8 * j + 2 * k + 1]);
-        st_bf16x8(p + 8 * j, o);
-      }
-    }
+    __syncwarp();
     return;
   }
+  if (row >= M) return;
+  float v[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[j]) * e.alpha;
   // scalar path (ragged right edge or unaligned pointers, e.g. gradients written straight into
   // a column block of a reference-layout weight matrix)
 #pragma unroll
@@ -314,7 +312,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_tcgen05_kernel(const __g
       uint32_t acc[32];
       tmem_ld_32x32(tmem_acc + (static_cast<uint32_t>(q * 32) << 16) + c0, acc);
       tmem_ld_wait();
-      if (row < p.M) epilogue_row32(p.epi, p.vec, p.M, p.N, row, n0 + c0, BN - c0 < 32 ? BN - c0 : 32, acc);
+      epilogue_row32(p.epi, p.vec, p.M, p.N, m0 + q * 32, n0 + c0, BN - c0 < 32 ? BN - c0 : 32, acc,
+                     reinterpret_cast<float*>(smem_a) + (warp - 2) * 32 * 36);
     }
   }
   tc_fence_before();
@@ -445,6 +444,21 @@ int gemm_bf16_tn(cudaStream_t stream, int M, int N, int nseg, const GemmSeg* seg
   // bytes in flight per SM, not by the tensor pipe. So: the widest N tile that still yields >= ~100 CTAs,
   // ~100 KB of TMA stages per CTA and two CTAs resident per SM (no wave-quantisation tail at 149..296 CTAs,
   // one CTA's epilogue overlaps the other's main loop).
+  if (const char* f = getenv("SSCVAE_GEMM_FORCE")) {      // tuning knob for tools/gemm_bench.py: "BN,STAGES"
+    int bn = 0, st = 0;
+    if (sscanf(f, "%d,%d", &bn, &st) == 2) {
+      if (bn == 256 && st == 4) return launch_tc<256, 4>(stream, prm, segs);
+      if (bn == 128 && st == 6) return launch_tc<128, 6>(stream, prm, segs);
+      if (bn == 128 && st == 3) return launch_tc<128, 3>(stream, prm, segs);
+      if (bn == 64 && st == 8) return launch_tc<64, 8>(stream, prm, segs);
+      if (bn == 64 && st == 4) return launch_tc<64, 4>(stream, prm, segs);
+      if (bn == 32 && st == 5) return launch_tc<32, 5>(stream, prm, segs);
+      if (bn == 32 && st == 10) return launch_tc<32, 10>(stream, prm, segs);
+      if (bn == 16 && st == 6) return launch_tc<16, 6>(stream, prm, segs);
+      set_error("SSCVAE_GEMM_FORCE=%s: no such instantiation", f);
+      return SSCVAE_ERR_BAD_ARG;
+    }
+  }
   const long mt = ceil_div(M, BM);
   if (mt * ceil_div(N, 128) >= 96) return launch_tc<128, 3>(stream, prm, segs);
   if (mt * ceil_div(N, 64) >= 96) return launch_tc<64, 4>(stream, prm, segs);
