@@ -124,7 +124,7 @@ static int decode_impl(Handle* h, int B, int N, int S, int K, int P, const char*
       AttnArgs aa; aa.R = rows; aa.N = N; aa.A = d.A; aa.Ap = d.Ap; aa.F = d.F; aa.Fp = Fp; aa.rowmap = rowmap;
       aa.q = Wf("q"); aa.ld_q = d.A; aa.proj = Wb("projb"); aa.feats = Wb("featsb"); aa.mask = Wf("mask");
       aa.w_a = W(SSCVAE_W_ATT_VEC);
-      TRY(attention_forward(s, aa, Wf("alpha"), Wb("XE"), KXe));
+      TRY(attention_forward(s, aa, Wf("alpha"), nullptr, Wb("XE"), KXe));
     }
     {  // eval: z ~ N(prior_mean, prior_var) (updown_cell.py:200-208); no encoder LSTM
       LatentArgs la; la.R = rows; la.Z = d.Z; la.Zp = d.Zp; la.sentiment_vae = d.sv; la.prior_var = d.prior_std * d.prior_std;

@@ -115,9 +115,16 @@ struct AttnArgs {
   const float* mask;                   // (images, N)
   const float* w_a;                    // (A)
 };
-int attention_forward(cudaStream_t s, const AttnArgs& a, float* alpha /*(R,N)*/, bf16* xhat, int ld_x);
-int attention_backward(cudaStream_t s, const AttnArgs& a, const float* alpha, const float* dxhat, int ld_dx,
-                       bf16* dq /*(R,Ap)*/, int ld_dq, float* dproj_acc /*(images,N,A) +=*/, float* dwa_acc /*(R,A) +=*/);
+// smx (R,N): softmax(u*m) before the mask renormalisation, saved for the backward (null in decode)
+int attention_forward(cudaStream_t s, const AttnArgs& a, float* alpha /*(R,N)*/, float* smx /*(R,N) or null*/, bf16* xhat,
+                      int ld_x);
+// per-step part of the backward: d q (bf16 GEMM operand) and d u (R,N), the score gradients kept for the deferred part
+int attention_backward(cudaStream_t s, const AttnArgs& a, const float* smx, const float* dxhat, int ld_dx,
+                       bf16* dq /*(R,Ap)*/, int ld_dq, float* du /*(R,N)*/);
+// once after the time loop (training layout, a.R = B images, rows t*B+b): d P (B,N,A) and per-image d w_a rows (B,A),
+// both overwritten
+int attention_backward_deferred(cudaStream_t s, const AttnArgs& a, int T, const float* q_all /*(T,B,A)*/,
+                                const float* du_all /*(T,B,N)*/, float* dproj, float* dwa_rows);
 
 extern unsigned long long g_launch_count_pw;   // launches from the non-GEMM kernels
 }  // namespace sscvae
