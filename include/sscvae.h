@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define SSCVAE_ABI_VERSION 1
+#define SSCVAE_ABI_VERSION 2
 
 #define SSCVAE_ERR_BAD_ARG (-1)
 #define SSCVAE_ERR_WORKSPACE (-2)
@@ -93,10 +93,13 @@ void sscvae_destroy(SscvaeHandle* h);
 
 /* Packed bf16 operand copies of the weights (K-padded, recurrent blocks folded, transposed twins for
  * backward). Re-run after every optimizer step. `weights_f32` = host array of SSCVAE_W_COUNT device
- * pointers in reference layout. */
+ * pointers in reference layout. `dirty` = NULL for the first pack of a buffer (zero-fills the padding and
+ * packs everything), else a host array of SSCVAE_W_COUNT flags: only blocks whose source weight is flagged
+ * are re-packed (frozen weights — the tied embedding, the decoder LSTM under the freeze schedule of
+ * var_updown/scripts/train.py:156-161 — cost nothing). */
 size_t sscvae_packed_bytes(const SscvaeHandle* h);
 int sscvae_pack_weights(SscvaeHandle* h, const void* const* weights_f32, void* packed, size_t packed_bytes,
-                        void* stream);
+                        const uint8_t* dirty, void* stream);
 
 /* ---- training: replaces UpDownCaptioner.forward, training branch (updown_captioner.py:263-323),
  * i.e. _decode_step x T (:371-455), UpDownCell.forward (var_updown/var_updown/modules/updown_cell.py:86-231),

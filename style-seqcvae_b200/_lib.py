@@ -78,7 +78,7 @@ def lib():
     L.sscvae_destroy.restype = None
     L.sscvae_packed_bytes.argtypes = [vp]
     L.sscvae_packed_bytes.restype = sz
-    L.sscvae_pack_weights.argtypes = [vp, C.POINTER(vp), vp, sz, vp]
+    L.sscvae_pack_weights.argtypes = [vp, C.POINTER(vp), vp, sz, C.POINTER(C.c_uint8), vp]
     L.sscvae_train_workspace_bytes.argtypes = [vp, i32, i32]
     L.sscvae_train_workspace_bytes.restype = sz
     L.sscvae_train_forward.argtypes = [vp, i32, i32, vp, C.POINTER(vp), vp, vp, vp, vp, u64, vp, sz, vp, vp, vp]
@@ -104,7 +104,7 @@ def lib():
         fn = getattr(L, name)
         if fn.restype is C.c_int and name not in ("sscvae_abi_version",):
             fn.restype = C.c_int
-    if L.sscvae_abi_version() != 1:
+    if L.sscvae_abi_version() != 2:
         raise ImportError("libsscvae_b200.so ABI version mismatch")
     _lib = L
     return L

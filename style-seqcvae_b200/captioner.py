@@ -245,14 +245,20 @@ class UpDownCaptioner(nn.Module):
 
     def _packed_weights(self) -> torch.Tensor:
         ws = self._weight_tensors()
+        # one key per weight: a weight is re-packed when its storage or its version counter changed (torch's own
+        # optimizers bump the counter; FusedClipSGD, which writes through raw pointers, does so explicitly)
         key = tuple((p.data_ptr(), p._version) for p in ws)
         if self._packed is None or key != self._packed_key or self._packed.device != ws[0].device:
             L = _lib.lib()
             nbytes = L.sscvae_packed_bytes(self._handle)
+            dirty = None
             if self._packed is None or self._packed.numel() != nbytes or self._packed.device != ws[0].device:
                 self._packed = torch.empty(nbytes, dtype=torch.uint8, device=ws[0].device)
+            elif self._packed_key is not None:
+                dirty = (C.c_uint8 * len(ws))(*[int(a != b) for a, b in zip(key, self._packed_key)])
             stream = C.c_void_p(torch.cuda.current_stream(ws[0].device).cuda_stream)
-            _lib.check(L.sscvae_pack_weights(self._handle, _lib.ptr_array(ws), _lib.ptr(self._packed), nbytes, stream))
+            _lib.check(L.sscvae_pack_weights(self._handle, _lib.ptr_array(ws), _lib.ptr(self._packed), nbytes, dirty,
+                                             stream))
             self._packed_key = key
         return self._packed
 

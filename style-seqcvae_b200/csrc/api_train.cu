@@ -192,33 +192,48 @@ const Plan& Handle::train_plan(int B, int N) {
 }
 
 // ---- weight packing ----------------------------------------------------------------------------
-static int pack_weights_impl(Handle* h, const void* const* wv, char* pk, cudaStream_t s) {
+static int pack_weights_impl(Handle* h, const void* const* wv, char* pk, const uint8_t* dirty, cudaStream_t s) {
   const Dims& d = h->d;
   const Plan& pp = h->pp;
   auto W = [&](int i) { return reinterpret_cast<const float*>(wv[i]); };
   auto Pb = [&](const char* n) { return reinterpret_cast<bf16*>(pk + pp.find(n)->off); };
   auto Pf = [&](const char* n) { return reinterpret_cast<float*>(pk + pp.find(n)->off); };
+  // dirty == NULL: first pack of this buffer (zero the K/N padding, pack everything); otherwise only the blocks
+  // whose fp32 source changed are re-packed (the padding stays zero, frozen weights are skipped)
+  auto need = [&](std::initializer_list<int> ids) {
+    if (!dirty) return true;
+    for (int i : ids) if (dirty[i]) return true;
+    return false;
+  };
   for (int i = 0; i < SSCVAE_W_COUNT; ++i) REQUIRE(wv[i] != nullptr, "weight pointer %d is NULL", i);
-  CUDA_TRY(cudaMemsetAsync(pk, 0, pp.total, s));
+  if (!dirty) CUDA_TRY(cudaMemsetAsync(pk, 0, pp.total, s));
   const int E = d.E, F = d.F, H = d.H, A = d.A, Z = d.Z, V = d.V, G = d.G, c = d.cond;
   // embedding (gather source and, tied, the vocabulary GEMM operand)
-  TRY(pack_block(s, Pb("embb"), d.Ep, 0, W(SSCVAE_W_EMBEDDING), E, V, E, nullptr, 0));
-  if (d.tied) TRY(pack_block(s, Pb("embT"), d.Vp, 1, W(SSCVAE_W_EMBEDDING), E, V, E, nullptr, 0));
+  if (need({SSCVAE_W_EMBEDDING})) {
+    TRY(pack_block(s, Pb("embb"), d.Ep, 0, W(SSCVAE_W_EMBEDDING), E, V, E, nullptr, 0));
+    if (d.tied) TRY(pack_block(s, Pb("embT"), d.Vp, 1, W(SSCVAE_W_EMBEDDING), E, V, E, nullptr, 0));
+  }
   // attention LSTM: W_ih columns [emb E | avg F | h1 H | h_dec H] (updown_cell.py:143-145); W_hh folded onto h1
   const int ldi = E + F + 2 * H;
   const float* wih = W(SSCVAE_W_ATT_IH);
-  TRY(pack_block(s, Pb("w_att_e"), d.Ep, 0, wih, ldi, G, E, nullptr, 0));
-  TRY(pack_block(s, Pb("w_att_eT"), d.Gp, 1, wih, ldi, G, E, nullptr, 0));
-  TRY(pack_block(s, Pb("w_att_f"), d.Fp, 0, wih + E, ldi, G, F, nullptr, 0));
-  TRY(pack_block(s, Pb("w_att_rec"), 2 * d.Hp, 0, wih + E + F, ldi, G, H, W(SSCVAE_W_ATT_HH), H));
-  TRY(pack_block(s, Pb("w_att_rec") + d.Hp, 2 * d.Hp, 0, wih + E + F + H, ldi, G, H, nullptr, 0));
-  TRY(pack_block(s, Pb("w_att_recT"), d.Gp, 1, wih + E + F, ldi, G, H, W(SSCVAE_W_ATT_HH), H));
-  TRY(pack_block(s, Pb("w_att_recT") + (size_t)d.Hp * d.Gp, d.Gp, 1, wih + E + F + H, ldi, G, H, nullptr, 0));
-  TRY(vec_add_f32(s, W(SSCVAE_W_ATT_BIH), W(SSCVAE_W_ATT_BHH), Pf("b_att"), G));
+  if (need({SSCVAE_W_ATT_IH, SSCVAE_W_ATT_HH})) {
+    TRY(pack_block(s, Pb("w_att_rec"), 2 * d.Hp, 0, wih + E + F, ldi, G, H, W(SSCVAE_W_ATT_HH), H));
+    TRY(pack_block(s, Pb("w_att_recT"), d.Gp, 1, wih + E + F, ldi, G, H, W(SSCVAE_W_ATT_HH), H));
+  }
+  if (need({SSCVAE_W_ATT_IH})) {
+    TRY(pack_block(s, Pb("w_att_e"), d.Ep, 0, wih, ldi, G, E, nullptr, 0));
+    TRY(pack_block(s, Pb("w_att_eT"), d.Gp, 1, wih, ldi, G, E, nullptr, 0));
+    TRY(pack_block(s, Pb("w_att_f"), d.Fp, 0, wih + E, ldi, G, F, nullptr, 0));
+    TRY(pack_block(s, Pb("w_att_rec") + d.Hp, 2 * d.Hp, 0, wih + E + F + H, ldi, G, H, nullptr, 0));
+    TRY(pack_block(s, Pb("w_att_recT") + (size_t)d.Hp * d.Gp, d.Gp, 1, wih + E + F + H, ldi, G, H, nullptr, 0));
+  }
+  if (need({SSCVAE_W_ATT_BIH, SSCVAE_W_ATT_BHH})) TRY(vec_add_f32(s, W(SSCVAE_W_ATT_BIH), W(SSCVAE_W_ATT_BHH), Pf("b_att"), G));
   // attention
-  TRY(pack_block(s, Pb("wq"), d.Hp, 0, W(SSCVAE_W_QUERY_PROJ), H, A, H, nullptr, 0));
-  TRY(pack_block(s, Pb("wqT"), d.Ap, 1, W(SSCVAE_W_QUERY_PROJ), H, A, H, nullptr, 0));
-  TRY(pack_block(s, Pb("wv"), d.Fp, 0, W(SSCVAE_W_IMAGE_PROJ), F, A, F, nullptr, 0));
+  if (need({SSCVAE_W_QUERY_PROJ})) {
+    TRY(pack_block(s, Pb("wq"), d.Hp, 0, W(SSCVAE_W_QUERY_PROJ), H, A, H, nullptr, 0));
+    TRY(pack_block(s, Pb("wqT"), d.Ap, 1, W(SSCVAE_W_QUERY_PROJ), H, A, H, nullptr, 0));
+  }
+  if (need({SSCVAE_W_IMAGE_PROJ})) TRY(pack_block(s, Pb("wv"), d.Fp, 0, W(SSCVAE_W_IMAGE_PROJ), F, A, F, nullptr, 0));
   // encoder LSTM: W_ih columns [xhat F | h1 H | h_dec H | cond c] (updown_cell.py:178-190)
   const int lde = F + 2 * H + c;
   const float* we = W(SSCVAE_W_ENC_IH);
@@ -226,38 +241,53 @@ static int pack_weights_impl(Handle* h, const void* const* wv, char* pk, cudaStr
   const int offs_src[3] = {0, F, F + H};
   const int offs_dst[3] = {0, d.Fp, d.Fp + d.Hp};
   const int widths[3] = {F, H, H};
-  for (int k = 0; k < 3; ++k) {
-    TRY(pack_block(s, wex + offs_dst[k], d.KX, 0, we + offs_src[k], lde, G, widths[k], nullptr, 0));
-    TRY(pack_block(s, wexT + (size_t)offs_dst[k] * d.Gp, d.Gp, 1, we + offs_src[k], lde, G, widths[k], nullptr, 0));
+  if (need({SSCVAE_W_ENC_IH})) {
+    for (int k = 0; k < 3; ++k) {
+      TRY(pack_block(s, wex + offs_dst[k], d.KX, 0, we + offs_src[k], lde, G, widths[k], nullptr, 0));
+      TRY(pack_block(s, wexT + (size_t)offs_dst[k] * d.Gp, d.Gp, 1, we + offs_src[k], lde, G, widths[k], nullptr, 0));
+    }
+    if (c) TRY(copy_block_f32(s, we + F + 2 * H, lde, Pf("scol_enc"), 1, G, 1));
   }
-  TRY(pack_block(s, Pb("w_enc_hh"), d.Hp, 0, W(SSCVAE_W_ENC_HH), H, G, H, nullptr, 0));
-  TRY(pack_block(s, Pb("w_enc_xhT") + (size_t)d.KX * d.Gp, d.Gp, 1, W(SSCVAE_W_ENC_HH), H, G, H, nullptr, 0));
-  TRY(vec_add_f32(s, W(SSCVAE_W_ENC_BIH), W(SSCVAE_W_ENC_BHH), Pf("b_enc"), G));
-  if (c) TRY(copy_block_f32(s, we + F + 2 * H, lde, Pf("scol_enc"), 1, G, 1));
+  if (need({SSCVAE_W_ENC_HH})) {
+    TRY(pack_block(s, Pb("w_enc_hh"), d.Hp, 0, W(SSCVAE_W_ENC_HH), H, G, H, nullptr, 0));
+    TRY(pack_block(s, Pb("w_enc_xhT") + (size_t)d.KX * d.Gp, d.Gp, 1, W(SSCVAE_W_ENC_HH), H, G, H, nullptr, 0));
+  }
+  if (need({SSCVAE_W_ENC_BIH, SSCVAE_W_ENC_BHH})) TRY(vec_add_f32(s, W(SSCVAE_W_ENC_BIH), W(SSCVAE_W_ENC_BHH), Pf("b_enc"), G));
   // decoder LSTM: W_ih columns [xhat F | h1 H | h_dec H | cond c | z Z] (updown_cell.py:211-224); W_hh folded onto h_dec
   const int ldd = F + 2 * H + c + Z;
   const float* wd = W(SSCVAE_W_DEC_IH);
   bf16* wdx = Pb("w_dec_x"); bf16* wdxT = Pb("w_dec_xzT");
-  for (int k = 0; k < 3; ++k) {
-    const float* fold = (k == 2) ? W(SSCVAE_W_DEC_HH) : nullptr;
-    TRY(pack_block(s, wdx + offs_dst[k], d.KX, 0, wd + offs_src[k], ldd, G, widths[k], fold, H));
-    TRY(pack_block(s, wdxT + (size_t)offs_dst[k] * d.Gp, d.Gp, 1, wd + offs_src[k], ldd, G, widths[k], fold, H));
+  if (need({SSCVAE_W_DEC_IH, SSCVAE_W_DEC_HH})) {
+    for (int k = 0; k < 3; ++k) {
+      if (k < 2 && !need({SSCVAE_W_DEC_IH})) continue;
+      const float* fold = (k == 2) ? W(SSCVAE_W_DEC_HH) : nullptr;
+      TRY(pack_block(s, wdx + offs_dst[k], d.KX, 0, wd + offs_src[k], ldd, G, widths[k], fold, H));
+      TRY(pack_block(s, wdxT + (size_t)offs_dst[k] * d.Gp, d.Gp, 1, wd + offs_src[k], ldd, G, widths[k], fold, H));
+    }
   }
-  TRY(pack_block(s, Pb("w_dec_z"), d.Zp, 0, wd + F + 2 * H + c, ldd, G, Z, nullptr, 0));
-  TRY(pack_block(s, Pb("w_dec_xzT") + (size_t)d.KX * d.Gp, d.Gp, 1, wd + F + 2 * H + c, ldd, G, Z, nullptr, 0));
-  TRY(vec_add_f32(s, W(SSCVAE_W_DEC_BIH), W(SSCVAE_W_DEC_BHH), Pf("b_dec"), G));
-  if (c) TRY(copy_block_f32(s, wd + F + 2 * H, ldd, Pf("scol_dec"), 1, G, 1));
+  if (need({SSCVAE_W_DEC_IH})) {
+    TRY(pack_block(s, Pb("w_dec_z"), d.Zp, 0, wd + F + 2 * H + c, ldd, G, Z, nullptr, 0));
+    TRY(pack_block(s, Pb("w_dec_xzT") + (size_t)d.KX * d.Gp, d.Gp, 1, wd + F + 2 * H + c, ldd, G, Z, nullptr, 0));
+    if (c) TRY(copy_block_f32(s, wd + F + 2 * H, ldd, Pf("scol_dec"), 1, G, 1));
+  }
+  if (need({SSCVAE_W_DEC_BIH, SSCVAE_W_DEC_BHH})) TRY(vec_add_f32(s, W(SSCVAE_W_DEC_BIH), W(SSCVAE_W_DEC_BHH), Pf("b_dec"), G));
   // latent heads stacked [fc_mean ; fc_log_var]
-  TRY(pack_block(s, Pb("w_fc"), d.Hp, 0, W(SSCVAE_W_FC_MEAN_W), H, Z, H, nullptr, 0));
-  TRY(pack_block(s, Pb("w_fc") + (size_t)Z * d.Hp, d.Hp, 0, W(SSCVAE_W_FC_LOGVAR_W), H, Z, H, nullptr, 0));
-  TRY(pack_block(s, Pb("w_fcT"), d.Z2p, 1, W(SSCVAE_W_FC_MEAN_W), H, Z, H, nullptr, 0));
-  TRY(pack_block(s, Pb("w_fcT") + Z, d.Z2p, 1, W(SSCVAE_W_FC_LOGVAR_W), H, Z, H, nullptr, 0));
-  TRY(copy_block_f32(s, W(SSCVAE_W_FC_MEAN_B), 1, Pf("b_fc"), 1, Z, 1));
-  TRY(copy_block_f32(s, W(SSCVAE_W_FC_LOGVAR_B), 1, Pf("b_fc") + Z, 1, Z, 1));
+  if (need({SSCVAE_W_FC_MEAN_W})) {
+    TRY(pack_block(s, Pb("w_fc"), d.Hp, 0, W(SSCVAE_W_FC_MEAN_W), H, Z, H, nullptr, 0));
+    TRY(pack_block(s, Pb("w_fcT"), d.Z2p, 1, W(SSCVAE_W_FC_MEAN_W), H, Z, H, nullptr, 0));
+  }
+  if (need({SSCVAE_W_FC_LOGVAR_W})) {
+    TRY(pack_block(s, Pb("w_fc") + (size_t)Z * d.Hp, d.Hp, 0, W(SSCVAE_W_FC_LOGVAR_W), H, Z, H, nullptr, 0));
+    TRY(pack_block(s, Pb("w_fcT") + Z, d.Z2p, 1, W(SSCVAE_W_FC_LOGVAR_W), H, Z, H, nullptr, 0));
+  }
+  if (need({SSCVAE_W_FC_MEAN_B})) TRY(copy_block_f32(s, W(SSCVAE_W_FC_MEAN_B), 1, Pf("b_fc"), 1, Z, 1));
+  if (need({SSCVAE_W_FC_LOGVAR_B})) TRY(copy_block_f32(s, W(SSCVAE_W_FC_LOGVAR_B), 1, Pf("b_fc") + Z, 1, Z, 1));
   // output head
   const int NO = d.tied ? E : V, NOp = d.tied ? d.Ep : d.Vp;
-  TRY(pack_block(s, Pb("w_out"), d.Hp, 0, W(SSCVAE_W_OUT_PROJ_W), H, NO, H, nullptr, 0));
-  TRY(pack_block(s, Pb("w_outT"), NOp, 1, W(SSCVAE_W_OUT_PROJ_W), H, NO, H, nullptr, 0));
+  if (need({SSCVAE_W_OUT_PROJ_W})) {
+    TRY(pack_block(s, Pb("w_out"), d.Hp, 0, W(SSCVAE_W_OUT_PROJ_W), H, NO, H, nullptr, 0));
+    TRY(pack_block(s, Pb("w_outT"), NOp, 1, W(SSCVAE_W_OUT_PROJ_W), H, NO, H, nullptr, 0));
+  }
   return 0;
 }
 
@@ -711,12 +741,13 @@ void sscvae_destroy(SscvaeHandle* h) { delete reinterpret_cast<Handle*>(h); }
 
 size_t sscvae_packed_bytes(const SscvaeHandle* h) { return reinterpret_cast<const Handle*>(h)->pp.total; }
 
-int sscvae_pack_weights(SscvaeHandle* hh, const void* const* weights, void* packed, size_t packed_bytes, void* stream) {
+int sscvae_pack_weights(SscvaeHandle* hh, const void* const* weights, void* packed, size_t packed_bytes,
+                        const uint8_t* dirty, void* stream) {
   Handle* h = reinterpret_cast<Handle*>(hh);
   REQUIRE(h && weights && packed, "NULL argument");
   if (packed_bytes < h->pp.total) { set_error("packed buffer too small: %zu < %zu", packed_bytes, h->pp.total); return SSCVAE_ERR_WORKSPACE; }
   REQUIRE((reinterpret_cast<uintptr_t>(packed) & 255) == 0, "packed buffer must be 256-byte aligned");
-  return pack_weights_impl(h, weights, reinterpret_cast<char*>(packed), reinterpret_cast<cudaStream_t>(stream));
+  return pack_weights_impl(h, weights, reinterpret_cast<char*>(packed), dirty, reinterpret_cast<cudaStream_t>(stream));
 }
 
 size_t sscvae_train_workspace_bytes(const SscvaeHandle* hh, int batch, int num_boxes) {

@@ -59,4 +59,7 @@ class FusedClipSGD:
             _lib.check(L.sscvae_sgd_step(_lib.ptr(p), _lib.ptr(g), _lib.ptr(self._mom[id(p)]), p.numel(), _lib.ptr(total),
                                          float(self.max_norm), float(self.lr), float(self.momentum),
                                          float(self.weight_decay), int(first), stream))
+            # the kernel wrote through a raw pointer: tell autograd (and the captioner's packed-weight cache,
+            # which is keyed on the version counters) that the parameter changed
+            torch.autograd.graph.increment_version(p)
         self.iteration += 1

@@ -123,6 +123,39 @@ def test_reference_rng_mode_replays_cpu_generator():
     assert ((out["loss"].cpu() - g["loss"]).abs() / g["loss"].abs().clamp(min=1)).max() < TOL_LOSS_VS_FP32_REF
 
 
+def test_optimizer_step_repacks_the_bf16_operand_copies():
+    """FusedClipSGD writes the fp32 parameters through raw pointers; the next forward must run on re-packed bf16
+    weights: it has to equal a fresh module built from the updated state_dict, not the previous step's loss."""
+    import sscvae
+    g = load_golden("train_tied_sv1")
+    cfg = g["cfg"]
+    m = module_from_cfg(cfg, g["params"])
+    m.train()
+    m._eps_override = g["eps"].cuda()
+    args = (g["image_features"].cuda(), None, None, g["caption_tokens"].cuda(), g["sentiment"].cuda())
+    opt = sscvae.FusedClipSGD([p for p in m.parameters() if p.requires_grad], lr=0.5, momentum=0.9, weight_decay=1e-3,
+                              max_norm=12.5, num_iterations=100)
+    out1 = m(*args)
+    (out1["loss"].mean() + out1["kld"].mean() / 750.0).backward()
+    before = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    grads = {k: p.grad.detach().clone() for k, p in m.named_parameters() if p.grad is not None}
+    opt.step()
+    # the update itself: clip_grad_norm_(12.5) + SGD(momentum, wd), first step (train.py:173-176)
+    norm = torch.sqrt(sum((v.double() ** 2).sum() for v in grads.values()))
+    coef = min(1.0, 12.5 / (norm.item() + 1e-6))
+    for k, p in m.named_parameters():
+        if k in grads:
+            want = before[k] - 0.5 * (grads[k] * coef + 1e-3 * before[k])
+            assert torch.allclose(p.detach(), want, rtol=1e-5, atol=1e-6), k
+    out2 = m(*args)
+    fresh = module_from_cfg(cfg, {k: v.detach().cpu() for k, v in m.state_dict().items()})
+    fresh.train()
+    fresh._eps_override = g["eps"].cuda()
+    out3 = fresh(*args)
+    assert torch.equal(out2["loss"], out3["loss"]) and torch.equal(out2["kld"], out3["kld"])
+    assert not torch.allclose(out2["loss"], out1["loss"])
+
+
 def test_full_size_properties():
     """BASELINE config 2 shape (B=256, 36x2048, V=10k, L=20, dims Y): size-independent properties."""
     torch.manual_seed(0)
