@@ -11,6 +11,9 @@
 
 namespace sscvae {
 
+constexpr int kPad = 64;   // elements: operand row strides / column blocks are multiples of 128 bytes (see init_dims)
+
+
 struct Dims {
   int F, E, H, A, Z, V, L, T;
   int sv, simple, tied, pad, boundary, cond;

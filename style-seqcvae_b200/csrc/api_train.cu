@@ -38,9 +38,13 @@ int init_dims(const SscvaeDims* in, Dims& d) {
   REQUIRE(d.prior_std > 0.f, "prior_std must be positive");
   d.T = d.L + 1;
   d.cond = (d.simple || d.sv == 0) ? 0 : 1;
-  d.Fp = round_up(d.F, 8); d.Ep = round_up(d.E, 8); d.Hp = round_up(d.H, 8); d.Ap = round_up(d.A, 8);
-  d.Zp = round_up(d.Z, 8); d.Vp = round_up(d.V, 8);
-  d.G = 4 * d.H; d.Gp = round_up(d.G, 8); d.Z2 = 2 * d.Z; d.Z2p = round_up(d.Z2, 8);
+  // Every bf16 operand row stride and column-block offset is a multiple of 64 elements = 128 bytes, so that each
+  // 128-byte row segment of a TMA box is exactly ONE cache line. With 16-byte granularity (the TMA minimum) a
+  // segment straddles two lines and the TMA unit pulls both whole lines into the SM: ncu showed 2.0x the operand
+  // bytes crossing the crossbar (profiles/README.md), and the per-step GEMMs are bound by exactly that ingest.
+  d.Fp = round_up(d.F, kPad); d.Ep = round_up(d.E, kPad); d.Hp = round_up(d.H, kPad); d.Ap = round_up(d.A, kPad);
+  d.Zp = round_up(d.Z, kPad); d.Vp = round_up(d.V, kPad);
+  d.G = 4 * d.H; d.Gp = round_up(d.G, kPad); d.Z2 = 2 * d.Z; d.Z2p = round_up(d.Z2, kPad);
   d.KX = d.Fp + 2 * d.Hp;
   return 0;
 }
@@ -95,8 +99,8 @@ static void plan_packed(const Dims& d, Plan& p) {
 
 static void plan_train(const Dims& d, int B, int N, Plan& p) {
   const size_t b = sizeof(bf16), f = 4;
-  const size_t T = d.T, TB = T * B, TBp = round_up((int)TB, 8), BN = (size_t)B * N, BNp = round_up((int)BN, 8);
-  const size_t Bp = round_up(B, 8);
+  const size_t T = d.T, TB = T * B, TBp = round_up((int)TB, kPad), BN = (size_t)B * N, BNp = round_up((int)BN, kPad);
+  const size_t Bp = round_up(B, kPad);
   // ---- forward, kept for backward
   p.add("tok", (size_t)B * (d.L + 2) * 4);
   p.add("tmask", TB * f);
@@ -479,8 +483,8 @@ static int train_backward_impl(Handle* h, int B, int N, const char* pk, const vo
     if (events && events[g]) CUDA_TRY(cudaEventRecord(reinterpret_cast<cudaEvent_t>(events[g]), s));
     return 0;
   };
-  const int T = d.T, TB = T * B, TBp = round_up(TB, 8), G = d.G, Gp = d.Gp, H = d.H, Hp = d.Hp, KX = d.KX, Fp = d.Fp;
-  const int E = d.E, F = d.F, A = d.A, Z = d.Z, V = d.V, c = d.cond, Bp = round_up(B, 8), BN = B * N, BNp = round_up(BN, 8);
+  const int T = d.T, TB = T * B, TBp = round_up(TB, kPad), G = d.G, Gp = d.Gp, H = d.H, Hp = d.Hp, KX = d.KX, Fp = d.Fp;
+  const int E = d.E, F = d.F, A = d.A, Z = d.Z, V = d.V, c = d.cond, Bp = round_up(B, kPad), BN = B * N, BNp = round_up(BN, kPad);
   const int* tok = Wi("tok");
   const float* tmask = Wf("tmask");
 
@@ -791,7 +795,21 @@ int sscvae_test_gemm(const void* A, int lda, const void* B, int ldb, int M, int 
                      const float* bias, int act_tanh, int accumulate, void* stream) {
   GemmSeg sg; sg.A = reinterpret_cast<const bf16*>(A); sg.lda = lda; sg.B = reinterpret_cast<const bf16*>(B); sg.ldb = ldb; sg.K = K;
   GemmEpi e; e.C32 = C32; e.ldc32 = ldc; e.bias = bias; e.act = act_tanh; e.accumulate = accumulate;
-  return gemm_bf16_tn(reinterpret_cast<cudaStream_t>(stream), M, N, 1, &sg, e);
+  int repeat = 1;                                   // tools/gemm_bench.py: back-to-back launches without Python in between
+  if (const char* r = getenv("SSCVAE_TEST_GEMM_REPEAT")) repeat = std::max(1, atoi(r));
+  for (int i = 0; i < repeat; ++i) TRY(gemm_bf16_tn(reinterpret_cast<cudaStream_t>(stream), M, N, 1, &sg, e));
+  return 0;
+}
+
+int sscvae_test_gemm_splitk(const void* A, int lda, const void* B, int ldb, int M, int N, int K, float* C32, int ldc,
+                            int splits, const float* bias, void* stream) {
+  GemmSeg sg; sg.A = reinterpret_cast<const bf16*>(A); sg.lda = lda; sg.B = reinterpret_cast<const bf16*>(B); sg.ldb = ldb; sg.K = K;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  GemmEpi e; e.C32 = C32; e.ldc32 = ldc; e.bias = bias; e.splits = splits;
+  int repeat = 1;
+  if (const char* r = getenv("SSCVAE_TEST_GEMM_REPEAT")) repeat = std::max(1, atoi(r));
+  for (int i = 0; i < repeat; ++i) TRY(gemm_bf16_tn(st, M, N, 1, &sg, e));
+  return 0;
 }
 
 }  // extern "C"

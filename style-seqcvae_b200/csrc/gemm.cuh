@@ -24,7 +24,14 @@ struct GemmEpi {
   float* C32 = nullptr; int ldc32 = 0; int accumulate = 0;   // C32[m,n] (+)= v
   bf16* C16 = nullptr; int ldc16 = 0;                  // C16[m,n] = bf16(v)
   const char* tag = "gemm";                            // kernel class for the optional profiler (prof.cuh)
+  // skinny GEMMs (M <= 256) run on the swapped-operand kernel with K split over a thread-block cluster; 0 = let the
+  // library choose the split count, 1/2/4 = force it (tools/gemm_bench.py)
+  int splits = 0;
 };
+
+// K-split (cluster size 1, 2 or 4) the swapped-operand kernel uses for a skinny GEMM (M <= 256)
+int gemm_suggest_splits(int M, int N, int K_total);
+
 
 // Launches on `stream`; returns 0 or an error code (message via get_error()).
 int gemm_bf16_tn(cudaStream_t stream, int M, int N, int nseg, const GemmSeg* segs, const GemmEpi& epi);

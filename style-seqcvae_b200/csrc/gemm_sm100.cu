@@ -12,6 +12,8 @@
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
+#include <unordered_map>
+#include <algorithm>
 
 namespace sscvae {
 
@@ -30,6 +32,11 @@ struct GemmParams {
   int nseg;
   int M, N;
   int vec;                                        // 1: every epilogue pointer allows 16-byte access
+  int splits;                                     // gridDim.z
+  int kb_per_split;                               // split-K: CTA z works on k-blocks [z*kb_per_split, ...) of the
+                                                  // concatenated segments and ADDS its partial tile into C32
+  int tma_store;                                  // 1: plain fp32 tile (+bias): the epilogue leaves through TMA stores of `tc`
+  CUtensorMap tc;                                 // fp32 output, box 32 columns x 32 rows, no swizzle
   GemmEpi epi;
 };
 
@@ -65,6 +72,18 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* tmap, 
       ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
 }
+// shared -> global tile store (bulk async group of the issuing thread); out-of-bounds parts of the box are clipped
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* tmap, uint32_t src_smem, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(tmap)),
+               "r"(src_smem), "r"(c0), "r"(c1)
+               : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* tmap) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tmap)) : "memory");
 }
@@ -97,6 +116,53 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint6
       "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// ---- CTA-pair (cta_group::2) variants: the two CTAs of a 2-cluster drive one 256-row MMA -------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// Executed by both CTAs of the pair; clearing the peer bit (bit 24 of the shared::cluster address) makes the
+// transaction bytes land on the LEADER CTA's mbarrier (cf. cute::SM100_TMA_2SM_LOAD_2D).
+__device__ __forceinline__ void tma_load_2d_2sm(void* dst, const CUtensorMap* tmap, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar) & 0xFEFFFFFFu), "r"(c0), "r"(c1)
+      : "memory");
+}
+template <int NCOLS>
+__device__ __forceinline__ void tmem_alloc_2sm(uint32_t* dst_smem) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)),
+               "n"(NCOLS)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+template <int NCOLS>
+__device__ __forceinline__ void tmem_dealloc_2sm(uint32_t taddr) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(NCOLS) : "memory");
+}
+// arrives (once the MMAs issued so far have completed) on the barrier at this shared-memory offset in BOTH CTAs
+__device__ __forceinline__ void umma_commit_2sm(uint64_t* bar) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+          smem_u32(bar)),
+      "h"(static_cast<uint16_t>(3))
+      : "memory");
+}
+__device__ __forceinline__ void umma_bf16_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                              uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
 __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -139,9 +205,155 @@ __device__ __forceinline__ float tanh_fast(float x) {
   return tanhf(x);
 }
 
-__device__ __forceinline__ void epilogue_row32(const GemmEpi& e, int vec, int M, int N, int row0, int col0, int ncols,
-                                               const uint32_t (&acc)[32], float* stage) {
+// explicit shared-memory accesses (32-bit shared addresses): pointers derived from the aligned dynamic-smem base are
+// treated as generic by the compiler, and generic LD/ST that resolve to shared memory are several times slower than
+// LDS/STS for a lone epilogue warp
+__device__ __forceinline__ void sts_f32(uint32_t a, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory"); }
+__device__ __forceinline__ void sts_v4(uint32_t a, const float4& v) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ float lds_f32(uint32_t a) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ float4 lds_v4(uint32_t a) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a) : "memory");
+  return v;
+}
+
+__device__ __forceinline__ void red_add_f32x4(float* p, const float4& v) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
+// Second half of the vector epilogue: the warp's 32x32 fp32 block sits in `stage` as [row][column] (pitch 36 floats);
+// 8 consecutive lanes own 32 consecutive columns of ONE output row (128 contiguous bytes), 4 rows per instruction,
+// for the addend loads and for the stores.
+// NOTE: GemmEpi is taken BY VALUE everywhere in the epilogue. Through a reference to the __grid_constant__ kernel
+// parameter the compiler must assume the output stores alias the struct and re-reads every field after each store
+// (measured: ~250 cycles per store, 2-3.4k cycles per 32x32 block instead of ~300).
+__device__ __forceinline__ void epilogue_block_vec(const GemmEpi e, int M, int row0, int col0, uint32_t stage,
+                                                   int splitk, bool add1_all) {
+  constexpr int PITCH = 36;
   const int lane = threadIdx.x & 31;
+  const int c4 = (lane & 7) * 4;
+  const int n = col0 + c4;
+  float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (e.bias) bias4 = *reinterpret_cast<const float4*>(e.bias + n);
+  // The epilogue warps run one per SM sub-partition, so the epilogue is bound by its own instruction count
+  // (measured: 3.4k cycles per 32x32 block when the tanh / dtanh / accumulate forms were compiled into the one loop).
+  // The common case - scaled accumulator + bias + addends -> fp32 and/or bf16 - gets its own lean loop.
+  if (!e.act && !e.dtanh && !e.accumulate && !splitk) {
+    const float alpha = e.alpha;
+    const float* a1 = add1_all ? e.add1 + n : nullptr;
+    const float* a2 = e.add2 ? e.add2 + n : nullptr;
+    float* c32 = e.C32 ? e.C32 + n : nullptr;
+    bf16* c16 = e.C16 ? e.C16 + n : nullptr;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int rr = k * 4 + (lane >> 3);
+      const int r = row0 + rr;
+      if (r < M) {
+        float4 v = lds_v4(stage + (rr * PITCH + c4) * 4);
+        v.x = fmaf(v.x, alpha, bias4.x); v.y = fmaf(v.y, alpha, bias4.y);
+        v.z = fmaf(v.z, alpha, bias4.z); v.w = fmaf(v.w, alpha, bias4.w);
+        if (a1) {
+          const float4 b = *reinterpret_cast<const float4*>(a1 + (size_t)r * e.ld1);
+          v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+        }
+        if (a2) {
+          const float4 b = *reinterpret_cast<const float4*>(a2 + (size_t)r * e.ld2);
+          v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+        }
+        if (c32) *reinterpret_cast<float4*>(c32 + (size_t)r * e.ldc32) = v;
+        if (c16) {
+          __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+          uint2 o;
+          o.x = *reinterpret_cast<uint32_t*>(&lo);
+          o.y = *reinterpret_cast<uint32_t*>(&hi);
+          *reinterpret_cast<uint2*>(c16 + (size_t)r * e.ldc16) = o;
+        }
+      }
+    }
+    return;
+  }
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int rr = k * 4 + (lane >> 3);
+    const int r = row0 + rr;
+    if (r < M) {
+      float4 v = lds_v4(stage + (rr * PITCH + c4) * 4);
+      v.x = v.x * e.alpha + bias4.x; v.y = v.y * e.alpha + bias4.y;
+      v.z = v.z * e.alpha + bias4.z; v.w = v.w * e.alpha + bias4.w;
+      if (add1_all) {
+        const float4 b = *reinterpret_cast<const float4*>(e.add1 + (size_t)r * e.ld1 + n);
+        v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+      }
+      if (e.add2) {
+        const float4 b = *reinterpret_cast<const float4*>(e.add2 + (size_t)r * e.ld2 + n);
+        v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+      }
+      if (e.act == 1) { v.x = tanh_fast(v.x); v.y = tanh_fast(v.y); v.z = tanh_fast(v.z); v.w = tanh_fast(v.w); }
+      if (e.dtanh) {
+        const float4 t = *reinterpret_cast<const float4*>(e.dtanh + (size_t)r * e.ldd + n);
+        v.x *= 1.0f - t.x * t.x; v.y *= 1.0f - t.y * t.y; v.z *= 1.0f - t.z * t.z; v.w *= 1.0f - t.w * t.w;
+      }
+      if (e.C32) {
+        float* p = e.C32 + (size_t)r * e.ldc32 + n;
+        if (splitk) {
+          red_add_f32x4(p, v);
+        } else {
+          if (e.accumulate) {
+            const float4 c = *reinterpret_cast<const float4*>(p);
+            v.x += c.x; v.y += c.y; v.z += c.z; v.w += c.w;
+          }
+          *reinterpret_cast<float4*>(p) = v;
+        }
+      }
+      if (e.C16) {
+        __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+        uint2 o;
+        o.x = *reinterpret_cast<uint32_t*>(&lo);
+        o.y = *reinterpret_cast<uint32_t*>(&hi);
+        *reinterpret_cast<uint2*>(e.C16 + (size_t)r * e.ldc16 + n) = o;
+      }
+    }
+  }
+}
+
+// Plain fp32 tile (+ bias): the warp's 32x32 block goes to shared memory as 32 rows of 128 bytes in the TMA
+// 128B-swizzle pattern (16-byte chunk c of row r at chunk c ^ (r & 7): 4-way instead of 32-way bank conflicts for
+// lane == row) and leaves with ONE asynchronous TMA store; rows / columns beyond the matrix are clipped by the TMA
+// unit. Plain STG.128 stores cost a lone epilogue warp ~220 cycles each (1.8k cycles per block, measured).
+__device__ __forceinline__ void epilogue_tma_row32(const GemmEpi e, const CUtensorMap* tc, int N, int row0, int col0,
+                                                   const uint32_t (&acc)[32], uint32_t stage) {
+  const int lane = threadIdx.x & 31;
+  if (lane == 0) tma_store_wait_read();                  // the previous store has finished reading this buffer
+  __syncwarp();
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (e.bias && col0 + 4 * j + 3 < N) b = *reinterpret_cast<const float4*>(e.bias + col0 + 4 * j);
+    else if (e.bias) {
+      if (col0 + 4 * j < N) b.x = e.bias[col0 + 4 * j];
+      if (col0 + 4 * j + 1 < N) b.y = e.bias[col0 + 4 * j + 1];
+      if (col0 + 4 * j + 2 < N) b.z = e.bias[col0 + 4 * j + 2];
+    }
+    const float4 v = make_float4(fmaf(__uint_as_float(acc[4 * j]), e.alpha, b.x), fmaf(__uint_as_float(acc[4 * j + 1]), e.alpha, b.y),
+                                 fmaf(__uint_as_float(acc[4 * j + 2]), e.alpha, b.z), fmaf(__uint_as_float(acc[4 * j + 3]), e.alpha, b.w));
+    sts_v4(stage + lane * 128 + ((j ^ (lane & 7)) << 4), v);
+  }
+  fence_proxy_async_smem();
+  __syncwarp();
+  if (lane == 0) tma_store_2d(tc, stage, col0, row0);
+}
+
+// splitk: 0 = plain store; 1 = this CTA holds a partial sum: add it into C32 (split 0 also applies the addends)
+__device__ __forceinline__ void epilogue_row32(GemmEpi e, int vec, int M, int N, int row0, int col0, int ncols,
+                                               const uint32_t (&acc)[32], uint32_t stage, int splitk, int first_split) {
+  const int lane = threadIdx.x & 31;
+  if (splitk && !first_split) { e.bias = nullptr; e.add1 = nullptr; e.add2 = nullptr; }
   const int row = row0 + lane;           // TMEM lane == output row of this thread's 32 accumulator columns
   // `ncols` < 32 only for the narrow (BN=16) tiles; add1 may cover just the first add1_cols columns
   const bool add1_all = e.add1 && (col0 + 32 <= e.add1_cols);
@@ -154,52 +366,11 @@ __device__ __forceinline__ void epilogue_row32(const GemmEpi& e, int vec, int M,
     constexpr int PITCH = 36;            // floats; keeps float4 alignment
 #pragma unroll
     for (int j = 0; j < 8; ++j)
-      *reinterpret_cast<float4*>(stage + lane * PITCH + 4 * j) =
-          make_float4(__uint_as_float(acc[4 * j]), __uint_as_float(acc[4 * j + 1]), __uint_as_float(acc[4 * j + 2]),
-                      __uint_as_float(acc[4 * j + 3]));
+      sts_v4(stage + (lane * PITCH + 4 * j) * 4,
+             make_float4(__uint_as_float(acc[4 * j]), __uint_as_float(acc[4 * j + 1]), __uint_as_float(acc[4 * j + 2]),
+                         __uint_as_float(acc[4 * j + 3])));
     __syncwarp();
-    const int c4 = (lane & 7) * 4;
-    const int n = col0 + c4;
-    float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (e.bias) bias4 = *reinterpret_cast<const float4*>(e.bias + n);
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      const int rr = k * 4 + (lane >> 3);
-      const int r = row0 + rr;
-      if (r < M) {
-        float4 v = *reinterpret_cast<const float4*>(stage + rr * PITCH + c4);
-        v.x = v.x * e.alpha + bias4.x; v.y = v.y * e.alpha + bias4.y;
-        v.z = v.z * e.alpha + bias4.z; v.w = v.w * e.alpha + bias4.w;
-        if (add1_all) {
-          const float4 b = *reinterpret_cast<const float4*>(e.add1 + (size_t)r * e.ld1 + n);
-          v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
-        }
-        if (e.add2) {
-          const float4 b = *reinterpret_cast<const float4*>(e.add2 + (size_t)r * e.ld2 + n);
-          v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
-        }
-        if (e.act == 1) { v.x = tanh_fast(v.x); v.y = tanh_fast(v.y); v.z = tanh_fast(v.z); v.w = tanh_fast(v.w); }
-        if (e.dtanh) {
-          const float4 t = *reinterpret_cast<const float4*>(e.dtanh + (size_t)r * e.ldd + n);
-          v.x *= 1.0f - t.x * t.x; v.y *= 1.0f - t.y * t.y; v.z *= 1.0f - t.z * t.z; v.w *= 1.0f - t.w * t.w;
-        }
-        if (e.C32) {
-          float* p = e.C32 + (size_t)r * e.ldc32 + n;
-          if (e.accumulate) {
-            const float4 c = *reinterpret_cast<const float4*>(p);
-            v.x += c.x; v.y += c.y; v.z += c.z; v.w += c.w;
-          }
-          *reinterpret_cast<float4*>(p) = v;
-        }
-        if (e.C16) {
-          __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
-          uint2 o;
-          o.x = *reinterpret_cast<uint32_t*>(&lo);
-          o.y = *reinterpret_cast<uint32_t*>(&hi);
-          *reinterpret_cast<uint2*>(e.C16 + (size_t)r * e.ldc16 + n) = o;
-        }
-      }
-    }
+    epilogue_block_vec(e, M, row0, col0, stage, splitk, add1_all);
     __syncwarp();
     return;
   }
@@ -221,7 +392,8 @@ __device__ __forceinline__ void epilogue_row32(const GemmEpi& e, int vec, int M,
       if (e.dtanh) { float t = e.dtanh[(size_t)row * e.ldd + n]; x *= 1.0f - t * t; }
       if (e.C32) {
         float* p = e.C32 + (size_t)row * e.ldc32 + n;
-        *p = e.accumulate ? (*p + x) : x;
+        if (splitk) atomicAdd(p, x);
+        else *p = e.accumulate ? (*p + x) : x;
       }
       if (e.C16) e.C16[(size_t)row * e.ldc16 + n] = __float2bfloat16_rn(x);
     }
@@ -237,8 +409,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_tcgen05_kernel(const __g
   constexpr uint32_t IDESC = make_idesc(BM, BN);
   constexpr int TMEM_COLS = BN < 32 ? 32 : BN;          // allocation granularity: power of two >= 32
   extern __shared__ uint8_t smem_raw[];
-  // 128B swizzle needs 1024-byte aligned tiles
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // 1024-byte alignment (128B swizzle) by POINTER arithmetic on the __shared__ array: a round trip through an integer
+  // loses the address space and every staging access becomes a generic LD/ST instead of LDS/STS
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + STAGES * A_STAGE_BYTES;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_b + STAGES * B_STAGE_BYTES);
@@ -254,6 +427,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_tcgen05_kernel(const __g
   int total_kb = 0;
 #pragma unroll
   for (int s = 0; s < MAX_SEG; ++s) total_kb += (s < p.nseg) ? p.kblocks[s] : 0;
+  const int kb_begin = blockIdx.z * p.kb_per_split;
+  const int kb_end = min(total_kb, kb_begin + p.kb_per_split);
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.nseg; ++s) { prefetch_tmap(&p.ta[s]); prefetch_tmap(&p.tb[s]); }
@@ -270,20 +445,21 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_tcgen05_kernel(const __g
   if (warp == 0) {
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
-      for (int s = 0; s < p.nseg; ++s) {
-        for (int kb = 0; kb < p.kblocks[s]; ++kb) {
-          mbar_wait(&empty_bar[stage], phase ^ 1);
-          mbar_expect_tx(&full_bar[stage], A_STAGE_BYTES + B_STAGE_BYTES);
-          tma_load_2d(smem_a + stage * A_STAGE_BYTES, &p.ta[s], &full_bar[stage], kb * BK, m0);
-          tma_load_2d(smem_b + stage * B_STAGE_BYTES, &p.tb[s], &full_bar[stage], kb * BK, n0);
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
-        }
+      int s = 0, base = 0;                              // segment of the current k-block, its first global index
+      for (int g = kb_begin; g < kb_end; ++g) {
+        while (g >= base + p.kblocks[s]) { base += p.kblocks[s]; ++s; }
+        const int kb = g - base;
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        mbar_expect_tx(&full_bar[stage], A_STAGE_BYTES + B_STAGE_BYTES);
+        tma_load_2d(smem_a + stage * A_STAGE_BYTES, &p.ta[s], &full_bar[stage], kb * BK, m0);
+        tma_load_2d(smem_b + stage * B_STAGE_BYTES, &p.tb[s], &full_bar[stage], kb * BK, n0);
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
-      for (int kb = 0; kb < total_kb; ++kb) {
+      for (int kb = kb_begin; kb < kb_end; ++kb) {
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
         const uint32_t a_base = smem_u32(smem_a + stage * A_STAGE_BYTES);
@@ -292,7 +468,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_tcgen05_kernel(const __g
         for (int k = 0; k < BK / 16; ++k) {
           // advance 16 elements (32 bytes) along K inside the 128B swizzle atom
           umma_bf16(tmem_acc, make_smem_desc(a_base + k * 32), make_smem_desc(b_base + k * 32), IDESC,
-                    (kb > 0 || k > 0) ? 1u : 0u);
+                    (kb > kb_begin || k > 0) ? 1u : 0u);
         }
         umma_commit(&empty_bar[stage]);          // frees the smem slot once these MMAs have read it
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -312,15 +488,346 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_tcgen05_kernel(const __g
       uint32_t acc[32];
       tmem_ld_32x32(tmem_acc + (static_cast<uint32_t>(q * 32) << 16) + c0, acc);
       tmem_ld_wait();
-      epilogue_row32(p.epi, p.vec, p.M, p.N, m0 + q * 32, n0 + c0, BN - c0 < 32 ? BN - c0 : 32, acc,
-                     reinterpret_cast<float*>(smem_a) + (warp - 2) * 32 * 36);
+      if (BN >= 32 && p.tma_store) {
+        epilogue_tma_row32(p.epi, &p.tc, p.N, m0 + q * 32, n0 + c0, acc, smem_u32(smem_a) + (warp - 2) * 4096);
+      } else {
+        epilogue_row32(p.epi, p.vec, p.M, p.N, m0 + q * 32, n0 + c0, BN - c0 < 32 ? BN - c0 : 32, acc,
+                       smem_u32(smem_a) + (warp - 2) * 32 * 36 * 4, gridDim.z > 1, blockIdx.z == 0);
+      }
     }
   }
+  if (p.tma_store && warp >= 2 && (threadIdx.x & 31) == 0) tma_store_wait_all();
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc<TMEM_COLS>(tmem_acc);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// CTA-pair kernel: a 2-CTA cluster computes one 256 x BN tile with tcgen05.mma.cta_group::2 (M = 256).
+// CTA r of the pair owns rows [128r, 128r+128) of the tile: it loads its own 128 x 64 slice of A and HALF of the
+// B tile (BN/2 rows), so per MMA each SM reads half the shared-memory bytes of the single-CTA kernel and the pair
+// pulls B through L2 once instead of twice. Only the leader (rank 0) issues MMAs; both CTAs' TMA loads complete on
+// the leader's `full` barrier; tcgen05.commit multicasts the `empty` / accumulator-ready arrivals to both CTAs.
+// ---------------------------------------------------------------------------------------------
+template <int BN, int STAGES>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
+gemm_tcgen05_2cta_kernel(const __grid_constant__ GemmParams p) {
+  constexpr int BH = BN / 2;                              // B rows loaded by each CTA
+  constexpr int B_STAGE_BYTES = BH * BK * 2;
+  constexpr uint32_t IDESC = make_idesc(2 * BM, BN);
+  constexpr int TMEM_COLS = BN < 32 ? 32 : BN;
+  extern __shared__ uint8_t smem_raw[];
+  // 1024-byte alignment (128B swizzle) by POINTER arithmetic on the __shared__ array: a round trip through an integer
+  // loses the address space and every staging access becomes a generic LD/ST instead of LDS/STS
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + STAGES * A_STAGE_BYTES;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_b + STAGES * B_STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* accum_bar = empty_bar + STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int m0 = blockIdx.y * (2 * BM) + (int)rank * BM;
+  const int n0 = (blockIdx.x >> 1) * BN;
+
+  int total_kb = 0;
+#pragma unroll
+  for (int s = 0; s < MAX_SEG; ++s) total_kb += (s < p.nseg) ? p.kblocks[s] : 0;
+  const int kb_begin = blockIdx.z * p.kb_per_split;
+  const int kb_end = min(total_kb, kb_begin + p.kb_per_split);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.nseg; ++s) { prefetch_tmap(&p.ta[s]); prefetch_tmap(&p.tb[s]); }
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    mbar_init(accum_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) tmem_alloc_2sm<TMEM_COLS>(tmem_slot);
+  tc_fence_before();
+  cluster_sync_all();                                     // both CTAs' barriers exist before any remote arrival
+  tc_fence_after();
+  const uint32_t tmem_acc = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      int s = 0, base = 0;
+      for (int g = kb_begin; g < kb_end; ++g) {
+        while (g >= base + p.kblocks[s]) { base += p.kblocks[s]; ++s; }
+        const int kb = g - base;
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * (A_STAGE_BYTES + B_STAGE_BYTES));
+        tma_load_2d_2sm(smem_a + stage * A_STAGE_BYTES, &p.ta[s], &full_bar[stage], kb * BK, m0);
+        tma_load_2d_2sm(smem_b + stage * B_STAGE_BYTES, &p.tb[s], &full_bar[stage], kb * BK, n0 + (int)rank * BH);
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (rank == 0 && lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int kb = kb_begin; kb < kb_end; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        const uint32_t a_base = smem_u32(smem_a + stage * A_STAGE_BYTES);
+        const uint32_t b_base = smem_u32(smem_b + stage * B_STAGE_BYTES);
+#pragma unroll
+        for (int k = 0; k < BK / 16; ++k) {
+          umma_bf16_2sm(tmem_acc, make_smem_desc(a_base + k * 32), make_smem_desc(b_base + k * 32), IDESC,
+                        (kb > kb_begin || k > 0) ? 1u : 0u);
+        }
+        umma_commit_2sm(&empty_bar[stage]);
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+      umma_commit_2sm(accum_bar);
+    }
+    __syncwarp();
+  } else {
+    const int q = warp & 3;
+    mbar_wait(accum_bar, 0);
+    tc_fence_after();
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+      if (n0 + c0 >= p.N) break;
+      uint32_t acc[32];
+      tmem_ld_32x32(tmem_acc + (static_cast<uint32_t>(q * 32) << 16) + c0, acc);
+      tmem_ld_wait();
+      if (BN >= 32 && p.tma_store) {
+        epilogue_tma_row32(p.epi, &p.tc, p.N, m0 + q * 32, n0 + c0, acc, smem_u32(smem_a) + (warp - 2) * 4096);
+      } else {
+        epilogue_row32(p.epi, p.vec, p.M, p.N, m0 + q * 32, n0 + c0, BN - c0 < 32 ? BN - c0 : 32, acc,
+                       smem_u32(smem_a) + (warp - 2) * 32 * 36 * 4, gridDim.z > 1, blockIdx.z == 0);
+      }
+    }
+  }
+  if (p.tma_store && warp >= 2 && (threadIdx.x & 31) == 0) tma_store_wait_all();
+  tc_fence_before();
+  cluster_sync_all();                                     // the peer may still be reading its half of the accumulator
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_2sm<TMEM_COLS>(tmem_acc);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Skinny-M kernel (M <= 256: the per-timestep recurrent GEMMs, M = batch): operands SWAPPED, K split over a
+// thread-block cluster, partial tiles reduced through distributed shared memory.
+//
+// Measured on B200 (tools/gemm_bench.py, profiles/README.md): an M=128 tcgen05.mma takes ~130 cycles whatever its
+// N, and one SM ingests TMA operands at ~77 GB/s at most. A skinny GEMM therefore wants (a) the <= 256 batch rows on
+// the MMA's N side so every instruction is a full 128x256x16, and (b) as few operand bytes per SM as possible.
+// A CTA owns 128 rows of the WEIGHT matrix (UMMA M) x all batch rows (UMMA N = 256) over 1/S of K: 48 KB of
+// operands per 128x256x64 k-block (the 128x64 tiling moves 24 KB per 128x64x64). The S CTAs of a cluster (1,1,S)
+// work on the same tile; afterwards CTA r owns the batch columns [r*256/S, (r+1)*256/S): every CTA pushes the other
+// CTAs' column slices of its partial accumulator into their shared memory (st.shared::cluster, coalesced), a
+// cluster barrier makes them visible, and the owner adds them to its own TMEM slice and runs the full epilogue.
+// The accumulator is transposed (TMEM lane = output column n, TMEM column = batch row), so for a fixed batch row the
+// 32 lanes of an epilogue warp hold 32 consecutive n: every global access is one coalesced 128-byte line.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t mapa_shared(uint32_t saddr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void st_shared_cluster_f32(uint32_t addr, float v) {
+  asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
+}
+
+// v[j] = value of output column n (this lane) at batch row b0 + j. The block is staged in shared memory as
+// [batch row][column] (lanes write consecutive words: conflict-free, no transpose needed) and leaves through the
+// same vector path as the other kernels, 16 bytes per lane. (With 4-byte stores from the 4 epilogue warps alone the
+// SM sustained ~5 B/clk: 3k cycles per 32x32 block.) Ragged / unaligned blocks take a scalar loop over the staged
+// block; nothing indexes the register array dynamically (that would push it to local memory).
+__device__ __forceinline__ void epilogue_swapped32(const GemmEpi e, int vec, int M, int N, int n_warp0, int b0,
+                                                   const float (&v)[32], uint32_t stage) {
+  const int lane = threadIdx.x & 31;
+#pragma unroll
+  for (int j = 0; j < 32; ++j) sts_f32(stage + (j * 36 + lane) * 4, v[j]);
+  __syncwarp();
+  const bool add1_all = e.add1 && (n_warp0 + 32 <= e.add1_cols);
+  const bool add1_none = !e.add1 || (n_warp0 >= e.add1_cols);
+  if (vec && n_warp0 + 32 <= N && (add1_all || add1_none)) {
+    epilogue_block_vec(e, M, b0, n_warp0, stage, 0, add1_all);
+  } else {
+    const int n = n_warp0 + lane;
+    if (n < N) {
+      const float bias = e.bias ? e.bias[n] : 0.f;
+      const bool add1 = e.add1 && n < e.add1_cols;
+      const int rows = min(32, M - b0);
+#pragma unroll 1
+      for (int j = 0; j < rows; ++j) {
+        const int b = b0 + j;
+        float x = lds_f32(stage + (j * 36 + lane) * 4) * e.alpha + bias;
+        if (add1) x += e.add1[(size_t)b * e.ld1 + n];
+        if (e.add2) x += e.add2[(size_t)b * e.ld2 + n];
+        if (e.act == 1) x = tanh_fast(x);
+        if (e.dtanh) { const float t = e.dtanh[(size_t)b * e.ldd + n]; x *= 1.0f - t * t; }
+        if (e.C32) {
+          float* q = e.C32 + (size_t)b * e.ldc32 + n;
+          *q = e.accumulate ? (*q + x) : x;
+        }
+        if (e.C16) e.C16[(size_t)b * e.ldc16 + n] = __float2bfloat16_rn(x);
+      }
+    }
+  }
+  __syncwarp();
+}
+
+template <int STAGES>
+__global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_swapped_kernel(const __grid_constant__ GemmParams p) {
+  constexpr int BW = 128, BX = 256;                     // weight rows per CTA (UMMA M), activation rows (UMMA N)
+  constexpr int W_STAGE_BYTES = BW * BK * 2, X_STAGE_BYTES = BX * BK * 2;
+  constexpr uint32_t IDESC = make_idesc(BW, BX);
+  extern __shared__ uint8_t smem_raw[];
+  // 1024-byte alignment (128B swizzle) by POINTER arithmetic on the __shared__ array: a round trip through an integer
+  // loses the address space and every staging access becomes a generic LD/ST instead of LDS/STS
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* smem_w = smem;
+  uint8_t* smem_x = smem + STAGES * W_STAGE_BYTES;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_x + STAGES * X_STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* accum_bar = empty_bar + STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int n0 = blockIdx.x * BW;
+  const int S = p.splits;                               // cluster size along z; this CTA's rank = blockIdx.z
+  const int rank = blockIdx.z;
+
+  int total_kb = 0;
+#pragma unroll
+  for (int s = 0; s < MAX_SEG; ++s) total_kb += (s < p.nseg) ? p.kblocks[s] : 0;
+  const int kb_begin = rank * p.kb_per_split;
+  const int kb_end = min(total_kb, kb_begin + p.kb_per_split);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.nseg; ++s) { prefetch_tmap(&p.ta[s]); prefetch_tmap(&p.tb[s]); }
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    mbar_init(accum_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) tmem_alloc<BX>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_acc = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      int s = 0, base = 0;
+      for (int g = kb_begin; g < kb_end; ++g) {
+        while (g >= base + p.kblocks[s]) { base += p.kblocks[s]; ++s; }
+        const int kb = g - base;
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        mbar_expect_tx(&full_bar[stage], W_STAGE_BYTES + X_STAGE_BYTES);
+        tma_load_2d(smem_w + stage * W_STAGE_BYTES, &p.tb[s], &full_bar[stage], kb * BK, n0);
+        tma_load_2d(smem_x + stage * X_STAGE_BYTES, &p.ta[s], &full_bar[stage], kb * BK, 0);
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int kb = kb_begin; kb < kb_end; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        const uint32_t w_base = smem_u32(smem_w + stage * W_STAGE_BYTES);
+        const uint32_t x_base = smem_u32(smem_x + stage * X_STAGE_BYTES);
+#pragma unroll
+        for (int k = 0; k < BK / 16; ++k)
+          umma_bf16(tmem_acc, make_smem_desc(w_base + k * 32), make_smem_desc(x_base + k * 32), IDESC,
+                    (kb > kb_begin || k > 0) ? 1u : 0u);
+        umma_commit(&empty_bar[stage]);
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+      umma_commit(accum_bar);
+    }
+    __syncwarp();
+  } else {
+    mbar_wait(accum_bar, 0);                            // this CTA's partial tile is complete in TMEM
+    tc_fence_after();
+  }
+
+  const int q = warp & 3;                               // epilogue warps 2..5 own TMEM lanes [32q, 32q+32)
+  const int tl = q * 32 + lane;                         // TMEM lane = column n0 + tl of the output
+  const int CW = BX / S;                                // batch columns owned by each CTA of the cluster
+  float* recv = reinterpret_cast<float*>(smem);         // [(S-1) sources][CW columns][128 lanes], over the dead stages
+  if (S > 1) {
+    // every CTA of the cluster has finished its main loop (its stage buffers are dead) before anyone pushes
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+    if (warp >= 2 && kb_end > kb_begin) {
+      for (int o = 0; o < S; ++o) {
+        if (o == rank) continue;
+        const int slot = rank < o ? rank : rank - 1;
+        const uint32_t rbase = mapa_shared(smem_u32(recv), (uint32_t)o);
+        for (int c = 0; c < CW; c += 32) {
+          if (o * CW + c >= p.M) break;                 // columns beyond the batch are never read
+          uint32_t acc[32];
+          tmem_ld_32x32(tmem_acc + (static_cast<uint32_t>(q * 32) << 16) + o * CW + c, acc);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            st_shared_cluster_f32(rbase + (uint32_t)(((slot * CW + c + j) * 128 + tl) * 4), __uint_as_float(acc[j]));
+        }
+      }
+    }
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+  }
+  if (warp >= 2) {
+    const GemmEpi epi = p.epi;                          // registers (see the note at epilogue_block_vec)
+    // which of the other CTAs actually had k-blocks (a trailing split can be empty when K is short)
+    for (int c = 0; c < CW; c += 32) {
+      const int b0 = rank * CW + c;
+      if (b0 >= p.M) break;
+      float v[32];
+      if (kb_end > kb_begin) {
+        uint32_t acc[32];
+        tmem_ld_32x32(tmem_acc + (static_cast<uint32_t>(q * 32) << 16) + b0, acc);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[j]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = 0.f;
+      }
+      for (int o = 0; o < S; ++o) {
+        if (o == rank || o * p.kb_per_split >= total_kb) continue;
+        const int slot = o < rank ? o : o - 1;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] += lds_f32(smem_u32(recv) + (uint32_t)(((slot * CW + c + j) * 128 + tl) * 4));
+      }
+      if (p.tma_store) {
+        // dense [32 batch rows][32 columns] block per warp -> one TMA store; the async engine writes it out while the
+        // warp goes on (plain STG.128 stores cost this lone warp ~220 cycles each: 1.8k cycles per block)
+        const uint32_t st = smem_u32(smem) + 96 * 1024 + (warp - 2) * 4096;
+        const float bias = (epi.bias && n0 + tl < p.N) ? epi.bias[n0 + tl] : 0.f;
+        if (lane == 0) tma_store_wait_read();           // the previous store has finished reading this buffer
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) sts_f32(st + (j * 32 + lane) * 4, fmaf(v[j], epi.alpha, bias));
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) tma_store_2d(&p.tc, st, n0 + q * 32, b0);
+      } else {
+        epilogue_swapped32(epi, p.vec, p.M, p.N, n0 + q * 32, b0, v,
+                           smem_u32(smem) + 96 * 1024 + (warp - 2) * 32 * 36 * 4);
+      }
+    }
+  }
+  if (p.tma_store && warp >= 2 && lane == 0) tma_store_wait_all();
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<BX>(tmem_acc);
   }
 }
 
@@ -367,7 +874,35 @@ static EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
+// cuTensorMapEncodeTiled costs microseconds of host time and a training step issues ~500 of them with the same
+// few hundred (pointer, shape) combinations every step: memoise the encoded descriptors.
+struct TmapKey {
+  const void* base; int rows, K, ld, box_rows;
+  bool operator==(const TmapKey& o) const { return base == o.base && rows == o.rows && K == o.K && ld == o.ld && box_rows == o.box_rows; }
+};
+struct TmapKeyHash {
+  size_t operator()(const TmapKey& k) const {
+    size_t h = reinterpret_cast<size_t>(k.base) * 0x9E3779B97F4A7C15ull;
+    h ^= ((size_t)k.rows << 40) ^ ((size_t)k.K << 20) ^ ((size_t)k.ld << 4) ^ (size_t)k.box_rows;
+    return h * 0xD6E8FEB86659FD93ull;
+  }
+};
+static std::unordered_map<TmapKey, CUtensorMap, TmapKeyHash> g_tmap_cache;
+static std::mutex g_tmap_mutex;
+
+static int encode_tmap_uncached(CUtensorMap* out, const bf16* base, int rows, int K, int ld, int box_rows);
 static int encode_tmap(CUtensorMap* out, const bf16* base, int rows, int K, int ld, int box_rows) {
+  const TmapKey key{base, rows, K, ld, box_rows};
+  std::lock_guard<std::mutex> lock(g_tmap_mutex);
+  auto it = g_tmap_cache.find(key);
+  if (it != g_tmap_cache.end()) { *out = it->second; return 0; }
+  TRY(encode_tmap_uncached(out, base, rows, K, ld, box_rows));
+  if (g_tmap_cache.size() > 8192) g_tmap_cache.clear();
+  g_tmap_cache.emplace(key, *out);
+  return 0;
+}
+
+static int encode_tmap_uncached(CUtensorMap* out, const bf16* base, int rows, int K, int ld, int box_rows) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) { set_error("cuTensorMapEncodeTiled not available from the driver"); return SSCVAE_ERR_DRIVER; }
   if ((reinterpret_cast<uintptr_t>(base) & 15) || (ld % 8) != 0) {
@@ -378,9 +913,14 @@ static int encode_tmap(CUtensorMap* out, const bf16* base, int rows, int K, int 
   cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
   cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
+  static const CUtensorMapL2promotion promo = [] {
+    const char* e = getenv("SSCVAE_TMA_L2_PROMOTION");      // tuning knob: 0 none, 64, 128, 256
+    const int v = e ? atoi(e) : 256;
+    return v == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE : v == 64 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B
+         : v == 128 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B : CU_TENSOR_MAP_L2_PROMOTION_L2_256B;
+  }();
   CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<bf16*>(base), dims, strides, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled failed (%d) rows=%d K=%d ld=%d box_rows=%d", (int)r, rows, K, ld, box_rows);
     return SSCVAE_ERR_DRIVER;
@@ -390,23 +930,124 @@ static int encode_tmap(CUtensorMap* out, const bf16* base, int rows, int K, int 
 
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
+static bool tma_store_eligible(const GemmParams& prm) {
+  static const bool off = [] { const char* v = getenv("SSCVAE_GEMM_NO_TMA_STORE"); return v && v[0] == '1'; }();
+  const GemmEpi& e = prm.epi;
+  return !off && prm.splits == 1 && e.C32 && !e.C16 && !e.act && !e.dtanh && !e.accumulate && !e.add1 && !e.add2 &&
+         aligned16(e.C32) && (e.ldc32 % 4) == 0 && (prm.N % 4) == 0 && (!e.bias || aligned16(e.bias));
+  // N % 4: the TMA unit clips stores at 16-byte granularity (measured: with N = 77 the columns 77..79 were written)
+}
+
+// fp32 output tile map for TMA stores: box = 32 columns x 32 rows, dense in shared memory
+static int encode_tmap_c32(CUtensorMap* out, const float* base, int rows, int cols, int ld, bool swizzle128) {
+  const TmapKey key{base, rows, cols, ld, swizzle128 ? -33 : -32};
+  std::lock_guard<std::mutex> lock(g_tmap_mutex);
+  auto it = g_tmap_cache.find(key);
+  if (it != g_tmap_cache.end()) { *out = it->second; return 0; }
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) { set_error("cuTensorMapEncodeTiled not available from the driver"); return SSCVAE_ERR_DRIVER; }
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+  cuuint32_t box[2] = {32, 32};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                  CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled (fp32 output) failed (%d) rows=%d cols=%d ld=%d", (int)r, rows, cols, ld);
+    return SSCVAE_ERR_DRIVER;
+  }
+  if (g_tmap_cache.size() > 8192) g_tmap_cache.clear();
+  g_tmap_cache.emplace(key, *out);
+  return 0;
+}
+
 template <int BN, int STAGES>
 static int launch_tc(cudaStream_t stream, GemmParams& prm, const GemmSeg* segs) {
   for (int s = 0; s < prm.nseg; ++s) {
     TRY(encode_tmap(&prm.ta[s], segs[s].A, prm.M, segs[s].K, segs[s].lda, BM));
     TRY(encode_tmap(&prm.tb[s], segs[s].B, prm.N, segs[s].K, segs[s].ldb, BN));
   }
+  prm.tma_store = BN >= 32 && tma_store_eligible(prm);
+  if (prm.tma_store) TRY(encode_tmap_c32(&prm.tc, prm.epi.C32, prm.M, prm.N, prm.epi.ldc32, true));
   constexpr int smem = 1024 + STAGES * (A_STAGE_BYTES + BN * BK * 2) + 256;
   static bool configured = false;
   if (!configured) {
     CUDA_TRY(cudaFuncSetAttribute(gemm_tcgen05_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = true;
   }
-  dim3 grid(ceil_div(prm.N, BN), ceil_div(prm.M, BM));
+  dim3 grid(ceil_div(prm.N, BN), ceil_div(prm.M, BM), prm.splits);
   gemm_tcgen05_kernel<BN, STAGES><<<grid, GEMM_THREADS, smem, stream>>>(prm);
   CUDA_TRY(cudaGetLastError());
   ++g_launch_count;
   return 0;
+}
+
+template <int BN, int STAGES>
+static int launch_tc2(cudaStream_t stream, GemmParams& prm, const GemmSeg* segs) {
+  for (int s = 0; s < prm.nseg; ++s) {
+    TRY(encode_tmap(&prm.ta[s], segs[s].A, prm.M, segs[s].K, segs[s].lda, BM));
+    TRY(encode_tmap(&prm.tb[s], segs[s].B, prm.N, segs[s].K, segs[s].ldb, BN / 2));
+  }
+  prm.tma_store = BN >= 32 && tma_store_eligible(prm);
+  if (prm.tma_store) TRY(encode_tmap_c32(&prm.tc, prm.epi.C32, prm.M, prm.N, prm.epi.ldc32, true));
+  constexpr int smem = 1024 + STAGES * (A_STAGE_BYTES + (BN / 2) * BK * 2) + 256;
+  static bool configured = false;
+  if (!configured) {
+    CUDA_TRY(cudaFuncSetAttribute(gemm_tcgen05_2cta_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured = true;
+  }
+  dim3 grid(2 * ceil_div(prm.N, BN), ceil_div(prm.M, 2 * BM), prm.splits);
+  gemm_tcgen05_2cta_kernel<BN, STAGES><<<grid, GEMM_THREADS, smem, stream>>>(prm);
+  CUDA_TRY(cudaGetLastError());
+  ++g_launch_count;
+  return 0;
+}
+
+template <int STAGES>
+static int launch_swapped(cudaStream_t stream, GemmParams& prm, const GemmSeg* segs) {
+  for (int s = 0; s < prm.nseg; ++s) {
+    TRY(encode_tmap(&prm.ta[s], segs[s].A, prm.M, segs[s].K, segs[s].lda, 256));
+    TRY(encode_tmap(&prm.tb[s], segs[s].B, prm.N, segs[s].K, segs[s].ldb, 128));
+  }
+  const GemmEpi& e = prm.epi;
+  static const bool no_tma_store = [] { const char* v = getenv("SSCVAE_GEMM_NO_TMA_STORE"); return v && v[0] == '1'; }();
+  prm.tma_store = !no_tma_store && e.C32 && !e.C16 && !e.act && !e.dtanh && !e.accumulate && !e.add1 && !e.add2 &&
+                  aligned16(e.C32) && (e.ldc32 % 4) == 0 && (prm.N % 4) == 0;
+  if (prm.tma_store) TRY(encode_tmap_c32(&prm.tc, e.C32, prm.M, prm.N, e.ldc32, false));
+  constexpr int smem = 1024 + STAGES * (128 + 256) * BK * 2 + 256;
+  static bool configured = false;
+  if (!configured) {
+    CUDA_TRY(cudaFuncSetAttribute(gemm_tcgen05_swapped_kernel<STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured = true;
+  }
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(ceil_div(prm.N, 128), 1, prm.splits);
+  cfg.blockDim = dim3(GEMM_THREADS, 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 1; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = prm.splits;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  CUDA_TRY(cudaLaunchKernelEx(&cfg, gemm_tcgen05_swapped_kernel<STAGES>, prm));
+  ++g_launch_count;
+  return 0;
+}
+
+int gemm_suggest_splits(int M, int N, int K_total) {
+  if (M > 256) return 1;
+  static int n_sm = 0;
+  if (n_sm == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
+      n_sm = 148;
+  }
+  const int tiles = ceil_div(N, 128), kb = ceil_div(K_total, BK);
+  int s = 1;
+  while (s < 4 && tiles * s * 2 <= n_sm && kb >= 4 * s * 2) s *= 2;   // power of two: the cluster splits 256 columns
+  return s;
 }
 
 int gemm_bf16_tn(cudaStream_t stream, int M, int N, int nseg, const GemmSeg* segs, const GemmEpi& epi) {
@@ -440,6 +1081,36 @@ int gemm_bf16_tn(cudaStream_t stream, int M, int N, int nseg, const GemmSeg* seg
   if (epi.C32) vec &= aligned16(epi.C32) && (epi.ldc32 % 4 == 0);
   if (epi.C16) vec &= aligned16(epi.C16) && (epi.ldc16 % 8 == 0);
   prm.vec = vec ? 1 : 0;
+  int total_kb = 0;
+  for (int s = 0; s < nseg; ++s) total_kb += prm.kblocks[s];
+  prm.splits = 1; prm.kb_per_split = total_kb;
+  // split-K: gridDim.z CTAs share one output tile, each adds its partial sum into C32 with vector reductions
+  // (red.global.add.v4.f32). Only for linear epilogues with an fp32 output; C32 is zeroed first unless accumulating.
+  auto use_splits = [&](int n) -> int {
+    if (n <= 1 || !epi.C32 || epi.C16 || epi.act || epi.dtanh) return 0;
+    n = std::min(n, std::max(1, total_kb / 2));
+    if (n <= 1) return 0;
+    prm.kb_per_split = ceil_div(total_kb, n);
+    prm.splits = ceil_div(total_kb, prm.kb_per_split);
+    if (!epi.accumulate)
+      CUDA_TRY(cudaMemset2DAsync(epi.C32, (size_t)epi.ldc32 * 4, 0, (size_t)N * 4, (size_t)M, stream));
+    return 0;
+  };
+  if (const char* e = getenv("SSCVAE_GEMM_SPLITK")) TRY(use_splits(atoi(e)));
+  static const bool no_swapped = [] { const char* e = getenv("SSCVAE_GEMM_NO_SWAPPED"); return e && e[0] == '1'; }();
+  // skinny and long-K (the per-timestep LSTM and BPTT GEMMs): swapped-operand cluster split-K. Measured on B200
+  // (tools/gemm_bench.py, GPU time inside a CUDA graph, us): 256x3600x4928: 17.0 vs 24.9 for the 128x64 tiling;
+  // 256x4160x3648: 16.0 vs 19.4; 256x1920x3648: 13.9 vs 18.8; short K (256x3600x1920: 12.6 vs 12.4) and narrow N
+  // (256x768x960: 10.2 vs 7.9) stay on the plain kernel.
+  const bool skinny = M <= 256 && N >= 1024 && total_kb >= 48;
+  if ((epi.splits > 0 || (skinny && !no_swapped)) && M <= 256 && !getenv("SSCVAE_GEMM_FORCE")) {
+    int S = epi.splits > 0 ? epi.splits : gemm_suggest_splits(M, N, total_kb * BK);
+    REQUIRE(S == 1 || S == 2 || S == 4, "gemm: split count %d (1, 2 or 4)", S);
+    while (S > 1 && total_kb < S) S /= 2;
+    prm.splits = S;
+    prm.kb_per_split = ceil_div(total_kb, S);
+    return launch_swapped<4>(stream, prm, segs);
+  }
   // The recurrent GEMMs have M = batch (two 128-row tiles) and stream their weights once: they are bound by
   // bytes in flight per SM, not by the tensor pipe. So: the widest N tile that still yields >= ~100 CTAs,
   // ~100 KB of TMA stages per CTA and two CTAs resident per SM (no wave-quantisation tail at 149..296 CTAs,
@@ -455,11 +1126,21 @@ int gemm_bf16_tn(cudaStream_t stream, int M, int N, int nseg, const GemmSeg* seg
       if (bn == 32 && st == 5) return launch_tc<32, 5>(stream, prm, segs);
       if (bn == 32 && st == 10) return launch_tc<32, 10>(stream, prm, segs);
       if (bn == 16 && st == 6) return launch_tc<16, 6>(stream, prm, segs);
+      // CTA-pair kernel: "2xBN,STAGES" is spelled with a leading 2 (e.g. 2256,6 = pair tile 256x256, 6 stages)
+      if (bn == 2256 && st == 6) return launch_tc2<256, 6>(stream, prm, segs);
+      if (bn == 2256 && st == 4) return launch_tc2<256, 4>(stream, prm, segs);
+      if (bn == 2128 && st == 8) return launch_tc2<128, 8>(stream, prm, segs);
+      if (bn == 2128 && st == 4) return launch_tc2<128, 4>(stream, prm, segs);
+      if (bn == 264 && st == 10) return launch_tc2<64, 10>(stream, prm, segs);
+      if (bn == 264 && st == 5) return launch_tc2<64, 5>(stream, prm, segs);
+      if (bn == 232 && st == 10) return launch_tc2<32, 10>(stream, prm, segs);
       set_error("SSCVAE_GEMM_FORCE=%s: no such instantiation", f);
       return SSCVAE_ERR_BAD_ARG;
     }
   }
   const long mt = ceil_div(M, BM);
+  // large and long-K (the batched weight-gradient GEMMs): CTA pairs, 256x128 tiles (3600x2048x5376: 68 vs 76 us)
+  if (M >= 1024 && N >= 512 && total_kb >= 32) return launch_tc2<128, 4>(stream, prm, segs);
   if (mt * ceil_div(N, 128) >= 96) return launch_tc<128, 3>(stream, prm, segs);
   if (mt * ceil_div(N, 64) >= 96) return launch_tc<64, 4>(stream, prm, segs);
   if (mt * ceil_div(N, 32) >= 96) return launch_tc<32, 5>(stream, prm, segs);

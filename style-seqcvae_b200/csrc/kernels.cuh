@@ -99,6 +99,9 @@ int copy_block_f32(cudaStream_t s, const float* src, int ld_src, float* dst, int
 int pack_block(cudaStream_t s, bf16* dst, int ld_dst, int transposed, const float* src, int ld_src, int rows, int cols,
                const float* src2, int ld_src2);
 int vec_add_f32(cudaStream_t s, const float* a, const float* b, float* out, int n);
+// dst (rows, cols; ld_dst) = sum of `nparts` split-K partial tiles parts + z*stride (rows, cols; ld); dst may be parts
+int sum_partials_f32(cudaStream_t s, float* dst, int ld_dst, const float* parts, size_t stride, int nparts, int rows,
+                     int cols, int ld);
 int scale_rows_f32(cudaStream_t s, const float* in, float scale, float* out, int n);
 // dEmb[tok[b,t], :] += dx[(t*B+b), :] skipping the padding index (nn.Embedding padding_idx)
 int embed_scatter_add(cudaStream_t s, const int* tok, int B, int L, int pad, const float* dx, int ld_dx, int E, float* demb);

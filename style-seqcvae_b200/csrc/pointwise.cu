@@ -620,6 +620,29 @@ int pack_block(cudaStream_t s, bf16* dst, int ld_dst, int transposed, const floa
   return 0;
 }
 
+// dst[r, c] = sum_z parts[z * stride + r * ld + c]   (split-K partial tiles -> result; dst may alias parts[0])
+__global__ void sum_partials_kernel(float* __restrict__ dst, int ld_dst, const float* __restrict__ parts, size_t stride,
+                                    int nparts, int rows, int cols4, int ld) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const int r = blockIdx.y;
+  if (c >= cols4) return;
+  float4 v = *reinterpret_cast<const float4*>(parts + (size_t)r * ld + 4 * c);
+  for (int z = 1; z < nparts; ++z) {
+    const float4 w = *reinterpret_cast<const float4*>(parts + z * stride + (size_t)r * ld + 4 * c);
+    v.x += w.x; v.y += w.y; v.z += w.z; v.w += w.w;
+  }
+  *reinterpret_cast<float4*>(dst + (size_t)r * ld_dst + 4 * c) = v;
+}
+int sum_partials_f32(cudaStream_t s, float* dst, int ld_dst, const float* parts, size_t stride, int nparts, int rows,
+                     int cols, int ld) {
+  PROF_SCOPE(s, "splitk_reduce", 0, (double)rows * cols * 4.0 * (nparts + 1));
+  REQUIRE(cols % 4 == 0 && ld % 4 == 0 && ld_dst % 4 == 0 && stride % 4 == 0, "sum_partials: shapes must be multiples of 4");
+  dim3 grid(ceil_div(cols / 4, 128), rows);
+  sum_partials_kernel<<<grid, 128, 0, s>>>(dst, ld_dst, parts, stride, nparts, rows, cols / 4, ld);
+  LAUNCHED();
+  return 0;
+}
+
 __global__ void vec_add_kernel(const float* a, const float* b, float* out, int n) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) out[i] = a[i] + (b ? b[i] : 0.f);
