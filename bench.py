@@ -138,6 +138,78 @@ def cpu_reference_run(steps, warmup, B=8):
                 seconds=dt)
 
 
+def synthetic_fsm(n_images, vocab, constraint_ids):
+    """(B, 2^k, 2^k, V) uint8 adjacency tensor of k single-word constraints (the shape the reference's
+    FiniteStateMachineBuilder hands to ConstrainedBeamSearch, updown-baseline/updown/utils/constraints.py:329-361):
+    fsm[b, s, s2, w] = 1 iff emitting word w moves state s -> s2. State = bitmask of satisfied constraints."""
+    k = len(constraint_ids)
+    S = 1 << k
+    fsm = torch.zeros(S, S, vocab, dtype=torch.uint8)
+    for s in range(S):
+        fsm[s, s, :] = 1
+        for i, ids in enumerate(constraint_ids):
+            if not (s >> i) & 1:
+                for w in ids:
+                    fsm[s, s, w] = 0
+                    fsm[s, s | (1 << i), w] = 1
+    return fsm[None].repeat(n_images, 1, 1, 1).contiguous()
+
+
+def decode_legs(sscvae, vocab, train_model, dev, world, max_over_ranks, barrier):
+    """BASELINE configs[3] and [4]: decode throughput through UpDownCaptioner.forward (eval), images sharded over
+    ranks with no collective. (a) diverse sampling: 100 latent samples per image, greedy decode - the reference loop
+    `for k in range(N_Z_SAMPLES): model(image_features, ...)` (var_updown/scripts/inference.py:138-167);
+    (b) constrained beam search, beam 5, 3 single-word constraints (8 FSM states, 40 rows per image)."""
+    out = {}
+    sd = train_model.state_dict()
+
+    def build(beam, cbs):
+        m = sscvae.UpDownCaptioner(vocab, DIMS["image_feature_size"], DIMS["embedding_size"], DIMS["hidden_size"],
+                                   DIMS["attention_projection_size"], max_caption_length=20, beam_size=beam, use_cbs=cbs,
+                                   min_constraints_to_satisfy=2, z_space=DIMS["z_space"], prior_std=1.0, simple_vae=False,
+                                   latent_embedding="glove", sentiment_vae=1, senti_prior_multip=0.5, cbs_simple=True,
+                                   device=dev).to(dev)
+        m.load_state_dict(sd)
+        m.eval()
+        return m
+
+    def timed(fn, calls, warm):
+        for _ in range(warm):
+            fn()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(calls):
+            fn()
+        e1.record()
+        barrier()
+        return max_over_ranks(e0.elapsed_time(e1))
+
+    g = torch.Generator().manual_seed(7)
+    # (a) diverse sampling, greedy
+    n_img, n_samples = 256, 100
+    feats = torch.rand(n_img, N_BOXES, DIMS["image_feature_size"], generator=g).to(dev)
+    sent = torch.randint(-1, 2, (n_img, 1), generator=g).float().to(dev)
+    m1 = build(1, False)
+    ms = timed(lambda: m1(feats, None, None, sentiment=sent)["predictions"], n_samples, 3)
+    out["sampling_greedy"] = {"value": n_img * n_samples * world / (ms / 1e3), "unit": "captions/s",
+                              "images_per_gpu": n_img, "samples_per_image": n_samples, "ms_per_call": ms / n_samples,
+                              "config": "BASELINE configs[3]: 100 latent samples per image, greedy decode, max length 20"}
+    del m1
+    # (b) CBS beam 5, 3 constraints -> 8 states
+    n_img, calls = 64, 5
+    feats = feats[:n_img].contiguous()
+    sent = sent[:n_img].contiguous()
+    fsm = synthetic_fsm(n_img, DIMS["vocab_size"], [[11, 12], [57], [300, 301, 302]]).to(dev)
+    nc = torch.full((n_img,), 3, dtype=torch.long, device=dev)
+    m5 = build(5, True)
+    ms = timed(lambda: m5(feats, None, None, fsm=fsm, num_constraints=nc, sentiment=sent)["predictions"], calls, 2)
+    out["cbs_beam5"] = {"value": n_img * calls * world / (ms / 1e3), "unit": "captions/s", "images_per_gpu": n_img,
+                        "fsm_states": 8, "beam": 5, "rows_per_image": 40, "ms_per_call": ms / calls,
+                        "config": "BASELINE configs[4]: constrained beam search, beam 5, 3 word constraints, max length 20"}
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -307,6 +379,10 @@ def main():
                 "share_of_step": gemm_ms / total_ms, "launches_per_step": gemm_n / args.profile_steps,
                 "avg_launch_us": 1e3 * gemm_ms / gemm_n}
 
+    decode = None
+    if not args.no_decode:
+        decode = decode_legs(sscvae, _Vocab(), model, dev, world, max_over_ranks, barrier)
+
     captions = B * world * args.steps
     value = captions / (ms_dev / 1e3)
     e2e_value = captions / (ms_e2e / 1e3)
@@ -330,6 +406,7 @@ def main():
                        "unit": "TFLOP/s", "frac": value * GFLOP_PER_CAPTION / 1e3 / (peaks["tf_sustained"] * world),
                        "note": "model FLOPs (8.10 GFLOP/caption, SURVEY §8d) / step time"},
         kernels=kernels,
+        decode=decode,
     )
     if not args.no_cpu_baseline and world == 1:
         r = cpu_reference_run(3, 1)

@@ -211,33 +211,34 @@ static int pack_weights_impl(Handle* h, const void* const* wv, char* pk, const u
   };
   for (int i = 0; i < SSCVAE_W_COUNT; ++i) REQUIRE(wv[i] != nullptr, "weight pointer %d is NULL", i);
   if (!dirty) CUDA_TRY(cudaMemsetAsync(pk, 0, pp.total, s));
+  PackJobList jobs;                                   // every bf16 block below is converted by ONE kernel launch
   const int E = d.E, F = d.F, H = d.H, A = d.A, Z = d.Z, V = d.V, G = d.G, c = d.cond;
   // embedding (gather source and, tied, the vocabulary GEMM operand)
   if (need({SSCVAE_W_EMBEDDING})) {
-    TRY(pack_block(s, Pb("embb"), d.Ep, 0, W(SSCVAE_W_EMBEDDING), E, V, E, nullptr, 0));
-    if (d.tied) TRY(pack_block(s, Pb("embT"), d.Vp, 1, W(SSCVAE_W_EMBEDDING), E, V, E, nullptr, 0));
+    TRY(jobs.add(Pb("embb"), d.Ep, 0, W(SSCVAE_W_EMBEDDING), E, V, E, nullptr, 0));
+    if (d.tied) TRY(jobs.add(Pb("embT"), d.Vp, 1, W(SSCVAE_W_EMBEDDING), E, V, E, nullptr, 0));
   }
   // attention LSTM: W_ih columns [emb E | avg F | h1 H | h_dec H] (updown_cell.py:143-145); W_hh folded onto h1
   const int ldi = E + F + 2 * H;
   const float* wih = W(SSCVAE_W_ATT_IH);
   if (need({SSCVAE_W_ATT_IH, SSCVAE_W_ATT_HH})) {
-    TRY(pack_block(s, Pb("w_att_rec"), 2 * d.Hp, 0, wih + E + F, ldi, G, H, W(SSCVAE_W_ATT_HH), H));
-    TRY(pack_block(s, Pb("w_att_recT"), d.Gp, 1, wih + E + F, ldi, G, H, W(SSCVAE_W_ATT_HH), H));
+    TRY(jobs.add(Pb("w_att_rec"), 2 * d.Hp, 0, wih + E + F, ldi, G, H, W(SSCVAE_W_ATT_HH), H));
+    TRY(jobs.add(Pb("w_att_recT"), d.Gp, 1, wih + E + F, ldi, G, H, W(SSCVAE_W_ATT_HH), H));
   }
   if (need({SSCVAE_W_ATT_IH})) {
-    TRY(pack_block(s, Pb("w_att_e"), d.Ep, 0, wih, ldi, G, E, nullptr, 0));
-    TRY(pack_block(s, Pb("w_att_eT"), d.Gp, 1, wih, ldi, G, E, nullptr, 0));
-    TRY(pack_block(s, Pb("w_att_f"), d.Fp, 0, wih + E, ldi, G, F, nullptr, 0));
-    TRY(pack_block(s, Pb("w_att_rec") + d.Hp, 2 * d.Hp, 0, wih + E + F + H, ldi, G, H, nullptr, 0));
-    TRY(pack_block(s, Pb("w_att_recT") + (size_t)d.Hp * d.Gp, d.Gp, 1, wih + E + F + H, ldi, G, H, nullptr, 0));
+    TRY(jobs.add(Pb("w_att_e"), d.Ep, 0, wih, ldi, G, E, nullptr, 0));
+    TRY(jobs.add(Pb("w_att_eT"), d.Gp, 1, wih, ldi, G, E, nullptr, 0));
+    TRY(jobs.add(Pb("w_att_f"), d.Fp, 0, wih + E, ldi, G, F, nullptr, 0));
+    TRY(jobs.add(Pb("w_att_rec") + d.Hp, 2 * d.Hp, 0, wih + E + F + H, ldi, G, H, nullptr, 0));
+    TRY(jobs.add(Pb("w_att_recT") + (size_t)d.Hp * d.Gp, d.Gp, 1, wih + E + F + H, ldi, G, H, nullptr, 0));
   }
   if (need({SSCVAE_W_ATT_BIH, SSCVAE_W_ATT_BHH})) TRY(vec_add_f32(s, W(SSCVAE_W_ATT_BIH), W(SSCVAE_W_ATT_BHH), Pf("b_att"), G));
   // attention
   if (need({SSCVAE_W_QUERY_PROJ})) {
-    TRY(pack_block(s, Pb("wq"), d.Hp, 0, W(SSCVAE_W_QUERY_PROJ), H, A, H, nullptr, 0));
-    TRY(pack_block(s, Pb("wqT"), d.Ap, 1, W(SSCVAE_W_QUERY_PROJ), H, A, H, nullptr, 0));
+    TRY(jobs.add(Pb("wq"), d.Hp, 0, W(SSCVAE_W_QUERY_PROJ), H, A, H, nullptr, 0));
+    TRY(jobs.add(Pb("wqT"), d.Ap, 1, W(SSCVAE_W_QUERY_PROJ), H, A, H, nullptr, 0));
   }
-  if (need({SSCVAE_W_IMAGE_PROJ})) TRY(pack_block(s, Pb("wv"), d.Fp, 0, W(SSCVAE_W_IMAGE_PROJ), F, A, F, nullptr, 0));
+  if (need({SSCVAE_W_IMAGE_PROJ})) TRY(jobs.add(Pb("wv"), d.Fp, 0, W(SSCVAE_W_IMAGE_PROJ), F, A, F, nullptr, 0));
   // encoder LSTM: W_ih columns [xhat F | h1 H | h_dec H | cond c] (updown_cell.py:178-190)
   const int lde = F + 2 * H + c;
   const float* we = W(SSCVAE_W_ENC_IH);
@@ -247,14 +248,14 @@ static int pack_weights_impl(Handle* h, const void* const* wv, char* pk, const u
   const int widths[3] = {F, H, H};
   if (need({SSCVAE_W_ENC_IH})) {
     for (int k = 0; k < 3; ++k) {
-      TRY(pack_block(s, wex + offs_dst[k], d.KX, 0, we + offs_src[k], lde, G, widths[k], nullptr, 0));
-      TRY(pack_block(s, wexT + (size_t)offs_dst[k] * d.Gp, d.Gp, 1, we + offs_src[k], lde, G, widths[k], nullptr, 0));
+      TRY(jobs.add(wex + offs_dst[k], d.KX, 0, we + offs_src[k], lde, G, widths[k], nullptr, 0));
+      TRY(jobs.add(wexT + (size_t)offs_dst[k] * d.Gp, d.Gp, 1, we + offs_src[k], lde, G, widths[k], nullptr, 0));
     }
     if (c) TRY(copy_block_f32(s, we + F + 2 * H, lde, Pf("scol_enc"), 1, G, 1));
   }
   if (need({SSCVAE_W_ENC_HH})) {
-    TRY(pack_block(s, Pb("w_enc_hh"), d.Hp, 0, W(SSCVAE_W_ENC_HH), H, G, H, nullptr, 0));
-    TRY(pack_block(s, Pb("w_enc_xhT") + (size_t)d.KX * d.Gp, d.Gp, 1, W(SSCVAE_W_ENC_HH), H, G, H, nullptr, 0));
+    TRY(jobs.add(Pb("w_enc_hh"), d.Hp, 0, W(SSCVAE_W_ENC_HH), H, G, H, nullptr, 0));
+    TRY(jobs.add(Pb("w_enc_xhT") + (size_t)d.KX * d.Gp, d.Gp, 1, W(SSCVAE_W_ENC_HH), H, G, H, nullptr, 0));
   }
   if (need({SSCVAE_W_ENC_BIH, SSCVAE_W_ENC_BHH})) TRY(vec_add_f32(s, W(SSCVAE_W_ENC_BIH), W(SSCVAE_W_ENC_BHH), Pf("b_enc"), G));
   // decoder LSTM: W_ih columns [xhat F | h1 H | h_dec H | cond c | z Z] (updown_cell.py:211-224); W_hh folded onto h_dec
@@ -265,33 +266,34 @@ static int pack_weights_impl(Handle* h, const void* const* wv, char* pk, const u
     for (int k = 0; k < 3; ++k) {
       if (k < 2 && !need({SSCVAE_W_DEC_IH})) continue;
       const float* fold = (k == 2) ? W(SSCVAE_W_DEC_HH) : nullptr;
-      TRY(pack_block(s, wdx + offs_dst[k], d.KX, 0, wd + offs_src[k], ldd, G, widths[k], fold, H));
-      TRY(pack_block(s, wdxT + (size_t)offs_dst[k] * d.Gp, d.Gp, 1, wd + offs_src[k], ldd, G, widths[k], fold, H));
+      TRY(jobs.add(wdx + offs_dst[k], d.KX, 0, wd + offs_src[k], ldd, G, widths[k], fold, H));
+      TRY(jobs.add(wdxT + (size_t)offs_dst[k] * d.Gp, d.Gp, 1, wd + offs_src[k], ldd, G, widths[k], fold, H));
     }
   }
   if (need({SSCVAE_W_DEC_IH})) {
-    TRY(pack_block(s, Pb("w_dec_z"), d.Zp, 0, wd + F + 2 * H + c, ldd, G, Z, nullptr, 0));
-    TRY(pack_block(s, Pb("w_dec_xzT") + (size_t)d.KX * d.Gp, d.Gp, 1, wd + F + 2 * H + c, ldd, G, Z, nullptr, 0));
+    TRY(jobs.add(Pb("w_dec_z"), d.Zp, 0, wd + F + 2 * H + c, ldd, G, Z, nullptr, 0));
+    TRY(jobs.add(Pb("w_dec_xzT") + (size_t)d.KX * d.Gp, d.Gp, 1, wd + F + 2 * H + c, ldd, G, Z, nullptr, 0));
     if (c) TRY(copy_block_f32(s, wd + F + 2 * H, ldd, Pf("scol_dec"), 1, G, 1));
   }
   if (need({SSCVAE_W_DEC_BIH, SSCVAE_W_DEC_BHH})) TRY(vec_add_f32(s, W(SSCVAE_W_DEC_BIH), W(SSCVAE_W_DEC_BHH), Pf("b_dec"), G));
   // latent heads stacked [fc_mean ; fc_log_var]
   if (need({SSCVAE_W_FC_MEAN_W})) {
-    TRY(pack_block(s, Pb("w_fc"), d.Hp, 0, W(SSCVAE_W_FC_MEAN_W), H, Z, H, nullptr, 0));
-    TRY(pack_block(s, Pb("w_fcT"), d.Z2p, 1, W(SSCVAE_W_FC_MEAN_W), H, Z, H, nullptr, 0));
+    TRY(jobs.add(Pb("w_fc"), d.Hp, 0, W(SSCVAE_W_FC_MEAN_W), H, Z, H, nullptr, 0));
+    TRY(jobs.add(Pb("w_fcT"), d.Z2p, 1, W(SSCVAE_W_FC_MEAN_W), H, Z, H, nullptr, 0));
   }
   if (need({SSCVAE_W_FC_LOGVAR_W})) {
-    TRY(pack_block(s, Pb("w_fc") + (size_t)Z * d.Hp, d.Hp, 0, W(SSCVAE_W_FC_LOGVAR_W), H, Z, H, nullptr, 0));
-    TRY(pack_block(s, Pb("w_fcT") + Z, d.Z2p, 1, W(SSCVAE_W_FC_LOGVAR_W), H, Z, H, nullptr, 0));
+    TRY(jobs.add(Pb("w_fc") + (size_t)Z * d.Hp, d.Hp, 0, W(SSCVAE_W_FC_LOGVAR_W), H, Z, H, nullptr, 0));
+    TRY(jobs.add(Pb("w_fcT") + Z, d.Z2p, 1, W(SSCVAE_W_FC_LOGVAR_W), H, Z, H, nullptr, 0));
   }
   if (need({SSCVAE_W_FC_MEAN_B})) TRY(copy_block_f32(s, W(SSCVAE_W_FC_MEAN_B), 1, Pf("b_fc"), 1, Z, 1));
   if (need({SSCVAE_W_FC_LOGVAR_B})) TRY(copy_block_f32(s, W(SSCVAE_W_FC_LOGVAR_B), 1, Pf("b_fc") + Z, 1, Z, 1));
   // output head
   const int NO = d.tied ? E : V, NOp = d.tied ? d.Ep : d.Vp;
   if (need({SSCVAE_W_OUT_PROJ_W})) {
-    TRY(pack_block(s, Pb("w_out"), d.Hp, 0, W(SSCVAE_W_OUT_PROJ_W), H, NO, H, nullptr, 0));
-    TRY(pack_block(s, Pb("w_outT"), NOp, 1, W(SSCVAE_W_OUT_PROJ_W), H, NO, H, nullptr, 0));
+    TRY(jobs.add(Pb("w_out"), d.Hp, 0, W(SSCVAE_W_OUT_PROJ_W), H, NO, H, nullptr, 0));
+    TRY(jobs.add(Pb("w_outT"), NOp, 1, W(SSCVAE_W_OUT_PROJ_W), H, NO, H, nullptr, 0));
   }
+  TRY(pack_blocks(s, jobs));
   return 0;
 }
 

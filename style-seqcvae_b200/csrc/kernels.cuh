@@ -98,6 +98,20 @@ int copy_block_f32(cudaStream_t s, const float* src, int ld_src, float* dst, int
 // weight packing: dst (bf16) <- src (+ src2) fp32, optionally transposed
 int pack_block(cudaStream_t s, bf16* dst, int ld_dst, int transposed, const float* src, int ld_src, int rows, int cols,
                const float* src2, int ld_src2);
+// the same for a whole list of blocks in ONE launch (the per-step weight re-pack is ~30 blocks)
+struct PackJob {
+  const float* src; const float* src2; bf16* dst;
+  int ld_src, ld_src2, ld_dst, rows, cols, transposed;
+  int tile0, tiles_x;                  // filled by pack_blocks: first tile index, tiles along the columns
+};
+constexpr int kMaxPackJobs = 40;
+struct PackJobList {
+  PackJob job[kMaxPackJobs];
+  int n = 0;
+  int add(bf16* dst, int ld_dst, int transposed, const float* src, int ld_src, int rows, int cols, const float* src2,
+          int ld_src2);
+};
+int pack_blocks(cudaStream_t s, PackJobList& jobs);
 int vec_add_f32(cudaStream_t s, const float* a, const float* b, float* out, int n);
 // dst (rows, cols; ld_dst) = sum of `nparts` split-K partial tiles parts + z*stride (rows, cols; ld); dst may be parts
 int sum_partials_f32(cudaStream_t s, float* dst, int ld_dst, const float* parts, size_t stride, int nparts, int rows,

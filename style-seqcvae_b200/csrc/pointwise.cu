@@ -643,6 +643,74 @@ int sum_partials_f32(cudaStream_t s, float* dst, int ld_dst, const float* parts,
   return 0;
 }
 
+// ---- batched weight packing: one launch for every block; a CTA converts one 64 x 64 tile ------------------
+int PackJobList::add(bf16* dst, int ld_dst, int transposed, const float* src, int ld_src, int rows, int cols,
+                     const float* src2, int ld_src2) {
+  REQUIRE(n < kMaxPackJobs, "pack job list full");
+  PackJob& j = job[n++];
+  j.src = src; j.src2 = src2; j.dst = dst; j.ld_src = ld_src; j.ld_src2 = ld_src2; j.ld_dst = ld_dst;
+  j.rows = rows; j.cols = cols; j.transposed = transposed; j.tile0 = 0; j.tiles_x = 0;
+  return 0;
+}
+
+struct PackJobTable { PackJob job[kMaxPackJobs]; int n; };
+
+__global__ void __launch_bounds__(256) pack_blocks_kernel(const __grid_constant__ PackJobTable t) {
+  __shared__ float tile[64][65];
+  int ji = 0;
+  while (ji + 1 < t.n && (int)blockIdx.x >= t.job[ji + 1].tile0) ++ji;
+  const PackJob& j = t.job[ji];
+  const int local = blockIdx.x - j.tile0;
+  const int r0 = (local / j.tiles_x) * 64, c0 = (local % j.tiles_x) * 64;
+  const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;          // 64 x 4
+  if (!j.transposed) {
+    for (int i = ty; i < 64; i += 4) {
+      const int r = r0 + i, c = c0 + tx;
+      if (r < j.rows && c < j.cols) {
+        float v = j.src[(size_t)r * j.ld_src + c];
+        if (j.src2) v += j.src2[(size_t)r * j.ld_src2 + c];
+        j.dst[(size_t)r * j.ld_dst + c] = __float2bfloat16_rn(v);
+      }
+    }
+    return;
+  }
+  for (int i = ty; i < 64; i += 4) {
+    const int r = r0 + i, c = c0 + tx;
+    float v = 0.f;
+    if (r < j.rows && c < j.cols) {
+      v = j.src[(size_t)r * j.ld_src + c];
+      if (j.src2) v += j.src2[(size_t)r * j.ld_src2 + c];
+    }
+    tile[i][tx] = v;
+  }
+  __syncthreads();
+  for (int i = ty; i < 64; i += 4) {
+    const int c = c0 + i, r = r0 + tx;                                // dst[c, r] = src[r, c]
+    if (c < j.cols && r < j.rows) j.dst[(size_t)c * j.ld_dst + r] = __float2bfloat16_rn(tile[tx][i]);
+  }
+}
+
+int pack_blocks(cudaStream_t s, PackJobList& jobs) {
+  if (jobs.n == 0) return 0;
+  PackJobTable t;
+  double bytes = 0;
+  int tiles = 0;
+  for (int i = 0; i < jobs.n; ++i) {
+    PackJob& j = jobs.job[i];
+    j.tiles_x = ceil_div(j.cols, 64);
+    j.tile0 = tiles;
+    tiles += j.tiles_x * ceil_div(j.rows, 64);
+    bytes += (double)j.rows * j.cols * 6.0;
+    t.job[i] = j;
+  }
+  t.n = jobs.n;
+  PROF_SCOPE(s, "pack_weights", 0, bytes);
+  pack_blocks_kernel<<<tiles, 256, 0, s>>>(t);
+  LAUNCHED();
+  jobs.n = 0;
+  return 0;
+}
+
 __global__ void vec_add_kernel(const float* a, const float* b, float* out, int n) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) out[i] = a[i] + (b ? b[i] : 0.f);
