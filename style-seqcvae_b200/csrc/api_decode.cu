@@ -13,6 +13,7 @@ static void plan_decode(const Dims& d, int B, int N, int S, int K, Plan& p) {
   const size_t b = sizeof(bf16), f = 4;
   const size_t R = (size_t)B * S * K, BN = (size_t)B * N;
   const int Pmax = K;
+  p.add("seed", 16);
   p.add("featsb", BN * d.Fp * b);
   p.add("mask", BN * f);
   p.add("avgb", (size_t)B * d.Fp * b);
@@ -79,6 +80,8 @@ static int decode_impl(Handle* h, int B, int N, int S, int K, int P, const char*
   auto Wi = [&](const char* n) { return reinterpret_cast<int*>(ws + dp.find(n)->off); };
   auto zero = [&](const char* n) { return cudaMemsetAsync(ws + dp.find(n)->off, 0, dp.find(n)->bytes, s); };
   const int SK = S * K, R = B * SK, G = d.G, H = d.H, Hp = d.Hp, Fp = d.Fp, KXe = d.Fp + d.Hp, KX = d.KX, L = d.L;
+  const unsigned long long* seed_dev = reinterpret_cast<const unsigned long long*>(ws + dp.find("seed")->off);
+  (void)seed;
 
   CUDA_TRY(zero("XA0")); CUDA_TRY(zero("XA1")); CUDA_TRY(zero("XE")); CUDA_TRY(zero("projb")); CUDA_TRY(zero("bp_hist"));
   if (d.tied) CUDA_TRY(zero("ob"));
@@ -129,7 +132,7 @@ static int decode_impl(Handle* h, int B, int N, int S, int K, int P, const char*
     {  // eval: z ~ N(prior_mean, prior_var) (updown_cell.py:200-208); no encoder LSTM
       LatentArgs la; la.R = rows; la.Z = d.Z; la.Zp = d.Zp; la.sentiment_vae = d.sv; la.prior_var = d.prior_std * d.prior_std;
       la.prior_mean_row = Wf("pm_row"); la.rowmap = rowmap;
-      TRY(latent_forward_eval(s, la, eps_t, eps_stride, seed, (unsigned long long)step, Wb("ZB"), d.Zp));
+      TRY(latent_forward_eval(s, la, eps_t, eps_stride, seed_dev, (unsigned long long)step, Wb("ZB"), d.Zp));
     }
     {
       GemmSeg sg[3] = {seg(Wb("XE"), KXe, Pb("w_dec_x"), KX, KXe),
@@ -267,11 +270,28 @@ int sscvae_decode(SscvaeHandle* hh, int batch, int num_boxes, int states, int be
                   int32_t* n_steps, void* stream) {
   Handle* h = reinterpret_cast<Handle*>(hh);
   REQUIRE(h && packed && weights && image_features && workspace && predictions && log_probs && best && n_steps, "NULL argument");
-  return decode_impl(h, batch, num_boxes, states, beam, per_node, reinterpret_cast<const char*>(packed), weights,
-                     image_features, sentiment, fsm, reinterpret_cast<const long long*>(num_constraints),
-                     min_constraints_to_satisfy, eps, seed, reinterpret_cast<char*>(workspace), workspace_bytes,
-                     reinterpret_cast<long long*>(predictions), log_probs, reinterpret_cast<long long*>(best), n_steps,
-                     reinterpret_cast<cudaStream_t>(stream));
+  REQUIRE(batch > 0 && num_boxes > 0 && states >= 1 && beam >= 1, "bad decode shape");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const Plan& dp = h->decode_plan(batch, num_boxes, states, beam);
+  if (workspace_bytes < dp.total) { set_error("workspace too small: %zu < %zu", workspace_bytes, dp.total); return SSCVAE_ERR_WORKSPACE; }
+  const unsigned long long seed_host = seed;
+  CUDA_TRY(cudaMemcpyAsync(reinterpret_cast<char*>(workspace) + dp.find("seed")->off, &seed_host, sizeof(seed_host),
+                           cudaMemcpyHostToDevice, st));
+  std::vector<uint64_t> key;
+  for (uint64_t v : {(uint64_t)batch, (uint64_t)num_boxes, (uint64_t)states, (uint64_t)beam, (uint64_t)per_node,
+                     (uint64_t)min_constraints_to_satisfy, (uint64_t)workspace_bytes})
+    key_add(key, v);
+  for (const void* q : {packed, (const void*)image_features, (const void*)sentiment, (const void*)fsm,
+                        (const void*)num_constraints, (const void*)eps, (const void*)workspace, (const void*)predictions,
+                        (const void*)log_probs, (const void*)best, (const void*)n_steps})
+    key_add(key, q);
+  for (int i = 0; i < SSCVAE_W_COUNT; ++i) key_add(key, weights[i]);
+  return run_with_graph(h->dec_graphs, key, st, true, [&](cudaStream_t s) {
+    return decode_impl(h, batch, num_boxes, states, beam, per_node, reinterpret_cast<const char*>(packed), weights,
+                       image_features, sentiment, fsm, reinterpret_cast<const long long*>(num_constraints),
+                       min_constraints_to_satisfy, eps, seed, reinterpret_cast<char*>(workspace), workspace_bytes,
+                       reinterpret_cast<long long*>(predictions), log_probs, reinterpret_cast<long long*>(best), n_steps, s);
+  });
 }
 
 }  // extern "C"

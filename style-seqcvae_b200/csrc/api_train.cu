@@ -102,6 +102,7 @@ static void plan_train(const Dims& d, int B, int N, Plan& p) {
   const size_t T = d.T, TB = T * B, TBp = round_up((int)TB, kPad), BN = (size_t)B * N, BNp = round_up((int)BN, kPad);
   const size_t Bp = round_up(B, kPad);
   // ---- forward, kept for backward
+  p.add("seed", 16);                                   // Philox seed of this call (device memory: graph replay)
   p.add("tok", (size_t)B * (d.L + 2) * 4);
   p.add("tmask", TB * f);
   p.add("lengths", B * f);
@@ -355,6 +356,8 @@ static int train_forward_impl(Handle* h, int B, int N, const char* pk, const voi
   auto Wi = [&](const char* n) { return reinterpret_cast<int*>(ws + tp.find(n)->off); };
   auto zero = [&](const char* n) { return cudaMemsetAsync(ws + tp.find(n)->off, 0, tp.find(n)->bytes, s); };
   const int T = d.T, TB = T * B, G = d.G, H = d.H, Hp = d.Hp, KX = d.KX, Fp = d.Fp;
+  const unsigned long long* seed_dev = reinterpret_cast<const unsigned long long*>(ws + tp.find("seed")->off);
+  (void)seed;                                          // copied to `seed_dev` by the caller, in front of the graph
 
   // keep the per-timestep weights L2-resident across the 21 steps (they are re-read every step)
   TRY(set_l2_window(s, pk + pp.find("w_att_rec")->off, pp.find("fwd_end")->off - pp.find("w_att_rec")->off));
@@ -429,7 +432,7 @@ static int train_forward_impl(Handle* h, int B, int N, const char* pk, const voi
       GemmEpi ef; ef.tag = "gemm.step"; ef.C32 = Wf("ml"); ef.ldc32 = d.Z2;
       TRY(gemm_bf16_tn(s, B, d.Z2, 1, &sf, ef));
       const size_t rZ = (size_t)t * B * d.Z;
-      TRY(latent_forward_train(s, la, Wf("ml"), d.Z2, Pf("b_fc"), eps ? eps + rZ : nullptr, seed, (unsigned long long)t,
+      TRY(latent_forward_train(s, la, Wf("ml"), d.Z2, Pf("b_fc"), eps ? eps + rZ : nullptr, seed_dev, (unsigned long long)t,
                                Wf("mean") + rZ, Wf("logvar") + rZ, Wf("eps") + rZ, ZB_t, d.Zp, Wf("kl") + (size_t)t * B));
     }
     {  // language (decoder) LSTM (updown_cell.py:211-229)
@@ -777,10 +780,23 @@ int sscvae_train_forward(SscvaeHandle* hh, int batch, int num_boxes, const void*
                          void* stream) {
   Handle* h = reinterpret_cast<Handle*>(hh);
   REQUIRE(h && packed && weights && image_features && caption_tokens && workspace && loss && kld, "NULL argument");
-  return train_forward_impl(h, batch, num_boxes, reinterpret_cast<const char*>(packed), weights, image_features,
-                            reinterpret_cast<const long long*>(caption_tokens), sentiment, eps, seed,
-                            reinterpret_cast<char*>(workspace), workspace_bytes, loss, kld,
-                            reinterpret_cast<cudaStream_t>(stream));
+  REQUIRE(batch > 0 && num_boxes > 0, "batch/num_boxes must be positive");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const Plan& tp = h->train_plan(batch, num_boxes);
+  if (workspace_bytes < tp.total) { set_error("workspace too small: %zu < %zu", workspace_bytes, tp.total); return SSCVAE_ERR_WORKSPACE; }
+  const unsigned long long seed_host = seed;
+  CUDA_TRY(cudaMemcpyAsync(reinterpret_cast<char*>(workspace) + tp.find("seed")->off, &seed_host, sizeof(seed_host),
+                           cudaMemcpyHostToDevice, st));
+  std::vector<uint64_t> key;
+  key_add(key, (uint64_t)batch); key_add(key, (uint64_t)num_boxes); key_add(key, packed); key_add(key, image_features);
+  key_add(key, caption_tokens); key_add(key, sentiment); key_add(key, eps); key_add(key, workspace);
+  key_add(key, (uint64_t)workspace_bytes); key_add(key, loss); key_add(key, kld);
+  for (int i = 0; i < SSCVAE_W_COUNT; ++i) key_add(key, weights[i]);
+  return run_with_graph(h->fwd_graphs, key, st, true, [&](cudaStream_t s) {
+    return train_forward_impl(h, batch, num_boxes, reinterpret_cast<const char*>(packed), weights, image_features,
+                              reinterpret_cast<const long long*>(caption_tokens), sentiment, eps, seed,
+                              reinterpret_cast<char*>(workspace), workspace_bytes, loss, kld, s);
+  });
 }
 
 int sscvae_train_backward(SscvaeHandle* hh, int batch, int num_boxes, const void* packed, const void* const* weights,
@@ -788,9 +804,17 @@ int sscvae_train_backward(SscvaeHandle* hh, int batch, int num_boxes, const void
                           void* const* grads, void* const* group_events, void* stream) {
   Handle* h = reinterpret_cast<Handle*>(hh);
   REQUIRE(h && packed && weights && workspace && grad_loss && grad_kld && grads, "NULL argument");
-  return train_backward_impl(h, batch, num_boxes, reinterpret_cast<const char*>(packed), weights,
-                             reinterpret_cast<char*>(workspace), workspace_bytes, grad_loss, grad_kld, grads, group_events,
-                             reinterpret_cast<cudaStream_t>(stream));
+  std::vector<uint64_t> key;
+  key_add(key, (uint64_t)batch); key_add(key, (uint64_t)num_boxes); key_add(key, packed); key_add(key, workspace);
+  key_add(key, (uint64_t)workspace_bytes); key_add(key, grad_loss); key_add(key, grad_kld);
+  for (int i = 0; i < SSCVAE_W_COUNT; ++i) { key_add(key, weights[i]); key_add(key, grads[i]); }
+  // the per-group events of the data-parallel wrapper are recorded for OTHER streams to wait on: not capturable
+  return run_with_graph(h->bwd_graphs, key, reinterpret_cast<cudaStream_t>(stream), group_events == nullptr,
+                        [&](cudaStream_t s) {
+    return train_backward_impl(h, batch, num_boxes, reinterpret_cast<const char*>(packed), weights,
+                               reinterpret_cast<char*>(workspace), workspace_bytes, grad_loss, grad_kld, grads,
+                               group_events, s);
+  });
 }
 
 int sscvae_test_gemm(const void* A, int lda, const void* B, int ldb, int M, int N, int K, float* C32, int ldc,

@@ -56,12 +56,13 @@ struct LatentArgs {
 };
 // training: ml (R,2Z) = [mean|log_var] pre-bias GEMM output
 int latent_forward_train(cudaStream_t s, const LatentArgs& a, const float* ml, int ld_ml, const float* bias_ml,
-                         const float* eps_in /*(R,Z) or null*/, unsigned long long seed, unsigned long long step,
+                         const float* eps_in /*(R,Z) or null*/, const unsigned long long* seed_dev, unsigned long long step,
                          float* mean_out, float* logvar_out, float* eps_out, bf16* zb, int ld_z, float* kl_out);
+// (the Philox seed is read from DEVICE memory so that a captured CUDA graph can be replayed with a new seed)
 // eval: z = eps * prior_std + prior_mean
 // eps row r is read at eps_in[r * eps_row_stride, :]
 int latent_forward_eval(cudaStream_t s, const LatentArgs& a, const float* eps_in, int eps_row_stride,
-                        unsigned long long seed, unsigned long long step, bf16* zb, int ld_z);
+                        const unsigned long long* seed_dev, unsigned long long step, bf16* zb, int ld_z);
 int fill_i32(cudaStream_t s, int* dst, int value, int n);
 int iota_div_i32(cudaStream_t s, int* dst, int n, int div);   // dst[i] = i / div
 int latent_backward(cudaStream_t s, const LatentArgs& a, const float* dz, int ld_dz, const float* eps,

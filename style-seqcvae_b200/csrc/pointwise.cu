@@ -193,7 +193,7 @@ __device__ __forceinline__ float philox_normal(unsigned long long seed, unsigned
 
 __global__ void latent_fwd_train_kernel(LatentArgs a, const float* __restrict__ ml, int ld_ml,
                                         const float* __restrict__ bias_ml, const float* __restrict__ eps_in,
-                                        unsigned long long seed, unsigned long long step, float* __restrict__ mean_out,
+                                        const unsigned long long* __restrict__ seed_dev, unsigned long long step, float* __restrict__ mean_out,
                                         float* __restrict__ logvar_out, float* __restrict__ eps_out, bf16* __restrict__ zb,
                                         int ld_z, float* __restrict__ kl_out) {
   __shared__ float red[32];
@@ -207,7 +207,7 @@ __global__ void latent_fwd_train_kernel(LatentArgs a, const float* __restrict__ 
       const float mu = ml[(size_t)r * ld_ml + z] + bias_ml[z];
       const float lv = ml[(size_t)r * ld_ml + Z + z] + bias_ml[Z + z];
       const float var = __expf(lv);
-      const float e = eps_in ? eps_in[(size_t)r * Z + z] : philox_normal(seed, step, r, z, Z);
+      const float e = eps_in ? eps_in[(size_t)r * Z + z] : philox_normal(*seed_dev, step, r, z, Z);
       const float zz = e * sqrtf(var) + mu;
       mean_out[(size_t)r * Z + z] = mu;
       logvar_out[(size_t)r * Z + z] = lv;
@@ -230,18 +230,18 @@ __global__ void latent_fwd_train_kernel(LatentArgs a, const float* __restrict__ 
 }
 
 int latent_forward_train(cudaStream_t s, const LatentArgs& a, const float* ml, int ld_ml, const float* bias_ml,
-                         const float* eps_in, unsigned long long seed, unsigned long long step, float* mean_out,
+                         const float* eps_in, const unsigned long long* seed_dev, unsigned long long step, float* mean_out,
                          float* logvar_out, float* eps_out, bf16* zb, int ld_z, float* kl_out) {
   PROF_SCOPE(s, "latent_fwd", 0, (double)a.R*a.Z*24.0);
   const int threads = min(256, round_up(a.Zp, 32));
-  latent_fwd_train_kernel<<<a.R, threads, 0, s>>>(a, ml, ld_ml, bias_ml, eps_in, seed, step, mean_out, logvar_out,
+  latent_fwd_train_kernel<<<a.R, threads, 0, s>>>(a, ml, ld_ml, bias_ml, eps_in, seed_dev, step, mean_out, logvar_out,
                                                  eps_out, zb, ld_z, kl_out);
   LAUNCHED();
   return 0;
 }
 
 __global__ void latent_fwd_eval_kernel(LatentArgs a, const float* __restrict__ eps_in, int eps_row_stride,
-                                       unsigned long long seed, unsigned long long step, bf16* __restrict__ zb,
+                                       const unsigned long long* __restrict__ seed_dev, unsigned long long step, bf16* __restrict__ zb,
                                        int ld_z) {
   const int r = blockIdx.x;
   const float pm = a.prior_mean_row ? a.prior_mean_row[a.rowmap ? a.rowmap[r] : r] : 0.f;
@@ -249,7 +249,7 @@ __global__ void latent_fwd_eval_kernel(LatentArgs a, const float* __restrict__ e
   for (int z = threadIdx.x; z < a.Zp; z += blockDim.x) {
     float v = 0.f;
     if (z < a.Z) {
-      const float e = eps_in ? eps_in[(size_t)r * eps_row_stride * a.Z + z] : philox_normal(seed, step, r, z, a.Z);
+      const float e = eps_in ? eps_in[(size_t)r * eps_row_stride * a.Z + z] : philox_normal(*seed_dev, step, r, z, a.Z);
       v = e * sd + pm;
     }
     zb[(size_t)r * ld_z + z] = __float2bfloat16_rn(v);
@@ -257,10 +257,10 @@ __global__ void latent_fwd_eval_kernel(LatentArgs a, const float* __restrict__ e
 }
 
 int latent_forward_eval(cudaStream_t s, const LatentArgs& a, const float* eps_in, int eps_row_stride,
-                        unsigned long long seed, unsigned long long step, bf16* zb, int ld_z) {
+                        const unsigned long long* seed_dev, unsigned long long step, bf16* zb, int ld_z) {
   PROF_SCOPE(s, "latent_fwd", 0, (double)a.R*a.Z*6.0);
   const int threads = min(256, round_up(a.Zp, 32));
-  latent_fwd_eval_kernel<<<a.R, threads, 0, s>>>(a, eps_in, eps_row_stride, seed, step, zb, ld_z);
+  latent_fwd_eval_kernel<<<a.R, threads, 0, s>>>(a, eps_in, eps_row_stride, seed_dev, step, zb, ld_z);
   LAUNCHED();
   return 0;
 }
