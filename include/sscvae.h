@@ -197,6 +197,13 @@ int sscvae_grad_sqnorm(const float* grads, size_t n, float* partial /*>= 1024 fl
 int sscvae_sgd_step(float* params, const float* grads, float* momentum_buf, size_t n, const float* sqnorm,
                     float max_norm, float lr, float momentum, float weight_decay, int first_step, void* stream);
 
+/* The same for ALL parameter tensors in three launches (squared-norm partials, final sum, update). Host arrays of
+ * `count` (<= 32) device pointers / sizes; scratch: device floats, at least sum(ceil(size_i / 16384)) + 1. The global
+ * norm is reduced with a fixed chunking and ordered sums (bit-reproducible). */
+int sscvae_sgd_step_multi(int count, void* const* params, const void* const* grads, void* const* momentum_bufs,
+                          const uint64_t* sizes, const int32_t* first_step, float max_norm, float lr, float momentum,
+                          float weight_decay, float* scratch, size_t scratch_floats, void* stream);
+
 /* Optional instrumentation (off by default): CUDA events around every kernel launch of the library,
  * aggregated per kernel class. report() synchronises the device and writes a JSON object
  * {"class": {"count", "ms", "flops", "bytes"}} (algorithmic FLOPs / bytes as declared at the call site). */

@@ -39,7 +39,7 @@ GRAD_GROUPS = 5
 # every symbol include/sscvae.h declares (tests/test_abi.py checks the library exports each one)
 SYMBOLS = [
     "sscvae_abi_version", "sscvae_last_error", "sscvae_launch_count", "sscvae_create", "sscvae_destroy",
-    "sscvae_packed_bytes", "sscvae_pack_weights", "sscvae_test_gemm_splitk", "sscvae_train_workspace_bytes", "sscvae_train_forward",
+    "sscvae_packed_bytes", "sscvae_pack_weights", "sscvae_test_gemm_splitk", "sscvae_sgd_step_multi", "sscvae_train_workspace_bytes", "sscvae_train_forward",
     "sscvae_train_backward", "sscvae_train_region", "sscvae_fsm_pack", "sscvae_search_first_step",
     "sscvae_search_step", "sscvae_search_scratch_bytes", "sscvae_search_finish",
     "sscvae_decode_workspace_bytes", "sscvae_decode", "sscvae_decode_region", "sscvae_grad_sqnorm", "sscvae_sgd_step", "sscvae_test_gemm",
@@ -96,6 +96,8 @@ def lib():
     L.sscvae_decode.argtypes = [vp, i32, i32, i32, i32, i32, vp, C.POINTER(vp), vp, vp, vp, vp, i32, vp, u64, vp, sz,
                                 vp, vp, vp, vp, vp]
     L.sscvae_test_gemm_splitk.argtypes = [vp, i32, vp, i32, i32, i32, i32, vp, i32, i32, vp, vp]
+    L.sscvae_sgd_step_multi.argtypes = [i32, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(u64), C.POINTER(i32),
+                                        C.c_float, C.c_float, C.c_float, C.c_float, vp, sz, vp]
     L.sscvae_grad_sqnorm.argtypes = [vp, sz, vp, vp, vp]
     L.sscvae_sgd_step.argtypes = [vp, vp, vp, sz, vp, f32, f32, f32, f32, i32, vp]
     L.sscvae_test_gemm.argtypes = [vp, i32, vp, i32, i32, i32, i32, vp, i32, vp, i32, i32, vp]

@@ -61,10 +61,90 @@ __global__ void sgd_kernel(float* __restrict__ p, const float* __restrict__ g, f
     p[i] = w - lr * d;
   }
 }
+// ---- multi-tensor form: every parameter of the model in three launches ---------------------------------
+static constexpr int MT_MAX = 32;
+static constexpr unsigned MT_CHUNK = 16384;            // elements per block
+struct MultiTensorTable {
+  float* p[MT_MAX]; const float* g[MT_MAX]; float* m[MT_MAX];
+  unsigned long long n[MT_MAX];
+  unsigned chunk0[MT_MAX + 1];                         // first chunk (block) of tensor i
+  int first[MT_MAX];
+  int count;
+};
+
+__device__ __forceinline__ int mt_find(const MultiTensorTable& t, unsigned block) {
+  int i = 0;
+  while (i + 1 < t.count && block >= t.chunk0[i + 1]) ++i;
+  return i;
+}
+
+__global__ void __launch_bounds__(256) mt_sqnorm_kernel(const __grid_constant__ MultiTensorTable t, float* __restrict__ partial) {
+  __shared__ float red[8];
+  const int ti = mt_find(t, blockIdx.x);
+  const size_t lo = (size_t)(blockIdx.x - t.chunk0[ti]) * MT_CHUNK;
+  const size_t hi = min((size_t)t.n[ti], lo + MT_CHUNK);
+  const float* g = t.g[ti];
+  float s = 0.f;
+  for (size_t i = lo + threadIdx.x; i < hi; i += 256) { const float v = g[i]; s += v * v; }
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float v = 0.f;
+    for (int w = 0; w < 8; ++w) v += red[w];
+    partial[blockIdx.x] = v;                           // fixed chunking + ordered sums: deterministic
+  }
+}
+
+__global__ void __launch_bounds__(256) mt_sgd_kernel(const __grid_constant__ MultiTensorTable t, const float* __restrict__ sqnorm,
+                                                     float max_norm, float lr, float momentum, float wd) {
+  const int ti = mt_find(t, blockIdx.x);
+  const size_t lo = (size_t)(blockIdx.x - t.chunk0[ti]) * MT_CHUNK;
+  const size_t hi = min((size_t)t.n[ti], lo + MT_CHUNK);
+  float coef = 1.f;
+  if (max_norm > 0.f) coef = fminf(1.f, max_norm / (sqrtf(*sqnorm) + 1e-6f));   // torch clip_grad_norm_
+  float* p = t.p[ti]; const float* g = t.g[ti]; float* m = t.m[ti];
+  const bool first = t.first[ti] != 0;
+  for (size_t i = lo + threadIdx.x; i < hi; i += 256) {
+    const float w = p[i];
+    float d = g[i] * coef + wd * w;
+    if (momentum != 0.f) {
+      const float b = first ? d : momentum * m[i] + d;
+      m[i] = b;
+      d = b;
+    }
+    p[i] = w - lr * d;
+  }
+}
 }  // namespace sscvae
 
 using namespace sscvae;
 extern "C" {
+int sscvae_sgd_step_multi(int count, void* const* params, const void* const* grads, void* const* momentum_bufs,
+                          const uint64_t* sizes, const int32_t* first_step, float max_norm, float lr, float momentum,
+                          float weight_decay, float* scratch, size_t scratch_floats, void* stream) {
+  REQUIRE(count > 0 && count <= MT_MAX && params && grads && sizes && first_step && scratch, "bad argument (at most %d tensors)", MT_MAX);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  MultiTensorTable t;
+  unsigned chunks = 0;
+  for (int i = 0; i < count; ++i) {
+    REQUIRE(params[i] && grads[i] && (momentum == 0.f || (momentum_bufs && momentum_bufs[i])), "NULL tensor %d", i);
+    t.p[i] = reinterpret_cast<float*>(params[i]); t.g[i] = reinterpret_cast<const float*>(grads[i]);
+    t.m[i] = momentum_bufs ? reinterpret_cast<float*>(momentum_bufs[i]) : nullptr;
+    t.n[i] = sizes[i]; t.first[i] = first_step[i]; t.chunk0[i] = chunks;
+    chunks += (unsigned)((sizes[i] + MT_CHUNK - 1) / MT_CHUNK);
+  }
+  t.chunk0[count] = chunks; t.count = count;
+  REQUIRE(scratch_floats >= (size_t)chunks + 1, "scratch too small: need %u floats", chunks + 1);
+  mt_sqnorm_kernel<<<chunks, 256, 0, st>>>(t, scratch);
+  LAUNCHED();
+  sqnorm_final_kernel<<<1, 1024, 0, st>>>(scratch, (int)chunks, scratch + chunks);
+  LAUNCHED();
+  mt_sgd_kernel<<<chunks, 256, 0, st>>>(t, scratch + chunks, max_norm, lr, momentum, weight_decay);
+  LAUNCHED();
+  return 0;
+}
+
 int sscvae_grad_sqnorm(const float* grads, size_t n, float* partial, float* sqnorm_out, void* stream) {
   REQUIRE(grads && partial && sqnorm_out, "NULL argument");
   REQUIRE((reinterpret_cast<uintptr_t>(grads) & 15) == 0, "grads must be 16-byte aligned");

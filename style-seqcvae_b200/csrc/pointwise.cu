@@ -428,8 +428,44 @@ __global__ void transpose_kernel(const TIn* __restrict__ in, int rows, int cols,
   }
 }
 
+// bf16 fast path: 64 x 64 tiles, 16-byte loads along the input rows and 16-byte stores along the output rows
+// (the 2-byte-per-thread form above moves 64-byte segments and ran at 1.5 TB/s)
+__global__ void __launch_bounds__(256) transpose_bf16_v8_kernel(const bf16* __restrict__ in, int rows, int cols, int ld_in,
+                                                                bf16* __restrict__ out, int ld_out) {
+  __shared__ bf16 tile[64][64 + 8];
+  const int r0 = blockIdx.x * 64, c0 = blockIdx.y * 64;
+  for (int v = threadIdx.x; v < 512; v += 256) {
+    const int i = v >> 3, cv = (v & 7) * 8;
+    const int r = r0 + i, c = c0 + cv;
+    bf16x8 x;
+    if (r < rows && c < cols) x = ld_bf16x8(in + (size_t)r * ld_in + c);      // cols % 8 == 0
+    else
+#pragma unroll
+      for (int k = 0; k < 4; ++k) x.v[k] = __floats2bfloat162_rn(0.f, 0.f);
+    *reinterpret_cast<bf16x8*>(&tile[i][cv]) = x;
+  }
+  __syncthreads();
+  for (int v = threadIdx.x; v < 512; v += 256) {
+    const int i = v >> 3, rv = (v & 7) * 8;                                   // output row c0 + i, columns r0 + rv ..
+    const int c = c0 + i, r = r0 + rv;
+    if (c < cols && r < ld_out) {
+      bf16x8 x;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) x.v[k] = __halves2bfloat162(tile[rv + 2 * k][i], tile[rv + 2 * k + 1][i]);
+      st_bf16x8(out + (size_t)c * ld_out + r, x);                             // ld_out % 8 == 0
+    }
+  }
+}
+
 int transpose_bf16(cudaStream_t s, const bf16* in, int rows, int cols, int ld_in, bf16* out, int ld_out) {
   PROF_SCOPE(s, "transpose", 0, (double)rows*cols*4.0);
+  if ((cols % 8) == 0 && (ld_in % 8) == 0 && (ld_out % 8) == 0 && (reinterpret_cast<uintptr_t>(in) & 15) == 0 &&
+      (reinterpret_cast<uintptr_t>(out) & 15) == 0) {
+    dim3 grid(ceil_div(ld_out, 64), ceil_div(cols, 64));
+    transpose_bf16_v8_kernel<<<grid, 256, 0, s>>>(in, rows, cols, ld_in, out, ld_out);
+    LAUNCHED();
+    return 0;
+  }
   dim3 grid(ceil_div(ld_out, 32), ceil_div(cols, 32));
   transpose_kernel<bf16><<<grid, dim3(32, 8), 0, s>>>(in, rows, cols, ld_in, out, ld_out);
   LAUNCHED();

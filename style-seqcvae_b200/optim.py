@@ -1,6 +1,6 @@
 """Fused training-step tail: clip_grad_norm_ + SGD(momentum, weight decay) + the
 linear-decay learning-rate schedule of var_updown/scripts/train.py:126-134,173-176, as three kernel
-launches over flat buffers instead of ~100 eager launches."""
+launches over all parameter tensors instead of ~100 eager launches."""
 import ctypes as C
 from typing import Iterable
 
@@ -42,24 +42,28 @@ class FusedClipSGD:
         if not ps[0].is_cuda:
             raise RuntimeError("FusedClipSGD runs only on CUDA parameters; there is no CPU fallback")
         stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
-        if self._partial is None:
-            self._partial = torch.empty(2048, dtype=torch.float32, device=dev)
-        sq = self._partial[1024:1025]
-        # total squared norm = sum over tensors (each reduced deterministically), accumulated on device
-        total = torch.zeros(1, dtype=torch.float32, device=dev)
-        for p in ps:
-            g = p.grad.contiguous()
-            _lib.check(L.sscvae_grad_sqnorm(_lib.ptr(g), g.numel(), _lib.ptr(self._partial), _lib.ptr(sq), stream))
-            total += sq
+        grads = [p.grad.contiguous() for p in ps]
+        firsts = []
         for p in ps:
             first = id(p) not in self._mom
             if first:
                 self._mom[id(p)] = torch.empty_like(p)
-            g = p.grad.contiguous()
-            _lib.check(L.sscvae_sgd_step(_lib.ptr(p), _lib.ptr(g), _lib.ptr(self._mom[id(p)]), p.numel(), _lib.ptr(total),
-                                         float(self.max_norm), float(self.lr), float(self.momentum),
-                                         float(self.weight_decay), int(first), stream))
-            # the kernel wrote through a raw pointer: tell autograd (and the captioner's packed-weight cache,
-            # which is keyed on the version counters) that the parameter changed
+            firsts.append(int(first))
+        # all tensors in three launches: squared-norm partials over a fixed chunking, their ordered sum, the update
+        if len(ps) > 32:
+            raise RuntimeError("FusedClipSGD handles at most 32 parameter tensors (the captioner has 21)")
+        n = len(ps)
+        chunks = sum((p.numel() + 16383) // 16384 for p in ps)
+        if self._partial is None or self._partial.numel() < chunks + 1 or self._partial.device != dev:
+            self._partial = torch.empty(chunks + 1, dtype=torch.float32, device=dev)
+        vp = C.c_void_p
+        _lib.check(L.sscvae_sgd_step_multi(
+            n, (vp * n)(*[p.data_ptr() for p in ps]), (vp * n)(*[g.data_ptr() for g in grads]),
+            (vp * n)(*[self._mom[id(p)].data_ptr() for p in ps]), (C.c_uint64 * n)(*[p.numel() for p in ps]),
+            (C.c_int32 * n)(*firsts), float(self.max_norm), float(self.lr), float(self.momentum), float(self.weight_decay),
+            _lib.ptr(self._partial), self._partial.numel(), stream))
+        for p in ps:
+            # the kernel wrote through raw pointers: tell autograd (and the captioner's packed-weight cache, which is
+            # keyed on the version counters) that the parameters changed
             torch.autograd.graph.increment_version(p)
         self.iteration += 1
