@@ -71,7 +71,9 @@ struct AttnSmem {
 
 __device__ __forceinline__ AttnSmem carve(uint8_t* raw, const AttnArgs& a, bool bwd) {
   AttnSmem s;
-  uint8_t* p = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(raw) + 127) & ~uintptr_t(127));
+  // no integer round trip on the pointer: it would lose the shared address space and turn every access below into a
+  // generic LD/ST with 64-bit address arithmetic (a third of the instructions of the first version of these kernels)
+  uint8_t* p = raw;
   s.stage = p; p += ATT_STAGES * ATT_STAGE_BYTES;
   s.full = reinterpret_cast<uint64_t*>(p); p += ATT_STAGES * 8;
   s.empty = reinterpret_cast<uint64_t*>(p); p += ATT_STAGES * 8;
@@ -104,15 +106,17 @@ struct Ring {
 };
 
 __device__ __forceinline__ void produce_block(const AttnSmem& sm, Ring& ring, const uint8_t* base, int N, int row_bytes,
-                                              int nchunks, int bper) {
+                                              int nchunks, int bper, uint64_t policy) {
   for (int c = 0; c < nchunks; ++c) {
     const int n0 = c * bper;
     const int nb = min(bper, N - n0);
     const uint32_t bytes = (uint32_t)nb * (uint32_t)row_bytes;
     ptx::mbar_wait(&sm.empty[ring.stage], ring.phase ^ 1);
     ptx::mbar_expect_tx(&sm.full[ring.stage], bytes);
-    ptx::bulk_g2s(sm.stage + (size_t)ring.stage * ATT_STAGE_BYTES, base + (size_t)n0 * row_bytes, bytes,
-                  &sm.full[ring.stage]);
+    // evict_first: the 52 MB of features + projections are read once per timestep and would otherwise push the
+    // recurrent weights (76 MB, re-read every step) out of the 126 MB L2
+    ptx::bulk_g2s_hint(sm.stage + (size_t)ring.stage * ATT_STAGE_BYTES, base + (size_t)n0 * row_bytes, bytes,
+                       &sm.full[ring.stage], policy);
     ring.advance();
   }
 }
@@ -229,7 +233,7 @@ __device__ __forceinline__ void attn_prologue(const AttnSmem& sm, const AttnArgs
 __global__ void __launch_bounds__(ATT_THREADS, 2)
 attention_fwd_kernel(AttnArgs a, AttnPlan pl, float* __restrict__ alpha, float* __restrict__ smx, bf16* __restrict__ xhat,
                      int ld_x) {
-  extern __shared__ uint8_t att_smem_raw[];
+  extern __shared__ __align__(128) uint8_t att_smem_raw[];
   const AttnSmem sm = carve(att_smem_raw, a, false);
   attn_prologue(sm, a, false);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -239,10 +243,11 @@ attention_fwd_kernel(AttnArgs a, AttnPlan pl, float* __restrict__ alpha, float* 
 
   if (warp == ATT_CWARPS) {                          // ---- producer
     if (lane == 0) {
+      const uint64_t pol = ptx::l2_policy_evict_first();
       for (int r = r_begin; r < r_end; ++r) {
         const int img = a.rowmap ? a.rowmap[r] : r;
-        produce_block(sm, ring, reinterpret_cast<const uint8_t*>(a.proj + (size_t)img * a.N * a.Ap), a.N, a.Ap * 2, pl.nP, pl.bP);
-        produce_block(sm, ring, reinterpret_cast<const uint8_t*>(a.feats + (size_t)img * a.N * a.Fp), a.N, a.Fp * 2, pl.nF, pl.bF);
+        produce_block(sm, ring, reinterpret_cast<const uint8_t*>(a.proj + (size_t)img * a.N * a.Ap), a.N, a.Ap * 2, pl.nP, pl.bP, pol);
+        produce_block(sm, ring, reinterpret_cast<const uint8_t*>(a.feats + (size_t)img * a.N * a.Fp), a.N, a.Fp * 2, pl.nF, pl.bF, pol);
       }
     }
     return;
@@ -374,7 +379,7 @@ int attention_forward(cudaStream_t s, const AttnArgs& a, float* alpha, float* sm
 __global__ void __launch_bounds__(ATT_THREADS, 2)
 attention_bwd_kernel(AttnArgs a, AttnPlan pl, const float* __restrict__ smx, const float* __restrict__ dxhat, int ld_dx,
                      bf16* __restrict__ dq, int ld_dq, float* __restrict__ du) {
-  extern __shared__ uint8_t att_smem_raw[];
+  extern __shared__ __align__(128) uint8_t att_smem_raw[];
   const AttnSmem sm = carve(att_smem_raw, a, true);
   attn_prologue(sm, a, true);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -384,10 +389,11 @@ attention_bwd_kernel(AttnArgs a, AttnPlan pl, const float* __restrict__ smx, con
 
   if (warp == ATT_CWARPS) {                          // ---- producer: region features first, then projections
     if (lane == 0) {
+      const uint64_t pol = ptx::l2_policy_evict_first();
       for (int r = r_begin; r < r_end; ++r) {
         const int img = a.rowmap ? a.rowmap[r] : r;
-        produce_block(sm, ring, reinterpret_cast<const uint8_t*>(a.feats + (size_t)img * a.N * a.Fp), a.N, a.Fp * 2, pl.nF, pl.bF);
-        produce_block(sm, ring, reinterpret_cast<const uint8_t*>(a.proj + (size_t)img * a.N * a.Ap), a.N, a.Ap * 2, pl.nP, pl.bP);
+        produce_block(sm, ring, reinterpret_cast<const uint8_t*>(a.feats + (size_t)img * a.N * a.Fp), a.N, a.Fp * 2, pl.nF, pl.bF, pol);
+        produce_block(sm, ring, reinterpret_cast<const uint8_t*>(a.proj + (size_t)img * a.N * a.Ap), a.N, a.Ap * 2, pl.nP, pl.bP, pol);
       }
     }
     return;

@@ -408,10 +408,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_tcgen05_kernel(const __g
   constexpr int B_STAGE_BYTES = BN * BK * 2;
   constexpr uint32_t IDESC = make_idesc(BM, BN);
   constexpr int TMEM_COLS = BN < 32 ? 32 : BN;          // allocation granularity: power of two >= 32
-  extern __shared__ uint8_t smem_raw[];
-  // 1024-byte alignment (128B swizzle) by POINTER arithmetic on the __shared__ array: a round trip through an integer
-  // loses the address space and every staging access becomes a generic LD/ST instead of LDS/STS
-  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw;                             // __align__(1024): the 128B swizzle needs 1024-byte aligned tiles
+  if (threadIdx.x == 0 && (smem_u32(smem) & 1023u)) __trap();
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + STAGES * A_STAGE_BYTES;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_b + STAGES * B_STAGE_BYTES);
@@ -519,10 +518,9 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ GemmParams p) {
   constexpr int B_STAGE_BYTES = BH * BK * 2;
   constexpr uint32_t IDESC = make_idesc(2 * BM, BN);
   constexpr int TMEM_COLS = BN < 32 ? 32 : BN;
-  extern __shared__ uint8_t smem_raw[];
-  // 1024-byte alignment (128B swizzle) by POINTER arithmetic on the __shared__ array: a round trip through an integer
-  // loses the address space and every staging access becomes a generic LD/ST instead of LDS/STS
-  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw;                             // __align__(1024): the 128B swizzle needs 1024-byte aligned tiles
+  if (threadIdx.x == 0 && (smem_u32(smem) & 1023u)) __trap();
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + STAGES * A_STAGE_BYTES;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_b + STAGES * B_STAGE_BYTES);
@@ -683,10 +681,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_swapped_kernel(c
   constexpr int BW = 128, BX = 256;                     // weight rows per CTA (UMMA M), activation rows (UMMA N)
   constexpr int W_STAGE_BYTES = BW * BK * 2, X_STAGE_BYTES = BX * BK * 2;
   constexpr uint32_t IDESC = make_idesc(BW, BX);
-  extern __shared__ uint8_t smem_raw[];
-  // 1024-byte alignment (128B swizzle) by POINTER arithmetic on the __shared__ array: a round trip through an integer
-  // loses the address space and every staging access becomes a generic LD/ST instead of LDS/STS
-  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw;                             // __align__(1024): the 128B swizzle needs 1024-byte aligned tiles
+  if (threadIdx.x == 0 && (smem_u32(smem) & 1023u)) __trap();
   uint8_t* smem_w = smem;
   uint8_t* smem_x = smem + STAGES * W_STAGE_BYTES;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_x + STAGES * X_STAGE_BYTES);
@@ -1142,8 +1139,10 @@ int gemm_bf16_tn(cudaStream_t stream, int M, int N, int nseg, const GemmSeg* seg
   // large and long-K (the batched weight-gradient GEMMs): CTA pairs, 256x128 tiles (3600x2048x5376: 68 vs 76 us)
   if (M >= 1024 && N >= 512 && total_kb >= 32) return launch_tc2<128, 4>(stream, prm, segs);
   if (mt * ceil_div(N, 128) >= 96) return launch_tc<128, 3>(stream, prm, segs);
-  if (mt * ceil_div(N, 64) >= 96) return launch_tc<64, 4>(stream, prm, segs);
-  if (mt * ceil_div(N, 32) >= 96) return launch_tc<32, 5>(stream, prm, segs);
+  // Small problems are latency-bound, not occupancy-bound: narrower tiles only add CTAs whose MMAs cost the same
+  // ~130 cycles and lose the TMA-store epilogue (256x768x960: 7.9 us with 64-wide tiles, 10.4 with 16-wide).
+  if (N > 32) return launch_tc<64, 4>(stream, prm, segs);
+  if (N > 16) return launch_tc<32, 5>(stream, prm, segs);
   return launch_tc<16, 6>(stream, prm, segs);
 }
 
