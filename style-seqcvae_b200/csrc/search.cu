@@ -48,7 +48,10 @@ __device__ __forceinline__ void list_insert(float (&val)[P], int (&idx)[P], floa
   }
 }
 
-template <int P, int SC>
+// VEC = 4: 16-byte loads of the log-probs and of the FSM words (V % 4 == 0, 16-byte aligned rows). A warp walks its
+// row with 313 dependent 4-byte loads per pass otherwise, which is latency-bound (341 us per step for 2560 rows of
+// 10 000 log-probs; the 205 MB involved take 34 us at HBM speed).
+template <int P, int SC, int VEC>
 __global__ void __launch_bounds__(128) search_rows_kernel(SearchRowsArgs a) {
   const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (r >= a.R) return;
@@ -57,13 +60,29 @@ __global__ void __launch_bounds__(128) search_rows_kernel(SearchRowsArgs a) {
   const int s_from = (a.rows_per_image == 1) ? 0 : (r % a.rows_per_image) / a.K;
   const float* __restrict__ x = a.logp + (size_t)r * a.ld;
   const bool forced = a.last_tokens != nullptr && a.last_tokens[r] == a.end_index;   // cbs.py:177-181
+  const int nv = a.V / VEC;
   float mx = 0.f, lsum = 0.f;
   if (!a.normalized && !forced) {
     float m = -INFINITY;
-    for (int w = lane; w < a.V; w += 32) m = fmaxf(m, x[w]);
+    if (VEC == 4) {
+      const float4* x4 = reinterpret_cast<const float4*>(x);
+#pragma unroll 4
+      for (int i = lane; i < nv; i += 32) { const float4 v = x4[i]; m = fmaxf(m, fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w))); }
+    } else {
+      for (int w = lane; w < a.V; w += 32) m = fmaxf(m, x[w]);
+    }
     m = warp_max(m);
     float s = 0.f;
-    for (int w = lane; w < a.V; w += 32) s += __expf(x[w] - m);
+    if (VEC == 4) {
+      const float4* x4 = reinterpret_cast<const float4*>(x);
+#pragma unroll 4
+      for (int i = lane; i < nv; i += 32) {
+        const float4 v = x4[i];
+        s += (__expf(v.x - m) + __expf(v.y - m)) + (__expf(v.z - m) + __expf(v.w - m));
+      }
+    } else {
+      for (int w = lane; w < a.V; w += 32) s += __expf(x[w] - m);
+    }
     s = warp_sum(s);
     mx = m; lsum = logf(s);
   }
@@ -74,14 +93,26 @@ __global__ void __launch_bounds__(128) search_rows_kernel(SearchRowsArgs a) {
     for (int i = 0; i < SC; ++i)
 #pragma unroll
       for (int p = 0; p < P; ++p) { val[i][p] = -INFINITY; idx[i][p] = INT_MAX; }
-    for (int w = lane; w < a.V; w += 32) {
+    auto visit = [&](float xv, uint32_t bw, int w) {
       float v;
       if (forced) v = (w == a.end_index) ? 0.f : -INFINITY;
-      else v = a.normalized ? x[w] : (x[w] - mx) - lsum;
-      const uint32_t b = bits ? (bits[w] >> c0) : 0xffffffffu;
+      else v = a.normalized ? xv : (xv - mx) - lsum;
+      const uint32_t b = bw >> c0;
 #pragma unroll
       for (int i = 0; i < SC; ++i)
         if (c0 + i < a.S) list_insert<P>(val[i], idx[i], ((b >> i) & 1u) ? v : a.neg_value, w);
+    };
+    if (VEC == 4) {
+      const float4* x4 = reinterpret_cast<const float4*>(x);
+      const uint4* b4 = reinterpret_cast<const uint4*>(bits);
+#pragma unroll 2
+      for (int i = lane; i < nv; i += 32) {
+        const float4 v = x4[i];
+        const uint4 bw = bits ? b4[i] : make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
+        visit(v.x, bw.x, 4 * i); visit(v.y, bw.y, 4 * i + 1); visit(v.z, bw.z, 4 * i + 2); visit(v.w, bw.w, 4 * i + 3);
+      }
+    } else {
+      for (int w = lane; w < a.V; w += 32) visit(x[w], bits ? bits[w] : 0xffffffffu, w);
     }
     const float add = a.last_scores ? a.last_scores[r] : 0.f;
 #pragma unroll
@@ -110,10 +141,142 @@ __global__ void __launch_bounds__(128) search_rows_kernel(SearchRowsArgs a) {
   }
 }
 
+// One CTA (8 warps) per row: the row is loaded ONCE into shared memory with every 16-byte load of the CTA in flight at
+// the same time (the warp-per-row form issues ~80 dependent loads per pass and is latency-bound); max, sum-exp and the
+// per-to-state selection then run from shared memory. Each warp keeps its own sorted lists over an interleaved
+// slice of the row; the 8 x P warp winners of a state are merged by one warp with the same (value desc, index asc)
+// order, so the result is identical to the warp-per-row kernel's.
+template <int P, int SC>
+__global__ void __launch_bounds__(256) search_rows_block_kernel(SearchRowsArgs a) {
+  extern __shared__ __align__(16) float srow[];
+  __shared__ float red[8];
+  __shared__ float cv[8][SC][P];
+  __shared__ int ci[8][SC][P];
+  const int r = blockIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int img = r / a.rows_per_image;
+  const int s_from = (a.rows_per_image == 1) ? 0 : (r % a.rows_per_image) / a.K;
+  const float4* __restrict__ x4 = reinterpret_cast<const float4*>(a.logp + (size_t)r * a.ld);
+  float4* s4 = reinterpret_cast<float4*>(srow);
+  const bool forced = a.last_tokens != nullptr && a.last_tokens[r] == a.end_index;   // cbs.py:177-181
+  const int nv = a.V >> 2;
+  float m = -INFINITY;
+  for (int i = threadIdx.x; i < nv; i += 256) {
+    const float4 v = x4[i];
+    s4[i] = v;
+    m = fmaxf(m, fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w)));
+  }
+  float mx = 0.f, lsum = 0.f;
+  if (!a.normalized && !forced) {
+    m = warp_max(m);
+    if (lane == 0) red[warp] = m;
+    __syncthreads();
+    m = red[0];
+#pragma unroll
+    for (int w = 1; w < 8; ++w) m = fmaxf(m, red[w]);
+    __syncthreads();
+    float sum = 0.f;
+    for (int i = threadIdx.x; i < nv; i += 256) {                       // own elements: no barrier needed yet
+      const float4 v = s4[i];
+      sum += (__expf(v.x - m) + __expf(v.y - m)) + (__expf(v.z - m) + __expf(v.w - m));
+    }
+    sum = warp_sum(sum);
+    if (lane == 0) red[warp] = sum;
+    __syncthreads();
+    sum = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) sum += red[w];
+    mx = m; lsum = logf(sum);
+  }
+  __syncthreads();
+  const uint4* __restrict__ b4 = a.fsm_bits
+      ? reinterpret_cast<const uint4*>(a.fsm_bits + ((size_t)img * a.S + s_from) * a.V) : nullptr;
+  const float add = a.last_scores ? a.last_scores[r] : 0.f;
+  for (int c0 = 0; c0 < a.S; c0 += SC) {
+    float val[SC][P]; int idx[SC][P];
+#pragma unroll
+    for (int i = 0; i < SC; ++i)
+#pragma unroll
+      for (int p = 0; p < P; ++p) { val[i][p] = -INFINITY; idx[i][p] = INT_MAX; }
+    auto visit = [&](float xv, uint32_t bw, int w) {
+      float v;
+      if (forced) v = (w == a.end_index) ? 0.f : -INFINITY;
+      else v = a.normalized ? xv : (xv - mx) - lsum;
+      const uint32_t b = bw >> c0;
+#pragma unroll
+      for (int i = 0; i < SC; ++i)
+        if (c0 + i < a.S) list_insert<P>(val[i], idx[i], ((b >> i) & 1u) ? v : a.neg_value, w);
+    };
+    for (int i = threadIdx.x; i < nv; i += 256) {
+      const float4 v = s4[i];
+      const uint4 bw = b4 ? b4[i] : make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
+      visit(v.x, bw.x, 4 * i); visit(v.y, bw.y, 4 * i + 1); visit(v.z, bw.z, 4 * i + 2); visit(v.w, bw.w, 4 * i + 3);
+    }
+    // the warp's P best per state
+#pragma unroll
+    for (int i = 0; i < SC; ++i) {
+      if (c0 + i >= a.S) break;
+      for (int p = 0; p < P; ++p) {
+        float bv = val[i][0]; int bi = idx[i][0];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+          const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+          if (better(ov, oi, bv, bi)) { bv = ov; bi = oi; }
+        }
+        if (idx[i][0] == bi) {
+#pragma unroll
+          for (int k = 0; k + 1 < P; ++k) { val[i][k] = val[i][k + 1]; idx[i][k] = idx[i][k + 1]; }
+          val[i][P - 1] = -INFINITY; idx[i][P - 1] = INT_MAX;
+        }
+        if (lane == 0) { cv[warp][i][p] = bv; ci[warp][i][p] = bi; }
+      }
+    }
+    __syncthreads();
+    // merge: warp i handles state c0 + i; a lane holds up to two of the 8*P warp winners
+    for (int i = warp; i < SC && c0 + i < a.S; i += 8) {
+      float v0 = -INFINITY, v1 = -INFINITY; int i0 = INT_MAX, i1 = INT_MAX;
+      if (lane < 8 * P) { v0 = cv[lane / P][i][lane % P]; i0 = ci[lane / P][i][lane % P]; }
+      if (lane + 32 < 8 * P) { v1 = cv[(lane + 32) / P][i][(lane + 32) % P]; i1 = ci[(lane + 32) / P][i][(lane + 32) % P]; }
+      if (better(v1, i1, v0, i0)) { const float tv = v0; v0 = v1; v1 = tv; const int ti = i0; i0 = i1; i1 = ti; }
+      for (int p = 0; p < P; ++p) {
+        float bv = v0; int bi = i0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+          const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+          if (better(ov, oi, bv, bi)) { bv = ov; bi = oi; }
+        }
+        if (i0 == bi && v0 == bv) { v0 = v1; i0 = i1; v1 = -INFINITY; i1 = INT_MAX; }
+        if (lane == 0) {
+          const size_t o = ((size_t)r * a.S + c0 + i) * P + p;
+          a.cand_val[o] = a.last_scores ? bv + add : bv;     // cbs.py:210-212
+          a.cand_tok[o] = bi;
+        }
+      }
+    }
+    __syncthreads();
+  }
+}
+
 template <int P>
 static int launch_rows(cudaStream_t st, const SearchRowsArgs& a) {
   constexpr int SC = P <= 2 ? 8 : (P <= 4 ? 4 : 2);
-  search_rows_kernel<P, SC><<<ceil_div(a.R, 4), 128, 0, st>>>(a);
+  const bool vec = (a.V % 4) == 0 && (a.ld % 4) == 0 && (reinterpret_cast<uintptr_t>(a.logp) & 15) == 0 &&
+                   (reinterpret_cast<uintptr_t>(a.fsm_bits) & 15) == 0;
+  const size_t row_bytes = (size_t)a.V * 4;
+  if (vec && row_bytes <= 200 * 1024) {
+    static size_t configured = 0;
+    if (row_bytes > 48 * 1024 && row_bytes > configured) {
+      CUDA_TRY(cudaFuncSetAttribute(search_rows_block_kernel<P, SC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)row_bytes));
+      configured = row_bytes;
+    }
+    search_rows_block_kernel<P, SC><<<a.R, 256, row_bytes, st>>>(a);
+  } else if (vec) {
+    search_rows_kernel<P, SC, 4><<<ceil_div(a.R, 4), 128, 0, st>>>(a);
+  } else {
+    search_rows_kernel<P, SC, 1><<<ceil_div(a.R, 4), 128, 0, st>>>(a);
+  }
   LAUNCHED();
   return 0;
 }
