@@ -1052,7 +1052,13 @@ int gemm_bf16_tn(cudaStream_t stream, int M, int N, int nseg, const GemmSeg* seg
   REQUIRE(epi.C32 || epi.C16, "gemm: no output");
   double ksum = 0;
   for (int i = 0; i < nseg; ++i) ksum += segs[i].K;
-  PROF_SCOPE(stream, epi.tag, 2.0 * M * N * ksum, 2.0 * (M + N) * ksum + (epi.C32 ? 4.0 : 2.0) * M * N);
+  // instrumentation class: the skinny long-K GEMMs of the recurrence (the dominant kernel of a training step) are
+  // reported on their own as "gemm.recurrent"
+  int kb_all = 0;
+  for (int i = 0; i < nseg; ++i) kb_all += ceil_div(segs[i].K, BK);
+  const bool recurrent = M <= 256 && N >= 1024 && kb_all >= 48;
+  PROF_SCOPE(stream, recurrent ? "gemm.recurrent" : epi.tag, 2.0 * M * N * ksum,
+             2.0 * (M + N) * ksum + (epi.C32 ? 4.0 : 2.0) * M * N);
   static const bool simt = [] { const char* e = getenv("SSCVAE_GEMM_DEBUG_SIMT"); return e && e[0] == '1'; }();
   if (simt) {
     GemmSeg z{nullptr, 0, nullptr, 0, 0};

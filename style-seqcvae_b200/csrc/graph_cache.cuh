@@ -77,7 +77,7 @@ int run_with_graph(GraphCache& c, const std::vector<uint64_t>& key, cudaStream_t
   if (e->state < 0) return body(s);
   // second sighting: capture on the library's own stream, instantiate, launch on the caller's stream
   if (!c.capture_stream) CUDA_TRY(cudaStreamCreateWithFlags(&c.capture_stream, cudaStreamNonBlocking));
-  const unsigned long long before = g_launch_count + g_launch_count_pw;
+  const unsigned long long before_gemm = g_launch_count, before_pw = g_launch_count_pw;
   if (cudaStreamBeginCapture(c.capture_stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
     cudaGetLastError();
     e->state = -1;
@@ -86,14 +86,15 @@ int run_with_graph(GraphCache& c, const std::vector<uint64_t>& key, cudaStream_t
   const int rc = body(c.capture_stream);
   cudaGraph_t graph = nullptr;
   const cudaError_t ce = cudaStreamEndCapture(c.capture_stream, &graph);
-  const unsigned long long captured = g_launch_count + g_launch_count_pw - before;
+  const unsigned long long captured = (g_launch_count - before_gemm) + (g_launch_count_pw - before_pw);
+  g_launch_count = before_gemm;                         // nothing has run yet: the launches are counted per replay
+  g_launch_count_pw = before_pw;
   if (rc != 0 || ce != cudaSuccess || !graph) {
     if (graph) cudaGraphDestroy(graph);
     cudaGetLastError();
     e->state = -1;
     return rc != 0 ? rc : body(s);
   }
-  g_launch_count -= captured > g_launch_count ? g_launch_count : captured;   // nothing ran yet; the launch below re-adds it
   if (cudaGraphInstantiate(&e->exec, graph, 0) != cudaSuccess) {
     cudaGraphDestroy(graph);
     cudaGetLastError();
