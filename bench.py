@@ -269,7 +269,11 @@ def main():
     opt = sscvae.FusedClipSGD([p for _, p in named], lr=0.015, momentum=0.9, weight_decay=0.001, max_norm=12.5,
                               num_iterations=70000)
     reducer = sscvae.BucketedGradReducer(named) if world > 1 else None
-    if world > 1:
+    # data-parallel mode: "events" (default): the backward records one event per gradient bucket as soon as it is final
+    # (external event-record nodes of the replayed graph) and the in-place all-reduce of that bucket starts on a side
+    # stream; "plain": all buckets are reduced after the backward has finished
+    dp_mode = os.environ.get("SSCVAE_BENCH_DP", "events")
+    if world > 1 and dp_mode == "events":
         model._group_events = [torch.cuda.Event() for _ in range(_lib.GRAD_GROUPS)]
 
     n_batches = 2
@@ -283,7 +287,7 @@ def main():
         loss = out["loss"].mean() + out["kld"].mean() / KLD_WEIGHT        # train.py:168-171
         loss.backward()
         if reducer is not None:
-            reducer.reduce(model._group_events)
+            reducer.reduce(model._group_events, buckets=model.grad_buckets())
         opt.step()                                                        # clip 12.5 + SGD + lr schedule
         return loss.detach()
 
@@ -382,9 +386,9 @@ def main():
     roofline = None
     if dom:
         share = dom["ms"] / total_ms
-        launches = dom["count"] / args.profile_steps
+        dom_launches = dom["count"] / args.profile_steps
         flops_per_step = dom["flops"] / args.profile_steps
-        dur_us = 1e3 * share * step_ms / launches
+        dur_us = 1e3 * share * step_ms / dom_launches
         roofline = {"kernel": "gemm_tcgen05_swapped_kernel (class gemm.recurrent)", "bound": "tensor",
                     "achieved": flops_per_step / (share * step_ms) / 1e9, "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
                     "frac": flops_per_step / (share * step_ms) / 1e9 / peaks["tf_sustained"],
@@ -392,7 +396,7 @@ def main():
                     # launch shapes (32.3, 41.9, 15.9 MB), launch-weighted; algorithmic = the bf16 weight block
                     "traffic": 30.0e6, "algorithmic_bytes_per_launch": dom["bytes"] / dom["count"],
                     "peak_source": peaks["src"] + " bf16_tflops_sustained", "share_of_step": share,
-                    "launches_per_step": launches, "avg_launch_us": dur_us,
+                    "launches_per_step": dom_launches, "avg_launch_us": dur_us,
                     "all_gemm_share_of_step": sum(v["ms"] for v in gemm_all) / total_ms,
                     "all_gemm_tflops": sum(v["flops"] for v in gemm_all) / args.profile_steps
                                        / (sum(v["ms"] for v in gemm_all) / total_ms * step_ms) / 1e9}

@@ -74,7 +74,18 @@ class _TrainStep(torch.autograd.Function):
         L = _lib.lib()
         params = module._weight_tensors()
         needs = ctx.needs_input_grad[6:]
-        grads = [torch.empty_like(p) if (need and p.requires_grad) else None for p, need in zip(params, needs)]
+        # Gradients are written into persistent per-bucket flat buffers (stable pointers: the backward graph is replayed,
+        # and the data-parallel all-reduce runs in place on the buckets). If a parameter still holds the previous
+        # gradient in that very storage (gradient accumulation without zero_grad), a fresh tensor is used instead.
+        views = module._grad_views()
+        grads = []
+        for p, need, v in zip(params, needs, views):
+            if not (need and p.requires_grad) or v is None:
+                grads.append(None)
+            elif p.grad is not None and p.grad.data_ptr() == v.data_ptr():
+                grads.append(torch.empty_like(p))
+            else:
+                grads.append(v)
         dev = grad_loss.device
         gl = (grad_loss if grad_loss is not None else torch.zeros(ctx.B, device=dev)).contiguous().float()
         gk = (grad_kld if grad_kld is not None else torch.zeros(ctx.B, device=dev)).contiguous().float()
@@ -179,6 +190,8 @@ class UpDownCaptioner(nn.Module):
         self._ws_cache: Dict[tuple, torch.Tensor] = {}
         self._ws_generation = 0
         self._group_events = None          # set by the data-parallel wrapper
+        self._grad_view_cache = None
+        self._grad_flat = {}
         self.rng_mode = "philox"           # "reference": draw eps from the CPU generator like updown_cell.py:206
         self._eps_override = None          # tests: explicit eps tensor
         self._call_counter = 0
@@ -261,6 +274,39 @@ class UpDownCaptioner(nn.Module):
                                              stream))
             self._packed_key = key
         return self._packed
+
+    def _grad_views(self):
+        """Per weight tensor (SSCVAE_W_* order): a view, shaped like the parameter, into the flat gradient buffer of its
+        data-parallel bucket (dp.GROUP_PREFIXES)."""
+        ws = self._weight_tensors()
+        dev = ws[0].device
+        if self._grad_view_cache is not None and self._grad_view_cache[0] == dev:
+            return self._grad_view_cache[1]
+        from .dp import group_of, GROUP_PREFIXES
+        names = {id(p): n for n, p in self.named_parameters()}
+        groups = [[] for _ in GROUP_PREFIXES]
+        for i, p in enumerate(ws):
+            n = names.get(id(p))
+            if n is not None:                      # every parameter, also currently frozen ones (train.py:156-161 toggles)
+                groups[group_of(n)].append(i)
+        views = [None] * len(ws)
+        self._grad_flat = {}
+        for g, idxs in enumerate(groups):
+            if not idxs:
+                continue
+            flat = torch.zeros(sum(ws[i].numel() for i in idxs), dtype=torch.float32, device=dev)
+            off = 0
+            for i in idxs:
+                views[i] = flat[off:off + ws[i].numel()].view_as(ws[i])
+                off += ws[i].numel()
+            self._grad_flat[g] = (flat, [(ws[i], views[i]) for i in idxs])
+        self._grad_view_cache = (dev, views)
+        return views
+
+    def grad_buckets(self):
+        """{bucket: (flat fp32 buffer, [(parameter, view into the buffer), ...])} for an in-place gradient all-reduce."""
+        self._grad_views()
+        return self._grad_flat
 
     def _train_workspace(self, B, N) -> torch.Tensor:
         dev = self._embedding_layer.weight.device

@@ -484,8 +484,14 @@ static int train_backward_impl(Handle* h, int B, int N, const char* pk, const vo
   auto Wf = [&](const char* n) { return reinterpret_cast<float*>(ws + tp.find(n)->off); };
   auto Wi = [&](const char* n) { return reinterpret_cast<int*>(ws + tp.find(n)->off); };
   auto zero = [&](const char* n) { return cudaMemsetAsync(ws + tp.find(n)->off, 0, tp.find(n)->bytes, s); };
+  // While the call is being captured into a graph the record becomes an EXTERNAL event-record node: every replay
+  // re-records the event and streams outside the graph (the all-reduce side stream) can wait on it.
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  CUDA_TRY(cudaStreamIsCapturing(s, &cap));
   auto event = [&](int g) -> int {
-    if (events && events[g]) CUDA_TRY(cudaEventRecord(reinterpret_cast<cudaEvent_t>(events[g]), s));
+    if (events && events[g])
+      CUDA_TRY(cudaEventRecordWithFlags(reinterpret_cast<cudaEvent_t>(events[g]), s,
+                                        cap == cudaStreamCaptureStatusActive ? cudaEventRecordExternal : cudaEventRecordDefault));
     return 0;
   };
   const int T = d.T, TB = T * B, TBp = round_up(TB, kPad), G = d.G, Gp = d.Gp, H = d.H, Hp = d.Hp, KX = d.KX, Fp = d.Fp;
@@ -808,9 +814,8 @@ int sscvae_train_backward(SscvaeHandle* hh, int batch, int num_boxes, const void
   key_add(key, (uint64_t)batch); key_add(key, (uint64_t)num_boxes); key_add(key, packed); key_add(key, workspace);
   key_add(key, (uint64_t)workspace_bytes); key_add(key, grad_loss); key_add(key, grad_kld);
   for (int i = 0; i < SSCVAE_W_COUNT; ++i) { key_add(key, weights[i]); key_add(key, grads[i]); }
-  // the per-group events of the data-parallel wrapper are recorded for OTHER streams to wait on: not capturable
-  return run_with_graph(h->bwd_graphs, key, reinterpret_cast<cudaStream_t>(stream), group_events == nullptr,
-                        [&](cudaStream_t s) {
+  for (int g = 0; g < SSCVAE_GRAD_GROUPS; ++g) key_add(key, group_events ? group_events[g] : nullptr);
+  return run_with_graph(h->bwd_graphs, key, reinterpret_cast<cudaStream_t>(stream), true, [&](cudaStream_t s) {
     return train_backward_impl(h, batch, num_boxes, reinterpret_cast<const char*>(packed), weights,
                                reinterpret_cast<char*>(workspace), workspace_bytes, grad_loss, grad_kld, grads,
                                group_events, s);

@@ -60,9 +60,13 @@ class BucketedGradReducer:
     def world(self) -> int:
         return dist.get_world_size(self.pg) if dist.is_initialized() else 1
 
-    def reduce(self, events: Optional[Sequence] = None):
+    def reduce(self, events: Optional[Sequence] = None, buckets: Optional[Dict] = None):
+        """`buckets` = UpDownCaptioner.grad_buckets(): when every gradient of a bucket is the captioner's own view into
+        the bucket's flat buffer (the normal case) the bucket is all-reduced IN PLACE: no flatten / copy-back."""
         world = self.world()
         if world == 1:
+            return
+        if buckets and self._reduce_in_place(buckets, world, events):
             return
         cuda = any(p.is_cuda for g in self.groups for p in g)
         if cuda and self._side_stream is None:
@@ -101,6 +105,35 @@ class BucketedGradReducer:
                     off += p.grad.numel()
         if cuda:
             torch.cuda.current_stream().wait_stream(self._side_stream)
+
+
+    def _reduce_in_place(self, buckets: Dict, world: int, events) -> bool:
+        for g, (flat, pairs) in buckets.items():
+            for p, v in pairs:
+                if p.grad is not None and p.grad.data_ptr() != v.data_ptr():
+                    return False
+        cuda = any(flat.is_cuda for flat, _ in buckets.values())
+        if cuda and self._side_stream is None:
+            self._side_stream = torch.cuda.Stream()
+        ctx = torch.cuda.stream(self._side_stream) if cuda else _NullCtx()
+        handles = []
+        with ctx:
+            for g in sorted(buckets):
+                flat, pairs = buckets[g]
+                if not any(p.grad is not None for p, _ in pairs):
+                    continue
+                if cuda:
+                    if events is not None:
+                        self._side_stream.wait_event(events[g])
+                    else:
+                        self._side_stream.wait_stream(torch.cuda.current_stream())
+                handles.append((dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.pg, async_op=True), flat))
+            for h, flat in handles:
+                h.wait()
+                flat.div_(world)
+        if cuda:
+            torch.cuda.current_stream().wait_stream(self._side_stream)
+        return True
 
 
 class _NullCtx:

@@ -45,6 +45,28 @@ def _worker(rank, world, port, out):
             ok &= p.grad is None
         else:
             ok &= bool(torch.allclose(p.grad, torch.full_like(p, float(i + 1)) * mean_factor))
+    # in-place path: gradients that are views into per-bucket flat buffers (UpDownCaptioner.grad_buckets)
+    buckets = {}
+    for i, (n, p) in enumerate(params):
+        if "decoder" in n:
+            continue
+        buckets.setdefault(dp.group_of(n), []).append((i, p))
+    flat = {}
+    for gidx, items in buckets.items():
+        buf = torch.zeros(sum(p.numel() for _, p in items))
+        off, pairs = 0, []
+        for i, p in items:
+            v = buf[off:off + p.numel()].view_as(p)
+            v.copy_(torch.full_like(p, float(i + 1)) * (rank + 1))
+            p.grad = v
+            pairs.append((p, v))
+            off += p.numel()
+        flat[gidx] = (buf, pairs)
+    red.reduce(buckets=flat)
+    for i, (n, p) in enumerate(params):
+        if "decoder" not in n:
+            ok &= bool(torch.allclose(p.grad, torch.full_like(p, float(i + 1)) * mean_factor))
+            ok &= p.grad.data_ptr() == [v for q, v in flat[dp.group_of(n)][1] if q is p][0].data_ptr()
     norm = sscvae.global_grad_norm([p for _, p in params])
     norms = [torch.zeros(()) for _ in range(world)]
     dist.all_gather(norms, norm)
