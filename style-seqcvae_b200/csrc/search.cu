@@ -198,14 +198,30 @@ __global__ void __launch_bounds__(256) search_rows_block_kernel(SearchRowsArgs a
     for (int i = 0; i < SC; ++i)
 #pragma unroll
       for (int p = 0; p < P; ++p) { val[i][p] = -INFINITY; idx[i][p] = INT_MAX; }
+    // A disallowed word enters a list with the constant neg_value. Once a thread has visited P words, every one of its
+    // lists holds P entries that are >= neg_value with lower indices, PROVIDED no allowed word it has seen was below
+    // neg_value (-inf log-probs, forced rows): from then on a disallowed word can never be inserted and only the set
+    // bits of the FSM word (usually one) need the list test. `masked_matter` keeps the general path otherwise.
+    bool masked_matter = true;
+    bool seen_low = forced;
+    int visited = 0;
     auto visit = [&](float xv, uint32_t bw, int w) {
       float v;
       if (forced) v = (w == a.end_index) ? 0.f : -INFINITY;
       else v = a.normalized ? xv : (xv - mx) - lsum;
       const uint32_t b = bw >> c0;
+      if (masked_matter) {
 #pragma unroll
-      for (int i = 0; i < SC; ++i)
-        if (c0 + i < a.S) list_insert<P>(val[i], idx[i], ((b >> i) & 1u) ? v : a.neg_value, w);
+        for (int i = 0; i < SC; ++i)
+          if (c0 + i < a.S) list_insert<P>(val[i], idx[i], ((b >> i) & 1u) ? v : a.neg_value, w);
+        seen_low |= !(v >= a.neg_value);
+        masked_matter = (++visited < P) || seen_low;
+      } else {
+        if (!(v >= a.neg_value)) { masked_matter = true; seen_low = true; }
+#pragma unroll
+        for (int i = 0; i < SC; ++i)
+          if (c0 + i < a.S && ((b >> i) & 1u)) list_insert<P>(val[i], idx[i], v, w);
+      }
     };
     for (int i = threadIdx.x; i < nv; i += 256) {
       const float4 v = s4[i];
