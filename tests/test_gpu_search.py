@@ -84,6 +84,34 @@ def test_large_vocab_random_fsm_exact():
     assert torch.equal(preds.cpu(), op) and torch.equal(scores.cpu(), os_)
 
 
+@pytest.mark.parametrize("ninf", [False, True])
+def test_block_kernel_random_fsm_exact(ninf):
+    """V % 4 == 0 selects the CTA-per-row kernel (row staged in shared memory, 16-byte loads, disallowed to-states
+    skipped once they provably cannot enter a list). Random non-deterministic FSM; with `ninf` a fifth of the
+    log-probs is -inf, which is BELOW the -1e20 of disallowed words and forces the general path."""
+    torch.manual_seed(3)
+    B, S, K, P, V, steps = 3, 8, 5, 2, 11444, 6
+    fsm = (torch.rand(B, S, S, V) < 0.2).to(torch.uint8)
+    fsm[:, :, :, 1] = torch.eye(S, dtype=torch.uint8)
+    tables = torch.randn(steps, 64, V)
+    drop = torch.rand(steps, 64, V) < 0.2
+
+    def mk(cuda):
+        ctr = {"t": 0}
+
+        def step(last, state):
+            t = ctr["t"]; ctr["t"] += 1
+            lp = torch.log_softmax(tables[t][last.cpu() % 64], dim=1)
+            if ninf:
+                lp = lp.masked_fill(drop[t][last.cpu() % 64], float("-inf"))
+            return (lp.cuda() if cuda else lp), {}
+        return step
+    cbs = sscvae.ConstrainedBeamSearch(1, max_steps=steps, beam_size=K, per_node_beam_size=P)
+    preds, scores = cbs.search(torch.ones(B, dtype=torch.long, device="cuda"), None, mk(True), fsm.cuda())
+    op, os_ = so.cbs_search(torch.ones(B, dtype=torch.long), mk(False), fsm, K, P, 1, steps)
+    assert torch.equal(preds.cpu(), op) and torch.equal(scores.cpu(), os_)
+
+
 def test_fused_log_softmax_mode_matches_normalized_mode():
     """normalized=0 (raw logits in, log-softmax fused into the selection) picks the same tokens."""
     import ctypes as C
