@@ -18,7 +18,7 @@ static void plan_decode(const Dims& d, int B, int N, int S, int K, Plan& p) {
   p.add("mask", BN * f);
   p.add("avgb", (size_t)B * d.Fp * b);
   p.add("projb", BN * d.Ap * b);
-  p.add("gavg", (size_t)B * d.G * f);
+  p.add("gavg", (size_t)B * d.GP * f);
   p.add("pm_row", B * f);
   p.add("sent", B * f);
   p.add("rowmap", R * 4);
@@ -33,7 +33,7 @@ static void plan_decode(const Dims& d, int B, int N, int S, int K, Plan& p) {
   p.add("XE", R * (d.Fp + d.Hp) * b);
   p.add("embb_r", R * d.Ep * b);
   p.add("ZB", R * d.Zp * b);
-  p.add("acc", R * d.G * f);
+  p.add("acc", R * d.GP * f);
   p.add("q", R * d.A * f);
   p.add("alpha", R * N * f);
   if (d.tied) p.add("ob", R * d.Ep * b);
@@ -79,7 +79,7 @@ static int decode_impl(Handle* h, int B, int N, int S, int K, int P, const char*
   auto Wf = [&](const char* n) { return reinterpret_cast<float*>(ws + dp.find(n)->off); };
   auto Wi = [&](const char* n) { return reinterpret_cast<int*>(ws + dp.find(n)->off); };
   auto zero = [&](const char* n) { return cudaMemsetAsync(ws + dp.find(n)->off, 0, dp.find(n)->bytes, s); };
-  const int SK = S * K, R = B * SK, G = d.G, H = d.H, Hp = d.Hp, Fp = d.Fp, KXe = d.Fp + d.Hp, KX = d.KX, L = d.L;
+  const int SK = S * K, R = B * SK, GP = d.GP, H = d.H, Hp = d.Hp, Fp = d.Fp, KXe = d.Fp + d.Hp, KX = d.KX, L = d.L;
   const unsigned long long* seed_dev = reinterpret_cast<const unsigned long long*>(ws + dp.find("seed")->off);
   (void)seed;
 
@@ -98,8 +98,8 @@ static int decode_impl(Handle* h, int B, int N, int S, int K, int P, const char*
     GemmEpi e; e.tag = "gemm.decode"; e.C16 = Wb("projb"); e.ldc16 = d.Ap;
     TRY(gemm_bf16_tn(s, B * N, d.A, 1, &sg, e));
     GemmSeg sa = seg(Wb("avgb"), Fp, Pb("w_att_f"), Fp, d.F);
-    GemmEpi ea; ea.tag = "gemm.decode"; ea.C32 = Wf("gavg"); ea.ldc32 = G; ea.bias = Pf("b_att");
-    TRY(gemm_bf16_tn(s, B, G, 1, &sa, ea));
+    GemmEpi ea; ea.tag = "gemm.decode"; ea.C32 = Wf("gavg"); ea.ldc32 = GP;
+    TRY(gemm_bf16_tn(s, B, GP, 1, &sa, ea));
   }
   int* tok_hist = Wi("tok_hist"); int* bp_hist = Wi("bp_hist"); float* score_hist = Wf("score_hist");
   bf16* XA[2] = {Wb("XA0"), Wb("XA1")};
@@ -111,14 +111,13 @@ static int decode_impl(Handle* h, int B, int N, int S, int K, int P, const char*
     // in = index 0, out = index 1
     TRY(embed_gather_rows(s, tokens, rows, Pb("embb"), d.Ep, Wb("embb_r")));
     {
-      GemmSeg sg[2] = {seg(Wb("embb_r"), d.Ep, Pb("w_att_e"), d.Ep, d.E), seg(XA[0], 2 * Hp, Pb("w_att_rec"), 2 * Hp, 2 * Hp)};
-      GemmEpi e; e.tag = "gemm.decode"; e.C32 = Wf("acc"); e.ldc32 = G;
-      TRY(gemm_bf16_tn(s, rows, G, first ? 1 : 2, sg, e));
       LstmFwdArgs l = {};
-      l.R = rows; l.H = H; l.acc = Wf("acc"); l.ld_acc = G; l.add2 = Wf("gavg"); l.ld2 = G; l.rowmap = rowmap;
+      l.R = rows; l.H = H; l.add2 = Wf("gavg"); l.ld2 = GP; l.rowmap = rowmap; l.bias = Pf("b_att");
       l.c_prev = first ? nullptr : c1[0]; l.c_out = c1[1];
       l.h1_dst = Wb("XE") + Fp; l.ld_h1 = KXe; l.h2_dst = XA[1]; l.ld_h2 = 2 * Hp;
-      TRY(lstm_forward(s, l));
+      GemmSeg sg[2] = {seg(Wb("embb_r"), d.Ep, Pb("w_att_e"), d.Ep, d.E), seg(XA[0], 2 * Hp, Pb("w_att_rec"), 2 * Hp, 2 * Hp)};
+      GemmEpi e; e.tag = "gemm.decode"; e.C32 = Wf("acc"); e.ldc32 = GP; e.lstm = &l;   // cell fused when rows <= 256
+      TRY(gemm_bf16_tn(s, rows, GP, first ? 1 : 2, sg, e));
     }
     {
       GemmSeg sg = seg(Wb("XE") + Fp, KXe, Pb("wq"), Hp, Hp);
@@ -138,14 +137,13 @@ static int decode_impl(Handle* h, int B, int N, int S, int K, int P, const char*
       GemmSeg sg[3] = {seg(Wb("XE"), KXe, Pb("w_dec_x"), KX, KXe),
                        seg(Wb("ZB"), d.Zp, Pb("w_dec_z"), d.Zp, d.Zp),
                        seg(XA[0] + Hp, 2 * Hp, Pb("w_dec_x") + KXe, KX, Hp)};
-      GemmEpi e; e.tag = "gemm.decode"; e.C32 = Wf("acc"); e.ldc32 = G;
-      TRY(gemm_bf16_tn(s, rows, G, first ? 2 : 3, sg, e));
       LstmFwdArgs l = {};
-      l.R = rows; l.H = H; l.acc = Wf("acc"); l.ld_acc = G; l.bias = Pf("b_dec"); l.rowmap = rowmap;
+      l.R = rows; l.H = H; l.bias = Pf("b_dec"); l.rowmap = rowmap;
       if (d.cond) { l.sent = Wf("sent"); l.scol = Pf("scol_dec"); }
       l.c_prev = first ? nullptr : cd[0]; l.c_out = cd[1];
       l.h1_dst = XA[1] + Hp; l.ld_h1 = 2 * Hp;
-      TRY(lstm_forward(s, l));
+      GemmEpi e; e.tag = "gemm.decode"; e.C32 = Wf("acc"); e.ldc32 = GP; e.lstm = &l;
+      TRY(gemm_bf16_tn(s, rows, GP, first ? 2 : 3, sg, e));
     }
     if (d.tied) {
       GemmSeg sg = seg(XA[1] + Hp, 2 * Hp, Pb("w_out"), Hp, Hp);

@@ -20,6 +20,7 @@ struct Dims {
   int sv, simple, tied, pad, boundary, cond;
   float prior_std, mult;
   int Fp, Ep, Hp, Ap, Zp, Vp, G, Gp, Z2, Z2p, KX;
+  int GP;                              // rows of a packed forward LSTM weight block: gate-interleaved, lstm_gate_rows(H)
 };
 int init_dims(const SscvaeDims* in, Dims& d);
 int set_l2_window(cudaStream_t s, const void* base, size_t bytes);

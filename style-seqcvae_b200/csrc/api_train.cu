@@ -46,6 +46,7 @@ int init_dims(const SscvaeDims* in, Dims& d) {
   d.Zp = round_up(d.Z, kPad); d.Vp = round_up(d.V, kPad);
   d.G = 4 * d.H; d.Gp = round_up(d.G, kPad); d.Z2 = 2 * d.Z; d.Z2p = round_up(d.Z2, kPad);
   d.KX = d.Fp + 2 * d.Hp;
+  d.GP = lstm_gate_rows(d.H);
   return 0;
 }
 
@@ -64,14 +65,16 @@ const Region* Plan::find(const char* name) const {
 static void plan_packed(const Dims& d, Plan& p) {
   const size_t b = sizeof(bf16);
   const int NO = d.tied ? d.E : d.V, NOp = d.tied ? d.Ep : d.Vp;
-  // --- weights streamed at every forward timestep, contiguous so one L2 access-policy window covers them
-  p.add("w_att_rec", (size_t)d.G * 2 * d.Hp * b);
+  // --- weights streamed at every forward timestep, contiguous so one L2 access-policy window covers them.
+  // Forward LSTM blocks hold GP = lstm_gate_rows(H) gate-interleaved rows (kernels.cuh: lstm_gate_row), so that one
+  // 128-row GEMM tile owns all four gates of 32 hidden units and the cell can run in the GEMM epilogue.
+  p.add("w_att_rec", (size_t)d.GP * 2 * d.Hp * b);
   p.add("wq", (size_t)d.A * d.Hp * b);
-  p.add("w_enc_x", (size_t)d.G * d.KX * b);
-  p.add("w_enc_hh", (size_t)d.G * d.Hp * b);
+  p.add("w_enc_x", (size_t)d.GP * d.KX * b);
+  p.add("w_enc_hh", (size_t)d.GP * d.Hp * b);
   p.add("w_fc", (size_t)d.Z2 * d.Hp * b);
-  p.add("w_dec_x", (size_t)d.G * d.KX * b);
-  p.add("w_dec_z", (size_t)d.G * d.Zp * b);
+  p.add("w_dec_x", (size_t)d.GP * d.KX * b);
+  p.add("w_dec_z", (size_t)d.GP * d.Zp * b);
   p.add("fwd_end", 0);
   // --- transposed twins streamed at every backward timestep
   p.add("w_dec_xzT", (size_t)(d.KX + d.Zp) * d.Gp * b);   // rows [0,KX): W_dec_x^T ; rows [KX,KX+Zp): W_dec_z^T
@@ -83,9 +86,9 @@ static void plan_packed(const Dims& d, Plan& p) {
   // --- used once per sequence
   p.add("embb", (size_t)d.V * d.Ep * b);
   if (d.tied) p.add("embT", (size_t)d.E * d.Vp * b);
-  p.add("w_att_e", (size_t)d.G * d.Ep * b);
+  p.add("w_att_e", (size_t)d.GP * d.Ep * b);
   p.add("w_att_eT", (size_t)d.Ep * d.Gp * b);
-  p.add("w_att_f", (size_t)d.G * d.Fp * b);
+  p.add("w_att_f", (size_t)d.GP * d.Fp * b);
   p.add("wv", (size_t)d.A * d.Fp * b);
   p.add("w_out", (size_t)NO * d.Hp * b);
   p.add("w_outT", (size_t)d.Hp * NOp * b);
@@ -113,13 +116,13 @@ static void plan_train(const Dims& d, int B, int N, Plan& p) {
   p.add("avgb", (size_t)B * d.Fp * b);
   p.add("projb", BN * d.Ap * b);
   p.add("embb_t", TB * d.Ep * b);
-  p.add("gx_att", TB * d.G * f);
-  p.add("gavg", (size_t)B * d.G * f);
+  p.add("gx_att", TB * d.GP * f);
+  p.add("gavg", (size_t)B * d.GP * f);
   p.add("XA", (T + 1) * B * 2 * d.Hp * b);
   p.add("XE", TB * d.KX * b);
   p.add("HE", (T + 1) * B * d.Hp * b);
   p.add("ZB", TB * d.Zp * b);
-  p.add("acc", (size_t)B * d.G * f);
+  p.add("acc", (size_t)B * d.GP * f);
   p.add("gates_att", TB * d.G * f);
   p.add("gates_enc", TB * d.G * f);
   p.add("gates_dec", TB * d.G * f);
@@ -223,14 +226,14 @@ static int pack_weights_impl(Handle* h, const void* const* wv, char* pk, const u
   const int ldi = E + F + 2 * H;
   const float* wih = W(SSCVAE_W_ATT_IH);
   if (need({SSCVAE_W_ATT_IH, SSCVAE_W_ATT_HH})) {
-    TRY(jobs.add(Pb("w_att_rec"), 2 * d.Hp, 0, wih + E + F, ldi, G, H, W(SSCVAE_W_ATT_HH), H));
+    TRY(jobs.add(Pb("w_att_rec"), 2 * d.Hp, 0, wih + E + F, ldi, G, H, W(SSCVAE_W_ATT_HH), H, H));
     TRY(jobs.add(Pb("w_att_recT"), d.Gp, 1, wih + E + F, ldi, G, H, W(SSCVAE_W_ATT_HH), H));
   }
   if (need({SSCVAE_W_ATT_IH})) {
-    TRY(jobs.add(Pb("w_att_e"), d.Ep, 0, wih, ldi, G, E, nullptr, 0));
+    TRY(jobs.add(Pb("w_att_e"), d.Ep, 0, wih, ldi, G, E, nullptr, 0, H));
     TRY(jobs.add(Pb("w_att_eT"), d.Gp, 1, wih, ldi, G, E, nullptr, 0));
-    TRY(jobs.add(Pb("w_att_f"), d.Fp, 0, wih + E, ldi, G, F, nullptr, 0));
-    TRY(jobs.add(Pb("w_att_rec") + d.Hp, 2 * d.Hp, 0, wih + E + F + H, ldi, G, H, nullptr, 0));
+    TRY(jobs.add(Pb("w_att_f"), d.Fp, 0, wih + E, ldi, G, F, nullptr, 0, H));
+    TRY(jobs.add(Pb("w_att_rec") + d.Hp, 2 * d.Hp, 0, wih + E + F + H, ldi, G, H, nullptr, 0, H));
     TRY(jobs.add(Pb("w_att_recT") + (size_t)d.Hp * d.Gp, d.Gp, 1, wih + E + F + H, ldi, G, H, nullptr, 0));
   }
   if (need({SSCVAE_W_ATT_BIH, SSCVAE_W_ATT_BHH})) TRY(vec_add_f32(s, W(SSCVAE_W_ATT_BIH), W(SSCVAE_W_ATT_BHH), Pf("b_att"), G));
@@ -249,13 +252,13 @@ static int pack_weights_impl(Handle* h, const void* const* wv, char* pk, const u
   const int widths[3] = {F, H, H};
   if (need({SSCVAE_W_ENC_IH})) {
     for (int k = 0; k < 3; ++k) {
-      TRY(jobs.add(wex + offs_dst[k], d.KX, 0, we + offs_src[k], lde, G, widths[k], nullptr, 0));
+      TRY(jobs.add(wex + offs_dst[k], d.KX, 0, we + offs_src[k], lde, G, widths[k], nullptr, 0, H));
       TRY(jobs.add(wexT + (size_t)offs_dst[k] * d.Gp, d.Gp, 1, we + offs_src[k], lde, G, widths[k], nullptr, 0));
     }
     if (c) TRY(copy_block_f32(s, we + F + 2 * H, lde, Pf("scol_enc"), 1, G, 1));
   }
   if (need({SSCVAE_W_ENC_HH})) {
-    TRY(jobs.add(Pb("w_enc_hh"), d.Hp, 0, W(SSCVAE_W_ENC_HH), H, G, H, nullptr, 0));
+    TRY(jobs.add(Pb("w_enc_hh"), d.Hp, 0, W(SSCVAE_W_ENC_HH), H, G, H, nullptr, 0, H));
     TRY(jobs.add(Pb("w_enc_xhT") + (size_t)d.KX * d.Gp, d.Gp, 1, W(SSCVAE_W_ENC_HH), H, G, H, nullptr, 0));
   }
   if (need({SSCVAE_W_ENC_BIH, SSCVAE_W_ENC_BHH})) TRY(vec_add_f32(s, W(SSCVAE_W_ENC_BIH), W(SSCVAE_W_ENC_BHH), Pf("b_enc"), G));
@@ -267,12 +270,12 @@ static int pack_weights_impl(Handle* h, const void* const* wv, char* pk, const u
     for (int k = 0; k < 3; ++k) {
       if (k < 2 && !need({SSCVAE_W_DEC_IH})) continue;
       const float* fold = (k == 2) ? W(SSCVAE_W_DEC_HH) : nullptr;
-      TRY(jobs.add(wdx + offs_dst[k], d.KX, 0, wd + offs_src[k], ldd, G, widths[k], fold, H));
+      TRY(jobs.add(wdx + offs_dst[k], d.KX, 0, wd + offs_src[k], ldd, G, widths[k], fold, H, H));
       TRY(jobs.add(wdxT + (size_t)offs_dst[k] * d.Gp, d.Gp, 1, wd + offs_src[k], ldd, G, widths[k], fold, H));
     }
   }
   if (need({SSCVAE_W_DEC_IH})) {
-    TRY(jobs.add(Pb("w_dec_z"), d.Zp, 0, wd + F + 2 * H + c, ldd, G, Z, nullptr, 0));
+    TRY(jobs.add(Pb("w_dec_z"), d.Zp, 0, wd + F + 2 * H + c, ldd, G, Z, nullptr, 0, H));
     TRY(jobs.add(Pb("w_dec_xzT") + (size_t)d.KX * d.Gp, d.Gp, 1, wd + F + 2 * H + c, ldd, G, Z, nullptr, 0));
     if (c) TRY(copy_block_f32(s, wd + F + 2 * H, ldd, Pf("scol_dec"), 1, G, 1));
   }
@@ -355,7 +358,7 @@ static int train_forward_impl(Handle* h, int B, int N, const char* pk, const voi
   auto Wf = [&](const char* n) { return reinterpret_cast<float*>(ws + tp.find(n)->off); };
   auto Wi = [&](const char* n) { return reinterpret_cast<int*>(ws + tp.find(n)->off); };
   auto zero = [&](const char* n) { return cudaMemsetAsync(ws + tp.find(n)->off, 0, tp.find(n)->bytes, s); };
-  const int T = d.T, TB = T * B, G = d.G, H = d.H, Hp = d.Hp, KX = d.KX, Fp = d.Fp;
+  const int T = d.T, TB = T * B, GP = d.GP, H = d.H, Hp = d.Hp, KX = d.KX, Fp = d.Fp;
   const unsigned long long* seed_dev = reinterpret_cast<const unsigned long long*>(ws + tp.find("seed")->off);
   (void)seed;                                          // copied to `seed_dev` by the caller, in front of the graph
 
@@ -379,13 +382,13 @@ static int train_forward_impl(Handle* h, int B, int N, const char* pk, const voi
   TRY(embed_gather_train(s, tok, B, d.L, Pb("embb"), d.Ep, Wb("embb_t")));
   {  // teacher-forced embedding block of the attention-LSTM gates for all T at once
     GemmSeg sg = seg(Wb("embb_t"), d.Ep, Pb("w_att_e"), d.Ep, d.E);
-    GemmEpi e; e.tag = "gemm.pre"; e.C32 = Wf("gx_att"); e.ldc32 = G;
-    TRY(gemm_bf16_tn(s, TB, G, 1, &sg, e));
+    GemmEpi e; e.tag = "gemm.pre"; e.C32 = Wf("gx_att"); e.ldc32 = GP;
+    TRY(gemm_bf16_tn(s, TB, GP, 1, &sg, e));
   }
-  {  // time-invariant mean-feature block + both biases
+  {  // time-invariant mean-feature block (the biases, kept in reference order, are added by the cell)
     GemmSeg sg = seg(Wb("avgb"), Fp, Pb("w_att_f"), Fp, d.F);
-    GemmEpi e; e.tag = "gemm.pre"; e.C32 = Wf("gavg"); e.ldc32 = G; e.bias = Pf("b_att");
-    TRY(gemm_bf16_tn(s, B, G, 1, &sg, e));
+    GemmEpi e; e.tag = "gemm.pre"; e.C32 = Wf("gavg"); e.ldc32 = GP;
+    TRY(gemm_bf16_tn(s, B, GP, 1, &sg, e));
   }
   LatentArgs la; la.R = B; la.Z = d.Z; la.Zp = d.Zp; la.sentiment_vae = d.sv; la.prior_var = d.prior_std * d.prior_std;
   la.prior_mean_row = Wf("pm_row"); la.rowmap = nullptr;
@@ -400,16 +403,16 @@ static int train_forward_impl(Handle* h, int B, int N, const char* pk, const voi
     bf16* HE_t = Wb("HE") + (size_t)t * B * Hp;
     bf16* HE_n = HE_t + (size_t)B * Hp;
     bf16* ZB_t = Wb("ZB") + (size_t)t * B * d.Zp;
-    const size_t rG = (size_t)t * B * G, rH = (size_t)t * B * H;
-    {  // attention LSTM (updown_cell.py:143-148)
-      GemmSeg sg = seg(XA_t, 2 * Hp, Pb("w_att_rec"), 2 * Hp, 2 * Hp);
-      GemmEpi e; e.tag = "gemm.step"; e.C32 = acc; e.ldc32 = G;
-      TRY(gemm_bf16_tn(s, B, G, 1, &sg, e));
+    const size_t rG = (size_t)t * B * d.G, rH = (size_t)t * B * H;
+    {  // attention LSTM (updown_cell.py:143-148): gate GEMM with the cell fused into its epilogue
       LstmFwdArgs l = {};
-      l.R = B; l.H = H; l.acc = acc; l.ld_acc = G; l.add1 = Wf("gx_att") + rG; l.ld1 = G; l.add2 = Wf("gavg"); l.ld2 = G;
+      l.R = B; l.H = H; l.add1 = Wf("gx_att") + (size_t)t * B * GP; l.ld1 = GP; l.add2 = Wf("gavg"); l.ld2 = GP;
+      l.bias = Pf("b_att");
       l.c_prev = t ? Wf("c1") + rH - (size_t)B * H : nullptr; l.c_out = Wf("c1") + rH; l.gates_out = Wf("gates_att") + rG;
       l.h1_dst = XE_t + Fp; l.ld_h1 = KX; l.h2_dst = XA_n; l.ld_h2 = 2 * Hp;
-      TRY(lstm_forward(s, l));
+      GemmSeg sg = seg(XA_t, 2 * Hp, Pb("w_att_rec"), 2 * Hp, 2 * Hp);
+      GemmEpi e; e.tag = "gemm.step"; e.C32 = acc; e.ldc32 = GP; e.lstm = &l;
+      TRY(gemm_bf16_tn(s, B, GP, 1, &sg, e));
     }
     {  // query projection + fused region attention (attention.py:69-93, updown_cell.py:156)
       GemmSeg sg = seg(XE_t + Fp, KX, Pb("wq"), Hp, Hp);
@@ -419,15 +422,14 @@ static int train_forward_impl(Handle* h, int B, int N, const char* pk, const voi
       TRY(attention_forward(s, aa, Wf("alpha") + (size_t)t * B * N, Wf("smx") + (size_t)t * B * N, XE_t, KX));
     }
     {  // posterior (encoder) LSTM + latent heads + reparameterised sample (updown_cell.py:176-208)
-      GemmSeg sg[2] = {seg(XE_t, KX, Pb("w_enc_x"), KX, KX), seg(HE_t, Hp, Pb("w_enc_hh"), Hp, Hp)};
-      GemmEpi e; e.tag = "gemm.step"; e.C32 = acc; e.ldc32 = G;
-      TRY(gemm_bf16_tn(s, B, G, 2, sg, e));
       LstmFwdArgs l = {};
-      l.R = B; l.H = H; l.acc = acc; l.ld_acc = G; l.bias = Pf("b_enc");
+      l.R = B; l.H = H; l.bias = Pf("b_enc");
       if (d.cond) { l.sent = sent; l.scol = Pf("scol_enc"); }
       l.c_prev = t ? Wf("c_enc") + rH - (size_t)B * H : nullptr; l.c_out = Wf("c_enc") + rH;
       l.gates_out = Wf("gates_enc") + rG; l.h1_dst = HE_n; l.ld_h1 = Hp;
-      TRY(lstm_forward(s, l));
+      GemmSeg sg[2] = {seg(XE_t, KX, Pb("w_enc_x"), KX, KX), seg(HE_t, Hp, Pb("w_enc_hh"), Hp, Hp)};
+      GemmEpi e; e.tag = "gemm.step"; e.C32 = acc; e.ldc32 = GP; e.lstm = &l;
+      TRY(gemm_bf16_tn(s, B, GP, 2, sg, e));
       GemmSeg sf = seg(HE_n, Hp, Pb("w_fc"), Hp, Hp);
       GemmEpi ef; ef.tag = "gemm.step"; ef.C32 = Wf("ml"); ef.ldc32 = d.Z2;
       TRY(gemm_bf16_tn(s, B, d.Z2, 1, &sf, ef));
@@ -436,16 +438,15 @@ static int train_forward_impl(Handle* h, int B, int N, const char* pk, const voi
                                Wf("mean") + rZ, Wf("logvar") + rZ, Wf("eps") + rZ, ZB_t, d.Zp, Wf("kl") + (size_t)t * B));
     }
     {  // language (decoder) LSTM (updown_cell.py:211-229)
-      GemmSeg sg[2] = {seg(XE_t, KX, Pb("w_dec_x"), KX, KX), seg(ZB_t, d.Zp, Pb("w_dec_z"), d.Zp, d.Zp)};
-      GemmEpi e; e.tag = "gemm.step"; e.C32 = acc; e.ldc32 = G;
-      TRY(gemm_bf16_tn(s, B, G, 2, sg, e));
       LstmFwdArgs l = {};
-      l.R = B; l.H = H; l.acc = acc; l.ld_acc = G; l.bias = Pf("b_dec");
+      l.R = B; l.H = H; l.bias = Pf("b_dec");
       if (d.cond) { l.sent = sent; l.scol = Pf("scol_dec"); }
       l.c_prev = t ? Wf("c_dec") + rH - (size_t)B * H : nullptr; l.c_out = Wf("c_dec") + rH;
       l.gates_out = Wf("gates_dec") + rG; l.h1_dst = XA_n + Hp; l.ld_h1 = 2 * Hp;
       if (XE_n) { l.h2_dst = XE_n + Fp + Hp; l.ld_h2 = KX; }
-      TRY(lstm_forward(s, l));
+      GemmSeg sg[2] = {seg(XE_t, KX, Pb("w_dec_x"), KX, KX), seg(ZB_t, d.Zp, Pb("w_dec_z"), d.Zp, d.Zp)};
+      GemmEpi e; e.tag = "gemm.step"; e.C32 = acc; e.ldc32 = GP; e.lstm = &l;
+      TRY(gemm_bf16_tn(s, B, GP, 2, sg, e));
     }
   }
   // output head over all T*B rows at once (updown_captioner.py:444-445)

@@ -115,8 +115,9 @@ __device__ __forceinline__ void produce_block(const AttnSmem& sm, Ring& ring, co
     ptx::mbar_expect_tx(&sm.full[ring.stage], bytes);
     // evict_first: the 52 MB of features + projections are read once per timestep and would otherwise push the
     // recurrent weights (76 MB, re-read every step) out of the 126 MB L2
-    ptx::bulk_g2s_hint(sm.stage + (size_t)ring.stage * ATT_STAGE_BYTES, base + (size_t)n0 * row_bytes, bytes,
-                       &sm.full[ring.stage], policy);
+    if (policy) ptx::bulk_g2s_hint(sm.stage + (size_t)ring.stage * ATT_STAGE_BYTES, base + (size_t)n0 * row_bytes, bytes,
+                                   &sm.full[ring.stage], policy);
+    else ptx::bulk_g2s(sm.stage + (size_t)ring.stage * ATT_STAGE_BYTES, base + (size_t)n0 * row_bytes, bytes, &sm.full[ring.stage]);
     ring.advance();
   }
 }
@@ -236,6 +237,8 @@ attention_fwd_kernel(AttnArgs a, AttnPlan pl, float* __restrict__ alpha, float* 
   extern __shared__ __align__(128) uint8_t att_smem_raw[];
   const AttnSmem sm = carve(att_smem_raw, a, false);
   attn_prologue(sm, a, false);
+  pdl_wait();                                        // the prologue overlaps the previous kernel's tail
+  pdl_launch_dependents();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int r_begin = blockIdx.x * pl.rows_per_cta;
   const int r_end = min(a.R, r_begin + pl.rows_per_cta);
@@ -243,7 +246,7 @@ attention_fwd_kernel(AttnArgs a, AttnPlan pl, float* __restrict__ alpha, float* 
 
   if (warp == ATT_CWARPS) {                          // ---- producer
     if (lane == 0) {
-      const uint64_t pol = ptx::l2_policy_evict_first();
+      const uint64_t pol = a.l2_policy == 1 ? ptx::l2_policy_evict_first() : a.l2_policy == 2 ? ptx::l2_policy_evict_last() : 0;
       for (int r = r_begin; r < r_end; ++r) {
         const int img = a.rowmap ? a.rowmap[r] : r;
         produce_block(sm, ring, reinterpret_cast<const uint8_t*>(a.proj + (size_t)img * a.N * a.Ap), a.N, a.Ap * 2, pl.nP, pl.bP, pol);
@@ -359,7 +362,16 @@ static int make_plan(const AttnArgs& a, AttnPlan& pl) {
   return 0;
 }
 
-int attention_forward(cudaStream_t s, const AttnArgs& a, float* alpha, float* smx, bf16* xhat, int ld_x) {
+static int attn_l2_policy() {
+  // SSCVAE_ATT_POLICY: 0 = no hint, 1 = evict_first (default: the stream must not push the recurrent weights out of L2),
+  // 2 = evict_last (with SSCVAE_W_EVICT_FIRST=1: keep the features resident, let the weights stream)
+  static const int v = [] { const char* e = getenv("SSCVAE_ATT_POLICY"); return e ? atoi(e) : 1; }();
+  return v;
+}
+
+int attention_forward(cudaStream_t s, const AttnArgs& a_in, float* alpha, float* smx, bf16* xhat, int ld_x) {
+  AttnArgs a = a_in;
+  a.l2_policy = attn_l2_policy();
   PROF_SCOPE(s, "attention_fwd", 0, (double)a.R*((double)a.N*(a.Ap+a.Fp)*2.0 + a.A*4.0 + a.Fp*2.0 + a.N*4.0));
   REQUIRE(a.R > 0 && (ld_x % 8) == 0 && (reinterpret_cast<uintptr_t>(xhat) & 15) == 0, "attention_forward: bad xhat layout");
   AttnPlan pl;
@@ -370,7 +382,7 @@ int attention_forward(cudaStream_t s, const AttnArgs& a, float* alpha, float* sm
     CUDA_TRY(cudaFuncSetAttribute(attention_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
     configured = true;
   }
-  attention_fwd_kernel<<<ceil_div(a.R, pl.rows_per_cta), ATT_THREADS, smem, s>>>(a, pl, alpha, smx, xhat, ld_x);
+  CUDA_TRY(launch_pdl(attention_fwd_kernel, dim3(ceil_div(a.R, pl.rows_per_cta)), dim3(ATT_THREADS), smem, s, a, pl, alpha, smx, xhat, ld_x));
   LAUNCHED();
   return 0;
 }
@@ -382,6 +394,8 @@ attention_bwd_kernel(AttnArgs a, AttnPlan pl, const float* __restrict__ smx, con
   extern __shared__ __align__(128) uint8_t att_smem_raw[];
   const AttnSmem sm = carve(att_smem_raw, a, true);
   attn_prologue(sm, a, true);
+  pdl_wait();                                        // the prologue overlaps the previous kernel's tail
+  pdl_launch_dependents();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int r_begin = blockIdx.x * pl.rows_per_cta;
   const int r_end = min(a.R, r_begin + pl.rows_per_cta);
@@ -389,7 +403,7 @@ attention_bwd_kernel(AttnArgs a, AttnPlan pl, const float* __restrict__ smx, con
 
   if (warp == ATT_CWARPS) {                          // ---- producer: region features first, then projections
     if (lane == 0) {
-      const uint64_t pol = ptx::l2_policy_evict_first();
+      const uint64_t pol = a.l2_policy == 1 ? ptx::l2_policy_evict_first() : a.l2_policy == 2 ? ptx::l2_policy_evict_last() : 0;
       for (int r = r_begin; r < r_end; ++r) {
         const int img = a.rowmap ? a.rowmap[r] : r;
         produce_block(sm, ring, reinterpret_cast<const uint8_t*>(a.feats + (size_t)img * a.N * a.Fp), a.N, a.Fp * 2, pl.nF, pl.bF, pol);
@@ -521,8 +535,10 @@ attention_bwd_kernel(AttnArgs a, AttnPlan pl, const float* __restrict__ smx, con
   }
 }
 
-int attention_backward(cudaStream_t s, const AttnArgs& a, const float* smx, const float* dxhat, int ld_dx, bf16* dq,
+int attention_backward(cudaStream_t s, const AttnArgs& a_in, const float* smx, const float* dxhat, int ld_dx, bf16* dq,
                        int ld_dq, float* du) {
+  AttnArgs a = a_in;
+  a.l2_policy = attn_l2_policy();
   PROF_SCOPE(s, "attention_bwd", 0, (double)a.R*((double)a.N*(a.Ap+a.Fp)*2.0 + a.Fp*4.0 + a.A*6.0 + a.N*8.0));
   REQUIRE(a.R > 0 && (ld_dq % 2) == 0 && (reinterpret_cast<uintptr_t>(dq) & 3) == 0, "attention_backward: bad dq layout");
   AttnPlan pl;
@@ -533,7 +549,8 @@ int attention_backward(cudaStream_t s, const AttnArgs& a, const float* smx, cons
     CUDA_TRY(cudaFuncSetAttribute(attention_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
     configured = true;
   }
-  attention_bwd_kernel<<<ceil_div(a.R, pl.rows_per_cta), ATT_THREADS, smem, s>>>(a, pl, smx, dxhat, ld_dx, dq, ld_dq, du);
+  CUDA_TRY(launch_pdl(attention_bwd_kernel, dim3(ceil_div(a.R, pl.rows_per_cta)), dim3(ATT_THREADS), smem, s, a, pl, smx, dxhat, ld_dx, dq,
+                      ld_dq, du));
   LAUNCHED();
   return 0;
 }

@@ -5,6 +5,8 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstdarg>
+#include <cstdlib>
+#include <cstring>
 
 typedef __nv_bfloat16 bf16;
 
@@ -45,6 +47,30 @@ const char* get_error();
 static inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
 static inline size_t round_up_sz(size_t x, size_t m) { return (x + m - 1) / m * m; }
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+
+// ---- programmatic dependent launch ----------------------------------------------------------------
+// The time loops are ~10 dependent kernels of 3-15 us per step; what separates them is the launch / drain gap.
+// Kernels of the loops are launched with cudaLaunchAttributeProgrammaticStreamSerialization (launch_pdl): the next
+// grid may be scheduled while the previous one drains, runs its prologue (barrier init, TMEM allocation, descriptor
+// prefetch, index math) and blocks in pdl_wait() until the previous grid has completed and flushed. Rule: a kernel
+// launched through launch_pdl executes pdl_wait() before its first global-memory access (reads AND writes).
+// Both instructions are no-ops in a kernel launched without the attribute. SSCVAE_PDL=0 disables the attribute.
+inline bool pdl_enabled() {
+  static const bool on = [] { const char* e = getenv("SSCVAE_PDL"); return !(e && e[0] == '0'); }();
+  return on;
+}
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 // ---- device utilities ---------------------------------------------------------------------------
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + __expf(-x)); }

@@ -7,6 +7,8 @@
 
 namespace sscvae {
 
+struct LstmFwdArgs;
+
 struct GemmSeg {
   const bf16* A; int lda;   // (M, K) row-major, lda in elements (multiple of 8, base 16B aligned)
   const bf16* B; int ldb;   // (N, K) row-major
@@ -27,6 +29,12 @@ struct GemmEpi {
   // skinny GEMMs (M <= 256) run on the swapped-operand kernel with K split over a thread-block cluster; 0 = let the
   // library choose the split count, 1/2/4 = force it (tools/gemm_bench.py)
   int splits = 0;
+  // Fused LSTM cell (forward): the N = lstm_gate_rows(H) output columns are gate pre-activations in the
+  // gate-interleaved order of the packed weights; `lstm` describes the addends, states and destinations exactly as
+  // for lstm_forward (its acc / ld_acc / perm are ignored). On the CTA-pair kernel (M <= 256) the cell runs in the
+  // GEMM epilogue and the pre-activations never leave the SM; otherwise the GEMM writes C32 (required, ldc32 >= N)
+  // and lstm_forward runs behind it.
+  const LstmFwdArgs* lstm = nullptr;
 };
 
 // K-split (cluster size 1, 2 or 4) the swapped-operand kernel uses for a skinny GEMM (M <= 256)

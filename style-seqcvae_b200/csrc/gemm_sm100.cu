@@ -7,12 +7,14 @@
 //                 fused bias / addends / tanh / dtanh -> fp32 and/or bf16 global stores
 // The accumulator never touches registers or shared memory until the epilogue.
 #include "gemm.cuh"
+#include "kernels.cuh"
 #include "prof.cuh"
 #include <cuda.h>
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <unordered_map>
+#include <vector>
 #include <algorithm>
 
 namespace sscvae {
@@ -38,6 +40,12 @@ struct GemmParams {
   int tma_store;                                  // 1: plain fp32 tile (+bias): the epilogue leaves through TMA stores of `tc`
   CUtensorMap tc;                                 // fp32 output, box 32 columns x 32 rows, no swizzle
   GemmEpi epi;
+  int w_policy;                                   // pair kernel: 1 = weight tiles are loaded with an L2 evict_first hint
+  int fuse_lstm;                                  // pair kernel: run the LSTM cell `lstm` in the epilogue
+  int lstm_tma;                                   // ... and its outputs leave through TMA stores of `tl`
+  long long* dbg;                                 // SSCVAE_GEMM_DBG=1: per-CTA clock64 stamps of the pair kernel's phases
+  LstmFwdArgs lstm;
+  CUtensorMap tl[7];                              // gates i,f,g,o (fp32), c (fp32), h -> h1_dst, h2_dst (bf16); box 32 units x 32 rows
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -131,6 +139,14 @@ __device__ __forceinline__ void tma_load_2d_2sm(void* dst, const CUtensorMap* tm
   asm volatile(
       "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
       ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar) & 0xFEFFFFFFu), "r"(c0), "r"(c1)
+      : "memory");
+}
+// the same with an L2 eviction-priority hint (createpolicy) for operands that are streamed once per launch
+__device__ __forceinline__ void tma_load_2d_2sm_hint(void* dst, const CUtensorMap* tmap, uint64_t* bar, int c0, int c1,
+                                                     uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar) & 0xFEFFFFFFu), "r"(c0), "r"(c1), "l"(policy)
       : "memory");
 }
 template <int NCOLS>
@@ -440,6 +456,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_tcgen05_kernel(const __g
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_acc = *tmem_slot;
+  pdl_wait();                                           // everything above overlaps the previous kernel's tail
+  pdl_launch_dependents();
 
   if (warp == 0) {
     if (lane == 0) {
@@ -551,6 +569,8 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ GemmParams p) {
   cluster_sync_all();                                     // both CTAs' barriers exist before any remote arrival
   tc_fence_after();
   const uint32_t tmem_acc = *tmem_slot;
+  pdl_wait();
+  pdl_launch_dependents();
 
   if (warp == 0) {
     if (lane == 0) {
@@ -714,6 +734,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_swapped_kernel(c
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_acc = *tmem_slot;
+  pdl_wait();
+  pdl_launch_dependents();
 
   if (warp == 0) {
     if (lane == 0) {
@@ -825,6 +847,320 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_swapped_kernel(c
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc<BX>(tmem_acc);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Skinny-M kernel, CTA-PAIR form: the swapped-operand cluster split-K kernel above with every 256 x 256 tile driven
+// by tcgen05.mma.cta_group::2. The chip-wide L2 -> SM rate (~6300 B/clk, B300_MICROARCH.md; measured here as
+// ~77 GB/s per SM with all SMs pulling) bounds these GEMMs, and in the single-CTA form 2/3 of every k-block's 48 KB
+// is the ACTIVATION tile, re-read by every one of the N/128 weight-row CTAs. A pair splits that tile: CTA x of the
+// pair loads its own 128 weight rows (16 KB) and HALF of the batch rows (16 KB), the MMA (M = 256 weight rows,
+// N = 256 batch rows) reads both halves across the pair. 32 KB instead of 48 KB per SM and k-block: the loads of a
+// 128x256x64 block (~415 ns at 77 GB/s) now hide behind its MMAs (~440 ns at the sustained tensor rate).
+// Cluster = (2, 1, S): x = the pair, z = the K split (S = 1..4); CTA (x, z) ends up owning the batch columns
+// [z*CW, z*CW+CW) of its 128 weight rows, receives the other splits' partial sums for them through distributed
+// shared memory and runs the epilogue, exactly as in the single-CTA form.
+// ---------------------------------------------------------------------------------------------
+// Fused LSTM cell (updown_cell.py:143-148 etc., nn.LSTMCell gate order i,f,g,o). A thread owns hidden unit j for 8
+// batch rows [r0, r0+8) of a 32-row block. Everything the cell needs besides the GEMM result - the addends of the four
+// gate pre-activations and c_{t-1} - does not depend on the GEMM, so it is loaded into registers one block AHEAD (before
+// the accumulator is ready / while the previous block is processed): the epilogue never waits on global memory.
+struct LstmCellPre { float pre[8][4]; float cp[8]; };
+
+// Branch-free forms for the epilogue: its four warps run one per SM sub-partition with nothing to hide instruction
+// latency behind, and tanhf / IEEE division are ~4x the instructions (measured: 850 cycles per cell with them).
+// Absolute error <= 2e-7, far inside the bf16 operand rounding of the next GEMM.
+__device__ __forceinline__ float cell_sigmoid(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+__device__ __forceinline__ float cell_tanh(float x) { return 1.0f - __fdividef(2.0f, 1.0f + __expf(2.0f * x)); }
+
+__device__ __forceinline__ void lstm_cell_prefetch(const LstmFwdArgs& a, int j, int r0, LstmCellPre& P) {
+  const int H = a.H;
+  if (j >= H) return;
+  float bias[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) bias[k] = a.bias ? a.bias[k * H + j] : 0.f;
+#pragma unroll
+  for (int t = 0; t < 8; ++t) {
+    const int r = min(r0 + t, a.R - 1);                 // clamped: rows beyond R are loaded but never stored
+    const int r2 = a.rowmap ? a.rowmap[r] : r;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int na = lstm_gate_row(k, j);
+      float v = bias[k];
+      if (a.add1) v += a.add1[(size_t)r * a.ld1 + na];
+      if (a.add2) v += a.add2[(size_t)r2 * a.ld2 + na];
+      if (a.sent) v += a.sent[r2] * a.scol[k * H + j];
+      P.pre[t][k] = v;
+    }
+    P.cp[t] = a.c_prev ? a.c_prev[(size_t)r * H + j] : 0.f;
+  }
+}
+
+// the pre-activation (GEMM part) of gate k, row r0+t sits at xch + (k*32*32 + t*32) floats.
+// stg != 0: the results are staged in shared memory as dense [32 rows][32 units] tiles (gates i,f,g,o and c in fp32 at
+// stg + o*4096, h in bf16 at stg + 20480) and leave through TMA stores issued by the caller: global stores cost a lone
+// epilogue warp ~220 cycles each (measured), and a cell has seven of them. Units beyond H stage zeros: the fp32 maps
+// clip them, the bf16 maps write them into the zero padding columns of the operand buffers.
+__device__ __forceinline__ void lstm_cell_rows(const LstmFwdArgs& a, int j, int r0, uint32_t xch, const LstmCellPre& P,
+                                               uint32_t stg, int rb0) {
+  const int H = a.H;
+  if (stg) {
+    const int lane = threadIdx.x & 31;
+    const bool valid = j < H;
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+      float g[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) g[k] = lds_f32(xch + (uint32_t)((k * 32 * 32 + t * 32) * 4)) + P.pre[t][k];
+      float i = cell_sigmoid(g[0]), f = cell_sigmoid(g[1]), gg = cell_tanh(g[2]), o = cell_sigmoid(g[3]);
+      float c = f * P.cp[t] + i * gg;
+      float h = o * cell_tanh(c);
+      if (!valid) { i = f = gg = o = c = h = 0.f; }
+      const uint32_t off = (uint32_t)(((rb0 + t) * 32 + lane) * 4);
+      sts_f32(stg + off, i); sts_f32(stg + 4096 + off, f); sts_f32(stg + 8192 + off, gg); sts_f32(stg + 12288 + off, o);
+      sts_f32(stg + 16384 + off, c);
+      const unsigned short hb = __bfloat16_as_ushort(__float2bfloat16_rn(h));
+      asm volatile("st.shared.u16 [%0], %1;" ::"r"(stg + 20480 + (off >> 1)), "h"(hb) : "memory");
+    }
+    return;
+  }
+  if (j >= H) return;
+#pragma unroll
+  for (int t = 0; t < 8; ++t) {
+    const int r = r0 + t;
+    if (r < a.R) {
+      float g[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) g[k] = lds_f32(xch + (uint32_t)((k * 32 * 32 + t * 32) * 4)) + P.pre[t][k];
+      const float i = cell_sigmoid(g[0]), f = cell_sigmoid(g[1]), gg = cell_tanh(g[2]), o = cell_sigmoid(g[3]);
+      const float c = f * P.cp[t] + i * gg;
+      const float h = o * cell_tanh(c);
+      a.c_out[(size_t)r * H + j] = c;
+      if (a.gates_out) {
+        float* go = a.gates_out + (size_t)r * 4 * H;
+        go[j] = i; go[H + j] = f; go[2 * H + j] = gg; go[3 * H + j] = o;
+      }
+      const bf16 hb = __float2bfloat16_rn(h);
+      if (a.h1_dst) a.h1_dst[(size_t)r * a.ld_h1 + j] = hb;
+      if (a.h2_dst) a.h2_dst[(size_t)r * a.ld_h2 + j] = hb;
+    }
+  }
+}
+
+__device__ __forceinline__ void umma_commit_2sm_mask(uint64_t* bar, uint16_t mask) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+          smem_u32(bar)),
+      "h"(mask)
+      : "memory");
+}
+
+#define DBG_STAMP(i)                                                                                         \
+  do {                                                                                                     \
+    if (p.dbg && warp == 2 && lane == 0)                                                                   \
+      p.dbg[((size_t)blockIdx.z * gridDim.x + blockIdx.x) * 16 + (i)] = clock64();                          \
+  } while (0)
+
+template <int STAGES>
+__global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_swapped_pair_kernel(const __grid_constant__ GemmParams p) {
+  constexpr int BW = 128, BXH = 128;                    // weight rows per CTA (half of UMMA M), batch rows LOADED per CTA
+  constexpr int W_STAGE_BYTES = BW * BK * 2, X_STAGE_BYTES = BXH * BK * 2;
+  constexpr uint32_t IDESC = make_idesc(2 * BW, 2 * BXH);
+  constexpr int TCOLS = 2 * BXH;                        // accumulator: 128 lanes (this CTA's weight rows) x 256 batch rows
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw;
+  if (threadIdx.x == 0 && (smem_u32(smem) & 1023u)) __trap();
+  uint8_t* smem_w = smem;
+  uint8_t* smem_x = smem + STAGES * W_STAGE_BYTES;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_x + STAGES * X_STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* accum_bar = empty_bar + STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int xr = blockIdx.x & 1;                        // position in the pair; cluster rank = xr + 2 * z
+  const int S = p.splits;
+  const int rank = blockIdx.z;                          // K split of this CTA (cluster z == grid z)
+  const int n0 = (blockIdx.x >> 1) * (2 * BW) + xr * BW;   // first weight row (output column) of this CTA
+  DBG_STAMP(0);
+
+  int total_kb = 0;
+#pragma unroll
+  for (int s = 0; s < MAX_SEG; ++s) total_kb += (s < p.nseg) ? p.kblocks[s] : 0;
+  const int kb_begin = rank * p.kb_per_split;
+  const int kb_end = min(total_kb, kb_begin + p.kb_per_split);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.nseg; ++s) { prefetch_tmap(&p.ta[s]); prefetch_tmap(&p.tb[s]); }
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    mbar_init(accum_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) tmem_alloc_2sm<TCOLS>(tmem_slot);
+  tc_fence_before();
+  cluster_sync_all();                                   // the peer's barriers exist before any remote arrival
+  tc_fence_after();
+  const uint32_t tmem_acc = *tmem_slot;
+  DBG_STAMP(1);
+  pdl_wait();                                           // everything above overlaps the previous kernel's tail
+  pdl_launch_dependents();
+  DBG_STAMP(2);
+  const int CW = S == 1 ? 256 : S == 2 ? 128 : S == 3 ? 96 : 64;   // batch columns owned by each K split
+  LstmCellPre cell_pre;                                 // fused LSTM: addends + c_{t-1} of this thread's next 8 cells
+  const LstmFwdArgs lstm = p.lstm;                      // registers (see the note at epilogue_block_vec)
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      int s = 0, base = 0;
+      uint64_t w_pol = 0;
+      if (p.w_policy) asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(w_pol));
+      for (int g = kb_begin; g < kb_end; ++g) {
+        while (g >= base + p.kblocks[s]) { base += p.kblocks[s]; ++s; }
+        const int kb = g - base;
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        if (xr == 0) mbar_expect_tx(&full_bar[stage], 2 * (W_STAGE_BYTES + X_STAGE_BYTES));
+        if (p.w_policy) tma_load_2d_2sm_hint(smem_w + stage * W_STAGE_BYTES, &p.tb[s], &full_bar[stage], kb * BK, n0, w_pol);
+        else tma_load_2d_2sm(smem_w + stage * W_STAGE_BYTES, &p.tb[s], &full_bar[stage], kb * BK, n0);
+        tma_load_2d_2sm(smem_x + stage * X_STAGE_BYTES, &p.ta[s], &full_bar[stage], kb * BK, xr * BXH);
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (xr == 0 && lane == 0) {
+      const uint16_t pair_mask = static_cast<uint16_t>(3u << (2 * rank));
+      int stage = 0; uint32_t phase = 0;
+      for (int kb = kb_begin; kb < kb_end; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        const uint32_t w_base = smem_u32(smem_w + stage * W_STAGE_BYTES);
+        const uint32_t x_base = smem_u32(smem_x + stage * X_STAGE_BYTES);
+#pragma unroll
+        for (int k = 0; k < BK / 16; ++k)
+          umma_bf16_2sm(tmem_acc, make_smem_desc(w_base + k * 32), make_smem_desc(x_base + k * 32), IDESC,
+                        (kb > kb_begin || k > 0) ? 1u : 0u);
+        umma_commit_2sm_mask(&empty_bar[stage], pair_mask);
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+      umma_commit_2sm_mask(accum_bar, pair_mask);
+    }
+    __syncwarp();
+  } else {
+    if (p.fuse_lstm) lstm_cell_prefetch(lstm, (n0 >> 2) + lane, rank * CW + (warp - 2) * 8, cell_pre);
+    DBG_STAMP(3);
+    mbar_wait(accum_bar, 0);                            // this pair's partial tile is complete in both CTAs' TMEM
+    tc_fence_after();
+    DBG_STAMP(4);
+  }
+
+  const int q = warp & 3;                               // epilogue warps 2..5 own TMEM lanes [32q, 32q+32)
+  const int tl = q * 32 + lane;                         // TMEM lane = column n0 + tl of the output
+  float* recv = reinterpret_cast<float*>(smem);         // [(S-1) sources][CW columns][128 lanes], over the dead stages
+  // every CTA of the cluster has finished its main loop (stage buffers dead, also the ones the PEER's MMAs read)
+  cluster_sync_all();
+  DBG_STAMP(5);
+  if (S > 1) {
+    if (warp >= 2 && kb_end > kb_begin) {
+      for (int o = 0; o < S; ++o) {
+        if (o == rank) continue;
+        const int slot = rank < o ? rank : rank - 1;
+        const uint32_t rbase = mapa_shared(smem_u32(recv), (uint32_t)(xr + 2 * o));
+        for (int c = 0; c < CW; c += 32) {
+          if (o * CW + c >= p.M || o * CW + c >= TCOLS) break;   // columns beyond the batch are never read
+          uint32_t acc[32];
+          tmem_ld_32x32(tmem_acc + (static_cast<uint32_t>(q * 32) << 16) + o * CW + c, acc);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            st_shared_cluster_f32(rbase + (uint32_t)(((slot * CW + c + j) * 128 + tl) * 4), __uint_as_float(acc[j]));
+        }
+      }
+    }
+    DBG_STAMP(6);
+    cluster_sync_all();
+    DBG_STAMP(7);
+  }
+  if (warp >= 2) {
+    const GemmEpi epi = p.epi;
+    for (int c = 0; c < CW; c += 32) {
+      const int b0 = rank * CW + c;
+      if (b0 >= p.M || b0 >= TCOLS) break;
+      float v[32];
+      if (kb_end > kb_begin) {
+        uint32_t acc[32];
+        tmem_ld_32x32(tmem_acc + (static_cast<uint32_t>(q * 32) << 16) + b0, acc);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[j]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = 0.f;
+      }
+      for (int o = 0; o < S; ++o) {
+        if (o == rank || o * p.kb_per_split >= total_kb) continue;
+        const int slot = o < rank ? o : o - 1;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] += lds_f32(smem_u32(recv) + (uint32_t)(((slot * CW + c + j) * 128 + tl) * 4));
+      }
+      if (p.fuse_lstm) {
+        // The 128 weight rows of this CTA are 4 gates x 32 hidden units (lstm_gate_row): warp q holds gate q of unit
+        // `lane` for 32 batch rows. Exchange through shared memory, then warp w runs the cell for 8 of the 32 batch
+        // rows with lane = unit, so every global access is 32 consecutive units of one row (128 / 64 bytes).
+        const uint32_t xch = smem_u32(smem) + 96 * 1024;          // [gate][batch row][unit] fp32, 16 KB
+        const uint32_t stg = p.lstm_tma ? smem_u32(smem) + 112 * 1024 : 0u;   // output tiles for the TMA stores, 22 KB
+#pragma unroll
+        for (int j = 0; j < 32; ++j) sts_f32(xch + ((q * 32 + j) * 32 + lane) * 4, v[j]);
+        if (c == 0) DBG_STAMP(8);
+        if (stg && warp == 2 && lane == 0) tma_store_wait_read();   // the previous block's stores have read the staging tiles
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (c == 0) DBG_STAMP(9);
+        const LstmCellPre cur = cell_pre;
+        if (c + 32 < CW && b0 + 32 < p.M && b0 + 32 < TCOLS)      // the next block's addends fly during this block's math
+          lstm_cell_prefetch(lstm, (n0 >> 2) + lane, b0 + 32 + (warp - 2) * 8, cell_pre);
+        lstm_cell_rows(lstm, (n0 >> 2) + lane, b0 + (warp - 2) * 8, xch + (uint32_t)((warp - 2) * 8 * 32 + lane) * 4, cur, stg,
+                       (warp - 2) * 8);
+        if (c == 0) DBG_STAMP(10);
+        if (stg) fence_proxy_async_smem();
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (c == 0) DBG_STAMP(11);
+        if (stg && warp == 2 && lane == 0 && n0 < p.N) {
+          const int j0 = n0 >> 2;
+          if (lstm.gates_out) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) tma_store_2d(&p.tl[k], stg + k * 4096, j0, b0);
+          }
+          tma_store_2d(&p.tl[4], stg + 16384, j0, b0);
+          if (lstm.h1_dst) tma_store_2d(&p.tl[5], stg + 20480, j0, b0);
+          if (lstm.h2_dst) tma_store_2d(&p.tl[6], stg + 20480, j0, b0);
+        }
+      } else if (p.tma_store) {
+        const uint32_t st = smem_u32(smem) + 96 * 1024 + (warp - 2) * 4096;
+        const float bias = (epi.bias && n0 + tl < p.N) ? epi.bias[n0 + tl] : 0.f;
+        if (lane == 0) tma_store_wait_read();
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) sts_f32(st + (j * 32 + lane) * 4, fmaf(v[j], epi.alpha, bias));
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0 && n0 + q * 32 < p.N) tma_store_2d(&p.tc, st, n0 + q * 32, b0);
+      } else if (n0 + q * 32 < p.N) {
+        epilogue_swapped32(epi, p.vec, p.M, p.N, n0 + q * 32, b0, v,
+                           smem_u32(smem) + 96 * 1024 + (warp - 2) * 32 * 36 * 4);
+      }
+    }
+  }
+  DBG_STAMP(12);
+  if ((p.tma_store || p.lstm_tma) && warp >= 2 && lane == 0) tma_store_wait_all();
+  DBG_STAMP(13);
+  tc_fence_before();
+  cluster_sync_all();                                   // nobody deallocates while the pair's MMAs / loads are in flight
+  DBG_STAMP(14);
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_2sm<TCOLS>(tmem_acc);
   }
 }
 
@@ -959,6 +1295,30 @@ static int encode_tmap_c32(CUtensorMap* out, const float* base, int rows, int co
   return 0;
 }
 
+// bf16 output tile map for TMA stores: box = 32 columns x 32 rows (64-byte rows), dense in shared memory
+static int encode_tmap_h16(CUtensorMap* out, const bf16* base, int rows, int cols, int ld) {
+  const TmapKey key{base, rows, cols, ld, -34};
+  std::lock_guard<std::mutex> lock(g_tmap_mutex);
+  auto it = g_tmap_cache.find(key);
+  if (it != g_tmap_cache.end()) { *out = it->second; return 0; }
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) { set_error("cuTensorMapEncodeTiled not available from the driver"); return SSCVAE_ERR_DRIVER; }
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {32, 32};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<bf16*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled (bf16 output) failed (%d) rows=%d cols=%d ld=%d", (int)r, rows, cols, ld);
+    return SSCVAE_ERR_DRIVER;
+  }
+  if (g_tmap_cache.size() > 8192) g_tmap_cache.clear();
+  g_tmap_cache.emplace(key, *out);
+  return 0;
+}
+
 template <int BN, int STAGES>
 static int launch_tc(cudaStream_t stream, GemmParams& prm, const GemmSeg* segs) {
   for (int s = 0; s < prm.nseg; ++s) {
@@ -974,8 +1334,7 @@ static int launch_tc(cudaStream_t stream, GemmParams& prm, const GemmSeg* segs) 
     configured = true;
   }
   dim3 grid(ceil_div(prm.N, BN), ceil_div(prm.M, BM), prm.splits);
-  gemm_tcgen05_kernel<BN, STAGES><<<grid, GEMM_THREADS, smem, stream>>>(prm);
-  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(launch_pdl(gemm_tcgen05_kernel<BN, STAGES>, grid, dim3(GEMM_THREADS), smem, stream, prm));
   ++g_launch_count;
   return 0;
 }
@@ -995,8 +1354,7 @@ static int launch_tc2(cudaStream_t stream, GemmParams& prm, const GemmSeg* segs)
     configured = true;
   }
   dim3 grid(2 * ceil_div(prm.N, BN), ceil_div(prm.M, 2 * BM), prm.splits);
-  gemm_tcgen05_2cta_kernel<BN, STAGES><<<grid, GEMM_THREADS, smem, stream>>>(prm);
-  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(launch_pdl(gemm_tcgen05_2cta_kernel<BN, STAGES>, grid, dim3(GEMM_THREADS), smem, stream, prm));
   ++g_launch_count;
   return 0;
 }
@@ -1018,18 +1376,142 @@ static int launch_swapped(cudaStream_t stream, GemmParams& prm, const GemmSeg* s
     CUDA_TRY(cudaFuncSetAttribute(gemm_tcgen05_swapped_kernel<STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = true;
   }
-  cudaLaunchConfig_t cfg;
-  memset(&cfg, 0, sizeof(cfg));
+  cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(ceil_div(prm.N, 128), 1, prm.splits);
   cfg.blockDim = dim3(GEMM_THREADS, 1, 1);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = 1; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = prm.splits;
   cfg.attrs = attr; cfg.numAttrs = 1;
+  if (pdl_enabled()) {
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.numAttrs = 2;
+  }
   CUDA_TRY(cudaLaunchKernelEx(&cfg, gemm_tcgen05_swapped_kernel<STAGES>, prm));
   ++g_launch_count;
+  return 0;
+}
+
+// max co-resident clusters of the pair kernel for a K split of S (cluster = 2*S CTAs); 0 if the query fails
+template <int STAGES>
+static int pair_max_clusters(int S, int smem) {
+  static int cache[5] = {-1, -1, -1, -1, -1};
+  if (cache[S] >= 0) return cache[S];
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(2 * 64, 1, S);
+  cfg.blockDim = dim3(GEMM_THREADS, 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = S;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  int n = 0;
+  if (cudaOccupancyMaxActiveClusters(&n, gemm_tcgen05_swapped_pair_kernel<STAGES>, &cfg) != cudaSuccess) {
+    cudaGetLastError();
+    n = 0;
+  }
+  cache[S] = n;
+  return n;
+}
+
+template <int STAGES>
+static int launch_swapped_pair(cudaStream_t stream, GemmParams& prm, const GemmSeg* segs, int forced_S) {
+  constexpr int smem = 1024 + STAGES * (128 + 128) * BK * 2 + 256;
+  static bool configured = false;
+  if (!configured) {
+    CUDA_TRY(cudaFuncSetAttribute(gemm_tcgen05_swapped_pair_kernel<STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured = true;
+  }
+  int total_kb = 0;
+  for (int s = 0; s < prm.nseg; ++s) total_kb += prm.kblocks[s];
+  const int pairs = ceil_div(prm.N, 256);
+  // the largest K split whose clusters are all co-resident (one wave) and that leaves every CTA >= 4 k-blocks
+  int S = 1;
+  if (forced_S > 0) S = forced_S;
+  else
+    for (int c = 4; c > 1; --c)
+      if (total_kb >= 4 * c && pairs <= pair_max_clusters<STAGES>(c, smem)) { S = c; break; }
+  while (S > 1 && total_kb < S) --S;
+  prm.kb_per_split = ceil_div(total_kb, S);
+  S = ceil_div(total_kb, prm.kb_per_split);             // no empty trailing split
+  prm.splits = S;
+  for (int s = 0; s < prm.nseg; ++s) {
+    TRY(encode_tmap(&prm.ta[s], segs[s].A, prm.M, segs[s].K, segs[s].lda, 128));
+    TRY(encode_tmap(&prm.tb[s], segs[s].B, prm.N, segs[s].K, segs[s].ldb, 128));
+  }
+  const GemmEpi& e = prm.epi;
+  static const bool no_tma_store = [] { const char* v = getenv("SSCVAE_GEMM_NO_TMA_STORE"); return v && v[0] == '1'; }();
+  prm.tma_store = !no_tma_store && e.C32 && !e.C16 && !e.act && !e.dtanh && !e.accumulate && !e.add1 && !e.add2 &&
+                  aligned16(e.C32) && (e.ldc32 % 4) == 0 && (prm.N % 4) == 0;
+  // The weights of the skinny GEMMs (76 MB per timestep) are streamed once per launch; marking them evict_first leaves
+  // L2 to the 52 MB of region features + projections the attention kernels re-read every step (measured: step
+  // 8.21 -> 8.08 ms, attention_fwd 25.1 -> 23.1 us). SSCVAE_W_EVICT_FIRST=0 turns the hint off.
+  static const bool w_evict_first = [] { const char* v = getenv("SSCVAE_W_EVICT_FIRST"); return !(v && v[0] == '0'); }();
+  prm.w_policy = w_evict_first ? 1 : 0;
+  prm.fuse_lstm = 0;
+  prm.lstm_tma = 0;
+  if (e.lstm) {
+    prm.fuse_lstm = 1;
+    prm.lstm = *e.lstm;
+    prm.tma_store = 0;
+    // outputs through TMA stores when every destination is 16-byte tileable (true for all training / decode buffers);
+    // the bf16 h destinations must have room for round_up(H, 32) columns (their K padding: Hp = round_up(H, 64))
+    const LstmFwdArgs& l = *e.lstm;
+    const int H = l.H, Hq = round_up(H, 32);
+    static const bool no_lstm_tma = [] { const char* v = getenv("SSCVAE_LSTM_TMA"); return v && v[0] == '0'; }();
+    bool ok = !no_lstm_tma && (H % 4) == 0 && aligned16(l.c_out) && (!l.gates_out || aligned16(l.gates_out));
+    ok = ok && (!l.h1_dst || (aligned16(l.h1_dst) && (l.ld_h1 % 8) == 0 && l.ld_h1 >= Hq));
+    ok = ok && (!l.h2_dst || (aligned16(l.h2_dst) && (l.ld_h2 % 8) == 0 && l.ld_h2 >= Hq));
+    if (ok) {
+      prm.lstm_tma = 1;
+      if (l.gates_out)
+        for (int k = 0; k < 4; ++k) TRY(encode_tmap_c32(&prm.tl[k], l.gates_out + (size_t)k * H, l.R, H, 4 * H, false));
+      TRY(encode_tmap_c32(&prm.tl[4], l.c_out, l.R, H, H, false));
+      if (l.h1_dst) TRY(encode_tmap_h16(&prm.tl[5], l.h1_dst, l.R, Hq, l.ld_h1));
+      if (l.h2_dst) TRY(encode_tmap_h16(&prm.tl[6], l.h2_dst, l.R, Hq, l.ld_h2));
+    }
+  }
+  if (prm.tma_store) TRY(encode_tmap_c32(&prm.tc, e.C32, prm.M, prm.N, e.ldc32, false));
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(2 * pairs, 1, S);
+  cfg.blockDim = dim3(GEMM_THREADS, 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = S;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  if (pdl_enabled()) {
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.numAttrs = 2;
+  }
+  static const bool dbg = [] { const char* v = getenv("SSCVAE_GEMM_DBG"); return v && v[0] == '1'; }();
+  static long long* dbg_buf = nullptr;
+  if (dbg) {                                            // bring-up aid: phase stamps of a few CTAs, printed per launch
+    if (!dbg_buf) CUDA_TRY(cudaMalloc(&dbg_buf, 16 * 8 * 1024));
+    CUDA_TRY(cudaMemsetAsync(dbg_buf, 0, 16 * 8 * 1024, stream));
+    prm.dbg = dbg_buf;
+  }
+  CUDA_TRY(cudaLaunchKernelEx(&cfg, gemm_tcgen05_swapped_pair_kernel<STAGES>, prm));
+  ++g_launch_count;
+  if (dbg) {
+    static int printed = 0;
+    CUDA_TRY(cudaStreamSynchronize(stream));
+    std::vector<long long> h(16 * 2 * pairs * S);
+    CUDA_TRY(cudaMemcpy(h.data(), dbg_buf, h.size() * 8, cudaMemcpyDeviceToHost));
+    if (printed++ < 400) {
+      for (int cta : {0, 2 * pairs * S - 2}) {
+        fprintf(stderr, "[pairdbg] M=%d N=%d kb=%d S=%d fuse=%d tma=%d cta=%d:", prm.M, prm.N, total_kb, S, prm.fuse_lstm,
+                prm.fuse_lstm ? prm.lstm_tma : prm.tma_store, cta);
+        for (int i = 1; i < 15; ++i) fprintf(stderr, " %lld", h[cta * 16 + i] ? h[cta * 16 + i] - h[cta * 16] : -1);
+        fprintf(stderr, "\n");
+      }
+    }
+  }
   return 0;
 }
 
@@ -1047,16 +1529,48 @@ int gemm_suggest_splits(int M, int N, int K_total) {
   return s;
 }
 
+static bool pair_kernel_disabled() {
+  static const bool off = [] {
+    const char* a = getenv("SSCVAE_GEMM_PAIR");
+    const char* b = getenv("SSCVAE_GEMM_NO_SWAPPED");
+    const char* c = getenv("SSCVAE_GEMM_DEBUG_SIMT");
+    return (a && a[0] == '0') || (b && b[0] == '1') || (c && c[0] == '1');
+  }();
+  return off || getenv("SSCVAE_GEMM_FORCE") != nullptr;
+}
+
 int gemm_bf16_tn(cudaStream_t stream, int M, int N, int nseg, const GemmSeg* segs, const GemmEpi& epi) {
   REQUIRE(M > 0 && N > 0 && nseg >= 1 && nseg <= MAX_SEG, "gemm: bad shape M=%d N=%d nseg=%d", M, N, nseg);
   REQUIRE(epi.C32 || epi.C16, "gemm: no output");
+  if (epi.lstm) {
+    REQUIRE(N == lstm_gate_rows(epi.lstm->H) && epi.lstm->R == M, "gemm: fused LSTM shape mismatch (N=%d H=%d M=%d R=%d)", N,
+            epi.lstm->H, M, epi.lstm->R);
+    REQUIRE(epi.C32 && epi.ldc32 >= N && !epi.C16 && !epi.bias && !epi.add1 && !epi.add2 && !epi.act && !epi.dtanh && !epi.accumulate,
+            "gemm: fused LSTM takes a plain fp32 accumulator buffer");
+    // SSCVAE_LSTM_FUSE: 0 (default) = cell kernel behind the GEMM, 1 = fuse cells without per-row addend matrices
+    // (encoder / decoder LSTM), 2 = fuse every cell. Measured on B200 (bench27, ms per training step): 0: 7.45,
+    // 1: 7.49, 2: 7.61. Phase stamps (SSCVAE_GEMM_DBG=1) show why: the four epilogue warps run one per SM
+    // sub-partition with nothing to hide latency behind - ~170 cycles per global load, ~400 cycles per cell even with
+    // branch-free math - while the separate cell kernel is one wave of 57 600 threads that takes 4 us. The fused
+    // form stays as an opt-in for shapes where launches, not the epilogue, dominate.
+    static const int fuse_mode = [] { const char* e = getenv("SSCVAE_LSTM_FUSE"); return e ? atoi(e) : 0; }();
+    const bool heavy = epi.lstm->add1 || epi.lstm->add2;
+    if (M > 256 || fuse_mode == 0 || (fuse_mode == 1 && heavy) || pair_kernel_disabled()) {   // unfused: cell kernel behind
+      GemmEpi e2 = epi;
+      e2.lstm = nullptr;
+      TRY(gemm_bf16_tn(stream, M, N, nseg, segs, e2));
+      LstmFwdArgs l = *epi.lstm;
+      l.acc = epi.C32; l.ld_acc = epi.ldc32; l.perm = 1;
+      return lstm_forward(stream, l);
+    }
+  }
   double ksum = 0;
   for (int i = 0; i < nseg; ++i) ksum += segs[i].K;
   // instrumentation class: the skinny long-K GEMMs of the recurrence (the dominant kernel of a training step) are
   // reported on their own as "gemm.recurrent"
   int kb_all = 0;
   for (int i = 0; i < nseg; ++i) kb_all += ceil_div(segs[i].K, BK);
-  const bool recurrent = M <= 256 && N >= 1024 && kb_all >= 48;
+  const bool recurrent = M <= 256 && N >= 1024 && kb_all >= 16;
   PROF_SCOPE(stream, recurrent ? "gemm.recurrent" : epi.tag, 2.0 * M * N * ksum,
              2.0 * (M + N) * ksum + (epi.C32 ? 4.0 : 2.0) * M * N);
   static const bool simt = [] { const char* e = getenv("SSCVAE_GEMM_DEBUG_SIMT"); return e && e[0] == '1'; }();
@@ -1106,6 +1620,16 @@ int gemm_bf16_tn(cudaStream_t stream, int M, int N, int nseg, const GemmSeg* seg
   // 256x4160x3648: 16.0 vs 19.4; 256x1920x3648: 13.9 vs 18.8; short K (256x3600x1920: 12.6 vs 12.4) and narrow N
   // (256x768x960: 10.2 vs 7.9) stay on the plain kernel.
   const bool skinny = M <= 256 && N >= 1024 && total_kb >= 48;
+  // CTA-pair form (see the kernel): every skinny GEMM with enough weight rows, short K included (the attention-LSTM
+  // recurrence, K = 2Hp). SSCVAE_GEMM_PAIR=0 falls back to the single-CTA swapped kernel; epi.splits < 0 forces the
+  // pair kernel with K split -epi.splits (tools/gemm_bench.py, tests).
+  static const bool no_pair = [] { const char* e = getenv("SSCVAE_GEMM_PAIR"); return e && e[0] == '0'; }();
+  const bool pair_shape = M <= 256 && N >= 1024 && total_kb >= 16;
+  if ((epi.lstm || epi.splits < 0 || (epi.splits == 0 && pair_shape && !no_pair && !no_swapped)) && M <= 256 &&
+      !getenv("SSCVAE_GEMM_FORCE")) {
+    REQUIRE(epi.splits >= -4, "gemm: pair split count %d (1..4)", -epi.splits);
+    return launch_swapped_pair<6>(stream, prm, segs, epi.splits < 0 ? -epi.splits : 0);
+  }
   if ((epi.splits > 0 || (skinny && !no_swapped)) && M <= 256 && !getenv("SSCVAE_GEMM_FORCE")) {
     int S = epi.splits > 0 ? epi.splits : gemm_suggest_splits(M, N, total_kb * BK);
     REQUIRE(S == 1 || S == 2 || S == 4, "gemm: split count %d (1, 2 or 4)", S);

@@ -31,7 +31,13 @@ struct LstmFwdArgs {
   float* gates_out;                    // optional (R,4H) activated gates, saved for BPTT
   bf16* h1_dst; int ld_h1;             // bf16 h -> up to two operand buffers
   bf16* h2_dst; int ld_h2;
+  // 1: the columns of the GEMM outputs `acc`, `add1`, `add2` are in the gate-interleaved order of the packed forward LSTM weights (lstm_gate_row): tile of
+  // 128 columns = 32 hidden units x 4 gates, so that one GEMM CTA owns all four gates of its units
+  int perm;
 };
+// packed row / GEMM output column of gate k (0..3 = i,f,g,o) of hidden unit j
+__host__ __device__ __forceinline__ int lstm_gate_row(int k, int j) { return (j >> 5) * 128 + k * 32 + (j & 31); }
+static inline int lstm_gate_rows(int H) { return ((H + 31) / 32) * 128; }
 int lstm_forward(cudaStream_t s, const LstmFwdArgs& a);
 
 struct LstmBwdArgs {
@@ -103,6 +109,7 @@ int pack_block(cudaStream_t s, bf16* dst, int ld_dst, int transposed, const floa
 struct PackJob {
   const float* src; const float* src2; bf16* dst;
   int ld_src, ld_src2, ld_dst, rows, cols, transposed;
+  int gate_H;                          // > 0: rows are (gate k, unit j) = r / gate_H, r % gate_H and go to row lstm_gate_row(k, j)
   int tile0, tiles_x;                  // filled by pack_blocks: first tile index, tiles along the columns
 };
 constexpr int kMaxPackJobs = 40;
@@ -110,7 +117,7 @@ struct PackJobList {
   PackJob job[kMaxPackJobs];
   int n = 0;
   int add(bf16* dst, int ld_dst, int transposed, const float* src, int ld_src, int rows, int cols, const float* src2,
-          int ld_src2);
+          int ld_src2, int gate_H = 0);
 };
 int pack_blocks(cudaStream_t s, PackJobList& jobs);
 int vec_add_f32(cudaStream_t s, const float* a, const float* b, float* out, int n);
@@ -132,6 +139,7 @@ struct AttnArgs {
   const bf16* feats;                   // (images, N, Fp)
   const float* mask;                   // (images, N)
   const float* w_a;                    // (A)
+  int l2_policy;                       // set by the launchers (SSCVAE_ATT_POLICY): 0 none, 1 evict_first, 2 evict_last
 };
 // smx (R,N): softmax(u*m) before the mask renormalisation, saved for the backward (null in decode)
 int attention_forward(cudaStream_t s, const AttnArgs& a, float* alpha /*(R,N)*/, float* smx /*(R,N) or null*/, bf16* xhat,

@@ -113,6 +113,8 @@ int embed_gather_rows(cudaStream_t s, const int* tokens, int R, const bf16* embb
 __global__ void lstm_fwd_kernel(LstmFwdArgs a) {
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   const int r = blockIdx.y;
+  pdl_wait();
+  pdl_launch_dependents();
   if (j >= a.H) return;
   const int H = a.H;
   const int r2 = a.rowmap ? a.rowmap[r] : r;
@@ -120,9 +122,10 @@ __global__ void lstm_fwd_kernel(LstmFwdArgs a) {
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
     const int n = k * H + j;
-    float v = a.acc[(size_t)r * a.ld_acc + n];
-    if (a.add1) v += a.add1[(size_t)r * a.ld1 + n];
-    if (a.add2) v += a.add2[(size_t)r2 * a.ld2 + n];
+    const int na = a.perm ? lstm_gate_row(k, j) : n;       // GEMM outputs (acc, add1, add2) share the packed row order
+    float v = a.acc[(size_t)r * a.ld_acc + na];
+    if (a.add1) v += a.add1[(size_t)r * a.ld1 + na];
+    if (a.add2) v += a.add2[(size_t)r2 * a.ld2 + na];
     if (a.bias) v += a.bias[n];
     if (a.sent) v += a.sent[r2] * a.scol[n];
     g[k] = v;
@@ -141,10 +144,73 @@ __global__ void lstm_fwd_kernel(LstmFwdArgs a) {
   if (a.h2_dst) a.h2_dst[(size_t)r * a.ld_h2 + j] = hb;
 }
 
+// 4 hidden units per thread, 16-byte accesses (H % 4 == 0 and 16-byte aligned rows: every training / decode buffer)
+__device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ void fma4(float4& v, float s, const float4& w) { v.x = fmaf(s, w.x, v.x); v.y = fmaf(s, w.y, v.y); v.z = fmaf(s, w.z, v.z); v.w = fmaf(s, w.w, v.w); }
+__device__ __forceinline__ void add4(float4& v, const float4& w) { v.x += w.x; v.y += w.y; v.z += w.z; v.w += w.w; }
+__device__ __forceinline__ void st_bf16x4(bf16* p, float a, float b, float c, float d) {
+  __nv_bfloat162 lo = __floats2bfloat162_rn(a, b), hi = __floats2bfloat162_rn(c, d);
+  uint2 o;
+  o.x = *reinterpret_cast<uint32_t*>(&lo);
+  o.y = *reinterpret_cast<uint32_t*>(&hi);
+  *reinterpret_cast<uint2*>(p) = o;
+}
+
+__global__ void __launch_bounds__(128) lstm_fwd_v4_kernel(LstmFwdArgs a) {
+  const int H = a.H, H4 = H >> 2;
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  pdl_wait();
+  pdl_launch_dependents();
+  if (idx >= a.R * H4) return;
+  const int r = idx / H4, j = (idx - r * H4) * 4;
+  const int r2 = a.rowmap ? a.rowmap[r] : r;
+  const float sv = a.sent ? a.sent[r2] : 0.f;
+  float4 g[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int n = k * H + j;
+    const int na = a.perm ? lstm_gate_row(k, j) : n;       // GEMM outputs (acc, add1, add2) share the packed row order
+    float4 v = ld4(a.acc + (size_t)r * a.ld_acc + na);
+    if (a.add1) add4(v, ld4(a.add1 + (size_t)r * a.ld1 + na));
+    if (a.add2) add4(v, ld4(a.add2 + (size_t)r2 * a.ld2 + na));
+    if (a.bias) add4(v, ld4(a.bias + n));
+    if (a.sent) fma4(v, sv, ld4(a.scol + n));
+    g[k] = v;
+  }
+  const float4 cp = a.c_prev ? ld4(a.c_prev + (size_t)r * H + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+  float4 gi, gf, gg, go, c, h;
+#define LSTM_LANE(X)                                                                       \
+  gi.X = sigmoidf_(g[0].X); gf.X = sigmoidf_(g[1].X); gg.X = tanhf(g[2].X); go.X = sigmoidf_(g[3].X); \
+  c.X = gf.X * cp.X + gi.X * gg.X; h.X = go.X * tanhf(c.X);
+  LSTM_LANE(x) LSTM_LANE(y) LSTM_LANE(z) LSTM_LANE(w)
+#undef LSTM_LANE
+  *reinterpret_cast<float4*>(a.c_out + (size_t)r * H + j) = c;
+  if (a.gates_out) {
+    float* o = a.gates_out + (size_t)r * 4 * H + j;
+    *reinterpret_cast<float4*>(o) = gi;
+    *reinterpret_cast<float4*>(o + H) = gf;
+    *reinterpret_cast<float4*>(o + 2 * H) = gg;
+    *reinterpret_cast<float4*>(o + 3 * H) = go;
+  }
+  if (a.h1_dst) st_bf16x4(a.h1_dst + (size_t)r * a.ld_h1 + j, h.x, h.y, h.z, h.w);
+  if (a.h2_dst) st_bf16x4(a.h2_dst + (size_t)r * a.ld_h2 + j, h.x, h.y, h.z, h.w);
+}
+
+static inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+static inline bool al8(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 7) == 0; }
+
 int lstm_forward(cudaStream_t s, const LstmFwdArgs& a) {
   PROF_SCOPE(s, "lstm_fwd", 0, (double)a.R*a.H*(4*4.0*2+4.0*2+2.0*2));
-  dim3 grid(ceil_div(a.H, 128), a.R);
-  lstm_fwd_kernel<<<grid, 128, 0, s>>>(a);
+  const bool v4 = (a.H % 4) == 0 && al16(a.acc) && (a.ld_acc % 4) == 0 && (!a.add1 || (al16(a.add1) && (a.ld1 % 4) == 0)) &&
+                  (!a.add2 || (al16(a.add2) && (a.ld2 % 4) == 0)) && (!a.bias || al16(a.bias)) && (!a.sent || al16(a.scol)) &&
+                  (!a.c_prev || al16(a.c_prev)) && al16(a.c_out) && (!a.gates_out || al16(a.gates_out)) &&
+                  (!a.h1_dst || (al8(a.h1_dst) && (a.ld_h1 % 4) == 0)) && (!a.h2_dst || (al8(a.h2_dst) && (a.ld_h2 % 4) == 0));
+  if (v4) {
+    CUDA_TRY(launch_pdl(lstm_fwd_v4_kernel, dim3(ceil_div(a.R * (a.H / 4), 128)), dim3(128), 0, s, a));
+  } else {
+    dim3 grid(ceil_div(a.H, 128), a.R);
+    CUDA_TRY(launch_pdl(lstm_fwd_kernel, grid, dim3(128), 0, s, a));
+  }
   LAUNCHED();
   return 0;
 }
@@ -153,6 +219,8 @@ __global__ void lstm_bwd_kernel(LstmBwdArgs a) {
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   const int r = blockIdx.y;
   const int H = a.H;
+  pdl_wait();
+  pdl_launch_dependents();
   if (j >= H) return;
   float dh = 0.f;
 #pragma unroll
@@ -174,10 +242,54 @@ __global__ void lstm_bwd_kernel(LstmBwdArgs a) {
   a.dc_prev[(size_t)r * H + j] = dc * f;
 }
 
+__global__ void __launch_bounds__(128) lstm_bwd_v4_kernel(LstmBwdArgs a) {
+  const int H = a.H, H4 = H >> 2;
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  pdl_wait();
+  pdl_launch_dependents();
+  if (idx >= a.R * H4) return;
+  const int r = idx / H4, j = (idx - r * H4) * 4;
+  float4 dh = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+  for (int k = 0; k < 3; ++k)
+    if (a.dh[k]) add4(dh, ld4(a.dh[k] + (size_t)r * a.ld_dh[k] + j));
+  const float* g = a.gates + (size_t)r * 4 * H + j;
+  const float4 gi = ld4(g), gf = ld4(g + H), gg = ld4(g + 2 * H), go = ld4(g + 3 * H);
+  const float4 c = ld4(a.c + (size_t)r * H + j);
+  const float4 cp = a.c_prev ? ld4(a.c_prev + (size_t)r * H + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+  const float4 dci = a.dc_in ? ld4(a.dc_in + (size_t)r * H + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+  float4 di, df, dg, d_o, dcp;
+#define LSTM_LANE(X)                                                                     \
+  {                                                                                      \
+    const float tc = tanhf(c.X);                                                         \
+    const float dc = dh.X * go.X * (1.f - tc * tc) + dci.X;                              \
+    di.X = dc * gg.X * gi.X * (1.f - gi.X);                                              \
+    df.X = dc * cp.X * gf.X * (1.f - gf.X);                                              \
+    dg.X = dc * gi.X * (1.f - gg.X * gg.X);                                              \
+    d_o.X = dh.X * tc * go.X * (1.f - go.X);                                             \
+    dcp.X = dc * gf.X;                                                                   \
+  }
+  LSTM_LANE(x) LSTM_LANE(y) LSTM_LANE(z) LSTM_LANE(w)
+#undef LSTM_LANE
+  bf16* o = a.dgates + (size_t)r * a.ld_dg + j;
+  st_bf16x4(o, di.x, di.y, di.z, di.w);
+  st_bf16x4(o + H, df.x, df.y, df.z, df.w);
+  st_bf16x4(o + 2 * H, dg.x, dg.y, dg.z, dg.w);
+  st_bf16x4(o + 3 * H, d_o.x, d_o.y, d_o.z, d_o.w);
+  *reinterpret_cast<float4*>(a.dc_prev + (size_t)r * H + j) = dcp;
+}
+
 int lstm_backward(cudaStream_t s, const LstmBwdArgs& a) {
   PROF_SCOPE(s, "lstm_bwd", 0, (double)a.R*a.H*(4*4.0+4*2.0+4.0*5));
-  dim3 grid(ceil_div(a.H, 128), a.R);
-  lstm_bwd_kernel<<<grid, 128, 0, s>>>(a);
+  bool v4 = (a.H % 4) == 0 && al16(a.gates) && al16(a.c) && (!a.c_prev || al16(a.c_prev)) && (!a.dc_in || al16(a.dc_in)) &&
+            al16(a.dc_prev) && al8(a.dgates) && (a.ld_dg % 4) == 0;
+  for (int k = 0; k < 3; ++k) v4 = v4 && (!a.dh[k] || (al16(a.dh[k]) && (a.ld_dh[k] % 4) == 0));
+  if (v4) {
+    CUDA_TRY(launch_pdl(lstm_bwd_v4_kernel, dim3(ceil_div(a.R * (a.H / 4), 128)), dim3(128), 0, s, a));
+  } else {
+    dim3 grid(ceil_div(a.H, 128), a.R);
+    CUDA_TRY(launch_pdl(lstm_bwd_kernel, grid, dim3(128), 0, s, a));
+  }
   LAUNCHED();
   return 0;
 }
@@ -199,6 +311,8 @@ __global__ void latent_fwd_train_kernel(LatentArgs a, const float* __restrict__ 
   __shared__ float red[32];
   const int r = blockIdx.x;
   const int Z = a.Z;
+  pdl_wait();
+  pdl_launch_dependents();
   const float pm = a.prior_mean_row ? a.prior_mean_row[a.rowmap ? a.rowmap[r] : r] : 0.f;
   const float log_pv = logf(a.prior_var);
   float part = 0.f;
@@ -234,8 +348,8 @@ int latent_forward_train(cudaStream_t s, const LatentArgs& a, const float* ml, i
                          float* logvar_out, float* eps_out, bf16* zb, int ld_z, float* kl_out) {
   PROF_SCOPE(s, "latent_fwd", 0, (double)a.R*a.Z*24.0);
   const int threads = min(256, round_up(a.Zp, 32));
-  latent_fwd_train_kernel<<<a.R, threads, 0, s>>>(a, ml, ld_ml, bias_ml, eps_in, seed_dev, step, mean_out, logvar_out,
-                                                 eps_out, zb, ld_z, kl_out);
+  CUDA_TRY(launch_pdl(latent_fwd_train_kernel, dim3(a.R), dim3(threads), 0, s, a, ml, ld_ml, bias_ml, eps_in, seed_dev, step,
+                      mean_out, logvar_out, eps_out, zb, ld_z, kl_out));
   LAUNCHED();
   return 0;
 }
@@ -244,6 +358,8 @@ __global__ void latent_fwd_eval_kernel(LatentArgs a, const float* __restrict__ e
                                        const unsigned long long* __restrict__ seed_dev, unsigned long long step, bf16* __restrict__ zb,
                                        int ld_z) {
   const int r = blockIdx.x;
+  pdl_wait();
+  pdl_launch_dependents();
   const float pm = a.prior_mean_row ? a.prior_mean_row[a.rowmap ? a.rowmap[r] : r] : 0.f;
   const float sd = sqrtf(a.prior_var);
   for (int z = threadIdx.x; z < a.Zp; z += blockDim.x) {
@@ -260,7 +376,7 @@ int latent_forward_eval(cudaStream_t s, const LatentArgs& a, const float* eps_in
                         const unsigned long long* seed_dev, unsigned long long step, bf16* zb, int ld_z) {
   PROF_SCOPE(s, "latent_fwd", 0, (double)a.R*a.Z*6.0);
   const int threads = min(256, round_up(a.Zp, 32));
-  latent_fwd_eval_kernel<<<a.R, threads, 0, s>>>(a, eps_in, eps_row_stride, seed_dev, step, zb, ld_z);
+  CUDA_TRY(launch_pdl(latent_fwd_eval_kernel, dim3(a.R), dim3(threads), 0, s, a, eps_in, eps_row_stride, seed_dev, step, zb, ld_z));
   LAUNCHED();
   return 0;
 }
@@ -271,6 +387,8 @@ __global__ void latent_bwd_kernel(LatentArgs a, const float* __restrict__ dz, in
                                   bf16* __restrict__ dml, int ld_dml) {
   const int r = blockIdx.x;
   const int Z = a.Z;
+  pdl_wait();
+  pdl_launch_dependents();
   const float pm = a.prior_mean_row ? a.prior_mean_row[a.rowmap ? a.rowmap[r] : r] : 0.f;
   const float w = gkld[r] * tmask_t[r];
   const float inv_pv = 1.0f / (a.prior_var + 0.00001f);
@@ -296,8 +414,8 @@ __global__ void latent_bwd_kernel(LatentArgs a, const float* __restrict__ dz, in
 int latent_backward(cudaStream_t s, const LatentArgs& a, const float* dz, int ld_dz, const float* eps, const float* mean,
                     const float* logvar, const float* gkld, const float* tmask_t, bf16* dml, int ld_dml) {
   PROF_SCOPE(s, "latent_bwd", 0, (double)a.R*a.Z*24.0);
-  latent_bwd_kernel<<<a.R, min(256, round_up(ld_dml, 32)), 0, s>>>(a, dz, ld_dz, eps, mean, logvar, gkld, tmask_t, dml,
-                                                                 ld_dml);
+  CUDA_TRY(launch_pdl(latent_bwd_kernel, dim3(a.R), dim3(min(256, round_up(ld_dml, 32))), 0, s, a, dz, ld_dz, eps, mean, logvar,
+                      gkld, tmask_t, dml, ld_dml));
   LAUNCHED();
   return 0;
 }
@@ -681,11 +799,12 @@ int sum_partials_f32(cudaStream_t s, float* dst, int ld_dst, const float* parts,
 
 // ---- batched weight packing: one launch for every block; a CTA converts one 64 x 64 tile ------------------
 int PackJobList::add(bf16* dst, int ld_dst, int transposed, const float* src, int ld_src, int rows, int cols,
-                     const float* src2, int ld_src2) {
+                     const float* src2, int ld_src2, int gate_H) {
   REQUIRE(n < kMaxPackJobs, "pack job list full");
+  REQUIRE(gate_H == 0 || (!transposed && rows == 4 * gate_H), "pack: gate interleaving needs a (4H, cols) row-major block");
   PackJob& j = job[n++];
   j.src = src; j.src2 = src2; j.dst = dst; j.ld_src = ld_src; j.ld_src2 = ld_src2; j.ld_dst = ld_dst;
-  j.rows = rows; j.cols = cols; j.transposed = transposed; j.tile0 = 0; j.tiles_x = 0;
+  j.rows = rows; j.cols = cols; j.transposed = transposed; j.gate_H = gate_H; j.tile0 = 0; j.tiles_x = 0;
   return 0;
 }
 
@@ -705,7 +824,8 @@ __global__ void __launch_bounds__(256) pack_blocks_kernel(const __grid_constant_
       if (r < j.rows && c < j.cols) {
         float v = j.src[(size_t)r * j.ld_src + c];
         if (j.src2) v += j.src2[(size_t)r * j.ld_src2 + c];
-        j.dst[(size_t)r * j.ld_dst + c] = __float2bfloat16_rn(v);
+        const int rd = j.gate_H ? lstm_gate_row(r / j.gate_H, r % j.gate_H) : r;
+        j.dst[(size_t)rd * j.ld_dst + c] = __float2bfloat16_rn(v);
       }
     }
     return;

@@ -84,3 +84,29 @@ def test_swapped_cluster_splitk_kernel(M, N, K, splits):
         ref = A.float() @ B.float().t() + bias
         assert (Cm[:, :N] - ref).abs().max().item() <= 2e-3 * (K ** 0.5)
         assert (Cm[:, N:] == -5.0).all()
+
+
+@pytest.mark.parametrize("splits", [1, 2, 3, 4])
+@pytest.mark.parametrize("M,N,K", [(256, 3600, 1920), (77, 1300, 4928), (256, 300, 960), (8, 4160, 3648), (129, 256, 512),
+                                   (256, 7200, 3968)])
+def test_swapped_pair_kernel(M, N, K, splits):
+    """The CTA-pair form of the swapped-operand kernel (tcgen05.mma.cta_group::2, cluster (2,1,S), DSMEM reduce-scatter),
+    forced with a negative split count; ragged weight rows (second CTA of the last pair fully out of range), batch rows
+    below one half tile, TMA-store and staged epilogues give the same bits."""
+    g = torch.Generator(device="cuda").manual_seed(M * 3 + N + K + splits)
+    A = torch.randn(M, K, device="cuda", generator=g).bfloat16()
+    B = torch.randn(N, K, device="cuda", generator=g).bfloat16()
+    bias = torch.randn(N, device="cuda", generator=g)
+    s = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    ref = A.float() @ B.float().t() + bias
+    outs = []
+    for ldc in (N + 1, N + 4):
+        Cm = torch.full((M, ldc), -5.0, device="cuda")
+        _lib.check(_lib.lib().sscvae_test_gemm_splitk(_lib.ptr(A), K, _lib.ptr(B), K, M, N, K, _lib.ptr(Cm), ldc, -splits,
+                                                      _lib.ptr(bias), s))
+        torch.cuda.synchronize()
+        assert (Cm[:, :N] - ref).abs().max().item() <= 2e-3 * (K ** 0.5)
+        assert (Cm[:, N:] == -5.0).all()
+        outs.append(Cm[:, :N].clone())
+    if N % 4 == 0:
+        assert torch.equal(outs[0], outs[1])

@@ -89,11 +89,11 @@ def main():
             def fn():
                 st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
                 _lib.check(L.sscvae_test_gemm(_lib.ptr(A), K, _lib.ptr(B), K, M, N, K, _lib.ptr(Cm), N, None, 0, 0, st))
-            if cfg is not None and cfg.startswith("sk"):
+            if cfg is not None and (cfg.startswith("sk") or cfg.startswith("pk")):
                 if M > 256 or N < 256:
                     continue
                 os.environ.pop("SSCVAE_GEMM_FORCE", None)
-                S = int(cfg[2:])
+                S = int(cfg[2:]) * (-1 if cfg.startswith("pk") else 1)      # pkN: CTA-pair kernel, K split N
 
                 def fn():
                     st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
