@@ -195,6 +195,14 @@ def decode_legs(sscvae, vocab, train_model, dev, world, max_over_ranks, barrier)
     out["sampling_greedy"] = {"value": n_img * n_samples * world / (ms / 1e3), "unit": "captions/s",
                               "images_per_gpu": n_img, "samples_per_image": n_samples, "ms_per_call": ms / n_samples,
                               "config": "BASELINE configs[3]: 100 latent samples per image, greedy decode, max length 20"}
+    # the same workload through the batched entry point (UpDownCaptioner.sample -> sscvae_decode_samples): the
+    # 100 sequences of an image are rows of one batch sharing its region features; 64 images x 100 samples per call
+    n_img_b, calls = 64, 3
+    fb, sb = feats[:n_img_b].contiguous(), sent[:n_img_b].contiguous()
+    ms = timed(lambda: m1.sample(fb, sentiment=sb, n_samples=n_samples)["predictions"], calls, 2)
+    out["sampling_greedy_batched"] = {"value": n_img_b * n_samples * calls * world / (ms / 1e3), "unit": "captions/s",
+                                      "images_per_gpu": n_img_b, "samples_per_image": n_samples, "ms_per_call": ms / calls,
+                                      "config": "BASELINE configs[3] in one call per 64 images: rows = images x 100 samples"}
     del m1
     # (b) CBS beam 5, 3 constraints -> 8 states
     n_img, calls = 64, 5

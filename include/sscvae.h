@@ -187,6 +187,21 @@ int sscvae_decode(SscvaeHandle* h, int batch, int num_boxes, int states, int bea
                   int32_t* n_steps,                   /* out device int32: valid leading steps */
                   void* stream);
 
+/* ---- diverse sampling: replaces the reference's loop `for k in range(N_Z_SAMPLES): model(image_features, ...)`
+ * (var_updown/scripts/inference.py:138-167) over the eval branch with beam_size 1: every image is decoded `samples`
+ * times with independent latent draws in ONE call. Row r = b*samples + j; rows of one image share its region
+ * features, so the per-step GEMMs run with batch*samples rows. eps: (max_steps, batch*samples, Z) or NULL -> Philox. */
+size_t sscvae_decode_samples_workspace_bytes(const SscvaeHandle* h, int batch, int samples, int num_boxes);
+int sscvae_decode_samples(SscvaeHandle* h, int batch, int samples, int num_boxes,
+                          const void* packed, const void* const* weights_f32,
+                          const float* image_features, const float* sentiment,
+                          const float* eps, uint64_t seed,
+                          void* workspace, size_t workspace_bytes,
+                          int64_t* predictions,               /* out (B,samples,L) */
+                          float* log_probs,                   /* out (B,samples) */
+                          int32_t* n_steps,                   /* out device int32: valid leading steps */
+                          void* stream);
+
 /* Named view into the decode workspace for tests ("tok_hist", "bp_hist", "score_hist" (L,B*S*K), "logits", ...). */
 int sscvae_decode_region(const SscvaeHandle* h, int batch, int num_boxes, int states, int beam, const char* name,
                          size_t* offset, size_t* bytes);

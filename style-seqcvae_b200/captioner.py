@@ -392,6 +392,55 @@ class UpDownCaptioner(nn.Module):
         return {"predictions": self._decode(image_features, sentiment, fsm, num_constraints)}
 
     @torch.no_grad()
+    def sample(self, image_features: torch.Tensor, sentiment=None, n_samples: int = 100):
+        """Diverse sampling: `n_samples` greedy captions per image with independent latent draws, in one call.
+
+        Replaces the reference's inference loop `for k in range(N_Z_SAMPLES): model(image_features, ...)`
+        (var_updown/scripts/inference.py:138-167) over the eval branch with beam_size 1: same per-sample computation
+        (`_decode_step` with z ~ N(prior_mean, prior_var), updown_cell.py:200-208; beam-1 search), but the
+        n_samples sequences of an image share its region features and run as rows of one batch.
+        Returns {"predictions": (B, n_samples, steps) int64, "log_probs": (B, n_samples)}."""
+        self._require_cuda(image_features)
+        if self._use_cbs:
+            raise ValueError("sample() is the unconstrained beam-1 path; use forward() for constrained beam search")
+        L = _lib.lib()
+        image_features = image_features.contiguous().float()
+        dev = image_features.device
+        B, N, F = image_features.shape
+        if F != self.image_feature_size:
+            raise ValueError(f"image_features last dim {F} != image_feature_size {self.image_feature_size}")
+        J, steps = int(n_samples), self._max_caption_length
+        if J < 1:
+            raise ValueError("n_samples must be >= 1")
+        if self.sentiment_vae == 1:
+            if sentiment is None:
+                raise ValueError("sentiment is required when sentiment_vae == 1")
+            sentiment = sentiment.to(dev).contiguous().float().view(B, 1)
+        else:
+            sentiment = None
+        eps = self._eps_override
+        if eps is not None:
+            eps = eps.to(dev).contiguous().float()
+            assert eps.shape == (steps, B * J, self.z_space)
+        nbytes = L.sscvae_decode_samples_workspace_bytes(self._handle, B, J, N)
+        key = ("decode", B, N, -J, 1, dev)
+        ws = self._ws_cache.get(key)
+        if ws is None:
+            self._ws_cache = {k: v for k, v in self._ws_cache.items() if k[0] != "decode"}
+            ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+            self._ws_cache[key] = ws
+        preds = torch.empty(B, J, steps, dtype=torch.long, device=dev)
+        scores = torch.empty(B, J, dtype=torch.float32, device=dev)
+        n_steps = torch.zeros(1, dtype=torch.int32, device=dev)
+        stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        _lib.check(L.sscvae_decode_samples(
+            self._handle, B, J, N, _lib.ptr(self._packed_weights()), _lib.ptr_array(self._weight_tensors()),
+            _lib.ptr(image_features), _lib.ptr(sentiment), _lib.ptr(eps), C.c_uint64(self._next_seed()), _lib.ptr(ws), nbytes,
+            _lib.ptr(preds), _lib.ptr(scores), _lib.ptr(n_steps), stream))
+        n = int(n_steps.item())
+        return {"predictions": preds[..., :n], "log_probs": scores}
+
+    @torch.no_grad()
     def _decode(self, image_features, sentiment, fsm, num_constraints):
         L = _lib.lib()
         dev = image_features.device

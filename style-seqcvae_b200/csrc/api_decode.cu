@@ -9,9 +9,13 @@
 
 namespace sscvae {
 
-static void plan_decode(const Dims& d, int B, int N, int S, int K, Plan& p) {
+// J > 1: "diverse sampling" (var_updown/scripts/inference.py:138-167 calls the model N_Z_SAMPLES times per image): every
+// image is decoded J times with independent latent draws in ONE call. The search sees Bv = B*J independent sequences
+// (virtual images); everything image-sized (features, projections, mean-feature gate block) stays at B and is shared
+// through the row -> image map, so the per-step GEMMs run with M = B*J rows instead of J launches with M = B.
+static void plan_decode(const Dims& d, int B, int N, int S, int K, int J, Plan& p) {
   const size_t b = sizeof(bf16), f = 4;
-  const size_t R = (size_t)B * S * K, BN = (size_t)B * N;
+  const size_t Bv = (size_t)B * J, R = Bv * S * K, BN = (size_t)B * N;
   const int Pmax = K;
   p.add("seed", 16);
   p.add("featsb", BN * d.Fp * b);
@@ -21,9 +25,10 @@ static void plan_decode(const Dims& d, int B, int N, int S, int K, Plan& p) {
   p.add("gavg", (size_t)B * d.GP * f);
   p.add("pm_row", B * f);
   p.add("sent", B * f);
-  p.add("rowmap", R * 4);
-  p.add("rowmap0", (size_t)B * 4);
-  p.add("start_tok", (size_t)B * 4);
+  p.add("rowmap", R * 4);                   // row -> image
+  p.add("rowmap_exp", R * 4);               // row -> its sequence's step-0 row
+  p.add("rowmap0", Bv * 4);                 // step-0 row -> image
+  p.add("start_tok", Bv * 4);
   p.add("XA0", R * 2 * d.Hp * b);
   p.add("XA1", R * 2 * d.Hp * b);
   p.add("c1a", R * d.H * f);
@@ -38,19 +43,20 @@ static void plan_decode(const Dims& d, int B, int N, int S, int K, Plan& p) {
   p.add("alpha", R * N * f);
   if (d.tied) p.add("ob", R * d.Ep * b);
   p.add("logits", R * d.V * f);
-  p.add("fsm_bits", (size_t)B * S * d.V * 4);
+  p.add("fsm_bits", Bv * S * d.V * 4);
   p.add("cand_val", R * S * Pmax * f);
   p.add("cand_tok", R * S * Pmax * 4);
   p.add("tok_hist", (size_t)d.L * R * 4);
   p.add("bp_hist", (size_t)d.L * R * 4);
   p.add("score_hist", (size_t)d.L * R * f);
+  p.add("best_samples", Bv * d.L * 8);                 // sscvae_decode_samples: the "best beam" copy of its predictions
 }
 
-const Plan& Handle::decode_plan(int B, int N, int S, int K) {
-  if (dp_B != B || dp_N != N || dp_S != S || dp_K != K) {
+const Plan& Handle::decode_plan(int B, int N, int S, int K, int J) {
+  if (dp_B != B || dp_N != N || dp_S != S || dp_K != K || dp_J != J) {
     dp = Plan();
-    plan_decode(d, B, N, S, K, dp);
-    dp_B = B; dp_N = N; dp_S = S; dp_K = K;
+    plan_decode(d, B, N, S, K, J, dp);
+    dp_B = B; dp_N = N; dp_S = S; dp_K = K; dp_J = J;
   }
   return dp;
 }
@@ -59,7 +65,7 @@ static inline GemmSeg seg(const bf16* A, int lda, const bf16* B, int ldb, int K)
   GemmSeg s; s.A = A; s.lda = lda; s.B = B; s.ldb = ldb; s.K = K; return s;
 }
 
-static int decode_impl(Handle* h, int B, int N, int S, int K, int P, const char* pk, const void* const* wv,
+static int decode_impl(Handle* h, int B, int J, int N, int S, int K, int P, const char* pk, const void* const* wv,
                        const float* feats, const float* sent, const uint8_t* fsm, const long long* num_constraints,
                        int min_sat, const float* eps, unsigned long long seed, char* ws, size_t ws_bytes,
                        long long* predictions, float* log_probs, long long* best, int32_t* n_steps, cudaStream_t s) {
@@ -67,7 +73,9 @@ static int decode_impl(Handle* h, int B, int N, int S, int K, int P, const char*
   REQUIRE(B > 0 && N > 0 && S >= 1 && S <= 32 && K >= 1 && K <= 8 && P >= 1 && P <= K, "bad decode shape B=%d N=%d S=%d K=%d P=%d", B, N, S, K, P);
   REQUIRE(d.cond == 0 || sent != nullptr, "sentiment is required when sentiment_vae == 1");
   REQUIRE(S == 1 || fsm != nullptr, "an FSM is required for more than one state");
-  const Plan& dp = h->decode_plan(B, N, S, K);
+  REQUIRE(J >= 1 && (J == 1 || (S == 1 && fsm == nullptr)), "samples per image > 1 needs the unconstrained search (S == 1)");
+  const Plan& dp = h->decode_plan(B, N, S, K, J);
+  const int Bv = B * J;
   if (ws_bytes < dp.total) { set_error("workspace too small: %zu < %zu", ws_bytes, dp.total); return SSCVAE_ERR_WORKSPACE; }
   REQUIRE((reinterpret_cast<uintptr_t>(ws) & 255) == 0 && (reinterpret_cast<uintptr_t>(pk) & 255) == 0,
           "workspace and packed weights must be 256-byte aligned");
@@ -79,7 +87,7 @@ static int decode_impl(Handle* h, int B, int N, int S, int K, int P, const char*
   auto Wf = [&](const char* n) { return reinterpret_cast<float*>(ws + dp.find(n)->off); };
   auto Wi = [&](const char* n) { return reinterpret_cast<int*>(ws + dp.find(n)->off); };
   auto zero = [&](const char* n) { return cudaMemsetAsync(ws + dp.find(n)->off, 0, dp.find(n)->bytes, s); };
-  const int SK = S * K, R = B * SK, GP = d.GP, H = d.H, Hp = d.Hp, Fp = d.Fp, KXe = d.Fp + d.Hp, KX = d.KX, L = d.L;
+  const int SK = S * K, R = Bv * SK, GP = d.GP, H = d.H, Hp = d.Hp, Fp = d.Fp, KXe = d.Fp + d.Hp, KX = d.KX, L = d.L;
   const unsigned long long* seed_dev = reinterpret_cast<const unsigned long long*>(ws + dp.find("seed")->off);
   (void)seed;
 
@@ -88,11 +96,12 @@ static int decode_impl(Handle* h, int B, int N, int S, int K, int P, const char*
   TRY(image_prep(s, feats, B, N, d.F, Wb("featsb"), Fp, Wf("mask"), Wb("avgb")));
   TRY(scale_rows_f32(s, d.cond ? sent : nullptr, d.mult, Wf("pm_row"), B));
   TRY(scale_rows_f32(s, d.cond ? sent : nullptr, 1.0f, Wf("sent"), B));
-  TRY(iota_div_i32(s, Wi("rowmap"), R, SK));
-  TRY(iota_div_i32(s, Wi("rowmap0"), B, 1));
-  TRY(fill_i32(s, Wi("start_tok"), d.boundary, B));                       // updown_captioner.py:326
+  TRY(iota_div_i32(s, Wi("rowmap"), R, SK * J));
+  TRY(iota_div_i32(s, Wi("rowmap_exp"), R, SK));
+  TRY(iota_div_i32(s, Wi("rowmap0"), Bv, J));
+  TRY(fill_i32(s, Wi("start_tok"), d.boundary, Bv));                       // updown_captioner.py:326
   const uint32_t* fsm_bits = nullptr;
-  if (fsm) { TRY(fsm_pack(s, fsm, B, S, d.V, reinterpret_cast<uint32_t*>(Wi("fsm_bits")))); fsm_bits = reinterpret_cast<uint32_t*>(Wi("fsm_bits")); }
+  if (fsm) { TRY(fsm_pack(s, fsm, Bv, S, d.V, reinterpret_cast<uint32_t*>(Wi("fsm_bits")))); fsm_bits = reinterpret_cast<uint32_t*>(Wi("fsm_bits")); }
   {  // once per image (the reference recomputes both every step in decode)
     GemmSeg sg = seg(Wb("featsb"), Fp, Pb("wv"), Fp, d.F);
     GemmEpi e; e.tag = "gemm.decode"; e.C16 = Wb("projb"); e.ldc16 = d.Ap;
@@ -161,17 +170,17 @@ static int decode_impl(Handle* h, int B, int N, int S, int K, int P, const char*
   };
 
   // ---- step 0: one row per image, zero states (cbs.py:127-155)
-  TRY(cell(B, Wi("start_tok"), Wi("rowmap0"), true, eps, SK, 0));
+  TRY(cell(Bv, Wi("start_tok"), Wi("rowmap0"), true, eps, SK, 0));
   {
     SearchRowsArgs a = {};
-    a.logp = Wf("logits"); a.ld = d.V; a.V = d.V; a.normalized = 0; a.fsm_bits = fsm_bits; a.R = B; a.S = S; a.K = K;
+    a.logp = Wf("logits"); a.ld = d.V; a.V = d.V; a.normalized = 0; a.fsm_bits = fsm_bits; a.R = Bv; a.S = S; a.K = K;
     a.rows_per_image = 1; a.P = K; a.end_index = d.boundary; a.neg_value = -INFINITY;
     a.cand_val = score_hist; a.cand_tok = tok_hist;
     TRY(search_rows(s, a));
   }
-  TRY(gather_rows_bf16(s, XA[1], Wi("rowmap"), R, 2 * Hp, 2 * Hp, XA[0]));
-  TRY(gather_rows_f32(s, c1[1], Wi("rowmap"), R, H, c1[0]));
-  TRY(gather_rows_f32(s, cd[1], Wi("rowmap"), R, H, cd[0]));
+  TRY(gather_rows_bf16(s, XA[1], Wi("rowmap_exp"), R, 2 * Hp, 2 * Hp, XA[0]));
+  TRY(gather_rows_f32(s, c1[1], Wi("rowmap_exp"), R, H, c1[0]));
+  TRY(gather_rows_f32(s, cd[1], Wi("rowmap_exp"), R, H, cd[0]));
   // ---- steps 1..L-1 on all R rows (cbs.py:161-250); the early exit is resolved at the end
   for (int t = 1; t < L; ++t) {
     TRY(cell(R, tok_hist + (size_t)(t - 1) * R, Wi("rowmap"), false, eps ? eps + (size_t)t * R * d.Z : nullptr, 1, t));
@@ -181,11 +190,11 @@ static int decode_impl(Handle* h, int B, int N, int S, int K, int P, const char*
     a.last_tokens = tok_hist + (size_t)(t - 1) * R; a.last_scores = score_hist + (size_t)(t - 1) * R;
     a.cand_val = Wf("cand_val"); a.cand_tok = Wi("cand_tok");
     TRY(search_rows(s, a));
-    TRY(search_merge(s, Wf("cand_val"), Wi("cand_tok"), B, S, K, P, tok_hist + (size_t)t * R, bp_hist + (size_t)t * R,
+    TRY(search_merge(s, Wf("cand_val"), Wi("cand_tok"), Bv, S, K, P, tok_hist + (size_t)t * R, bp_hist + (size_t)t * R,
                      score_hist + (size_t)t * R));
     TRY(state_gather(s, bp_hist + (size_t)t * R, R, SK, XA[1], XA[0], 2 * Hp, c1[1], c1[0], cd[1], cd[0], H));
   }
-  TRY(search_finish(s, tok_hist, bp_hist, score_hist, L, B, S, K, d.boundary, num_constraints, min_sat, predictions,
+  TRY(search_finish(s, tok_hist, bp_hist, score_hist, L, Bv, S, K, d.boundary, num_constraints, min_sat, predictions,
                     log_probs, best, n_steps));
   return 0;
 }
@@ -248,14 +257,20 @@ int sscvae_search_finish(const int32_t* tokens_hist, const int32_t* backptr_hist
 size_t sscvae_decode_workspace_bytes(const SscvaeHandle* hh, int batch, int num_boxes, int states, int beam) {
   Handle* h = const_cast<Handle*>(reinterpret_cast<const Handle*>(hh));
   if (!h || batch <= 0 || num_boxes <= 0 || states <= 0 || beam <= 0) return 0;
-  return h->decode_plan(batch, num_boxes, states, beam).total;
+  return h->decode_plan(batch, num_boxes, states, beam, 1).total;
+}
+
+size_t sscvae_decode_samples_workspace_bytes(const SscvaeHandle* hh, int batch, int samples, int num_boxes) {
+  Handle* h = const_cast<Handle*>(reinterpret_cast<const Handle*>(hh));
+  if (!h || batch <= 0 || num_boxes <= 0 || samples <= 0) return 0;
+  return h->decode_plan(batch, num_boxes, 1, 1, samples).total;
 }
 
 int sscvae_decode_region(const SscvaeHandle* hh, int batch, int num_boxes, int states, int beam, const char* name,
                          size_t* offset, size_t* bytes) {
   Handle* h = const_cast<Handle*>(reinterpret_cast<const Handle*>(hh));
   REQUIRE(h && name && offset && bytes, "NULL argument");
-  const Region* r = h->decode_plan(batch, num_boxes, states, beam).find(name);
+  const Region* r = h->decode_plan(batch, num_boxes, states, beam, 1).find(name);
   REQUIRE(r != nullptr, "unknown workspace region '%s'", name);
   *offset = r->off; *bytes = r->bytes;
   return 0;
@@ -270,7 +285,7 @@ int sscvae_decode(SscvaeHandle* hh, int batch, int num_boxes, int states, int be
   REQUIRE(h && packed && weights && image_features && workspace && predictions && log_probs && best && n_steps, "NULL argument");
   REQUIRE(batch > 0 && num_boxes > 0 && states >= 1 && beam >= 1, "bad decode shape");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  const Plan& dp = h->decode_plan(batch, num_boxes, states, beam);
+  const Plan& dp = h->decode_plan(batch, num_boxes, states, beam, 1);
   if (workspace_bytes < dp.total) { set_error("workspace too small: %zu < %zu", workspace_bytes, dp.total); return SSCVAE_ERR_WORKSPACE; }
   const unsigned long long seed_host = seed;
   CUDA_TRY(cudaMemcpyAsync(reinterpret_cast<char*>(workspace) + dp.find("seed")->off, &seed_host, sizeof(seed_host),
@@ -285,10 +300,39 @@ int sscvae_decode(SscvaeHandle* hh, int batch, int num_boxes, int states, int be
     key_add(key, q);
   for (int i = 0; i < SSCVAE_W_COUNT; ++i) key_add(key, weights[i]);
   return run_with_graph(h->dec_graphs, key, st, true, [&](cudaStream_t s) {
-    return decode_impl(h, batch, num_boxes, states, beam, per_node, reinterpret_cast<const char*>(packed), weights,
+    return decode_impl(h, batch, 1, num_boxes, states, beam, per_node, reinterpret_cast<const char*>(packed), weights,
                        image_features, sentiment, fsm, reinterpret_cast<const long long*>(num_constraints),
                        min_constraints_to_satisfy, eps, seed, reinterpret_cast<char*>(workspace), workspace_bytes,
                        reinterpret_cast<long long*>(predictions), log_probs, reinterpret_cast<long long*>(best), n_steps, s);
+  });
+}
+
+int sscvae_decode_samples(SscvaeHandle* hh, int batch, int samples, int num_boxes, const void* packed,
+                          const void* const* weights, const float* image_features, const float* sentiment, const float* eps,
+                          uint64_t seed, void* workspace, size_t workspace_bytes, int64_t* predictions, float* log_probs,
+                          int32_t* n_steps, void* stream) {
+  Handle* h = reinterpret_cast<Handle*>(hh);
+  REQUIRE(h && packed && weights && image_features && workspace && predictions && log_probs && n_steps, "NULL argument");
+  REQUIRE(batch > 0 && num_boxes > 0 && samples >= 1, "bad decode shape");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const Plan& dp = h->decode_plan(batch, num_boxes, 1, 1, samples);
+  if (workspace_bytes < dp.total) { set_error("workspace too small: %zu < %zu", workspace_bytes, dp.total); return SSCVAE_ERR_WORKSPACE; }
+  const unsigned long long seed_host = seed;
+  CUDA_TRY(cudaMemcpyAsync(reinterpret_cast<char*>(workspace) + dp.find("seed")->off, &seed_host, sizeof(seed_host),
+                           cudaMemcpyHostToDevice, st));
+  std::vector<uint64_t> key;
+  for (uint64_t v : {(uint64_t)batch, (uint64_t)num_boxes, (uint64_t)samples, (uint64_t)0x5a5a, (uint64_t)workspace_bytes})
+    key_add(key, v);
+  for (const void* q : {packed, (const void*)image_features, (const void*)sentiment, (const void*)eps, (const void*)workspace,
+                        (const void*)predictions, (const void*)log_probs, (const void*)n_steps})
+    key_add(key, q);
+  for (int i = 0; i < SSCVAE_W_COUNT; ++i) key_add(key, weights[i]);
+  char* wsb = reinterpret_cast<char*>(workspace);
+  long long* best = reinterpret_cast<long long*>(wsb + dp.find("best_samples")->off);
+  return run_with_graph(h->dec_graphs, key, st, true, [&](cudaStream_t s) {
+    return decode_impl(h, batch, samples, num_boxes, 1, 1, 1, reinterpret_cast<const char*>(packed), weights, image_features,
+                       sentiment, nullptr, nullptr, 0, eps, seed, wsb, workspace_bytes, reinterpret_cast<long long*>(predictions),
+                       log_probs, best, n_steps, s);
   });
 }
 

@@ -37,10 +37,10 @@ struct Handle {
   Dims d;
   Plan pp;                 // packed weights
   Plan tp; int tp_B = -1, tp_N = -1;   // training workspace for the last (B,N)
-  Plan dp; int dp_B = -1, dp_N = -1, dp_S = -1, dp_K = -1;   // decode workspace
+  Plan dp; int dp_B = -1, dp_N = -1, dp_S = -1, dp_K = -1, dp_J = -1;   // decode workspace
   GraphCache fwd_graphs, bwd_graphs, dec_graphs;
   const Plan& train_plan(int B, int N);
-  const Plan& decode_plan(int B, int N, int S, int K);
+  const Plan& decode_plan(int B, int N, int S, int K, int J);
 };
 
 }  // namespace sscvae

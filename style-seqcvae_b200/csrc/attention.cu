@@ -238,7 +238,7 @@ attention_fwd_kernel(AttnArgs a, AttnPlan pl, float* __restrict__ alpha, float* 
   const AttnSmem sm = carve(att_smem_raw, a, false);
   attn_prologue(sm, a, false);
   pdl_wait();                                        // the prologue overlaps the previous kernel's tail
-  pdl_launch_dependents();
+  pdl_launch_dependents(2);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int r_begin = blockIdx.x * pl.rows_per_cta;
   const int r_end = min(a.R, r_begin + pl.rows_per_cta);
@@ -395,7 +395,7 @@ attention_bwd_kernel(AttnArgs a, AttnPlan pl, const float* __restrict__ smx, con
   const AttnSmem sm = carve(att_smem_raw, a, true);
   attn_prologue(sm, a, true);
   pdl_wait();                                        // the prologue overlaps the previous kernel's tail
-  pdl_launch_dependents();
+  pdl_launch_dependents(2);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int r_begin = blockIdx.x * pl.rows_per_cta;
   const int r_end = min(a.R, r_begin + pl.rows_per_cta);

@@ -55,6 +55,7 @@ static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 // prefetch, index math) and blocks in pdl_wait() until the previous grid has completed and flushed. Rule: a kernel
 // launched through launch_pdl executes pdl_wait() before its first global-memory access (reads AND writes).
 // Both instructions are no-ops in a kernel launched without the attribute. SSCVAE_PDL=0 disables the attribute.
+// The early trigger is conditional, see pdl_launch_dependents().
 inline bool pdl_enabled() {
   static const bool on = [] { const char* e = getenv("SSCVAE_PDL"); return !(e && e[0] == '0'); }();
   return on;
@@ -70,7 +71,15 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
-__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+// Early trigger ONLY when every CTA of this grid is resident at once (`ctas_per_sm` = how many of them one SM holds).
+// A dependent grid that starts while CTAs of the primary are still waiting for an SM takes the resources those CTAs
+// need and then blocks in pdl_wait() for a primary that can no longer finish: observed as a hang of the decode path
+// at 1024 rows (two-wave GEMMs followed by cell kernels). A multi-wave grid keeps the implicit trigger at exit.
+__device__ __forceinline__ void pdl_launch_dependents(unsigned ctas_per_sm) {
+  unsigned nsm;
+  asm volatile("mov.u32 %0, %%nsmid;" : "=r"(nsm));
+  if (gridDim.x * gridDim.y * gridDim.z <= nsm * ctas_per_sm) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
 
 // ---- device utilities ---------------------------------------------------------------------------
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + __expf(-x)); }

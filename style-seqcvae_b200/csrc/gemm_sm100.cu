@@ -457,7 +457,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_tcgen05_kernel(const __g
   tc_fence_after();
   const uint32_t tmem_acc = *tmem_slot;
   pdl_wait();                                           // everything above overlaps the previous kernel's tail
-  pdl_launch_dependents();
+  pdl_launch_dependents(1);
 
   if (warp == 0) {
     if (lane == 0) {
@@ -570,7 +570,7 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ GemmParams p) {
   tc_fence_after();
   const uint32_t tmem_acc = *tmem_slot;
   pdl_wait();
-  pdl_launch_dependents();
+  pdl_launch_dependents(1);
 
   if (warp == 0) {
     if (lane == 0) {
@@ -735,7 +735,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_swapped_kernel(c
   tc_fence_after();
   const uint32_t tmem_acc = *tmem_slot;
   pdl_wait();
-  pdl_launch_dependents();
+  pdl_launch_dependents(1);
 
   if (warp == 0) {
     if (lane == 0) {
@@ -1005,7 +1005,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_swapped_pair_ker
   const uint32_t tmem_acc = *tmem_slot;
   DBG_STAMP(1);
   pdl_wait();                                           // everything above overlaps the previous kernel's tail
-  pdl_launch_dependents();
+  pdl_launch_dependents(1);
   DBG_STAMP(2);
   const int CW = S == 1 ? 256 : S == 2 ? 128 : S == 3 ? 96 : 64;   // batch columns owned by each K split
   LstmCellPre cell_pre;                                 // fused LSTM: addends + c_{t-1} of this thread's next 8 cells

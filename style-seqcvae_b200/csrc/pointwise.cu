@@ -114,7 +114,7 @@ __global__ void lstm_fwd_kernel(LstmFwdArgs a) {
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   const int r = blockIdx.y;
   pdl_wait();
-  pdl_launch_dependents();
+  pdl_launch_dependents(8);
   if (j >= a.H) return;
   const int H = a.H;
   const int r2 = a.rowmap ? a.rowmap[r] : r;
@@ -160,7 +160,7 @@ __global__ void __launch_bounds__(128) lstm_fwd_v4_kernel(LstmFwdArgs a) {
   const int H = a.H, H4 = H >> 2;
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   pdl_wait();
-  pdl_launch_dependents();
+  pdl_launch_dependents(8);
   if (idx >= a.R * H4) return;
   const int r = idx / H4, j = (idx - r * H4) * 4;
   const int r2 = a.rowmap ? a.rowmap[r] : r;
@@ -220,7 +220,7 @@ __global__ void lstm_bwd_kernel(LstmBwdArgs a) {
   const int r = blockIdx.y;
   const int H = a.H;
   pdl_wait();
-  pdl_launch_dependents();
+  pdl_launch_dependents(8);
   if (j >= H) return;
   float dh = 0.f;
 #pragma unroll
@@ -246,7 +246,7 @@ __global__ void __launch_bounds__(128) lstm_bwd_v4_kernel(LstmBwdArgs a) {
   const int H = a.H, H4 = H >> 2;
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   pdl_wait();
-  pdl_launch_dependents();
+  pdl_launch_dependents(8);
   if (idx >= a.R * H4) return;
   const int r = idx / H4, j = (idx - r * H4) * 4;
   float4 dh = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -312,7 +312,7 @@ __global__ void latent_fwd_train_kernel(LatentArgs a, const float* __restrict__ 
   const int r = blockIdx.x;
   const int Z = a.Z;
   pdl_wait();
-  pdl_launch_dependents();
+  pdl_launch_dependents(8);
   const float pm = a.prior_mean_row ? a.prior_mean_row[a.rowmap ? a.rowmap[r] : r] : 0.f;
   const float log_pv = logf(a.prior_var);
   float part = 0.f;
@@ -359,7 +359,7 @@ __global__ void latent_fwd_eval_kernel(LatentArgs a, const float* __restrict__ e
                                        int ld_z) {
   const int r = blockIdx.x;
   pdl_wait();
-  pdl_launch_dependents();
+  pdl_launch_dependents(8);
   const float pm = a.prior_mean_row ? a.prior_mean_row[a.rowmap ? a.rowmap[r] : r] : 0.f;
   const float sd = sqrtf(a.prior_var);
   for (int z = threadIdx.x; z < a.Zp; z += blockDim.x) {
@@ -388,7 +388,7 @@ __global__ void latent_bwd_kernel(LatentArgs a, const float* __restrict__ dz, in
   const int r = blockIdx.x;
   const int Z = a.Z;
   pdl_wait();
-  pdl_launch_dependents();
+  pdl_launch_dependents(8);
   const float pm = a.prior_mean_row ? a.prior_mean_row[a.rowmap ? a.rowmap[r] : r] : 0.f;
   const float w = gkld[r] * tmask_t[r];
   const float inv_pv = 1.0f / (a.prior_var + 0.00001f);

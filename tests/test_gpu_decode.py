@@ -148,3 +148,38 @@ def test_plain_beam_and_greedy_run_without_fsm():
         out = m(torch.rand(4, 5, 64).cuda(), sentiment=torch.zeros(4, 1).cuda())["predictions"]
         assert out.dtype == torch.long and out.shape[0] == 4 and 1 <= out.shape[1] <= 20
         assert (out >= 0).all() and (out < 300).all()
+
+
+@pytest.mark.parametrize("H", [32, 40])
+def test_sample_equals_the_reference_loop_over_latent_draws(H):
+    """sample(n) = the reference's `for k in range(N_Z_SAMPLES): model(image_features)` (inference.py:138-167): with
+    the same normals, sample j of image b is exactly the caption the j-th greedy call returns for image b."""
+    cfg = dict(vocab_size=300, image_feature_size=64, embedding_size=600, hidden_size=H, attention_projection_size=24,
+               z_space=16, sentiment_vae=1, simple_vae=False, max_caption_length=20, prior_std=1.0, senti_prior_multip=0.5)
+    torch.manual_seed(1)
+    B, J, Z, L = 3, 5, 16, 20
+    m = module_from_cfg(cfg, beam_size=1, use_cbs=False)
+    m.eval()
+    gen = torch.Generator().manual_seed(4)
+    feats = torch.rand(B, 6, 64, generator=gen)
+    feats[2, 2:] = 0
+    sent = torch.tensor([[1.0], [-1.0], [0.0]])
+    eps = torch.randn(L, B * J, Z, generator=gen)
+    m._eps_override = eps.cuda()
+    out = m.sample(feats.cuda(), sentiment=sent.cuda(), n_samples=J)
+    pred = out["predictions"].cpu()
+    assert pred.shape[:2] == (B, J)
+    differ = 0
+    for j in range(J):
+        m._eps_override = eps[:, j::J].contiguous().cuda()          # row b*J + j of the batched call
+        one = m(feats.cuda(), sentiment=sent.cuda())["predictions"].cpu()
+        n = min(one.shape[1], pred.shape[2])
+        assert torch.equal(one[:, :n], pred[:, j, :n]), j
+        assert bool((pred[:, j, n:] == 1).all()) and bool((one[:, n:] == 1).all())   # beyond either early exit: boundary
+        differ += int(j > 0 and not torch.equal(pred[:, j], pred[:, 0]))
+    m._eps_override = None
+    assert differ > 0                                               # different latent draws give different captions
+    # device Philox draws: rows are independent sequences, deterministic under a fixed seed
+    torch.manual_seed(5)
+    a = m.sample(feats.cuda(), sentiment=sent.cuda(), n_samples=J)["predictions"].cpu()
+    assert a.shape[:2] == (B, J) and (a >= 0).all() and (a < 300).all()
