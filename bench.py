@@ -384,8 +384,8 @@ def main():
         if v["bytes"] > 0:
             e["gbs"] = round(v["bytes"] / v["ms"] / 1e6, 1)
         kernels[k] = e
-    # Dominant kernel: the swapped-operand cluster split-K GEMM of the recurrence (class "gemm.recurrent": the
-    # encoder / decoder LSTM gate GEMMs and the three BPTT data-gradient GEMMs, M = batch = 256). The per-launch
+    # Dominant kernel: the swapped-operand CTA-pair cluster split-K GEMM of the recurrence (class "gemm.recurrent":
+    # the three LSTM gate GEMMs and the three BPTT data-gradient GEMMs of a timestep, M = batch = 256). The per-launch
     # instrumentation serialises the stream (its step is ~25 % slower than the timed one), so the class's SHARE of
     # the instrumented step is applied to the timed step: duration = share x ms_per_step.
     step_ms = ms_dev / args.steps
@@ -395,14 +395,20 @@ def main():
     if dom:
         share = dom["ms"] / total_ms
         dom_launches = dom["count"] / args.profile_steps
-        flops_per_step = dom["flops"] / args.profile_steps
+        # ALGORITHMIC flops of the class (unpadded dims; the kernels execute ~6 % more on K / N padding): per timestep
+        # the attention-LSTM recurrence [h1|h_dec](2H), the encoder LSTM [xhat|h1|h_dec|h_enc](F+3H) and the decoder
+        # LSTM [xhat|h1|h_dec|z](F+2H+Z, W_hh folded) gate GEMMs, 4H outputs each, plus their three data gradients
+        Hh, Ff, Zz, Tt = DIMS["hidden_size"], DIMS["image_feature_size"], DIMS["z_space"], 21
+        flops_per_step = 2.0 * 2.0 * B * 4 * Hh * (2 * Hh + (Ff + 3 * Hh) + (Ff + 2 * Hh + Zz)) * Tt
         dur_us = 1e3 * share * step_ms / dom_launches
-        roofline = {"kernel": "gemm_tcgen05_swapped_kernel (class gemm.recurrent)", "bound": "tensor",
+        roofline = {"kernel": "gemm_tcgen05_swapped_pair_kernel (class gemm.recurrent)", "bound": "tensor",
                     "achieved": flops_per_step / (share * step_ms) / 1e9, "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
                     "frac": flops_per_step / (share * step_ms) / 1e9 / peaks["tf_sustained"],
-                    # ncu --set full, profiles/ncu_full_r01_step_slice.json: dram read+write of the three captured
-                    # launch shapes (32.3, 41.9, 15.9 MB), launch-weighted; algorithmic = the bf16 weight block
+                    # ncu --set full, profiles/ncu_full_r01c_kernels.json: dram read+write of the three forward launch
+                    # shapes (39.4, 33.1, 15.3 MB; the five backward / forward shapes average ~30 MB); algorithmic =
+                    # the bf16 weight block + operands
                     "traffic": 30.0e6, "algorithmic_bytes_per_launch": dom["bytes"] / dom["count"],
+                    "flops_per_launch": flops_per_step / dom_launches,
                     "peak_source": peaks["src"] + " bf16_tflops_sustained", "share_of_step": share,
                     "launches_per_step": dom_launches, "avg_launch_us": dur_us,
                     "all_gemm_share_of_step": sum(v["ms"] for v in gemm_all) / total_ms,
@@ -439,7 +445,7 @@ def main():
         decode=decode,
     )
     if not args.no_cpu_baseline and world == 1:
-        r = cpu_reference_run(3, 1)
+        r = cpu_reference_run(20, 1)           # ~12 s of host work
         line["cpu_baseline"] = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
     else:
         line["cpu_baseline"] = None

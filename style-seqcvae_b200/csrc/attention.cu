@@ -61,6 +61,7 @@ struct AttnSmem {
   float* wa;             // Ap
   float* q0;             // 2 x Ap (double buffer, prefetched one row ahead)
   float* u;              // ATT_CWARPS x N4 partial scores (d alpha in backward): [sub-warp][box]
+  float* alw;            // ATT_CWARPS x N4: every consumer warp's own copy of alpha (broadcast reads in the weighted sum)
   float* dx0;            // 2 x Fp (backward only)
   float* sv0;            // 2 x N4 (backward only: saved softmax)
   int Ap, Fp, N4;
@@ -82,6 +83,7 @@ __device__ __forceinline__ AttnSmem carve(uint8_t* raw, const AttnArgs& a, bool 
   s.wa = f; f += a.Ap;
   s.q0 = f; f += 2 * a.Ap;
   s.u = f; f += ATT_CWARPS * s.N4;
+  s.alw = f; f += ATT_CWARPS * s.N4;
   s.dx0 = s.sv0 = nullptr;
   if (bwd) {
     s.dx0 = f; f += 2 * a.Fp;
@@ -91,7 +93,7 @@ __device__ __forceinline__ AttnSmem carve(uint8_t* raw, const AttnArgs& a, bool 
 }
 size_t attn_smem_bytes(const AttnArgs& a, bool bwd) {
   size_t n = 128 + (size_t)ATT_STAGES * ATT_STAGE_BYTES + 2 * ATT_STAGES * 8;
-  n += (size_t)(3 * a.Ap + ATT_CWARPS * ((a.N + 3) & ~3)) * 4;
+  n += (size_t)(3 * a.Ap + 2 * ATT_CWARPS * ((a.N + 3) & ~3)) * 4;
   if (bwd) n += (size_t)(2 * a.Fp + 2 * ((a.N + 3) & ~3)) * 4;
   return n;
 }
@@ -293,7 +295,19 @@ attention_fwd_kernel(AttnArgs a, AttnPlan pl, float* __restrict__ alpha, float* 
         }
       }
     }
-    // weighted sum: a thread owns 8 consecutive features (one 16-byte vector per box row)
+    // weighted sum: a thread owns 8 consecutive features (one 16-byte vector per box row). The inner loop is the
+    // instruction hot spot of the kernel (ncu: 39 % of all issued instructions, 46 per 8 FMAs when alpha came out of
+    // registers through a select chain + shuffle): alpha is read as a shared-memory broadcast from the warp's own
+    // copy, bf16 -> fp32 is one shift / one mask per element, and the box loop is unrolled.
+    {
+      float* mine = sm.alw + warp * sm.N4;
+#pragma unroll
+      for (int k = 0; k < ATT_NREG; ++k)
+        if (lane + 32 * k < a.N) mine[lane + 32 * k] = al[k];
+      __syncwarp();
+    }
+    const float* alw = sm.alw + warp * sm.N4;
+    const bool two = nfv > ATT_CONSUMERS;            // uniform: a second vector per thread only when Fp > 2048
     float acc[ATT_FV][8];
 #pragma unroll
     for (int v = 0; v < ATT_FV; ++v)
@@ -302,22 +316,34 @@ attention_fwd_kernel(AttnArgs a, AttnPlan pl, float* __restrict__ alpha, float* 
     for (int c = 0; c < pl.nF; ++c) {
       const int n0 = c * pl.bF, nb = min(pl.bF, a.N - n0);
       ptx::mbar_wait(&sm.full[ring.stage], ring.phase);
-      const bf16x8* buf = reinterpret_cast<const bf16x8*>(sm.stage + (size_t)ring.stage * ATT_STAGE_BYTES);
-      for (int j = 0; j < nb; ++j) {
-        const int n = n0 + j;
-        const float w = __shfl_sync(0xffffffffu, pick(al, n >> 5), n & 31);
-#pragma unroll
-        for (int v = 0; v < ATT_FV; ++v) {
-          const int vec = threadIdx.x + ATT_CONSUMERS * v;
-          if (vec < nfv) {
-            const bf16x8 x = buf[(size_t)j * nfv + vec];
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              const float2 f = __bfloat1622float2(x.v[k]);
-              acc[v][2 * k] += w * f.x;
-              acc[v][2 * k + 1] += w * f.y;
-            }
-          }
+      const uint4* buf = reinterpret_cast<const uint4*>(sm.stage + (size_t)ring.stage * ATT_STAGE_BYTES);
+      if (threadIdx.x < nfv) {
+#pragma unroll 4
+        for (int j = 0; j < nb; ++j) {
+          const float w = alw[n0 + j];
+          const uint4 x = buf[(size_t)j * nfv + threadIdx.x];
+          acc[0][0] = fmaf(w, __uint_as_float(x.x << 16), acc[0][0]);
+          acc[0][1] = fmaf(w, __uint_as_float(x.x & 0xffff0000u), acc[0][1]);
+          acc[0][2] = fmaf(w, __uint_as_float(x.y << 16), acc[0][2]);
+          acc[0][3] = fmaf(w, __uint_as_float(x.y & 0xffff0000u), acc[0][3]);
+          acc[0][4] = fmaf(w, __uint_as_float(x.z << 16), acc[0][4]);
+          acc[0][5] = fmaf(w, __uint_as_float(x.z & 0xffff0000u), acc[0][5]);
+          acc[0][6] = fmaf(w, __uint_as_float(x.w << 16), acc[0][6]);
+          acc[0][7] = fmaf(w, __uint_as_float(x.w & 0xffff0000u), acc[0][7]);
+        }
+      }
+      if (two && threadIdx.x + ATT_CONSUMERS < nfv) {
+        for (int j = 0; j < nb; ++j) {
+          const float w = alw[n0 + j];
+          const uint4 x = buf[(size_t)j * nfv + threadIdx.x + ATT_CONSUMERS];
+          acc[1][0] = fmaf(w, __uint_as_float(x.x << 16), acc[1][0]);
+          acc[1][1] = fmaf(w, __uint_as_float(x.x & 0xffff0000u), acc[1][1]);
+          acc[1][2] = fmaf(w, __uint_as_float(x.y << 16), acc[1][2]);
+          acc[1][3] = fmaf(w, __uint_as_float(x.y & 0xffff0000u), acc[1][3]);
+          acc[1][4] = fmaf(w, __uint_as_float(x.z << 16), acc[1][4]);
+          acc[1][5] = fmaf(w, __uint_as_float(x.z & 0xffff0000u), acc[1][5]);
+          acc[1][6] = fmaf(w, __uint_as_float(x.w << 16), acc[1][6]);
+          acc[1][7] = fmaf(w, __uint_as_float(x.w & 0xffff0000u), acc[1][7]);
         }
       }
       __syncwarp();

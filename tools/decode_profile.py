@@ -1,4 +1,5 @@
-"""Per-kernel-class time of one CBS decode call and one greedy call (library instrumentation, no CUDA graphs)."""
+"""Per-kernel-class time of one CBS decode call, one greedy call and one batched sampling call (library
+instrumentation, no CUDA graphs)."""
 import os, sys, json
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
@@ -42,3 +43,19 @@ for name, beam, cbs, n_img in (("cbs_beam5", 5, True, 64), ("greedy", 1, False, 
     print(name, "images", n_img, "total ms", round(tot, 3))
     for k, v in sorted(rep.items(), key=lambda kv: -kv[1]["ms"]):
         print(f"  {k:20s} {v['count']:5d} {v['ms']:8.3f} ms  {v['ms'] / tot * 100:5.1f}%")
+
+# batched diverse sampling: 64 images x 100 samples in one call
+n_img, J = 64, 100
+feats = torch.rand(n_img, 36, 2048, generator=g).to(dev)
+sent = torch.randint(-1, 2, (n_img, 1), generator=g).float().to(dev)
+m = build(1, False)
+for _ in range(2):
+    m.sample(feats, sentiment=sent, n_samples=J)
+_lib.profile(True)
+m.sample(feats, sentiment=sent, n_samples=J)
+rep = _lib.profile_report()
+_lib.profile(False)
+tot = sum(v["ms"] for v in rep.values())
+print("sampling_batched images", n_img, "samples", J, "total ms", round(tot, 3))
+for k, v in sorted(rep.items(), key=lambda kv: -kv[1]["ms"]):
+    print(f"  {k:20s} {v['count']:5d} {v['ms']:8.3f} ms  {v['ms'] / tot * 100:5.1f}%")
