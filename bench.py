@@ -229,6 +229,9 @@ def main():
     ap.add_argument("--no-decode", action="store_true")
     ap.add_argument("--profile-steps", type=int, default=2)
     args = ap.parse_args()
+    # a stalled run ends itself with every thread's stack on stderr instead of waiting for the caller's timeout
+    import faulthandler
+    faulthandler.dump_traceback_later(int(os.environ.get("SSCVAE_BENCH_WATCHDOG_S", "540")), exit=True)
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -266,6 +269,11 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     B = args.batch
+
+    def progress(msg):                 # stderr breadcrumbs: where a multi-rank run is when something stalls
+        if rank == 0:
+            print(f"[bench {time.strftime('%H:%M:%S')}] {msg}", file=sys.stderr, flush=True)
+    progress(f"process group up: world {world}")
     torch.manual_seed(0)
     model = sscvae.UpDownCaptioner(
         _Vocab(), DIMS["image_feature_size"], DIMS["embedding_size"], DIMS["hidden_size"],
@@ -315,6 +323,7 @@ def main():
     for i in range(warmup):
         train_step(*resident[i % n_batches])
     barrier()
+    progress("warm-up done")
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
@@ -328,6 +337,7 @@ def main():
     barrier()
     ms_dev = max_over_ranks(e0.elapsed_time(e1))
     launches = _lib.launch_count() - launches0
+    progress(f"device-resident arm done: {ms_dev / args.steps:.3f} ms/step")
 
     # ---------------------------------------------------------------- end-to-end arm (host buffers)
     copy_stream = torch.cuda.Stream()
@@ -365,6 +375,7 @@ def main():
     barrier()
     ms_e2e = max_over_ranks(e0.elapsed_time(e1))
     clocks = sampler.stop() if rank == 0 else None
+    progress(f"end-to-end arm done: {ms_e2e / args.steps:.3f} ms/step")
     assert torch.isfinite(loss_host).all(), "non-finite loss in the end-to-end arm"
 
     # ---------------------------------------------------------------- instrumented steps -> roofline
@@ -415,9 +426,11 @@ def main():
                     "all_gemm_tflops": sum(v["flops"] for v in gemm_all) / args.profile_steps
                                        / (sum(v["ms"] for v in gemm_all) / total_ms * step_ms) / 1e9}
 
+    progress("instrumented steps done")
     decode = None
     if not args.no_decode:
         decode = decode_legs(sscvae, _Vocab(), model, dev, world, max_over_ranks, barrier)
+        progress("decode legs done")
 
     captions = B * world * args.steps
     value = captions / (ms_dev / 1e3)
