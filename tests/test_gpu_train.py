@@ -205,3 +205,18 @@ def test_full_size_properties():
     m._eps_override = eps[:, perm].contiguous().cuda()
     o2 = m(feats[perm].cuda(), None, None, toks[perm].cuda(), sent[perm].cuda())
     assert torch.allclose(o2["loss"], loss[perm.cuda()], rtol=2e-3, atol=2e-2)
+
+
+@pytest.mark.parametrize("mode", ["1", "2"])
+def test_fused_lstm_epilogue_keeps_parity(mode):
+    """SSCVAE_LSTM_FUSE=1/2 runs the LSTM cells in the epilogue of the CTA-pair gate GEMMs (opt-in; read once per
+    process, hence the subprocess): forward, gradient and full-size property tests must hold unchanged."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, SSCVAE_LSTM_FUSE=mode)
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(root, "tests", "test_gpu_train.py"), "-q", "-x", "-m", "gpu",
+                        "-k", "matches or full_size", "-p", "no:cacheprovider"], env=env, cwd=root, capture_output=True,
+                       text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
