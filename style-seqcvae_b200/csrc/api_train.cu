@@ -7,7 +7,8 @@
 //   ZB  (TB, Zp)      bf16  z_t
 // Hidden states exist only as bf16 GEMM operands (written once by the LSTM pointwise kernel into
 // every buffer that consumes them); cell states, gate activations, softmax/KL/CE stay fp32.
-// "p" suffixes are sizes rounded up to 8 elements so every row stride is a multiple of 16 bytes (TMA).
+// "p" suffixes are sizes rounded up to 64 elements: every bf16 row stride and column block is a multiple of 128 bytes
+// (one TMA box row = one cache line, see init_dims).
 #include "api_internal.cuh"
 
 namespace sscvae {

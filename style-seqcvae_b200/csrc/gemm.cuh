@@ -26,8 +26,9 @@ struct GemmEpi {
   float* C32 = nullptr; int ldc32 = 0; int accumulate = 0;   // C32[m,n] (+)= v
   bf16* C16 = nullptr; int ldc16 = 0;                  // C16[m,n] = bf16(v)
   const char* tag = "gemm";                            // kernel class for the optional profiler (prof.cuh)
-  // skinny GEMMs (M <= 256) run on the swapped-operand kernel with K split over a thread-block cluster; 0 = let the
-  // library choose the split count, 1/2/4 = force it (tools/gemm_bench.py)
+  // skinny GEMMs (M <= 256) run on the swapped-operand kernels with K split over a thread-block cluster; 0 = let the
+  // library choose kernel and split count, 1/2/4 = force the single-CTA kernel with that split, -1..-4 = force the
+  // CTA-pair kernel with split 1..4 (tools/gemm_bench.py, tests)
   int splits = 0;
   // Fused LSTM cell (forward): the N = lstm_gate_rows(H) output columns are gate pre-activations in the
   // gate-interleaved order of the packed weights; `lstm` describes the addends, states and destinations exactly as
