@@ -7,10 +7,10 @@ through the repo-root shim: `import sscvae` (sscvae.py), which registers this pa
 """
 from . import _lib
 from .captioner import UpDownCaptioner
-from .search import (BeamSearch, ConstrainedBeamSearch, select_best_beam, select_best_beam_with_constraints)
+from .search import (BeamSearch, ConstrainedBeamSearch, select_best_beam, select_best_beam_with_constraints, pad_fsm_batch)
 from .dp import BucketedGradReducer, shard_batch, global_grad_norm
 from .optim import FusedClipSGD
 
 __all__ = ["UpDownCaptioner", "ConstrainedBeamSearch", "BeamSearch", "select_best_beam",
-           "select_best_beam_with_constraints", "BucketedGradReducer", "shard_batch", "global_grad_norm",
+           "select_best_beam_with_constraints", "pad_fsm_batch", "BucketedGradReducer", "shard_batch", "global_grad_norm",
            "FusedClipSGD"]

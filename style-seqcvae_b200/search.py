@@ -128,3 +128,36 @@ def select_best_beam_with_constraints(beams, beam_log_probabilities, given_const
         best.append(vb[torch.argmax(vl)])
         valid.append(vb)
     return torch.stack(best).long(), torch.stack(valid)
+
+
+def pad_fsm_batch(fsms, num_constraints=None):
+    """Batch per-image finite-state machines with DIFFERENT state counts.
+
+    The reference builds one trimmed `(S_i, S_i, V)` uint8 FSM per image (constraints.py:329-478, trimmed at
+    datasets.py:611-613) and its evaluation collate can therefore only stack a batch of ONE image
+    (datasets.py:604-620). Padding with zeros up to the largest state count is exact: a padded state has no incoming
+    transition, so its beams keep the masked score forever - the same thing that happens to the unreachable main
+    states the reference itself carries when an image has fewer constraints than `max_given_constraints` - and the
+    best-beam selection only looks at the `2**num_constraints` main states of each image (decoding.py:82-134).
+
+    fsms: sequence of (S_i, S_i, V) uint8 / bool tensors; num_constraints: optional sequence of ints.
+    Returns (fsm (B, S, S, V) uint8, num_constraints (B,) int64 or None)."""
+    if len(fsms) == 0:
+        raise ValueError("empty FSM batch")
+    V = fsms[0].shape[-1]
+    S = max(int(f.shape[0]) for f in fsms)
+    out = torch.zeros(len(fsms), S, S, V, dtype=torch.uint8, device=fsms[0].device)
+    for i, f in enumerate(fsms):
+        if f.dim() != 3 or f.shape[0] != f.shape[1] or f.shape[2] != V:
+            raise ValueError(f"FSM {i} has shape {tuple(f.shape)}, expected (S, S, {V})")
+        si = f.shape[0]
+        out[i, :si, :si] = f.to(torch.uint8)
+    nc = None
+    if num_constraints is not None:
+        if len(num_constraints) != len(fsms):
+            raise ValueError("one constraint count per FSM")
+        nc = torch.as_tensor([int(n) for n in num_constraints], dtype=torch.long, device=fsms[0].device)
+        for i, f in enumerate(fsms):
+            if 2 ** int(nc[i]) > f.shape[0]:
+                raise ValueError(f"FSM {i} has {f.shape[0]} states, fewer than the 2**{int(nc[i])} main states")
+    return out, nc
