@@ -139,6 +139,8 @@ static void plan_train(const Dims& d, int B, int N, Plan& p) {
   p.add("logvar", TB * d.Z * f);
   p.add("eps", TB * d.Z * f);
   p.add("kl", TB * f);
+  p.add("kl_part", TB * recurrent_forward_kl_parts(d.Z) * f);   // persistent recurrent kernel: per-tile KL partial sums
+  p.add("rf_flags", 256);                                       // ... and its dataflow counters
   if (d.tied) {
     p.add("ob", TB * d.Ep * b);
     p.add("o32", TB * d.E * f);
@@ -366,7 +368,7 @@ static int train_forward_impl(Handle* h, int B, int N, const char* pk, const voi
   // keep the per-timestep weights L2-resident across the 21 steps (they are re-read every step)
   TRY(set_l2_window(s, pk + pp.find("w_att_rec")->off, pp.find("fwd_end")->off - pp.find("w_att_rec")->off));
   // operand buffers carry zero padding columns and the zero initial states (updown_cell.py:131-140)
-  CUDA_TRY(zero("XA")); CUDA_TRY(zero("XE")); CUDA_TRY(zero("HE")); CUDA_TRY(zero("projb"));
+  CUDA_TRY(zero("XA")); CUDA_TRY(zero("XE")); CUDA_TRY(zero("HE")); CUDA_TRY(zero("projb")); CUDA_TRY(zero("ZB"));
   if (d.tied) CUDA_TRY(zero("ob"));
 
   int* tok = Wi("tok");
@@ -395,59 +397,79 @@ static int train_forward_impl(Handle* h, int B, int N, const char* pk, const voi
   la.prior_mean_row = Wf("pm_row"); la.rowmap = nullptr;
   AttnArgs aa; aa.R = B; aa.N = N; aa.A = d.A; aa.Ap = d.Ap; aa.F = d.F; aa.Fp = Fp; aa.rowmap = nullptr;
   aa.proj = Wb("projb"); aa.feats = Wb("featsb"); aa.mask = Wf("mask"); aa.w_a = W(SSCVAE_W_ATT_VEC); aa.ld_q = d.A;
-  float* acc = Wf("acc");
-  for (int t = 0; t < T; ++t) {
-    bf16* XA_t = Wb("XA") + (size_t)t * B * 2 * Hp;
-    bf16* XA_n = XA_t + (size_t)B * 2 * Hp;
-    bf16* XE_t = Wb("XE") + (size_t)t * B * KX;
-    bf16* XE_n = (t + 1 < T) ? XE_t + (size_t)B * KX : nullptr;
-    bf16* HE_t = Wb("HE") + (size_t)t * B * Hp;
-    bf16* HE_n = HE_t + (size_t)B * Hp;
-    bf16* ZB_t = Wb("ZB") + (size_t)t * B * d.Zp;
-    const size_t rG = (size_t)t * B * d.G, rH = (size_t)t * B * H;
-    {  // attention LSTM (updown_cell.py:143-148): gate GEMM with the cell fused into its epilogue
-      LstmFwdArgs l = {};
-      l.R = B; l.H = H; l.add1 = Wf("gx_att") + (size_t)t * B * GP; l.ld1 = GP; l.add2 = Wf("gavg"); l.ld2 = GP;
-      l.bias = Pf("b_att");
-      l.c_prev = t ? Wf("c1") + rH - (size_t)B * H : nullptr; l.c_out = Wf("c1") + rH; l.gates_out = Wf("gates_att") + rG;
-      l.h1_dst = XE_t + Fp; l.ld_h1 = KX; l.h2_dst = XA_n; l.ld_h2 = 2 * Hp;
-      GemmSeg sg = seg(XA_t, 2 * Hp, Pb("w_att_rec"), 2 * Hp, 2 * Hp);
-      GemmEpi e; e.tag = "gemm.step"; e.C32 = acc; e.ldc32 = GP; e.lstm = &l;
-      TRY(gemm_bf16_tn(s, B, GP, 1, &sg, e));
-    }
-    {  // query projection + fused region attention (attention.py:69-93, updown_cell.py:156)
-      GemmSeg sg = seg(XE_t + Fp, KX, Pb("wq"), Hp, Hp);
-      GemmEpi e; e.tag = "gemm.step"; e.C32 = Wf("q") + (size_t)t * B * d.A; e.ldc32 = d.A;
-      TRY(gemm_bf16_tn(s, B, d.A, 1, &sg, e));
-      aa.q = Wf("q") + (size_t)t * B * d.A;
-      TRY(attention_forward(s, aa, Wf("alpha") + (size_t)t * B * N, Wf("smx") + (size_t)t * B * N, XE_t, KX));
-    }
-    {  // posterior (encoder) LSTM + latent heads + reparameterised sample (updown_cell.py:176-208)
-      LstmFwdArgs l = {};
-      l.R = B; l.H = H; l.bias = Pf("b_enc");
-      if (d.cond) { l.sent = sent; l.scol = Pf("scol_enc"); }
-      l.c_prev = t ? Wf("c_enc") + rH - (size_t)B * H : nullptr; l.c_out = Wf("c_enc") + rH;
-      l.gates_out = Wf("gates_enc") + rG; l.h1_dst = HE_n; l.ld_h1 = Hp;
-      GemmSeg sg[2] = {seg(XE_t, KX, Pb("w_enc_x"), KX, KX), seg(HE_t, Hp, Pb("w_enc_hh"), Hp, Hp)};
-      GemmEpi e; e.tag = "gemm.step"; e.C32 = acc; e.ldc32 = GP; e.lstm = &l;
-      TRY(gemm_bf16_tn(s, B, GP, 2, sg, e));
-      GemmSeg sf = seg(HE_n, Hp, Pb("w_fc"), Hp, Hp);
-      GemmEpi ef; ef.tag = "gemm.step"; ef.C32 = Wf("ml"); ef.ldc32 = d.Z2;
-      TRY(gemm_bf16_tn(s, B, d.Z2, 1, &sf, ef));
-      const size_t rZ = (size_t)t * B * d.Z;
-      TRY(latent_forward_train(s, la, Wf("ml"), d.Z2, Pf("b_fc"), eps ? eps + rZ : nullptr, seed_dev, (unsigned long long)t,
-                               Wf("mean") + rZ, Wf("logvar") + rZ, Wf("eps") + rZ, ZB_t, d.Zp, Wf("kl") + (size_t)t * B));
-    }
-    {  // language (decoder) LSTM (updown_cell.py:211-229)
-      LstmFwdArgs l = {};
-      l.R = B; l.H = H; l.bias = Pf("b_dec");
-      if (d.cond) { l.sent = sent; l.scol = Pf("scol_dec"); }
-      l.c_prev = t ? Wf("c_dec") + rH - (size_t)B * H : nullptr; l.c_out = Wf("c_dec") + rH;
-      l.gates_out = Wf("gates_dec") + rG; l.h1_dst = XA_n + Hp; l.ld_h1 = 2 * Hp;
-      if (XE_n) { l.h2_dst = XE_n + Fp + Hp; l.ld_h2 = KX; }
-      GemmSeg sg[2] = {seg(XE_t, KX, Pb("w_dec_x"), KX, KX), seg(ZB_t, d.Zp, Pb("w_dec_z"), d.Zp, d.Zp)};
-      GemmEpi e; e.tag = "gemm.step"; e.C32 = acc; e.ldc32 = GP; e.lstm = &l;
-      TRY(gemm_bf16_tn(s, B, GP, 2, sg, e));
+  // ---- the T-step recurrence: one persistent cooperative kernel (recurrent_fwd.cu) when the shape allows it,
+  //      otherwise ~10 launches per timestep
+  RecFwdArgs rf = {};
+  rf.B = B; rf.T = T; rf.H = H; rf.Hp = Hp; rf.Fp = Fp; rf.Zp = d.Zp; rf.Z = d.Z; rf.A = d.A; rf.KX = KX; rf.GP = GP;
+  rf.sentiment_vae = d.sv; rf.prior_var = d.prior_std * d.prior_std;
+  rf.w_att_rec = Pb("w_att_rec"); rf.wq = Pb("wq"); rf.w_enc_x = Pb("w_enc_x"); rf.w_enc_hh = Pb("w_enc_hh");
+  rf.w_fc = Pb("w_fc"); rf.w_dec_x = Pb("w_dec_x"); rf.w_dec_z = Pb("w_dec_z");
+  rf.gx_att = Wf("gx_att"); rf.gavg = Wf("gavg"); rf.b_att = Pf("b_att"); rf.b_enc = Pf("b_enc"); rf.b_dec = Pf("b_dec");
+  rf.sent = d.cond ? sent : nullptr; rf.scol_enc = Pf("scol_enc"); rf.scol_dec = Pf("scol_dec");
+  rf.c1 = Wf("c1"); rf.c_enc = Wf("c_enc"); rf.c_dec = Wf("c_dec");
+  rf.gates_att = Wf("gates_att"); rf.gates_enc = Wf("gates_enc"); rf.gates_dec = Wf("gates_dec");
+  rf.XA = Wb("XA"); rf.XE = Wb("XE"); rf.HE = Wb("HE"); rf.ZB = Wb("ZB");
+  rf.q = Wf("q"); rf.b_fc = Pf("b_fc"); rf.eps_in = eps; rf.seed = seed_dev; rf.pm_row = Wf("pm_row");
+  rf.mean = Wf("mean"); rf.logvar = Wf("logvar"); rf.eps_out = Wf("eps"); rf.kl_part = Wf("kl_part"); rf.kl = Wf("kl");
+  rf.att = aa; rf.alpha = Wf("alpha"); rf.smx = Wf("smx");
+  rf.flags = reinterpret_cast<unsigned int*>(ws + tp.find("rf_flags")->off);
+  if (recurrent_forward_supported(rf)) {
+    TRY(recurrent_forward(s, rf));
+  } else {
+    float* acc = Wf("acc");
+    for (int t = 0; t < T; ++t) {
+      bf16* XA_t = Wb("XA") + (size_t)t * B * 2 * Hp;
+      bf16* XA_n = XA_t + (size_t)B * 2 * Hp;
+      bf16* XE_t = Wb("XE") + (size_t)t * B * KX;
+      bf16* XE_n = (t + 1 < T) ? XE_t + (size_t)B * KX : nullptr;
+      bf16* HE_t = Wb("HE") + (size_t)t * B * Hp;
+      bf16* HE_n = HE_t + (size_t)B * Hp;
+      bf16* ZB_t = Wb("ZB") + (size_t)t * B * d.Zp;
+      const size_t rG = (size_t)t * B * d.G, rH = (size_t)t * B * H;
+      {  // attention LSTM (updown_cell.py:143-148): gate GEMM with the cell fused into its epilogue
+        LstmFwdArgs l = {};
+        l.R = B; l.H = H; l.add1 = Wf("gx_att") + (size_t)t * B * GP; l.ld1 = GP; l.add2 = Wf("gavg"); l.ld2 = GP;
+        l.bias = Pf("b_att");
+        l.c_prev = t ? Wf("c1") + rH - (size_t)B * H : nullptr; l.c_out = Wf("c1") + rH; l.gates_out = Wf("gates_att") + rG;
+        l.h1_dst = XE_t + Fp; l.ld_h1 = KX; l.h2_dst = XA_n; l.ld_h2 = 2 * Hp;
+        GemmSeg sg = seg(XA_t, 2 * Hp, Pb("w_att_rec"), 2 * Hp, 2 * Hp);
+        GemmEpi e; e.tag = "gemm.step"; e.C32 = acc; e.ldc32 = GP; e.lstm = &l;
+        TRY(gemm_bf16_tn(s, B, GP, 1, &sg, e));
+      }
+      {  // query projection + fused region attention (attention.py:69-93, updown_cell.py:156)
+        GemmSeg sg = seg(XE_t + Fp, KX, Pb("wq"), Hp, Hp);
+        GemmEpi e; e.tag = "gemm.step"; e.C32 = Wf("q") + (size_t)t * B * d.A; e.ldc32 = d.A;
+        TRY(gemm_bf16_tn(s, B, d.A, 1, &sg, e));
+        aa.q = Wf("q") + (size_t)t * B * d.A;
+        TRY(attention_forward(s, aa, Wf("alpha") + (size_t)t * B * N, Wf("smx") + (size_t)t * B * N, XE_t, KX));
+      }
+      {  // posterior (encoder) LSTM + latent heads + reparameterised sample (updown_cell.py:176-208)
+        LstmFwdArgs l = {};
+        l.R = B; l.H = H; l.bias = Pf("b_enc");
+        if (d.cond) { l.sent = sent; l.scol = Pf("scol_enc"); }
+        l.c_prev = t ? Wf("c_enc") + rH - (size_t)B * H : nullptr; l.c_out = Wf("c_enc") + rH;
+        l.gates_out = Wf("gates_enc") + rG; l.h1_dst = HE_n; l.ld_h1 = Hp;
+        GemmSeg sg[2] = {seg(XE_t, KX, Pb("w_enc_x"), KX, KX), seg(HE_t, Hp, Pb("w_enc_hh"), Hp, Hp)};
+        GemmEpi e; e.tag = "gemm.step"; e.C32 = acc; e.ldc32 = GP; e.lstm = &l;
+        TRY(gemm_bf16_tn(s, B, GP, 2, sg, e));
+        GemmSeg sf = seg(HE_n, Hp, Pb("w_fc"), Hp, Hp);
+        GemmEpi ef; ef.tag = "gemm.step"; ef.C32 = Wf("ml"); ef.ldc32 = d.Z2;
+        TRY(gemm_bf16_tn(s, B, d.Z2, 1, &sf, ef));
+        const size_t rZ = (size_t)t * B * d.Z;
+        TRY(latent_forward_train(s, la, Wf("ml"), d.Z2, Pf("b_fc"), eps ? eps + rZ : nullptr, seed_dev, (unsigned long long)t,
+                                 Wf("mean") + rZ, Wf("logvar") + rZ, Wf("eps") + rZ, ZB_t, d.Zp, Wf("kl") + (size_t)t * B));
+      }
+      {  // language (decoder) LSTM (updown_cell.py:211-229)
+        LstmFwdArgs l = {};
+        l.R = B; l.H = H; l.bias = Pf("b_dec");
+        if (d.cond) { l.sent = sent; l.scol = Pf("scol_dec"); }
+        l.c_prev = t ? Wf("c_dec") + rH - (size_t)B * H : nullptr; l.c_out = Wf("c_dec") + rH;
+        l.gates_out = Wf("gates_dec") + rG; l.h1_dst = XA_n + Hp; l.ld_h1 = 2 * Hp;
+        if (XE_n) { l.h2_dst = XE_n + Fp + Hp; l.ld_h2 = KX; }
+        GemmSeg sg[2] = {seg(XE_t, KX, Pb("w_dec_x"), KX, KX), seg(ZB_t, d.Zp, Pb("w_dec_z"), d.Zp, d.Zp)};
+        GemmEpi e; e.tag = "gemm.step"; e.C32 = acc; e.ldc32 = GP; e.lstm = &l;
+        TRY(gemm_bf16_tn(s, B, GP, 2, sg, e));
+      }
     }
   }
   // output head over all T*B rows at once (updown_captioner.py:444-445)

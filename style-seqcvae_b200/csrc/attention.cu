@@ -25,213 +25,14 @@
 #include "kernels.cuh"
 #include "prof.cuh"
 #include "ptx.cuh"
+#include "attention_dev.cuh"
 
 namespace sscvae {
 
 #define LAUNCHED() do { CUDA_TRY(cudaGetLastError()); ++g_launch_count_pw; } while (0)
 
-__device__ __forceinline__ float tanh_approx(float x) {
-  float y;
-  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
+using namespace attn;
 
-namespace {
-
-constexpr int ATT_CONSUMERS = 256;                 // 8 consumer warps
-constexpr int ATT_CWARPS = ATT_CONSUMERS / 32;
-constexpr int ATT_THREADS = ATT_CONSUMERS + 32;    // + 1 producer warp
-constexpr int ATT_STAGES = 4;
-constexpr int ATT_STAGE_BYTES = 16384;             // two CTAs per SM: their phases overlap
-constexpr int ATT_MAXB = 8;                        // boxes per chunk (<= consumer warps: one box per warp and chunk)
-constexpr int ATT_NREG = 4;                        // boxes per lane in the softmax: N <= 128
-constexpr int ATT_FV = 2;                          // 16-byte feature vectors per thread: Fp <= 4096
-constexpr int ATT_PV = 2;                          // projection column pairs per thread: Ap <= 1024
-
-struct AttnPlan {
-  int nP, bP;            // chunks / boxes per chunk of the projected features
-  int nF, bF;            // same for the region features
-  int rows_per_cta;
-};
-
-struct AttnSmem {
-  uint8_t* stage;        // ATT_STAGES x ATT_STAGE_BYTES
-  uint64_t* full;        // [ATT_STAGES]
-  uint64_t* empty;       // [ATT_STAGES]
-  float* wa;             // Ap
-  float* q0;             // 2 x Ap (double buffer, prefetched one row ahead)
-  float* u;              // ATT_CWARPS x N4 partial scores (d alpha in backward): [sub-warp][box]
-  float* alw;            // ATT_CWARPS x N4: every consumer warp's own copy of alpha (broadcast reads in the weighted sum)
-  float* dx0;            // 2 x Fp (backward only)
-  float* sv0;            // 2 x N4 (backward only: saved softmax)
-  int Ap, Fp, N4;
-  __device__ __forceinline__ float* q(int slot) const { return q0 + slot * Ap; }
-  __device__ __forceinline__ float* dx(int slot) const { return dx0 + slot * Fp; }
-  __device__ __forceinline__ float* sv(int slot) const { return sv0 + slot * N4; }
-};
-
-__device__ __forceinline__ AttnSmem carve(uint8_t* raw, const AttnArgs& a, bool bwd) {
-  AttnSmem s;
-  // no integer round trip on the pointer: it would lose the shared address space and turn every access below into a
-  // generic LD/ST with 64-bit address arithmetic (a third of the instructions of the first version of these kernels)
-  uint8_t* p = raw;
-  s.stage = p; p += ATT_STAGES * ATT_STAGE_BYTES;
-  s.full = reinterpret_cast<uint64_t*>(p); p += ATT_STAGES * 8;
-  s.empty = reinterpret_cast<uint64_t*>(p); p += ATT_STAGES * 8;
-  float* f = reinterpret_cast<float*>(p);
-  s.Ap = a.Ap; s.Fp = a.Fp; s.N4 = (a.N + 3) & ~3;
-  s.wa = f; f += a.Ap;
-  s.q0 = f; f += 2 * a.Ap;
-  s.u = f; f += ATT_CWARPS * s.N4;
-  s.alw = f; f += ATT_CWARPS * s.N4;
-  s.dx0 = s.sv0 = nullptr;
-  if (bwd) {
-    s.dx0 = f; f += 2 * a.Fp;
-    s.sv0 = f; f += 2 * s.N4;
-  }
-  return s;
-}
-size_t attn_smem_bytes(const AttnArgs& a, bool bwd) {
-  size_t n = 128 + (size_t)ATT_STAGES * ATT_STAGE_BYTES + 2 * ATT_STAGES * 8;
-  n += (size_t)(3 * a.Ap + 2 * ATT_CWARPS * ((a.N + 3) & ~3)) * 4;
-  if (bwd) n += (size_t)(2 * a.Fp + 2 * ((a.N + 3) & ~3)) * 4;
-  return n;
-}
-
-// ring bookkeeping shared by producer and consumers (both walk the same chunk sequence)
-struct Ring {
-  int stage = 0;
-  uint32_t phase = 0;
-  __device__ __forceinline__ void advance() {
-    if (++stage == ATT_STAGES) { stage = 0; phase ^= 1; }
-  }
-};
-
-__device__ __forceinline__ void produce_block(const AttnSmem& sm, Ring& ring, const uint8_t* base, int N, int row_bytes,
-                                              int nchunks, int bper, uint64_t policy) {
-  for (int c = 0; c < nchunks; ++c) {
-    const int n0 = c * bper;
-    const int nb = min(bper, N - n0);
-    const uint32_t bytes = (uint32_t)nb * (uint32_t)row_bytes;
-    ptx::mbar_wait(&sm.empty[ring.stage], ring.phase ^ 1);
-    ptx::mbar_expect_tx(&sm.full[ring.stage], bytes);
-    // evict_first: the 52 MB of features + projections are read once per timestep and would otherwise push the
-    // recurrent weights (76 MB, re-read every step) out of the 126 MB L2
-    if (policy) ptx::bulk_g2s_hint(sm.stage + (size_t)ring.stage * ATT_STAGE_BYTES, base + (size_t)n0 * row_bytes, bytes,
-                                   &sm.full[ring.stage], policy);
-    else ptx::bulk_g2s(sm.stage + (size_t)ring.stage * ATT_STAGE_BYTES, base + (size_t)n0 * row_bytes, bytes, &sm.full[ring.stage]);
-    ring.advance();
-  }
-}
-
-// row-vector prefetch (cp.async, 4 bytes per op: no alignment requirement on the row stride)
-__device__ __forceinline__ void prefetch_vec(float* dst, const float* src, int n) {
-  for (int i = threadIdx.x; i < n; i += ATT_CONSUMERS) ptx::cp_async4(dst + i, src + i);
-}
-
-template <int K>
-__device__ __forceinline__ float pick(const float (&v)[K], int k) {
-  float r = v[0];
-#pragma unroll
-  for (int i = 1; i < K; ++i) r = (k == i) ? v[i] : r;
-  return r;
-}
-
-// A chunk holds nb <= ATT_MAXB boxes; 8/pow2ceil(nb) warps share one box (each a slice of the vectors), so all
-// consumer warps stay busy whatever the chunk size. Partial sums land in part[sub][n] and are added by the readers.
-__device__ __forceinline__ int warps_per_box(int nb) { return nb > 4 ? 1 : nb > 2 ? 2 : nb > 1 ? 4 : 8; }
-__device__ __forceinline__ float gather_partial(const float* part, int N4, int N, int bper, int n) {
-  const int n0 = (n / bper) * bper;
-  const int wpb = warps_per_box(min(bper, N - n0));
-  float s = 0.f;
-  for (int k = 0; k < wpb; ++k) s += part[k * N4 + n];
-  return s;
-}
-
-// scores u_n of the boxes of one P chunk
-__device__ __forceinline__ void chunk_scores(const AttnArgs& a, const bf16* buf, int n0, int nb, const float* mask_img,
-                                             const float* q_s, const float* wa_s, float* part, int N4) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int nvec = a.Ap >> 3;
-  const int wpb = warps_per_box(nb);
-  const int j = warp / wpb, sub = warp % wpb;
-  if (j >= nb) return;
-  const int n = n0 + j;
-  float s = 0.f;
-  if (mask_img[n] != 0.f) {                        // masked boxes enter the softmax as u*m = 0
-    const bf16x8* p = reinterpret_cast<const bf16x8*>(buf + (size_t)j * a.Ap);
-    for (int i = sub * 32 + lane; i < nvec; i += 32 * wpb) {
-      const bf16x8 v = p[i];
-      const float4 qa = *reinterpret_cast<const float4*>(q_s + i * 8);
-      const float4 qb = *reinterpret_cast<const float4*>(q_s + i * 8 + 4);
-      const float4 wa = *reinterpret_cast<const float4*>(wa_s + i * 8);
-      const float4 wb = *reinterpret_cast<const float4*>(wa_s + i * 8 + 4);
-      const float2 f0 = __bfloat1622float2(v.v[0]), f1 = __bfloat1622float2(v.v[1]);
-      const float2 f2 = __bfloat1622float2(v.v[2]), f3 = __bfloat1622float2(v.v[3]);
-      s += wa.x * tanh_approx(qa.x + f0.x) + wa.y * tanh_approx(qa.y + f0.y);
-      s += wa.z * tanh_approx(qa.z + f1.x) + wa.w * tanh_approx(qa.w + f1.y);
-      s += wb.x * tanh_approx(qb.x + f2.x) + wb.y * tanh_approx(qb.y + f2.y);
-      s += wb.z * tanh_approx(qb.z + f3.x) + wb.w * tanh_approx(qb.w + f3.y);
-    }
-    s = warp_sum(s);
-  }
-  if (lane == 0) part[sub * N4 + n] = s;
-}
-
-// masked softmax, redundantly per warp; lane holds boxes lane, lane+32, ...
-// sft[k] = softmax(u*m)[n], al[k] = alpha[n]; returns R = sum_n sft*m + 1e-13 (allennlp masked_softmax)
-__device__ __forceinline__ float warp_masked_softmax(int N, const float* mask_img, const float* part, int N4, int bper,
-                                                     float (&m)[ATT_NREG], float (&sft)[ATT_NREG], float (&al)[ATT_NREG]) {
-  const int lane = threadIdx.x & 31;
-  float x[ATT_NREG];
-  float mx = -INFINITY;
-#pragma unroll
-  for (int k = 0; k < ATT_NREG; ++k) {
-    const int n = lane + 32 * k;
-    m[k] = (n < N) ? mask_img[n] : 0.f;
-    x[k] = (n < N) ? gather_partial(part, N4, N, bper, n) * m[k] : -INFINITY;
-    mx = fmaxf(mx, x[k]);
-  }
-  mx = warp_max(mx);
-  float se = 0.f;
-#pragma unroll
-  for (int k = 0; k < ATT_NREG; ++k) {
-    x[k] = (lane + 32 * k < N) ? __expf(x[k] - mx) : 0.f;
-    se += x[k];
-  }
-  se = warp_sum(se);
-  float sr = 0.f;
-#pragma unroll
-  for (int k = 0; k < ATT_NREG; ++k) {
-    sft[k] = x[k] / se;
-    sr += sft[k] * m[k];
-  }
-  sr = warp_sum(sr);
-  const float Rn = sr + 1e-13f;
-#pragma unroll
-  for (int k = 0; k < ATT_NREG; ++k) al[k] = sft[k] * m[k] / Rn;
-  return Rn;
-}
-
-__device__ __forceinline__ void attn_prologue(const AttnSmem& sm, const AttnArgs& a, bool bwd) {
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < ATT_STAGES; ++s) {
-      ptx::mbar_init(&sm.full[s], 1);
-      ptx::mbar_init(&sm.empty[s], ATT_CWARPS);
-    }
-    ptx::mbar_fence_init();
-  }
-  for (int i = threadIdx.x; i < a.Ap; i += blockDim.x) {
-    sm.wa[i] = (i < a.A) ? a.w_a[i] : 0.f;
-    sm.q0[i] = 0.f;                                 // padding columns [A, Ap) stay zero: cp.async never writes them
-    sm.q0[a.Ap + i] = 0.f;
-  }
-  if (bwd)
-    for (int i = threadIdx.x; i < 2 * a.Fp; i += blockDim.x) sm.dx0[i] = 0.f;
-  __syncthreads();
-}
-
-}  // namespace
 
 __global__ void __launch_bounds__(ATT_THREADS, 2)
 attention_fwd_kernel(AttnArgs a, AttnPlan pl, float* __restrict__ alpha, float* __restrict__ smx, bf16* __restrict__ xhat,
@@ -258,7 +59,6 @@ attention_fwd_kernel(AttnArgs a, AttnPlan pl, float* __restrict__ alpha, float* 
     return;
   }
   // ---- consumers
-  const int nfv = a.Fp >> 3;
   if (r_begin < r_end) {
     prefetch_vec(sm.q(0), a.q + (size_t)r_begin * a.ld_q, a.A);
     ptx::cp_async_commit();
@@ -266,100 +66,8 @@ attention_fwd_kernel(AttnArgs a, AttnPlan pl, float* __restrict__ alpha, float* 
   int cur = 0;
   for (int r = r_begin; r < r_end; ++r, cur ^= 1) {
     const int img = a.rowmap ? a.rowmap[r] : r;
-    const float* mask_img = a.mask + (size_t)img * a.N;
-    ptx::cp_async_wait_all();
-    ptx::bar_sync(1, ATT_CONSUMERS);                 // q[cur] landed; everybody is done with the previous row
-    if (r + 1 < r_end) {
-      prefetch_vec(sm.q(cur ^ 1), a.q + (size_t)(r + 1) * a.ld_q, a.A);
-      ptx::cp_async_commit();
-    }
-    for (int c = 0; c < pl.nP; ++c) {
-      const int n0 = c * pl.bP, nb = min(pl.bP, a.N - n0);
-      ptx::mbar_wait(&sm.full[ring.stage], ring.phase);
-      chunk_scores(a, reinterpret_cast<const bf16*>(sm.stage + (size_t)ring.stage * ATT_STAGE_BYTES), n0, nb, mask_img,
-                   sm.q(cur), sm.wa, sm.u, sm.N4);
-      __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(&sm.empty[ring.stage]);
-      ring.advance();
-    }
-    ptx::bar_sync(1, ATT_CONSUMERS);                 // all N scores are in shared memory
-    float m[ATT_NREG], sft[ATT_NREG], al[ATT_NREG];
-    warp_masked_softmax(a.N, mask_img, sm.u, sm.N4, pl.bP, m, sft, al);
-    if (warp == 0) {
-#pragma unroll
-      for (int k = 0; k < ATT_NREG; ++k) {
-        const int n = lane + 32 * k;
-        if (n < a.N) {
-          alpha[(size_t)r * a.N + n] = al[k];
-          if (smx) smx[(size_t)r * a.N + n] = sft[k];
-        }
-      }
-    }
-    // weighted sum: a thread owns 8 consecutive features (one 16-byte vector per box row). The inner loop is the
-    // instruction hot spot of the kernel (ncu: 39 % of all issued instructions, 46 per 8 FMAs when alpha came out of
-    // registers through a select chain + shuffle): alpha is read as a shared-memory broadcast from the warp's own
-    // copy, bf16 -> fp32 is one shift / one mask per element, and the box loop is unrolled.
-    {
-      float* mine = sm.alw + warp * sm.N4;
-#pragma unroll
-      for (int k = 0; k < ATT_NREG; ++k)
-        if (lane + 32 * k < a.N) mine[lane + 32 * k] = al[k];
-      __syncwarp();
-    }
-    const float* alw = sm.alw + warp * sm.N4;
-    const bool two = nfv > ATT_CONSUMERS;            // uniform: a second vector per thread only when Fp > 2048
-    float acc[ATT_FV][8];
-#pragma unroll
-    for (int v = 0; v < ATT_FV; ++v)
-#pragma unroll
-      for (int k = 0; k < 8; ++k) acc[v][k] = 0.f;
-    for (int c = 0; c < pl.nF; ++c) {
-      const int n0 = c * pl.bF, nb = min(pl.bF, a.N - n0);
-      ptx::mbar_wait(&sm.full[ring.stage], ring.phase);
-      const uint4* buf = reinterpret_cast<const uint4*>(sm.stage + (size_t)ring.stage * ATT_STAGE_BYTES);
-      if (threadIdx.x < nfv) {
-#pragma unroll 4
-        for (int j = 0; j < nb; ++j) {
-          const float w = alw[n0 + j];
-          const uint4 x = buf[(size_t)j * nfv + threadIdx.x];
-          acc[0][0] = fmaf(w, __uint_as_float(x.x << 16), acc[0][0]);
-          acc[0][1] = fmaf(w, __uint_as_float(x.x & 0xffff0000u), acc[0][1]);
-          acc[0][2] = fmaf(w, __uint_as_float(x.y << 16), acc[0][2]);
-          acc[0][3] = fmaf(w, __uint_as_float(x.y & 0xffff0000u), acc[0][3]);
-          acc[0][4] = fmaf(w, __uint_as_float(x.z << 16), acc[0][4]);
-          acc[0][5] = fmaf(w, __uint_as_float(x.z & 0xffff0000u), acc[0][5]);
-          acc[0][6] = fmaf(w, __uint_as_float(x.w << 16), acc[0][6]);
-          acc[0][7] = fmaf(w, __uint_as_float(x.w & 0xffff0000u), acc[0][7]);
-        }
-      }
-      if (two && threadIdx.x + ATT_CONSUMERS < nfv) {
-        for (int j = 0; j < nb; ++j) {
-          const float w = alw[n0 + j];
-          const uint4 x = buf[(size_t)j * nfv + threadIdx.x + ATT_CONSUMERS];
-          acc[1][0] = fmaf(w, __uint_as_float(x.x << 16), acc[1][0]);
-          acc[1][1] = fmaf(w, __uint_as_float(x.x & 0xffff0000u), acc[1][1]);
-          acc[1][2] = fmaf(w, __uint_as_float(x.y << 16), acc[1][2]);
-          acc[1][3] = fmaf(w, __uint_as_float(x.y & 0xffff0000u), acc[1][3]);
-          acc[1][4] = fmaf(w, __uint_as_float(x.z << 16), acc[1][4]);
-          acc[1][5] = fmaf(w, __uint_as_float(x.z & 0xffff0000u), acc[1][5]);
-          acc[1][6] = fmaf(w, __uint_as_float(x.w << 16), acc[1][6]);
-          acc[1][7] = fmaf(w, __uint_as_float(x.w & 0xffff0000u), acc[1][7]);
-        }
-      }
-      __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(&sm.empty[ring.stage]);
-      ring.advance();
-    }
-#pragma unroll
-    for (int v = 0; v < ATT_FV; ++v) {
-      const int vec = threadIdx.x + ATT_CONSUMERS * v;
-      if (vec < nfv) {
-        bf16x8 o;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) o.v[k] = __floats2bfloat162_rn(acc[v][2 * k], acc[v][2 * k + 1]);
-        st_bf16x8(xhat + (size_t)r * ld_x + vec * 8, o);
-      }
-    }
+    attn_fwd_row(a, pl, sm, ring, cur, a.mask + (size_t)img * a.N, r + 1 < r_end ? a.q + (size_t)(r + 1) * a.ld_q : nullptr,
+                 alpha + (size_t)r * a.N, smx ? smx + (size_t)r * a.N : nullptr, xhat + (size_t)r * ld_x);
   }
 }
 

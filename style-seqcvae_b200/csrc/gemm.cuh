@@ -45,6 +45,9 @@ int gemm_suggest_splits(int M, int N, int K_total);
 // Launches on `stream`; returns 0 or an error code (message via get_error()).
 int gemm_bf16_tn(cudaStream_t stream, int M, int N, int nseg, const GemmSeg* segs, const GemmEpi& epi);
 
+// cuTensorMapEncodeTiled resolved through the runtime (null if the driver does not export it)
+void* tma_encode_fn();
+
 // number of kernels launched by this translation unit since load (bench.py's gpu_launches)
 extern unsigned long long g_launch_count;
 

@@ -152,5 +152,29 @@ int attention_backward(cudaStream_t s, const AttnArgs& a, const float* smx, cons
 int attention_backward_deferred(cudaStream_t s, const AttnArgs& a, int T, const float* q_all /*(T,B,A)*/,
                                 const float* du_all /*(T,B,N)*/, float* dproj, float* dwa_rows);
 
+// ---- persistent recurrent kernel of the training forward pass (recurrent_fwd.cu) -----------------
+// One cooperative launch runs all T timesteps of the UpDown cell for B <= 256 rows (training layout: row t*B + b,
+// image b). Buffers and packed weights exactly as api_train.cu lays them out; the per-step outputs saved for BPTT
+// (gates, cell states, q, alpha, softmax, mean / log_var / eps, kl) are the ones the per-launch path writes.
+struct RecFwdArgs {
+  int B, T, H, Hp, Fp, Zp, Z, A, KX, GP;
+  int sentiment_vae; float prior_var;
+  const bf16* w_att_rec; const bf16* wq; const bf16* w_enc_x; const bf16* w_enc_hh; const bf16* w_fc; const bf16* w_dec_x;
+  const bf16* w_dec_z;
+  const float* gx_att; const float* gavg; const float* b_att; const float* b_enc; const float* b_dec;
+  const float* sent; const float* scol_enc; const float* scol_dec;   // sent == null: no conditioning column
+  float* c1; float* c_enc; float* c_dec; float* gates_att; float* gates_enc; float* gates_dec;
+  bf16* XA; bf16* XE; bf16* HE; bf16* ZB;
+  float* q;
+  const float* b_fc; const float* eps_in; const unsigned long long* seed; const float* pm_row;
+  float* mean; float* logvar; float* eps_out; float* kl_part; float* kl;
+  AttnArgs att;                        // R = B, rowmap = null; q / ld_q unused
+  float* alpha; float* smx;
+  unsigned int* flags;                 // >= 64 bytes of scratch for the dataflow counters
+};
+bool recurrent_forward_supported(const RecFwdArgs& r);
+size_t recurrent_forward_kl_parts(int Z);   // number of per-row KL partial sums per timestep
+int recurrent_forward(cudaStream_t s, const RecFwdArgs& r);
+
 extern unsigned long long g_launch_count_pw;   // launches from the non-GEMM kernels
 }  // namespace sscvae
