@@ -291,6 +291,9 @@ def main():
     dp_mode = os.environ.get("SSCVAE_BENCH_DP", "events")
     if world > 1 and dp_mode == "events":
         model._group_events = [torch.cuda.Event() for _ in range(_lib.GRAD_GROUPS)]
+        for e in model._group_events:      # torch creates the cudaEvent_t at the first record: a handle of 0 would be skipped
+            e.record()
+        assert all(e.cuda_event for e in model._group_events)
 
     n_batches = 2
     host = [synthetic_batch(B, 100 * rank + i, True) for i in range(n_batches)]

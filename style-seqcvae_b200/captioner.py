@@ -104,11 +104,30 @@ class _TrainStep(torch.autograd.Function):
         events = module._group_events
         ev = None
         if events is not None:
-            ev = (C.c_void_p * _lib.GRAD_GROUPS)(*[e.cuda_event for e in events])
+            # torch creates the underlying cudaEvent_t lazily, at the first record(): an event that was never recorded has
+            # handle 0, the library would skip its record and a later wait_event() on it would be a no-op (the all-reduce
+            # would then race with the backward kernels). Force creation here; the library re-records them.
+            for e in events:
+                if not e.cuda_event:
+                    e.record(torch.cuda.current_stream(dev))
+            handles = [e.cuda_event for e in events]
+            if len(handles) != _lib.GRAD_GROUPS or not all(handles):
+                raise RuntimeError("sscvae: gradient-bucket events must be %d created CUDA events" % _lib.GRAD_GROUPS)
+            ev = (C.c_void_p * _lib.GRAD_GROUPS)(*handles)
         _lib.check(L.sscvae_train_backward(
             module._handle, ctx.B, ctx.N, _lib.ptr(module._packed_weights()), _lib.ptr_array(params), _lib.ptr(ws),
             ws.numel(), _lib.ptr(gl), _lib.ptr(gk), _lib.ptr_array(grads), ev, stream))
-        return (None, None, None, None, None, None) + tuple(grads)
+        # A gradient that was written into the bucket view becomes `.grad` directly (autograd's AccumulateGrad would
+        # clone a tensor that somebody else still references, and the in-place all-reduce of the buckets relies on
+        # p.grad being the view itself); anything else goes through autograd's normal accumulation.
+        out = []
+        for p, g, v in zip(params, grads, views):
+            if g is not None and g is v and p.grad is None:
+                p.grad = v
+                out.append(None)
+            else:
+                out.append(g)
+        return (None, None, None, None, None, None) + tuple(out)
 
 
 class UpDownCaptioner(nn.Module):
@@ -363,8 +382,14 @@ class UpDownCaptioner(nn.Module):
         return bufs
 
     def _next_seed(self) -> int:
+        """Philox seed of the next call: (torch seed, call counter, data-parallel rank). The rank term gives every
+        replica its own noise stream even when all ranks call torch.manual_seed with the same value (SURVEY 8e:
+        disjoint per-rank eps streams)."""
         self._call_counter += 1
-        return (int(torch.initial_seed()) * 1000003 + self._call_counter) & 0xFFFFFFFFFFFFFFFF
+        seed = (int(torch.initial_seed()) * 1000003 + self._call_counter) & 0xFFFFFFFFFFFFFFFF
+        if torch.distributed.is_available() and torch.distributed.is_initialized():
+            seed ^= ((torch.distributed.get_rank() + 1) * 0x9E3779B97F4A7C15) & 0xFFFFFFFFFFFFFFFF
+        return seed
 
     # ------------------------------------------------------------------------------------------
     def forward(
@@ -396,6 +421,10 @@ class UpDownCaptioner(nn.Module):
             caption_tokens = caption_tokens.to(image_features.device).contiguous().long()
             if caption_tokens.shape != (B, self._max_caption_length):
                 raise ValueError(f"caption_tokens must be (B, {self._max_caption_length}), got {tuple(caption_tokens.shape)}")
+            # nn.Embedding raises on an out-of-range id; the kernels index the table unchecked, so check on the device
+            # (asynchronous: no host sync on the training path)
+            torch._assert_async(((caption_tokens >= 0) & (caption_tokens < self._vocab_size)).all(),
+                                "caption_tokens contains an id outside [0, vocab_size)")
             T = self._max_caption_length + 1
             eps = self._eps_override
             if eps is None and self.rng_mode == "reference":

@@ -342,6 +342,16 @@ static inline GemmSeg seg(const bf16* A, int lda, const bf16* B, int ldb, int K)
   GemmSeg s; s.A = A; s.lda = lda; s.B = B; s.ldb = ldb; s.K = K; return s;
 }
 
+// Does the training forward of this shape run as the persistent recurrent kernel (recurrent_fwd.cu)? The backward asks
+// the same question: the persistent kernel saves the LSTM state in the row-tiled layout.
+static bool persistent_forward(const Dims& d, int B, int N) {
+  RecFwdArgs rf = {};
+  rf.B = B; rf.T = d.T; rf.H = d.H; rf.Hp = d.Hp; rf.Fp = d.Fp; rf.Zp = d.Zp; rf.Z = d.Z; rf.A = d.A; rf.KX = d.KX; rf.GP = d.GP;
+  rf.Ep = d.Ep;
+  rf.att.R = B; rf.att.N = N; rf.att.A = d.A; rf.att.Ap = d.Ap; rf.att.F = d.F; rf.att.Fp = d.Fp;
+  return recurrent_forward_supported(rf);
+}
+
 // ---- training forward --------------------------------------------------------------------------
 static int train_forward_impl(Handle* h, int B, int N, const char* pk, const void* const* wv, const float* feats,
                               const long long* cap, const float* sent, const float* eps, unsigned long long seed,
@@ -383,7 +393,8 @@ static int train_forward_impl(Handle* h, int B, int N, const char* pk, const voi
     TRY(gemm_bf16_tn(s, B * N, d.A, 1, &sg, e));
   }
   TRY(embed_gather_train(s, tok, B, d.L, Pb("embb"), d.Ep, Wb("embb_t")));
-  {  // teacher-forced embedding block of the attention-LSTM gates for all T at once
+  const bool persistent = persistent_forward(d, B, N);
+  if (!persistent) {  // teacher-forced embedding block of the attention-LSTM gates for all T at once
     GemmSeg sg = seg(Wb("embb_t"), d.Ep, Pb("w_att_e"), d.Ep, d.E);
     GemmEpi e; e.tag = "gemm.pre"; e.C32 = Wf("gx_att"); e.ldc32 = GP;
     TRY(gemm_bf16_tn(s, TB, GP, 1, &sg, e));
@@ -400,11 +411,12 @@ static int train_forward_impl(Handle* h, int B, int N, const char* pk, const voi
   // ---- the T-step recurrence: one persistent cooperative kernel (recurrent_fwd.cu) when the shape allows it,
   //      otherwise ~10 launches per timestep
   RecFwdArgs rf = {};
-  rf.B = B; rf.T = T; rf.H = H; rf.Hp = Hp; rf.Fp = Fp; rf.Zp = d.Zp; rf.Z = d.Z; rf.A = d.A; rf.KX = KX; rf.GP = GP;
+  rf.B = B; rf.T = T; rf.H = H; rf.Hp = Hp; rf.Fp = Fp; rf.Zp = d.Zp; rf.Z = d.Z; rf.A = d.A; rf.KX = KX; rf.GP = GP; rf.Ep = d.Ep;
+  rf.embb_t = Wb("embb_t"); rf.w_att_e = Pb("w_att_e");
   rf.sentiment_vae = d.sv; rf.prior_var = d.prior_std * d.prior_std;
   rf.w_att_rec = Pb("w_att_rec"); rf.wq = Pb("wq"); rf.w_enc_x = Pb("w_enc_x"); rf.w_enc_hh = Pb("w_enc_hh");
   rf.w_fc = Pb("w_fc"); rf.w_dec_x = Pb("w_dec_x"); rf.w_dec_z = Pb("w_dec_z");
-  rf.gx_att = Wf("gx_att"); rf.gavg = Wf("gavg"); rf.b_att = Pf("b_att"); rf.b_enc = Pf("b_enc"); rf.b_dec = Pf("b_dec");
+  rf.gavg = Wf("gavg"); rf.b_att = Pf("b_att"); rf.b_enc = Pf("b_enc"); rf.b_dec = Pf("b_dec");
   rf.sent = d.cond ? sent : nullptr; rf.scol_enc = Pf("scol_enc"); rf.scol_dec = Pf("scol_dec");
   rf.c1 = Wf("c1"); rf.c_enc = Wf("c_enc"); rf.c_dec = Wf("c_dec");
   rf.gates_att = Wf("gates_att"); rf.gates_enc = Wf("gates_enc"); rf.gates_dec = Wf("gates_dec");
@@ -413,7 +425,7 @@ static int train_forward_impl(Handle* h, int B, int N, const char* pk, const voi
   rf.mean = Wf("mean"); rf.logvar = Wf("logvar"); rf.eps_out = Wf("eps"); rf.kl_part = Wf("kl_part"); rf.kl = Wf("kl");
   rf.att = aa; rf.alpha = Wf("alpha"); rf.smx = Wf("smx");
   rf.flags = reinterpret_cast<unsigned int*>(ws + tp.find("rf_flags")->off);
-  if (recurrent_forward_supported(rf)) {
+  if (persistent) {
     TRY(recurrent_forward(s, rf));
   } else {
     float* acc = Wf("acc");
@@ -523,6 +535,7 @@ static int train_backward_impl(Handle* h, int B, int N, const char* pk, const vo
   const int* tok = Wi("tok");
   const float* tmask = Wf("tmask");
 
+  const int tiled = persistent_forward(d, B, N) ? 1 : 0;
   TRY(set_l2_window(s, pk + pp.find("w_dec_xzT")->off, pp.find("bwd_end")->off - pp.find("w_dec_xzT")->off));
   const char* zl[] = {"dc1", "dc_enc", "dc_dec", "dXEH0", "dXEH1", "dXA0", "dXA1",
                       "dG_att", "dG_enc", "dG_dec", "dqb"};
@@ -585,7 +598,7 @@ static int train_backward_impl(Handle* h, int B, int N, const char* pk, const vo
       l.dh[2] = dXA[nxt] + Hp; l.ld_dh[2] = 2 * Hp;
       l.dc_in = Wf("dc_dec"); l.dc_prev = Wf("dc_dec");
       l.gates = Wf("gates_dec") + rG; l.c = Wf("c_dec") + rH; l.c_prev = t ? Wf("c_dec") + rH - (size_t)B * H : nullptr;
-      l.dgates = dGd; l.ld_dg = Gp;
+      l.dgates = dGd; l.ld_dg = Gp; l.tiled = tiled;
       TRY(lstm_backward(s, l));
     }
     {  // decoder part of d[xhat|h1|h_dec_{t-1}] and d z in ONE GEMM (N = KX+Zp), then d mean / d log_var
@@ -607,7 +620,7 @@ static int train_backward_impl(Handle* h, int B, int N, const char* pk, const vo
       l.dh[1] = dXE[nxt] + KX; l.ld_dh[1] = KXH;
       l.dc_in = Wf("dc_enc"); l.dc_prev = Wf("dc_enc");
       l.gates = Wf("gates_enc") + rG; l.c = Wf("c_enc") + rH; l.c_prev = t ? Wf("c_enc") + rH - (size_t)B * H : nullptr;
-      l.dgates = dGe; l.ld_dg = Gp;
+      l.dgates = dGe; l.ld_dg = Gp; l.tiled = tiled;
       TRY(lstm_backward(s, l));
     }
     {  // encoder part of d[xhat|h1|h_dec_{t-1}] (added onto the decoder part) and d h_enc_{t-1}: one GEMM, N = KX+Hp
@@ -632,7 +645,7 @@ static int train_backward_impl(Handle* h, int B, int N, const char* pk, const vo
       l.dh[2] = dXA[nxt]; l.ld_dh[2] = 2 * Hp;
       l.dc_in = Wf("dc1"); l.dc_prev = Wf("dc1");
       l.gates = Wf("gates_att") + rG; l.c = Wf("c1") + rH; l.c_prev = t ? Wf("c1") + rH - (size_t)B * H : nullptr;
-      l.dgates = dGa; l.ld_dg = Gp;
+      l.dgates = dGa; l.ld_dg = Gp; l.tiled = tiled;
       TRY(lstm_backward(s, l));
       GemmSeg sg = seg(dGa, Gp, Pb("w_att_recT"), Gp, G);
       GemmEpi e; e.tag = "gemm.step_bwd"; e.C32 = dXA[cur]; e.ldc32 = 2 * Hp;
@@ -834,6 +847,8 @@ int sscvae_train_backward(SscvaeHandle* hh, int batch, int num_boxes, const void
                           void* const* grads, void* const* group_events, void* stream) {
   Handle* h = reinterpret_cast<Handle*>(hh);
   REQUIRE(h && packed && weights && workspace && grad_loss && grad_kld && grads, "NULL argument");
+  if (group_events)                                   // a NULL entry would be silently skipped and baked into the replayed graph
+    for (int g = 0; g < SSCVAE_GRAD_GROUPS; ++g) REQUIRE(group_events[g] != nullptr, "group_events[%d] is NULL (pass NULL for the whole array to disable)", g);
   std::vector<uint64_t> key;
   key_add(key, (uint64_t)batch); key_add(key, (uint64_t)num_boxes); key_add(key, packed); key_add(key, workspace);
   key_add(key, (uint64_t)workspace_bytes); key_add(key, grad_loss); key_add(key, grad_kld);

@@ -49,6 +49,7 @@ struct LstmBwdArgs {
   const float* c;                      // (R,H)
   bf16* dgates; int ld_dg;             // (R,4H) bf16 pre-activation grads (GEMM operand)
   float* dc_prev;                      // (R,H)
+  int tiled;                           // 1: gates / c / c_prev are blocks in the row-tiled layout (lstm_tiled_*_offset, B = R)
 };
 int lstm_backward(cudaStream_t s, const LstmBwdArgs& a);
 
@@ -155,13 +156,15 @@ int attention_backward_deferred(cudaStream_t s, const AttnArgs& a, int T, const 
 // ---- persistent recurrent kernel of the training forward pass (recurrent_fwd.cu) -----------------
 // One cooperative launch runs all T timesteps of the UpDown cell for B <= 256 rows (training layout: row t*B + b,
 // image b). Buffers and packed weights exactly as api_train.cu lays them out; the per-step outputs saved for BPTT
-// (gates, cell states, q, alpha, softmax, mean / log_var / eps, kl) are the ones the per-launch path writes.
+// (q, alpha, softmax, mean / log_var / eps, kl) are the ones the per-launch path writes; the activated gates and cell
+// states are saved in the ROW-TILED layout below (lstm_backward: LstmBwdArgs::tiled).
 struct RecFwdArgs {
-  int B, T, H, Hp, Fp, Zp, Z, A, KX, GP;
+  int B, T, H, Hp, Fp, Zp, Z, A, KX, GP, Ep;
   int sentiment_vae; float prior_var;
+  const bf16* embb_t; const bf16* w_att_e;   // teacher-forced embeddings (T*B, Ep) and their attention-LSTM weight block
   const bf16* w_att_rec; const bf16* wq; const bf16* w_enc_x; const bf16* w_enc_hh; const bf16* w_fc; const bf16* w_dec_x;
   const bf16* w_dec_z;
-  const float* gx_att; const float* gavg; const float* b_att; const float* b_enc; const float* b_dec;
+  const float* gavg; const float* b_att; const float* b_enc; const float* b_dec;
   const float* sent; const float* scol_enc; const float* scol_dec;   // sent == null: no conditioning column
   float* c1; float* c_enc; float* c_dec; float* gates_att; float* gates_enc; float* gates_dec;
   bf16* XA; bf16* XE; bf16* HE; bf16* ZB;
@@ -172,6 +175,13 @@ struct RecFwdArgs {
   float* alpha; float* smx;
   unsigned int* flags;                 // >= 64 bytes of scratch for the dataflow counters
 };
+// Row-tiled layout of the saved LSTM state of ONE timestep (B rows, H % 4 == 0 units): 4 consecutive units of a row are
+// 16 contiguous bytes and consecutive rows follow each other, so warps whose lanes are batch rows (the TMEM epilogues)
+// access 512 contiguous bytes per instruction. Offsets in floats from the block of the timestep.
+__host__ __device__ __forceinline__ size_t lstm_tiled_c_offset(int B, int b, int j) { return ((size_t)(j >> 2) * B + b) * 4 + (j & 3); }
+__host__ __device__ __forceinline__ size_t lstm_tiled_gate_offset(int B, int b, int k, int j) {
+  return (((size_t)(j >> 2) * 4 + k) * B + b) * 4 + (j & 3);
+}
 bool recurrent_forward_supported(const RecFwdArgs& r);
 size_t recurrent_forward_kl_parts(int Z);   // number of per-row KL partial sums per timestep
 int recurrent_forward(cudaStream_t s, const RecFwdArgs& r);

@@ -85,7 +85,8 @@ __global__ void __launch_bounds__(256) mt_sqnorm_kernel(const __grid_constant__ 
   const size_t hi = min((size_t)t.n[ti], lo + MT_CHUNK);
   const float* g = t.g[ti];
   float s = 0.f;
-  for (size_t i = lo + threadIdx.x; i < hi; i += 256) { const float v = g[i]; s += v * v; }
+  if (g)                                               // NULL gradient = all zeros (see sscvae_sgd_step_multi)
+    for (size_t i = lo + threadIdx.x; i < hi; i += 256) { const float v = g[i]; s += v * v; }
   s = warp_sum(s);
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
   __syncthreads();
@@ -107,7 +108,7 @@ __global__ void __launch_bounds__(256) mt_sgd_kernel(const __grid_constant__ Mul
   const bool first = t.first[ti] != 0;
   for (size_t i = lo + threadIdx.x; i < hi; i += 256) {
     const float w = p[i];
-    float d = g[i] * coef + wd * w;
+    float d = (g ? g[i] * coef : 0.f) + wd * w;
     if (momentum != 0.f) {
       const float b = first ? d : momentum * m[i] + d;
       m[i] = b;
@@ -128,7 +129,9 @@ int sscvae_sgd_step_multi(int count, void* const* params, const void* const* gra
   MultiTensorTable t;
   unsigned chunks = 0;
   for (int i = 0; i < count; ++i) {
-    REQUIRE(params[i] && grads[i] && (momentum == 0.f || (momentum_bufs && momentum_bufs[i])), "NULL tensor %d", i);
+    // grads[i] == NULL: a zero gradient (torch 1.1's zero_grad() leaves ZERO tensors behind, so a parameter frozen by
+    // train.py:156-161 keeps decaying and coasting on its momentum; see FusedClipSGD(legacy_zero_grad=True))
+    REQUIRE(params[i] && (momentum == 0.f || (momentum_bufs && momentum_bufs[i])), "NULL tensor %d", i);
     t.p[i] = reinterpret_cast<float*>(params[i]); t.g[i] = reinterpret_cast<const float*>(grads[i]);
     t.m[i] = momentum_bufs ? reinterpret_cast<float*>(momentum_bufs[i]) : nullptr;
     t.n[i] = sizes[i]; t.first[i] = first_step[i]; t.chunk0[i] = chunks;

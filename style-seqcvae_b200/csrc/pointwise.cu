@@ -253,10 +253,19 @@ __global__ void __launch_bounds__(128) lstm_bwd_v4_kernel(LstmBwdArgs a) {
 #pragma unroll
   for (int k = 0; k < 3; ++k)
     if (a.dh[k]) add4(dh, ld4(a.dh[k] + (size_t)r * a.ld_dh[k] + j));
-  const float* g = a.gates + (size_t)r * 4 * H + j;
-  const float4 gi = ld4(g), gf = ld4(g + H), gg = ld4(g + 2 * H), go = ld4(g + 3 * H);
-  const float4 c = ld4(a.c + (size_t)r * H + j);
-  const float4 cp = a.c_prev ? ld4(a.c_prev + (size_t)r * H + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+  float4 gi, gf, gg, go, c, cp = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (a.tiled) {
+    const float* g = a.gates + lstm_tiled_gate_offset(a.R, r, 0, j);
+    const size_t gs = (size_t)a.R * 4;
+    gi = ld4(g); gf = ld4(g + gs); gg = ld4(g + 2 * gs); go = ld4(g + 3 * gs);
+    c = ld4(a.c + lstm_tiled_c_offset(a.R, r, j));
+    if (a.c_prev) cp = ld4(a.c_prev + lstm_tiled_c_offset(a.R, r, j));
+  } else {
+    const float* g = a.gates + (size_t)r * 4 * H + j;
+    gi = ld4(g); gf = ld4(g + H); gg = ld4(g + 2 * H); go = ld4(g + 3 * H);
+    c = ld4(a.c + (size_t)r * H + j);
+    if (a.c_prev) cp = ld4(a.c_prev + (size_t)r * H + j);
+  }
   const float4 dci = a.dc_in ? ld4(a.dc_in + (size_t)r * H + j) : make_float4(0.f, 0.f, 0.f, 0.f);
   float4 di, df, dg, d_o, dcp;
 #define LSTM_LANE(X)                                                                     \
@@ -284,6 +293,7 @@ int lstm_backward(cudaStream_t s, const LstmBwdArgs& a) {
   bool v4 = (a.H % 4) == 0 && al16(a.gates) && al16(a.c) && (!a.c_prev || al16(a.c_prev)) && (!a.dc_in || al16(a.dc_in)) &&
             al16(a.dc_prev) && al8(a.dgates) && (a.ld_dg % 4) == 0;
   for (int k = 0; k < 3; ++k) v4 = v4 && (!a.dh[k] || (al16(a.dh[k]) && (a.ld_dh[k] % 4) == 0));
+  REQUIRE(!a.tiled || v4, "lstm_backward: the row-tiled state layout needs H %% 4 == 0 and 16-byte aligned buffers");
   if (v4) {
     CUDA_TRY(launch_pdl(lstm_bwd_v4_kernel, dim3(ceil_div(a.R * (a.H / 4), 128)), dim3(128), 0, s, a));
   } else {

@@ -38,6 +38,7 @@
 #include <curand_kernel.h>
 #include <mutex>
 #include <unordered_map>
+#include <vector>
 
 namespace sscvae {
 
@@ -48,18 +49,21 @@ namespace {
 constexpr int RF_CWARPS = 8;                                   // compute warps (epilogues + attention consumers)
 constexpr int RF_THREADS = 32 * (2 + RF_CWARPS + 1);           // + TMA producer, MMA issuer, attention producer
 constexpr int RF_CTHREADS = 32 * RF_CWARPS;
-constexpr int RF_STAGES = 5;
+constexpr int RF_STAGES = 6;
 constexpr int RF_X_BYTES = 128 * 64 * 2;                       // activation tile: 128 batch rows x 64 k (bf16)
 constexpr int RF_W_BYTES = 64 * 64 * 2;                        // weight tile half: <= 64 rows x 64 k
 constexpr int RF_STAGE_BYTES = RF_X_BYTES + RF_W_BYTES;
 constexpr int RF_TMEM_COLS = 512;
 
 enum { FLAG_H1 = 0, FLAG_HDEC, FLAG_HENC, FLAG_XHAT, FLAG_Q, FLAG_Z, FLAG_ABORT, FLAG_COUNT };
-enum { MAP_XA = 0, MAP_XE, MAP_HE, MAP_ZB, NUM_AMAPS };
-enum { WMAP_ATT = 0, WMAP_Q, WMAP_ENC_X, WMAP_ENC_HH, WMAP_FC, WMAP_DEC_X, WMAP_DEC_Z, NUM_WMAPS };
+enum { MAP_XA = 0, MAP_XE, MAP_HE, MAP_ZB, MAP_EMB, NUM_AMAPS };
+enum { WMAP_ATT = 0, WMAP_Q, WMAP_ENC_X, WMAP_ENC_HH, WMAP_FC, WMAP_DEC_X, WMAP_DEC_Z, WMAP_ATT_E, NUM_WMAPS };
 enum { SLOT_ATT = 0, SLOT_LSTM, SLOT_Q, SLOT_FC, NUM_SLOTS };
 enum { ROLE_ENC = 0, ROLE_DEC, ROLE_SPARE };
-constexpr int TMEM_COL_ATT = 0, TMEM_COL_LSTM = 128, TMEM_COL_Q = 256, TMEM_COL_FC = 384;
+// TMEM columns. LSTM pairs: two accumulators and the time-invariant addends of their gate pre-activations (biases,
+// mean-feature block, sentiment column), written once at kernel start; the other pairs: q and [mean | log_var].
+constexpr int TMEM_COL_ATT = 0, TMEM_COL_LSTM = 128, TMEM_COL_ATT_CONST = 256, TMEM_COL_LSTM_CONST = 384;
+constexpr int TMEM_COL_Q = 0, TMEM_COL_FC = 128;
 
 struct RfSeg {
   int amap, wmap;          // activation / weight tensor map
@@ -82,14 +86,14 @@ struct RfJob {
 struct RfParams {
   CUtensorMap amap[NUM_AMAPS];     // 3-D (k, batch row, t), box 64 x 128 x 1, 128B swizzle
   CUtensorMap wmap[NUM_WMAPS];     // 2-D (k, weight row), box 64 x w_box_rows
-  int B, T, H, Hp, Fp, Zp, Z, A, KX, GP;
+  int B, T, H, Hp, Fp, Zp, Z, A, KX, GP, Ep;
   int nt;                          // tiles per LSTM = GP / 128
   int nq, Nq;                      // query-projection tiles and their width
   int nfc;                         // latent tiles (16 dimensions each)
   int sentiment_vae;
   float prior_var;
   // LSTM cell epilogues
-  const float* gx_att; const float* gavg;
+  const float* gavg;
   const float* b_att; const float* b_enc; const float* b_dec;
   const float* sent; const float* scol_enc; const float* scol_dec;
   float* c1; float* c_enc; float* c_dec;
@@ -105,7 +109,14 @@ struct RfParams {
   unsigned int* flags;
   int w_policy;
   unsigned long long timeout_ns;
+  unsigned long long* dbg;         // SSCVAE_RF_DBG=1: globaltimer stamps of step dbg_t, 32 per CTA
+  int dbg_t;
 };
+
+#define RF_STAMP(cond, i)                                                                   \
+  do {                                                                                     \
+    if (p.dbg && t == p.dbg_t && (cond)) p.dbg[(size_t)blockIdx.x * 32 + (i)] = globaltimer_ns(); \
+  } while (0)
 
 // ---- bounded waits --------------------------------------------------------------------------------------------
 __device__ __forceinline__ unsigned long long globaltimer_ns() {
@@ -175,6 +186,10 @@ __device__ __forceinline__ void tma_load_3d_2sm(void* dst, const CUtensorMap* tm
       ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar) & 0xFEFFFFFFu), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
+__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* tmap, int c0, int c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(reinterpret_cast<uint64_t>(tmap)), "r"(c0), "r"(c1)
+               : "memory");
+}
 __device__ __forceinline__ void tmem_ld_x8(uint32_t taddr, float (&v)[8]) {
   uint32_t r[8];
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
@@ -222,8 +237,59 @@ __device__ __forceinline__ void st_bf16x4_rf(bf16* p, const float* h) {
   *reinterpret_cast<uint2*>(p) = o;
 }
 
+__device__ __forceinline__ void tmem_st_x8(uint32_t taddr, const float (&v)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr),
+               "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),
+               "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7]))
+               : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// Branch-free gate nonlinearities: the epilogue warps run two per SM sub-partition with little to hide instruction
+// latency behind, and tanhf / IEEE division are ~4x the instructions. Absolute error <= 2e-7, far inside the bf16
+// operand rounding of the next GEMM.
+__device__ __forceinline__ float cell_sigmoid(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+__device__ __forceinline__ float cell_tanh(float x) { return 1.0f - __fdividef(2.0f, 1.0f + __expf(2.0f * x)); }
+
+// Saved LSTM state in the "row-tiled" layout of the persistent kernels (kernels.cuh: lstm_tiled_*): within the block of
+// one timestep, 4 consecutive hidden units of one batch row are 16 contiguous bytes and consecutive rows follow each
+// other, so a warp whose lanes are 32 batch rows stores 512 contiguous bytes per instruction.
+
+// Time-invariant part of the gate pre-activations of this thread's row, written to TMEM once: b_ih + b_hh, and for the
+// attention LSTM the mean-feature block W_ih[:, avg] x_avg (hoisted GEMM `gavg`), for the encoder / decoder LSTM the
+// sentiment column sent[b] * W_ih[:, cond] (updown_cell.py:143-148, 178-194, 211-229).
+template <int WHICH>
+__device__ __forceinline__ void init_lstm_const(const RfParams& p, int tile, uint32_t tmem_base, int cw, int lane, int rank) {
+  const int qd = (cw + 2) & 3, half = cw >> 2;
+  const int b = rank * 128 + qd * 32 + lane;
+  const bool ok = b < p.B;
+  const int H = p.H;
+  const float* bias = WHICH == 0 ? p.b_att : WHICH == 1 ? p.b_enc : p.b_dec;
+  const float* scol = WHICH == 1 ? p.scol_enc : WHICH == 2 ? p.scol_dec : nullptr;
+  const float sv = (WHICH != 0 && p.sent && ok) ? p.sent[b] : 0.f;
+  const uint32_t taddr = tmem_base + (static_cast<uint32_t>(qd * 32) << 16) + (WHICH == 0 ? TMEM_COL_ATT_CONST : TMEM_COL_LSTM_CONST);
+#pragma unroll 1
+  for (int k = 0; k < 4; ++k)
+#pragma unroll 1
+    for (int c = 0; c < 2; ++c) {
+      const int u0 = half * 16 + c * 8, j0 = tile * 32 + u0;
+      float v[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        v[i] = 0.f;
+        if (ok && j0 + i < H) {
+          v[i] = bias[k * H + j0 + i];
+          if (WHICH == 0) v[i] += p.gavg[(size_t)b * p.GP + tile * 128 + k * 32 + u0 + i];
+          else if (p.sent) v[i] = fmaf(sv, scol[k * H + j0 + i], v[i]);
+        }
+      }
+      tmem_st_x8(taddr + k * 32 + u0, v);
+    }
+  tmem_st_wait();
+}
+
 // LSTM cell epilogue (torch.nn.LSTMCell, gate order i,f,g,o; updown_cell.py:143-148, 192-194, 226-229) of one 128-column
-// tile (32 hidden units x 4 gates). WHICH: 0 attention LSTM, 1 encoder, 2 decoder.
+// tile (32 hidden units x 4 gates). WHICH: 0 attention LSTM, 1 encoder, 2 decoder. A thread = one batch row x 16 units.
 template <int WHICH>
 __device__ __forceinline__ void epi_lstm(const RfParams& p, const RfSmem& sm, int t, int tile, uint32_t tmem_base, int cw, int lane,
                                          int rank) {
@@ -231,90 +297,69 @@ __device__ __forceinline__ void epi_lstm(const RfParams& p, const RfSmem& sm, in
   const int half = cw >> 2;                            // which 16 of the tile's 32 units
   const int b = rank * 128 + qd * 32 + lane;
   const bool ok = b < p.B;
-  const int H = p.H;
-  const size_t r = (size_t)t * p.B + b;
-  const float* bias = WHICH == 0 ? p.b_att : WHICH == 1 ? p.b_enc : p.b_dec;
-  const float* scol = WHICH == 1 ? p.scol_enc : WHICH == 2 ? p.scol_dec : nullptr;
-  float* cbuf = WHICH == 0 ? p.c1 : WHICH == 1 ? p.c_enc : p.c_dec;
-  float* gbuf = WHICH == 0 ? p.gates_att : WHICH == 1 ? p.gates_enc : p.gates_dec;
-  const int tcol = WHICH == 0 ? TMEM_COL_ATT : TMEM_COL_LSTM;
-  const float sv = (WHICH != 0 && p.sent && ok) ? p.sent[b] : 0.f;
-  const uint32_t taddr = tmem_base + (static_cast<uint32_t>(qd * 32) << 16) + tcol;
-#pragma unroll 1
+  const int H = p.H, H4 = H >> 2, B = p.B;
+  const size_t r = (size_t)t * B + b;
+  float* cbuf = (WHICH == 0 ? p.c1 : WHICH == 1 ? p.c_enc : p.c_dec) + (size_t)t * B * H;           // block of step t
+  float* gbuf = (WHICH == 0 ? p.gates_att : WHICH == 1 ? p.gates_enc : p.gates_dec) + (size_t)t * B * 4 * H;
+  const uint32_t tlane = tmem_base + (static_cast<uint32_t>(qd * 32) << 16);
+  const uint32_t tacc = tlane + (WHICH == 0 ? TMEM_COL_ATT : TMEM_COL_LSTM);
+  const uint32_t tcon = tlane + (WHICH == 0 ? TMEM_COL_ATT_CONST : TMEM_COL_LSTM_CONST);
+  // c_{t-1} of this thread's 16 units: independent of the accumulator, loaded before waiting for it
+  float cp[2][8];
+#pragma unroll
+  for (int chunk = 0; chunk < 2; ++chunk) {
+    const int jq0 = (tile * 32 + half * 16 + chunk * 8) >> 2;
+#pragma unroll
+    for (int v4 = 0; v4 < 2; ++v4) {
+      float4 c4 = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (ok && t > 0 && jq0 + v4 < H4) c4 = ld4g(cbuf - (size_t)B * H + ((size_t)(jq0 + v4) * B + b) * 4);
+      cp[chunk][v4 * 4] = c4.x; cp[chunk][v4 * 4 + 1] = c4.y; cp[chunk][v4 * 4 + 2] = c4.z; cp[chunk][v4 * 4 + 3] = c4.w;
+    }
+  }
+  mbar_wait_bounded(p, &sm.tfull[WHICH == 0 ? SLOT_ATT : SLOT_LSTM], (uint32_t)(t & 1), 10 + WHICH, t);
+  tc_fence_after();
+  RF_STAMP(cw == 0 && lane == 0, WHICH == 0 ? 8 : 9);
+#pragma unroll
   for (int chunk = 0; chunk < 2; ++chunk) {
     const int u0 = half * 16 + chunk * 8;              // unit inside the tile
     const int j0 = tile * 32 + u0;                     // hidden unit
     const int nv = min(8, max(0, H - j0));             // valid units of this chunk (H % 4 == 0)
-    float pre[4][8], cp[8];
+    float acc[4][8], pre[4][8];
 #pragma unroll
-    for (int k = 0; k < 4; ++k)
-#pragma unroll
-      for (int i = 0; i < 8; ++i) pre[k][i] = 0.f;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) cp[i] = 0.f;
-    if (ok) {
-#pragma unroll
-      for (int v4 = 0; v4 < 2; ++v4) {
-        if (v4 * 4 < nv) {
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            float* dst = &pre[k][v4 * 4];
-            add4v(dst, ld4g(bias + k * H + j0 + v4 * 4));
-            if (WHICH == 0) {
-              const int col = tile * 128 + k * 32 + u0 + v4 * 4;
-              add4v(dst, ld4g(p.gx_att + r * p.GP + col));
-              add4v(dst, ld4g(p.gavg + (size_t)b * p.GP + col));
-            } else if (p.sent) {
-              fma4v(dst, sv, ld4g(scol + k * H + j0 + v4 * 4));
-            }
-          }
-          if (t > 0) {
-            const float4 c4 = ld4g(cbuf + (r - p.B) * H + j0 + v4 * 4);
-            cp[v4 * 4] = c4.x; cp[v4 * 4 + 1] = c4.y; cp[v4 * 4 + 2] = c4.z; cp[v4 * 4 + 3] = c4.w;
-          }
-        }
-      }
-    }
-    if (chunk == 0) {
-      mbar_wait_bounded(p, &sm.tfull[WHICH == 0 ? SLOT_ATT : SLOT_LSTM], (uint32_t)(t & 1), 10 + WHICH, t);
-      tc_fence_after();
-    }
-    float acc[4][8];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) tmem_ld_x8(taddr + k * 32 + u0, acc[k]);
+    for (int k = 0; k < 4; ++k) { tmem_ld_x8(tacc + k * 32 + u0, acc[k]); tmem_ld_x8(tcon + k * 32 + u0, pre[k]); }
     tmem_ld_wait();
     if (ok && nv > 0) {
       float gi[8], gf[8], gg[8], go[8], c[8], h[8];
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
-        gi[i] = sigmoidf_(acc[0][i] + pre[0][i]);
-        gf[i] = sigmoidf_(acc[1][i] + pre[1][i]);
-        gg[i] = tanhf(acc[2][i] + pre[2][i]);
-        go[i] = sigmoidf_(acc[3][i] + pre[3][i]);
-        c[i] = gf[i] * cp[i] + gi[i] * gg[i];
-        h[i] = go[i] * tanhf(c[i]);
+        gi[i] = cell_sigmoid(acc[0][i] + pre[0][i]);
+        gf[i] = cell_sigmoid(acc[1][i] + pre[1][i]);
+        gg[i] = cell_tanh(acc[2][i] + pre[2][i]);
+        go[i] = cell_sigmoid(acc[3][i] + pre[3][i]);
+        c[i] = gf[i] * cp[chunk][i] + gi[i] * gg[i];
+        h[i] = go[i] * cell_tanh(c[i]);
       }
-      float* go_row = gbuf + r * 4 * H + j0;
-      float* c_row = cbuf + r * H + j0;
       bf16* h1 = nullptr; bf16* h2 = nullptr;
       if (WHICH == 0) {                                // h1_t -> XE_t[:, Fp + j] and XA_{t+1}[:, j]
         h1 = p.XE + r * p.KX + p.Fp + j0;
-        h2 = p.XA + (r + p.B) * 2 * p.Hp + j0;
+        h2 = p.XA + (r + B) * 2 * p.Hp + j0;
       } else if (WHICH == 1) {                         // h_enc_t -> HE_{t+1}
-        h1 = p.HE + (r + p.B) * p.Hp + j0;
+        h1 = p.HE + (r + B) * p.Hp + j0;
       } else {                                         // h_dec_t -> XA_{t+1}[:, Hp + j] and XE_{t+1}[:, Fp + Hp + j]
-        h1 = p.XA + (r + p.B) * 2 * p.Hp + p.Hp + j0;
-        if (t + 1 < p.T) h2 = p.XE + (r + p.B) * p.KX + p.Fp + p.Hp + j0;
+        h1 = p.XA + (r + B) * 2 * p.Hp + p.Hp + j0;
+        if (t + 1 < p.T) h2 = p.XE + (r + B) * p.KX + p.Fp + p.Hp + j0;
       }
 #pragma unroll
       for (int v4 = 0; v4 < 2; ++v4) {
         if (v4 * 4 < nv) {
           const int o = v4 * 4;
-          *reinterpret_cast<float4*>(go_row + o) = make_float4(gi[o], gi[o + 1], gi[o + 2], gi[o + 3]);
-          *reinterpret_cast<float4*>(go_row + H + o) = make_float4(gf[o], gf[o + 1], gf[o + 2], gf[o + 3]);
-          *reinterpret_cast<float4*>(go_row + 2 * H + o) = make_float4(gg[o], gg[o + 1], gg[o + 2], gg[o + 3]);
-          *reinterpret_cast<float4*>(go_row + 3 * H + o) = make_float4(go[o], go[o + 1], go[o + 2], go[o + 3]);
-          *reinterpret_cast<float4*>(c_row + o) = make_float4(c[o], c[o + 1], c[o + 2], c[o + 3]);
+          const size_t jq = (size_t)((j0 >> 2) + v4);
+          float* gq = gbuf + (jq * 4 * B + b) * 4;     // lstm_tiled_gate_offset(B, b, k, j) = ((jq*4 + k)*B + b)*4
+          *reinterpret_cast<float4*>(gq) = make_float4(gi[o], gi[o + 1], gi[o + 2], gi[o + 3]);
+          *reinterpret_cast<float4*>(gq + (size_t)B * 4) = make_float4(gf[o], gf[o + 1], gf[o + 2], gf[o + 3]);
+          *reinterpret_cast<float4*>(gq + (size_t)B * 8) = make_float4(gg[o], gg[o + 1], gg[o + 2], gg[o + 3]);
+          *reinterpret_cast<float4*>(gq + (size_t)B * 12) = make_float4(go[o], go[o + 1], go[o + 2], go[o + 3]);
+          *reinterpret_cast<float4*>(cbuf + (jq * B + b) * 4) = make_float4(c[o], c[o + 1], c[o + 2], c[o + 3]);
           st_bf16x4_rf(h1 + o, &h[o]);
           if (h2) st_bf16x4_rf(h2 + o, &h[o]);
         }
@@ -333,6 +378,7 @@ __device__ __forceinline__ void epi_q(const RfParams& p, const RfSmem& sm, int t
   const uint32_t taddr = tmem_base + (static_cast<uint32_t>(qd * 32) << 16) + TMEM_COL_Q;
   mbar_wait_bounded(p, &sm.tfull[SLOT_Q], (uint32_t)(t & 1), 13, t);
   tc_fence_after();
+  RF_STAMP(cw == 0 && lane == 0, 8);
   float* qrow = p.q + ((size_t)t * p.B + b) * p.A;
 #pragma unroll 1
   for (int c = half * hw; c < (half + 1) * hw; c += 8) {
@@ -356,26 +402,45 @@ __device__ __forceinline__ void epi_q(const RfParams& p, const RfSmem& sm, int t
 
 // mean / log_var heads, reparameterised sample and the per-step KL terms (updown_cell.py:196-208,
 // updown_captioner.py:295-303) of 16 latent dimensions: accumulator columns [0,16) = mean, [16,32) = log_var.
+// eps does not depend on the accumulator: it is drawn (or loaded) before waiting for it.
 __device__ __forceinline__ void epi_latent(const RfParams& p, const RfSmem& sm, int t, int tile, uint32_t tmem_base, int cw, int lane,
                                            int rank) {
   const int qd = (cw + 2) & 3, half = cw >> 2;
   const int b = rank * 128 + qd * 32 + lane;
   const bool ok = b < p.B;
   const int Z = p.Z;
+  const size_t r = (size_t)t * p.B + b;
+  const int z0 = tile * 16 + half * 8;
+  float e[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) e[i] = 0.f;
+  if (ok) {
+    if (p.eps_in) {
+#pragma unroll
+      for (int i = 0; i < 8; i += 2)
+        if (z0 + i < Z) {                              // Z even, z0 even: pairs never straddle the end
+          const float2 v = *reinterpret_cast<const float2*>(p.eps_in + r * Z + z0 + i);
+          e[i] = v.x; e[i + 1] = v.y;
+        }
+    } else {
+      const unsigned long long seed = *p.seed;
+#pragma unroll 1
+      for (int i = 0; i < 8; ++i)
+        if (z0 + i < Z) e[i] = philox_normal_rf(seed, (unsigned long long)t, b, z0 + i, Z);
+    }
+  }
   const uint32_t taddr = tmem_base + (static_cast<uint32_t>(qd * 32) << 16) + TMEM_COL_FC;
   mbar_wait_bounded(p, &sm.tfull[SLOT_FC], (uint32_t)(t & 1), 14, t);
   tc_fence_after();
+  RF_STAMP(cw == 0 && lane == 0, 9);
   float mu[8], lv[8];
   tmem_ld_x8(taddr + half * 8, mu);
   tmem_ld_x8(taddr + 16 + half * 8, lv);
   tmem_ld_wait();
   tc_fence_before();
   if (!ok) return;
-  const size_t r = (size_t)t * p.B + b;
-  const int z0 = tile * 16 + half * 8;
   const float pm = p.pm_row ? p.pm_row[b] : 0.f;
   const float log_pv = logf(p.prior_var);
-  const unsigned long long seed = p.eps_in ? 0ull : *p.seed;
   float part = 0.f;
   float zz[8];
 #pragma unroll
@@ -383,18 +448,21 @@ __device__ __forceinline__ void epi_latent(const RfParams& p, const RfSmem& sm, 
     const int z = z0 + i;
     zz[i] = 0.f;
     if (z < Z) {
-      const float m = mu[i] + p.b_fc[z];
-      const float l = lv[i] + p.b_fc[Z + z];
-      const float var = __expf(l);
-      const float e = p.eps_in ? p.eps_in[r * Z + z] : philox_normal_rf(seed, (unsigned long long)t, b, z, Z);
-      zz[i] = e * sqrtf(var) + m;
-      p.mean[r * Z + z] = m;
-      p.logvar[r * Z + z] = l;
-      p.eps_out[r * Z + z] = e;
-      if (p.sentiment_vae == 0) part += 1.f + l - m * m - var;
-      else part += 1.f + l - log_pv - ((m - pm) * (m - pm) + var) / (p.prior_var + 0.00001f);
+      mu[i] += p.b_fc[z];
+      lv[i] += p.b_fc[Z + z];
+      const float var = __expf(lv[i]);
+      zz[i] = e[i] * sqrtf(var) + mu[i];
+      if (p.sentiment_vae == 0) part += 1.f + lv[i] - mu[i] * mu[i] - var;
+      else part += 1.f + lv[i] - log_pv - ((mu[i] - pm) * (mu[i] - pm) + var) / (p.prior_var + 0.00001f);
     }
   }
+#pragma unroll
+  for (int i = 0; i < 8; i += 2)
+    if (z0 + i < Z) {
+      *reinterpret_cast<float2*>(p.mean + r * Z + z0 + i) = make_float2(mu[i], mu[i + 1]);
+      *reinterpret_cast<float2*>(p.logvar + r * Z + z0 + i) = make_float2(lv[i], lv[i + 1]);
+      *reinterpret_cast<float2*>(p.eps_out + r * Z + z0 + i) = make_float2(e[i], e[i + 1]);
+    }
   if (z0 < p.Zp) {
     bf16x8 o;
 #pragma unroll
@@ -418,10 +486,11 @@ __device__ void build_jobs(const RfParams& p, int pair, RfJob* jobs, int* njobs)
   const int n_rows = min((int)gridDim.x, p.B);         // CTAs that signal attention rows
   int n = 0;
   if (pair < nt) {
-    RfJob& a = jobs[n++];                              // attention LSTM tile: [h1_{t-1} | h_dec_{t-1}] W_att_rec^T
-    a.nseg = 2;
-    a.seg[0] = make_seg(MAP_XA, 0, WMAP_ATT, 0, kbH, 0, FLAG_H1, n_lstm, 0);
-    a.seg[1] = make_seg(MAP_XA, p.Hp, WMAP_ATT, p.Hp, kbH, 0, FLAG_HDEC, n_lstm, 0);
+    RfJob& a = jobs[n++];                              // attention LSTM tile: emb_t W_e^T + [h1_{t-1} | h_dec_{t-1}] W_att_rec^T
+    a.nseg = 3;                                        // teacher-forced embedding block first: it needs no flag
+    a.seg[0] = make_seg(MAP_EMB, 0, WMAP_ATT_E, 0, p.Ep >> 6, 0, -1, 0, 0);
+    a.seg[1] = make_seg(MAP_XA, 0, WMAP_ATT, 0, kbH, 0, FLAG_H1, n_lstm, 0);
+    a.seg[2] = make_seg(MAP_XA, p.Hp, WMAP_ATT, p.Hp, kbH, 0, FLAG_HDEC, n_lstm, 0);
     a.w_row[0] = pair * 128; a.w_row[1] = pair * 128 + 64; a.w_box_rows = 64; a.N = 128;
     a.tmem_col = TMEM_COL_ATT; a.slot = SLOT_ATT;
     RfJob& e = jobs[n++];                              // encoder LSTM tile: h_enc_{t-1}, h_dec_{t-1}, h1_t, x_hat_t
@@ -517,6 +586,10 @@ recurrent_fwd_kernel(const __grid_constant__ RfParams p) {
           const uint32_t tx = 2u * (uint32_t)(RF_X_BYTES + job.w_box_rows * 128);
           for (int s = 0; s < job.nseg; ++s) {
             const RfSeg sg = job.seg[s];
+            // The weight tiles of a segment do not depend on any flag: pull them into L2 while the activations they
+            // multiply are still being produced (the ring alone keeps only RF_STAGES tiles in flight, which left the
+            // weight stream HBM-latency bound: ~0.4 us per k-block).
+            for (int kb = 0; kb < sg.kblocks; ++kb) tma_prefetch_2d(&p.wmap[sg.wmap], sg.wcol0 + kb * 64, job.w_row[rank]);
             if (sg.flag >= 0) {
               const unsigned int target = (unsigned int)((t + sg.flag_toff) * sg.flag_mult);
               if (target) {
@@ -524,6 +597,7 @@ recurrent_fwd_kernel(const __grid_constant__ RfParams p) {
                 fence_proxy_async_global();
               }
             }
+            RF_STAMP(true, 10 + j * 4 + s);
             for (int kb = 0; kb < sg.kblocks; ++kb) {
               mbar_wait_bounded(p, &sm.empty[stage], phase ^ 1, 1, t);
               if (rank == 0) mbar_expect_tx(&sm.full[stage], tx);
@@ -567,6 +641,7 @@ recurrent_fwd_kernel(const __grid_constant__ RfParams p) {
             }
           }
           umma_commit_2sm(&sm.tfull[job.slot]);
+          RF_STAMP(true, 20 + j);
         }
       }
     }
@@ -580,17 +655,28 @@ recurrent_fwd_kernel(const __grid_constant__ RfParams p) {
     const bool has_q = role == ROLE_SPARE && s_idx < p.nq;
     const bool has_fc = role == ROLE_SPARE && s_idx < p.nfc;
     const int tile = role == ROLE_ENC ? pair : role == ROLE_DEC ? pair - p.nt : s_idx;
+    if (role == ROLE_ENC) {
+      init_lstm_const<0>(p, tile, tmem_base, cw, lane, rank);
+      init_lstm_const<1>(p, tile, tmem_base, cw, lane, rank);
+    } else if (role == ROLE_DEC) {
+      init_lstm_const<2>(p, tile, tmem_base, cw, lane, rank);
+    }
+    tc_fence_before();
     for (int t = 0; t < T; ++t) {
+      RF_STAMP(ctid == 0, 0);
       if (role == ROLE_ENC) {
         epi_lstm<0>(p, sm, t, tile, tmem_base, cw, lane, rank);
+        RF_STAMP(ctid == 0, 1);
         signal_done(p, FLAG_H1, ctid);
       } else if (has_q) {
         epi_q(p, sm, t, tile, tmem_base, cw, lane, rank);
+        RF_STAMP(ctid == 0, 1);
         signal_done(p, FLAG_Q, ctid);
       }
       // ---- region attention of this CTA's rows (attention.py:69-93, updown_cell.py:156)
       if (cta < p.B) {
         if (ctid == 0) wait_flag(p, FLAG_Q, (unsigned int)((t + 1) * 2 * p.nq), 20, t);
+        RF_STAMP(ctid == 0, 3);
         ptx::bar_sync(1, RF_CTHREADS);
         const float* q_t = p.q + (size_t)t * p.B * p.A;
         prefetch_vec(asm_.q(0), q_t + (size_t)cta * p.A, a.A);
@@ -601,18 +687,24 @@ recurrent_fwd_kernel(const __grid_constant__ RfParams p) {
           attn_fwd_row(a, p.plan, asm_, ring, cur, a.mask + (size_t)b * a.N, b + G < p.B ? q_t + (size_t)(b + G) * p.A : nullptr,
                        p.alpha + r * a.N, p.smx + r * a.N, p.XE + r * p.KX);
         }
+        RF_STAMP(ctid == 0, 4);
         signal_done(p, FLAG_XHAT, ctid);
       }
+      RF_STAMP(ctid == 0, 5);
       if (role == ROLE_ENC) {
         epi_lstm<1>(p, sm, t, tile, tmem_base, cw, lane, rank);
+        RF_STAMP(ctid == 0, 6);
         signal_done(p, FLAG_HENC, ctid);
       } else if (role == ROLE_DEC) {
         epi_lstm<2>(p, sm, t, tile, tmem_base, cw, lane, rank);
+        RF_STAMP(ctid == 0, 6);
         signal_done(p, FLAG_HDEC, ctid);
       } else if (has_fc) {
         epi_latent(p, sm, t, tile, tmem_base, cw, lane, rank);
+        RF_STAMP(ctid == 0, 6);
         signal_done(p, FLAG_Z, ctid);
       }
+      RF_STAMP(ctid == 0, 7);
     }
   } else {
     // ================= attention producer: streams P and the region features of this CTA's rows =================
@@ -708,7 +800,7 @@ size_t recurrent_forward_kl_parts(int Z) { return 2 * (size_t)((Z + 15) / 16); }
 bool recurrent_forward_supported(const RecFwdArgs& r) {
   static const bool off = [] { const char* e = getenv("SSCVAE_PERSISTENT"); return e && e[0] == '0'; }();
   if (off) return false;
-  if (r.B > 256 || r.B < 1 || (r.H & 3) || r.GP % 128 || (r.Hp & 63) || (r.Fp & 63) || (r.Zp & 63)) return false;
+  if (r.B > 256 || r.B < 1 || (r.H & 3) || r.GP % 128 || (r.Hp & 63) || (r.Fp & 63) || (r.Zp & 63) || (r.Ep & 63) || (r.Z & 1)) return false;
   AttnArgs a = r.att;
   if (a.N > 32 * ATT_NREG || a.Fp > 8 * ATT_CONSUMERS * ATT_FV || a.Ap * 2 > ATT_STAGE_BYTES || a.Fp * 2 > ATT_STAGE_BYTES ||
       (a.Ap % 8) || (a.Fp % 8))
@@ -736,6 +828,7 @@ int recurrent_forward(cudaStream_t s, const RecFwdArgs& r) {
   REQUIRE(NP > 0, "recurrent_fwd: no co-resident CTA pairs");
   const int nt = r.GP / 128, spare = NP - 2 * nt;
   p.B = r.B; p.T = r.T; p.H = r.H; p.Hp = r.Hp; p.Fp = r.Fp; p.Zp = r.Zp; p.Z = r.Z; p.A = r.A; p.KX = r.KX; p.GP = r.GP;
+  p.Ep = r.Ep;
   p.nt = nt;
   p.Nq = round_up(ceil_div(r.A, spare), 16);
   p.nq = ceil_div(r.A, p.Nq);
@@ -745,6 +838,7 @@ int recurrent_forward(cudaStream_t s, const RecFwdArgs& r) {
   TRY(encode_act3d(&p.amap[MAP_XE], r.XE, r.KX, r.B, r.T, r.KX));
   TRY(encode_act3d(&p.amap[MAP_HE], r.HE, r.Hp, r.B, r.T + 1, r.Hp));
   TRY(encode_act3d(&p.amap[MAP_ZB], r.ZB, r.Zp, r.B, r.T, r.Zp));
+  TRY(encode_act3d(&p.amap[MAP_EMB], r.embb_t, r.Ep, r.B, r.T, r.Ep));
   TRY(encode_w2d(&p.wmap[WMAP_ATT], r.w_att_rec, 2 * r.Hp, r.GP, 2 * r.Hp, 64));
   TRY(encode_w2d(&p.wmap[WMAP_Q], r.wq, r.Hp, r.A, r.Hp, p.Nq / 2));
   TRY(encode_w2d(&p.wmap[WMAP_ENC_X], r.w_enc_x, r.KX, r.GP, r.KX, 64));
@@ -752,7 +846,8 @@ int recurrent_forward(cudaStream_t s, const RecFwdArgs& r) {
   TRY(encode_w2d(&p.wmap[WMAP_FC], r.w_fc, r.Hp, 2 * r.Z, r.Hp, 16));
   TRY(encode_w2d(&p.wmap[WMAP_DEC_X], r.w_dec_x, r.KX, r.GP, r.KX, 64));
   TRY(encode_w2d(&p.wmap[WMAP_DEC_Z], r.w_dec_z, r.Zp, r.GP, r.Zp, 64));
-  p.gx_att = r.gx_att; p.gavg = r.gavg; p.b_att = r.b_att; p.b_enc = r.b_enc; p.b_dec = r.b_dec;
+  TRY(encode_w2d(&p.wmap[WMAP_ATT_E], r.w_att_e, r.Ep, r.GP, r.Ep, 64));
+  p.gavg = r.gavg; p.b_att = r.b_att; p.b_enc = r.b_enc; p.b_dec = r.b_dec;
   p.sent = r.sent; p.scol_enc = r.scol_enc; p.scol_dec = r.scol_dec;
   p.c1 = r.c1; p.c_enc = r.c_enc; p.c_dec = r.c_dec;
   p.gates_att = r.gates_att; p.gates_enc = r.gates_enc; p.gates_dec = r.gates_dec;
@@ -775,8 +870,16 @@ int recurrent_forward(cudaStream_t s, const RecFwdArgs& r) {
     p.plan.rows_per_cta = 0;
   }
   // model FLOPs of the loop (un-hoisted parts only): the three gate GEMMs, q, fc; bytes: the attention stream
-  const double flops = 2.0 * r.B * r.T * ((double)r.GP * (2 * r.Hp + r.KX + r.Hp + r.KX + r.Zp) + (double)r.A * r.Hp + 2.0 * r.Z * r.Hp);
+  const double flops = 2.0 * r.B * r.T * ((double)r.GP * (r.Ep + 2 * r.Hp + r.KX + r.Hp + r.KX + r.Zp) + (double)r.A * r.Hp + 2.0 * r.Z * r.Hp);
   PROF_SCOPE(s, "recurrent_fwd", flops, (double)r.B * r.T * a.N * (a.Ap + a.Fp) * 2.0);
+  static const bool dbg = [] { const char* e = getenv("SSCVAE_RF_DBG"); return e && e[0] == '1'; }();
+  static unsigned long long* dbg_buf = nullptr;
+  if (dbg) {
+    if (!dbg_buf) CUDA_TRY(cudaMalloc(&dbg_buf, 32 * 8 * 2 * 128));
+    CUDA_TRY(cudaMemsetAsync(dbg_buf, 0, 32 * 8 * 2 * 128, s));
+    p.dbg = dbg_buf;
+    p.dbg_t = r.T / 2;
+  }
   CUDA_TRY(cudaMemsetAsync(r.flags, 0, FLAG_COUNT * sizeof(unsigned int), s));
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(2 * NP); cfg.blockDim = dim3(RF_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = s;
@@ -786,6 +889,23 @@ int recurrent_forward(cudaStream_t s, const RecFwdArgs& r) {
   cfg.attrs = attr; cfg.numAttrs = 1;
   CUDA_TRY(cudaLaunchKernelEx(&cfg, recurrent_fwd_kernel, p));
   ++g_launch_count;
+  if (dbg) {
+    static int printed = 0;
+    CUDA_TRY(cudaStreamSynchronize(s));
+    std::vector<unsigned long long> h(32 * 2 * NP);
+    CUDA_TRY(cudaMemcpy(h.data(), dbg_buf, h.size() * 8, cudaMemcpyDeviceToHost));
+    if (printed++ < 6) {
+      unsigned long long t0 = ~0ull;
+      for (int c = 0; c < 2 * NP; ++c) if (h[c * 32] && h[c * 32] < t0) t0 = h[c * 32];
+      const int show[] = {0, 1, 2 * nt - 2, 2 * nt, 4 * nt - 2, 4 * nt, 4 * nt + 2 * p.nfc, 2 * NP - 2};
+      for (int c : show) {
+        if (c < 0 || c >= 2 * NP) continue;
+        fprintf(stderr, "[rfdbg] B=%d t=%d cta=%3d:", r.B, p.dbg_t, c);
+        for (int i = 0; i < 24; ++i) fprintf(stderr, " %d:%.1f", i, h[c * 32 + i] ? (double)(h[c * 32 + i] - t0) / 1e3 : -1.0);
+        fprintf(stderr, "\n");
+      }
+    }
+  }
   const int TB = r.T * r.B;
   kl_sum_parts_kernel<<<ceil_div(TB, 256), 256, 0, s>>>(r.kl_part, 2 * p.nfc, r.B, TB, r.kl);
   CUDA_TRY(cudaGetLastError());

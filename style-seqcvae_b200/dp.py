@@ -84,10 +84,7 @@ class BucketedGradReducer:
             ctx = torch.cuda.stream(self._side_stream) if cuda else _NullCtx()
             with ctx:
                 if cuda:
-                    if events is not None:
-                        self._side_stream.wait_event(events[g])
-                    else:
-                        self._side_stream.wait_stream(torch.cuda.current_stream())
+                    self._wait_for_group(events, g)
                 off = 0
                 for p in ps:
                     flat[off:off + p.grad.numel()].copy_(p.grad.reshape(-1))
@@ -107,6 +104,14 @@ class BucketedGradReducer:
             torch.cuda.current_stream().wait_stream(self._side_stream)
 
 
+    def _wait_for_group(self, events, g):
+        """Order the side stream behind the backward kernels that produce bucket `g`. An event that was never recorded
+        has no CUDA handle and wait_event() on it is a no-op: fall back to waiting for the whole backward stream."""
+        if events is not None and getattr(events[g], "cuda_event", 0):
+            self._side_stream.wait_event(events[g])
+        else:
+            self._side_stream.wait_stream(torch.cuda.current_stream())
+
     def _reduce_in_place(self, buckets: Dict, world: int, events) -> bool:
         for g, (flat, pairs) in buckets.items():
             for p, v in pairs:
@@ -123,10 +128,7 @@ class BucketedGradReducer:
                 if not any(p.grad is not None for p, _ in pairs):
                     continue
                 if cuda:
-                    if events is not None:
-                        self._side_stream.wait_event(events[g])
-                    else:
-                        self._side_stream.wait_stream(torch.cuda.current_stream())
+                    self._wait_for_group(events, g)
                 handles.append((dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.pg, async_op=True), flat))
             for h, flat in handles:
                 h.wait()
