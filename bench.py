@@ -138,6 +138,52 @@ def cpu_reference_run(steps, warmup, B=8):
                 seconds=dt)
 
 
+def gpu_eager_reference_run(dev, B, steps=3, warmup=2):
+    """SURVEY 8(d) last sentence / BASELINE.md 3.5: "the reference PyTorch path on the B200" - the pinned oracle port of
+    the reference module (plain torch ops, autograd BPTT) run by torch eager ON THE GPU, same workload as the timed
+    arm: batch B, fwd + loss + backward + clip_grad_norm_(12.5) + torch.optim.SGD(momentum, wd). Three arithmetic
+    modes: fp32 (the reference's own), tf32 matmuls, bf16 autocast. Baseline leg only: never on the product path."""
+    from oracle import updown_oracle as uo
+    out = {}
+    cfg = uo.OracleConfig(**DIMS)
+    feats, toks, sent = (t.to(dev) for t in synthetic_batch(B, 0, False))
+    for mode in ("fp32", "tf32", "bf16_autocast"):
+        torch.backends.cuda.matmul.allow_tf32 = mode == "tf32"
+        p = {k: v.to(dev) for k, v in uo.init_params(cfg, seed=0).items()}
+        train = [v.requires_grad_(True) for k, v in p.items()
+                 if not (cfg.tied and k in ("_embedding_layer.weight", "_output_layer.weight"))]
+        opt = torch.optim.SGD(train, lr=0.015, momentum=0.9, weight_decay=0.001)
+        g = torch.Generator(device=dev).manual_seed(1234)
+
+        def step():
+            opt.zero_grad()
+            eps = torch.randn(21, B, DIMS["z_space"], generator=g, device=dev)
+            with torch.device(dev), torch.autocast("cuda", dtype=torch.bfloat16, enabled=mode == "bf16_autocast"):
+                o = uo.train_forward(p, cfg, feats, toks, sent, eps)
+            uo.train_objective(o, KLD_WEIGHT).backward()
+            torch.nn.utils.clip_grad_norm_(train, 12.5)
+            opt.step()
+        try:
+            for _ in range(warmup):
+                step()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            e0.record()
+            for _ in range(steps):
+                step()
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / steps
+            out[mode] = {"value": B / (ms / 1e3), "unit": "captions/s", "ms_per_step": ms}
+        except Exception as ex:                                     # e.g. an op autocast cannot handle
+            out[mode] = {"error": f"{type(ex).__name__}: {ex}"[:200]}
+        del p, train, opt
+    torch.backends.cuda.matmul.allow_tf32 = False
+    out["what"] = (f"oracle port of var_updown UpDownCaptioner (oracle/updown_oracle.py, pinned to the reference by tests/golden) "
+                   f"in torch {torch.__version__} eager on this GPU, batch {B}, fwd+loss+bwd+clip+SGD, {steps} timed steps")
+    return out
+
+
 def synthetic_fsm(n_images, vocab, constraint_ids):
     """(B, 2^k, 2^k, V) uint8 adjacency tensor of k single-word constraints (the shape the reference's
     FiniteStateMachineBuilder hands to ConstrainedBeamSearch, updown-baseline/updown/utils/constraints.py:329-361):
@@ -227,6 +273,7 @@ def main():
     ap.add_argument("--batch", type=int, default=256, help="captions per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-decode", action="store_true")
+    ap.add_argument("--no-gpu-eager", action="store_true")
     ap.add_argument("--profile-steps", type=int, default=2)
     args = ap.parse_args()
     # a stalled run ends itself with every thread's stack on stderr instead of waiting for the caller's timeout
@@ -398,36 +445,52 @@ def main():
         if v["bytes"] > 0:
             e["gbs"] = round(v["bytes"] / v["ms"] / 1e6, 1)
         kernels[k] = e
-    # Dominant kernel: the swapped-operand CTA-pair cluster split-K GEMM of the recurrence (class "gemm.recurrent":
-    # the three LSTM gate GEMMs and the three BPTT data-gradient GEMMs of a timestep, M = batch = 256). The per-launch
-    # instrumentation serialises the stream (its step is ~25 % slower than the timed one), so the class's SHARE of
-    # the instrumented step is applied to the timed step: duration = share x ms_per_step.
+    # Dominant kernel = the instrumented class with the largest share of the step. Since round 2 that is the persistent
+    # recurrent kernel of the forward pass (class "recurrent_fwd": all 21 timesteps in one cooperative launch), followed
+    # by the skinny BPTT data-gradient GEMMs (class "gemm.recurrent"). The per-launch instrumentation serialises the
+    # stream, so a class's SHARE of the instrumented step is applied to the timed step: duration = share x ms_per_step.
     step_ms = ms_dev / args.steps
-    dom = rep.get("gemm.recurrent")
+    Hh, Ff, Zz, Ee, Aa, Tt = (DIMS["hidden_size"], DIMS["image_feature_size"], DIMS["z_space"], DIMS["embedding_size"],
+                              DIMS["attention_projection_size"], 21)
+    # ALGORITHMIC flops per training step (reference math, unpadded dims, 2 flops per MAC):
+    #   recurrent_fwd : per row and timestep the in-loop part of the three LSTMs (attention: emb + h1 + h_dec + W_hh h1
+    #                   columns; encoder: xhat + h1 + h_dec + W_hh h_enc; decoder: xhat + h1 + h_dec + z + W_hh h_dec), the
+    #                   query projection, fc_mean / fc_log_var and the region attention (scores + weighted sum)
+    #   gemm.recurrent: the three BPTT data gradients dX = dG W of the same LSTM blocks
+    alg = {
+        "recurrent_fwd": 2.0 * B * Tt * (4 * Hh * ((Ee + 3 * Hh) + (Ff + 3 * Hh) + (Ff + 3 * Hh + Zz)) + Hh * Aa + 2 * Hh * Zz
+                                         + N_BOXES * (Aa + Ff)),
+        "gemm.recurrent": 2.0 * B * Tt * 4 * Hh * (2 * Hh + (Ff + 3 * Hh) + (Ff + 2 * Hh + Zz)),
+    }
+    names = {"recurrent_fwd": "recurrent_fwd_kernel (persistent cooperative kernel, all T steps of the UpDown cell)",
+             "gemm.recurrent": "gemm_tcgen05_swapped_pair_kernel (BPTT data-gradient GEMMs, M = batch)"}
+    traffic_file = os.path.join(ROOT, "profiles", "ncu_traffic_r02.json")        # dram read+write per launch, from ncu --set full
+    traffic = json.load(open(traffic_file)) if os.path.exists(traffic_file) else {}
     gemm_all = [v for k, v in rep.items() if k.startswith("gemm")]
-    roofline = None
-    if dom:
-        share = dom["ms"] / total_ms
-        dom_launches = dom["count"] / args.profile_steps
-        # ALGORITHMIC flops of the class (unpadded dims; the kernels execute ~6 % more on K / N padding): per timestep
-        # the attention-LSTM recurrence [h1|h_dec](2H), the encoder LSTM [xhat|h1|h_dec|h_enc](F+3H) and the decoder
-        # LSTM [xhat|h1|h_dec|z](F+2H+Z, W_hh folded) gate GEMMs, 4H outputs each, plus their three data gradients
-        Hh, Ff, Zz, Tt = DIMS["hidden_size"], DIMS["image_feature_size"], DIMS["z_space"], 21
-        flops_per_step = 2.0 * 2.0 * B * 4 * Hh * (2 * Hh + (Ff + 3 * Hh) + (Ff + 2 * Hh + Zz)) * Tt
-        dur_us = 1e3 * share * step_ms / dom_launches
-        roofline = {"kernel": "gemm_tcgen05_swapped_pair_kernel (class gemm.recurrent)", "bound": "tensor",
-                    "achieved": flops_per_step / (share * step_ms) / 1e9, "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
-                    "frac": flops_per_step / (share * step_ms) / 1e9 / peaks["tf_sustained"],
-                    # ncu --set full, profiles/ncu_full_r01c_kernels.json: dram read+write of the three forward launch
-                    # shapes (39.4, 33.1, 15.3 MB; the five backward / forward shapes average ~30 MB); algorithmic =
-                    # the bf16 weight block + operands
-                    "traffic": 30.0e6, "algorithmic_bytes_per_launch": dom["bytes"] / dom["count"],
-                    "flops_per_launch": flops_per_step / dom_launches,
-                    "peak_source": peaks["src"] + " bf16_tflops_sustained", "share_of_step": share,
-                    "launches_per_step": dom_launches, "avg_launch_us": dur_us,
-                    "all_gemm_share_of_step": sum(v["ms"] for v in gemm_all) / total_ms,
-                    "all_gemm_tflops": sum(v["flops"] for v in gemm_all) / args.profile_steps
-                                       / (sum(v["ms"] for v in gemm_all) / total_ms * step_ms) / 1e9}
+    roofline, roofline_other = None, {}
+    ranked = sorted((k for k in rep if k in alg), key=lambda k: -rep[k]["ms"])
+    for k in ranked:
+        v = rep[k]
+        share = v["ms"] / total_ms
+        n_launch = v["count"] / args.profile_steps
+        r = {"kernel": names[k], "class": k, "bound": "tensor", "achieved": alg[k] / (share * step_ms) / 1e9,
+             "peak": peaks["tf_sustained"], "unit": "TFLOP/s", "frac": alg[k] / (share * step_ms) / 1e9 / peaks["tf_sustained"],
+             "traffic": traffic.get(k), "flops_per_launch": alg[k] / n_launch, "executed_flops_per_launch": v["flops"] / v["count"],
+             "peak_source": peaks["src"] + " bf16_tflops_sustained", "share_of_step": share, "launches_per_step": n_launch,
+             "avg_launch_us": 1e3 * share * step_ms / n_launch}
+        if roofline is None:
+            roofline = r
+        else:
+            roofline_other[k] = r
+    if roofline is not None:
+        roofline["all_gemm_share_of_step"] = sum(v["ms"] for v in gemm_all) / total_ms
+        roofline["other_classes"] = roofline_other
+    for k in ("attention_bwd", "attention_fwd", "ce_fwd", "ce_bwd"):            # HBM-bound classes: achieved GB/s of their algorithmic bytes
+        if k in rep and rep[k]["bytes"] > 0:
+            share = rep[k]["ms"] / total_ms
+            gbs = rep[k]["bytes"] / args.profile_steps / (share * step_ms) / 1e6
+            roofline_other[k] = {"class": k, "bound": "hbm", "achieved": gbs, "peak": peaks["hbm"], "unit": "GB/s",
+                                 "frac": gbs / peaks["hbm"], "share_of_step": share}
 
     progress("instrumented steps done")
     decode = None
@@ -460,6 +523,11 @@ def main():
         kernels=kernels,
         decode=decode,
     )
+    if not args.no_gpu_eager and world == 1:
+        del model, opt
+        torch.cuda.empty_cache()
+        line["gpu_eager_baseline"] = gpu_eager_reference_run(dev, B)
+        progress("gpu eager reference leg done")
     if not args.no_cpu_baseline and world == 1:
         r = cpu_reference_run(20, 1)           # ~12 s of host work
         line["cpu_baseline"] = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}

@@ -140,7 +140,7 @@ static void plan_train(const Dims& d, int B, int N, Plan& p) {
   p.add("eps", TB * d.Z * f);
   p.add("kl", TB * f);
   p.add("kl_part", TB * recurrent_forward_kl_parts(d.Z) * f);   // persistent recurrent kernel: per-tile KL partial sums
-  p.add("rf_flags", 256);                                       // ... and its dataflow counters
+  p.add("rf_flags", 1024);                                      // ... and its dataflow counters
   if (d.tied) {
     p.add("ob", TB * d.Ep * b);
     p.add("o32", TB * d.E * f);

@@ -173,7 +173,7 @@ struct RecFwdArgs {
   float* mean; float* logvar; float* eps_out; float* kl_part; float* kl;
   AttnArgs att;                        // R = B, rowmap = null; q / ld_q unused
   float* alpha; float* smx;
-  unsigned int* flags;                 // >= 64 bytes of scratch for the dataflow counters
+  unsigned int* flags;                 // >= 1 KB of scratch for the dataflow counters
 };
 // Row-tiled layout of the saved LSTM state of ONE timestep (B rows, H % 4 == 0 units): 4 consecutive units of a row are
 // 16 contiguous bytes and consecutive rows follow each other, so warps whose lanes are batch rows (the TMEM epilogues)

@@ -56,6 +56,10 @@ constexpr int RF_STAGE_BYTES = RF_X_BYTES + RF_W_BYTES;
 constexpr int RF_TMEM_COLS = 512;
 
 enum { FLAG_H1 = 0, FLAG_HDEC, FLAG_HENC, FLAG_XHAT, FLAG_Q, FLAG_Z, FLAG_ABORT, FLAG_COUNT };
+// The three hidden states (families FLAG_H1, FLAG_HDEC, FLAG_HENC) are produced tile by tile (32 units per LSTM tile) and
+// consumed k-block by k-block (64 units = 2 tiles): they are tracked per TILE, counter = 2 per timestep (both CTAs of the
+// owning pair), so that a consumer streams the k-blocks whose tiles are done while the other epilogues still run.
+constexpr int TILE_FLAG_BASE = 16, TILE_FLAG_STRIDE = 64, RF_FLAG_WORDS = TILE_FLAG_BASE + 3 * TILE_FLAG_STRIDE;
 enum { MAP_XA = 0, MAP_XE, MAP_HE, MAP_ZB, MAP_EMB, NUM_AMAPS };
 enum { WMAP_ATT = 0, WMAP_Q, WMAP_ENC_X, WMAP_ENC_HH, WMAP_FC, WMAP_DEC_X, WMAP_DEC_Z, WMAP_ATT_E, NUM_WMAPS };
 enum { SLOT_ATT = 0, SLOT_LSTM, SLOT_Q, SLOT_FC, NUM_SLOTS };
@@ -70,7 +74,8 @@ struct RfSeg {
   int acol0, wcol0;        // first K column (elements) in each
   int kblocks;
   int t_off;               // the activation is read at time index t + t_off
-  int flag;                // counter that must reach (t + flag_toff) * flag_mult before the segment is loaded (-1: none)
+  int flag;                // counter that must reach (t + flag_toff) * flag_mult before the segment is loaded (-1: none);
+                           // FLAG_H1 / FLAG_HDEC / FLAG_HENC: per-tile counters, k-block kb waits for tiles 2kb, 2kb+1
   int flag_mult, flag_toff;
 };
 struct RfJob {
@@ -108,6 +113,8 @@ struct RfParams {
   float* alpha; float* smx;
   unsigned int* flags;
   int w_policy;
+  int tile_flags;                  // 1: per-tile counters for the hidden states (SSCVAE_RF_TILE_FLAGS=1; measured slower: 2.18 vs 1.95 ms)
+  int stages;                      // ring stages in use (<= RF_STAGES; SSCVAE_RF_STAGES, tuning knob)
   unsigned long long timeout_ns;
   unsigned long long* dbg;         // SSCVAE_RF_DBG=1: globaltimer stamps of step dbg_t, 32 per CTA
   int dbg_t;
@@ -153,7 +160,6 @@ __device__ __forceinline__ void wait_flag(const RfParams& p, int flag, unsigned 
       if (t0 == 0) t0 = now;
       if (now - t0 > p.timeout_ns || ld_acquire_u32(p.flags + FLAG_ABORT)) rf_abort(p, code, t, v, target);
     }
-    __nanosleep(32);
   }
 }
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
@@ -224,6 +230,25 @@ __device__ __forceinline__ void signal_done(const RfParams& p, int flag, int cti
   if (ctid == 0) red_release_add(p.flags + flag, 1u);
 }
 
+__device__ __forceinline__ void signal_tile_done(const RfParams& p, int family, int tile, int ctid) {
+  fence_proxy_async_global();
+  __threadfence();
+  ptx::bar_sync(2, RF_CTHREADS);
+  if (ctid == 0) red_release_add(p.tile_flags ? p.flags + TILE_FLAG_BASE + family * TILE_FLAG_STRIDE + tile : p.flags + family, 1u);
+}
+// Number of leading k-blocks of a hidden-state segment whose producer tiles have reached `target` (polled by the
+// TMA producer thread: all counters of the family are read with independent loads, one fence orders them).
+__device__ __forceinline__ int ready_kblocks(const RfParams& p, int family, int nt, int kblocks, unsigned int target) {
+  const unsigned int* f = p.flags + TILE_FLAG_BASE + family * TILE_FLAG_STRIDE;
+  int first_not_ready = nt;
+  for (int i = nt - 1; i >= 0; --i) {
+    unsigned int v;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(f + i) : "memory");
+    if ((int)(v - target) < 0) first_not_ready = i;
+  }
+  asm volatile("fence.acq_rel.gpu;" ::: "memory");
+  return first_not_ready >= nt ? kblocks : min(kblocks, first_not_ready >> 1);
+}
 __device__ __forceinline__ float4 ld4g(const float* p) { return *reinterpret_cast<const float4*>(p); }
 __device__ __forceinline__ void add4v(float* v, const float4& w) { v[0] += w.x; v[1] += w.y; v[2] += w.z; v[3] += w.w; }
 __device__ __forceinline__ void fma4v(float* v, float s, const float4& w) {
@@ -429,6 +454,9 @@ __device__ __forceinline__ void epi_latent(const RfParams& p, const RfSmem& sm, 
         if (z0 + i < Z) e[i] = philox_normal_rf(seed, (unsigned long long)t, b, z0 + i, Z);
     }
   }
+  // pin the draws in front of the wait (the compiler would otherwise sink the register-only Philox arithmetic to its first use)
+#pragma unroll
+  for (int i = 0; i < 8; ++i) asm volatile("" : "+f"(e[i]));
   const uint32_t taddr = tmem_base + (static_cast<uint32_t>(qd * 32) << 16) + TMEM_COL_FC;
   mbar_wait_bounded(p, &sm.tfull[SLOT_FC], (uint32_t)(t & 1), 14, t);
   tc_fence_after();
@@ -482,22 +510,21 @@ __device__ __forceinline__ RfSeg make_seg(int amap, int acol0, int wmap, int wco
 // the jobs of this pair, in issue order
 __device__ void build_jobs(const RfParams& p, int pair, RfJob* jobs, int* njobs) {
   const int nt = p.nt, kbH = p.Hp >> 6, kbF = p.Fp >> 6, kbZ = p.Zp >> 6;
-  const int n_lstm = 2 * nt;                           // CTAs that signal an LSTM tile
   const int n_rows = min((int)gridDim.x, p.B);         // CTAs that signal attention rows
   int n = 0;
   if (pair < nt) {
     RfJob& a = jobs[n++];                              // attention LSTM tile: emb_t W_e^T + [h1_{t-1} | h_dec_{t-1}] W_att_rec^T
     a.nseg = 3;                                        // teacher-forced embedding block first: it needs no flag
     a.seg[0] = make_seg(MAP_EMB, 0, WMAP_ATT_E, 0, p.Ep >> 6, 0, -1, 0, 0);
-    a.seg[1] = make_seg(MAP_XA, 0, WMAP_ATT, 0, kbH, 0, FLAG_H1, n_lstm, 0);
-    a.seg[2] = make_seg(MAP_XA, p.Hp, WMAP_ATT, p.Hp, kbH, 0, FLAG_HDEC, n_lstm, 0);
+    a.seg[1] = make_seg(MAP_XA, 0, WMAP_ATT, 0, kbH, 0, FLAG_H1, 2, 0);
+    a.seg[2] = make_seg(MAP_XA, p.Hp, WMAP_ATT, p.Hp, kbH, 0, FLAG_HDEC, 2, 0);
     a.w_row[0] = pair * 128; a.w_row[1] = pair * 128 + 64; a.w_box_rows = 64; a.N = 128;
     a.tmem_col = TMEM_COL_ATT; a.slot = SLOT_ATT;
     RfJob& e = jobs[n++];                              // encoder LSTM tile: h_enc_{t-1}, h_dec_{t-1}, h1_t, x_hat_t
     e.nseg = 4;
-    e.seg[0] = make_seg(MAP_HE, 0, WMAP_ENC_HH, 0, kbH, 0, FLAG_HENC, n_lstm, 0);
-    e.seg[1] = make_seg(MAP_XE, p.Fp + p.Hp, WMAP_ENC_X, p.Fp + p.Hp, kbH, 0, FLAG_HDEC, n_lstm, 0);
-    e.seg[2] = make_seg(MAP_XE, p.Fp, WMAP_ENC_X, p.Fp, kbH, 0, FLAG_H1, n_lstm, 1);
+    e.seg[0] = make_seg(MAP_HE, 0, WMAP_ENC_HH, 0, kbH, 0, FLAG_HENC, 2, 0);
+    e.seg[1] = make_seg(MAP_XE, p.Fp + p.Hp, WMAP_ENC_X, p.Fp + p.Hp, kbH, 0, FLAG_HDEC, 2, 0);
+    e.seg[2] = make_seg(MAP_XE, p.Fp, WMAP_ENC_X, p.Fp, kbH, 0, FLAG_H1, 2, 1);
     e.seg[3] = make_seg(MAP_XE, 0, WMAP_ENC_X, 0, kbF, 0, FLAG_XHAT, n_rows, 1);
     e.w_row[0] = pair * 128; e.w_row[1] = pair * 128 + 64; e.w_box_rows = 64; e.N = 128;
     e.tmem_col = TMEM_COL_LSTM; e.slot = SLOT_LSTM;
@@ -505,8 +532,8 @@ __device__ void build_jobs(const RfParams& p, int pair, RfJob* jobs, int* njobs)
     const int tile = pair - nt;
     RfJob& d = jobs[n++];                              // decoder LSTM tile: h_dec_{t-1}, h1_t, x_hat_t, z_t
     d.nseg = 4;
-    d.seg[0] = make_seg(MAP_XE, p.Fp + p.Hp, WMAP_DEC_X, p.Fp + p.Hp, kbH, 0, FLAG_HDEC, n_lstm, 0);
-    d.seg[1] = make_seg(MAP_XE, p.Fp, WMAP_DEC_X, p.Fp, kbH, 0, FLAG_H1, n_lstm, 1);
+    d.seg[0] = make_seg(MAP_XE, p.Fp + p.Hp, WMAP_DEC_X, p.Fp + p.Hp, kbH, 0, FLAG_HDEC, 2, 0);
+    d.seg[1] = make_seg(MAP_XE, p.Fp, WMAP_DEC_X, p.Fp, kbH, 0, FLAG_H1, 2, 1);
     d.seg[2] = make_seg(MAP_XE, 0, WMAP_DEC_X, 0, kbF, 0, FLAG_XHAT, n_rows, 1);
     d.seg[3] = make_seg(MAP_ZB, 0, WMAP_DEC_Z, 0, kbZ, 0, FLAG_Z, 2 * p.nfc, 1);
     d.w_row[0] = tile * 128; d.w_row[1] = tile * 128 + 64; d.w_box_rows = 64; d.N = 128;
@@ -516,14 +543,14 @@ __device__ void build_jobs(const RfParams& p, int pair, RfJob* jobs, int* njobs)
     if (s < p.nq) {
       RfJob& q = jobs[n++];                            // query projection tile: h1_t W_q^T
       q.nseg = 1;
-      q.seg[0] = make_seg(MAP_XE, p.Fp, WMAP_Q, 0, kbH, 0, FLAG_H1, n_lstm, 1);
+      q.seg[0] = make_seg(MAP_XE, p.Fp, WMAP_Q, 0, kbH, 0, FLAG_H1, 2, 1);
       q.w_row[0] = s * p.Nq; q.w_row[1] = s * p.Nq + (p.Nq >> 1); q.w_box_rows = p.Nq >> 1; q.N = p.Nq;
       q.tmem_col = TMEM_COL_Q; q.slot = SLOT_Q;
     }
     if (s < p.nfc) {
       RfJob& f = jobs[n++];                            // latent heads tile: h_enc_t [W_mean ; W_logvar]^T
       f.nseg = 1;
-      f.seg[0] = make_seg(MAP_HE, 0, WMAP_FC, 0, kbH, 1, FLAG_HENC, n_lstm, 1);
+      f.seg[0] = make_seg(MAP_HE, 0, WMAP_FC, 0, kbH, 1, FLAG_HENC, 2, 1);
       f.w_row[0] = s * 16; f.w_row[1] = p.Z + s * 16; f.w_box_rows = 16; f.N = 32;
       f.tmem_col = TMEM_COL_FC; f.slot = SLOT_FC;
     }
@@ -590,15 +617,29 @@ recurrent_fwd_kernel(const __grid_constant__ RfParams p) {
             // multiply are still being produced (the ring alone keeps only RF_STAGES tiles in flight, which left the
             // weight stream HBM-latency bound: ~0.4 us per k-block).
             for (int kb = 0; kb < sg.kblocks; ++kb) tma_prefetch_2d(&p.wmap[sg.wmap], sg.wcol0 + kb * 64, job.w_row[rank]);
-            if (sg.flag >= 0) {
-              const unsigned int target = (unsigned int)((t + sg.flag_toff) * sg.flag_mult);
-              if (target) {
+            const bool hidden = sg.flag == FLAG_H1 || sg.flag == FLAG_HDEC || sg.flag == FLAG_HENC;
+            const bool tiled = hidden && p.tile_flags;
+            // hidden states: 2 signals per tile and step (per-tile counters) or 2 * nt per step (one counter per family)
+            const unsigned int target = sg.flag >= 0 ? (unsigned int)((t + sg.flag_toff) * sg.flag_mult * (hidden && !tiled ? p.nt : 1)) : 0u;
+            int ready = sg.kblocks;
+            if (target) {
+              if (tiled) {
+                ready = 0;
+              } else {
                 wait_flag(p, sg.flag, target, 100 + j * 10 + s, t);
                 fence_proxy_async_global();
               }
             }
             RF_STAMP(true, 10 + j * 4 + s);
+            unsigned long long t0 = 0;
             for (int kb = 0; kb < sg.kblocks; ++kb) {
+              while (kb >= ready) {                    // hidden-state segment: stream the k-blocks whose tiles are done
+                ready = ready_kblocks(p, sg.flag, p.nt, sg.kblocks, target);
+                if (kb < ready) { fence_proxy_async_global(); break; }
+                const unsigned long long now = globaltimer_ns();
+                if (t0 == 0) t0 = now;
+                if (now - t0 > p.timeout_ns || ld_acquire_u32(p.flags + FLAG_ABORT)) rf_abort(p, 100 + j * 10 + s, t, (unsigned)ready, target);
+              }
               mbar_wait_bounded(p, &sm.empty[stage], phase ^ 1, 1, t);
               if (rank == 0) mbar_expect_tx(&sm.full[stage], tx);
               uint8_t* xs = sm.ring + (size_t)stage * RF_STAGE_BYTES;
@@ -607,7 +648,7 @@ recurrent_fwd_kernel(const __grid_constant__ RfParams p) {
                 tma_load_2d_2sm_hint(xs + RF_X_BYTES, &p.wmap[sg.wmap], &sm.full[stage], sg.wcol0 + kb * 64, job.w_row[rank], w_pol);
               else
                 tma_load_2d_2sm(xs + RF_X_BYTES, &p.wmap[sg.wmap], &sm.full[stage], sg.wcol0 + kb * 64, job.w_row[rank]);
-              if (++stage == RF_STAGES) { stage = 0; phase ^= 1; }
+              if (++stage == p.stages) { stage = 0; phase ^= 1; }
             }
           }
         }
@@ -637,7 +678,7 @@ recurrent_fwd_kernel(const __grid_constant__ RfParams p) {
                 first = false;
               }
               umma_commit_2sm(&sm.empty[stage]);
-              if (++stage == RF_STAGES) { stage = 0; phase ^= 1; }
+              if (++stage == p.stages) { stage = 0; phase ^= 1; }
             }
           }
           umma_commit_2sm(&sm.tfull[job.slot]);
@@ -667,7 +708,7 @@ recurrent_fwd_kernel(const __grid_constant__ RfParams p) {
       if (role == ROLE_ENC) {
         epi_lstm<0>(p, sm, t, tile, tmem_base, cw, lane, rank);
         RF_STAMP(ctid == 0, 1);
-        signal_done(p, FLAG_H1, ctid);
+        signal_tile_done(p, FLAG_H1, tile, ctid);
       } else if (has_q) {
         epi_q(p, sm, t, tile, tmem_base, cw, lane, rank);
         RF_STAMP(ctid == 0, 1);
@@ -694,11 +735,11 @@ recurrent_fwd_kernel(const __grid_constant__ RfParams p) {
       if (role == ROLE_ENC) {
         epi_lstm<1>(p, sm, t, tile, tmem_base, cw, lane, rank);
         RF_STAMP(ctid == 0, 6);
-        signal_done(p, FLAG_HENC, ctid);
+        signal_tile_done(p, FLAG_HENC, tile, ctid);
       } else if (role == ROLE_DEC) {
         epi_lstm<2>(p, sm, t, tile, tmem_base, cw, lane, rank);
         RF_STAMP(ctid == 0, 6);
-        signal_done(p, FLAG_HDEC, ctid);
+        signal_tile_done(p, FLAG_HDEC, tile, ctid);
       } else if (has_fc) {
         epi_latent(p, sm, t, tile, tmem_base, cw, lane, rank);
         RF_STAMP(ctid == 0, 6);
@@ -820,7 +861,9 @@ int recurrent_forward(cudaStream_t s, const RecFwdArgs& r) {
   RfParams p;
   memset(&p, 0, sizeof(p));
   AttnArgs a = r.att;
-  static const int att_pol = [] { const char* e = getenv("SSCVAE_ATT_POLICY"); return e ? atoi(e) : 0; }();
+  // measured (bench.py, ms per training step / ms of this kernel): no hint 7.06 / 2.035, evict_last 7.08 / 2.038,
+  // evict_first 6.90 / 1.950
+  static const int att_pol = [] { const char* e = getenv("SSCVAE_ATT_POLICY"); return e ? atoi(e) : 1; }();
   static const int w_pol = [] { const char* e = getenv("SSCVAE_RF_W_POLICY"); return e ? atoi(e) : 1; }();
   a.l2_policy = att_pol;
   const size_t smem = rf_smem_bytes(a);
@@ -857,6 +900,10 @@ int recurrent_forward(cudaStream_t s, const RecFwdArgs& r) {
   p.att = a; p.alpha = r.alpha; p.smx = r.smx;
   p.flags = r.flags;
   p.w_policy = w_pol;
+  static const int n_stages = [] { const char* e = getenv("SSCVAE_RF_STAGES"); return e ? std::min(RF_STAGES, std::max(2, atoi(e))) : RF_STAGES; }();
+  p.stages = n_stages;
+  static const int tile_flags = [] { const char* e = getenv("SSCVAE_RF_TILE_FLAGS"); return e && e[0] == '1' ? 1 : 0; }();
+  p.tile_flags = tile_flags;
   static const unsigned long long timeout_ms = [] { const char* e = getenv("SSCVAE_RF_TIMEOUT_MS"); return e ? (unsigned long long)atoll(e) : 4000ull; }();
   p.timeout_ns = timeout_ms * 1000000ull;
   {  // chunking of the attention streams (as attention.cu: make_plan)
@@ -880,7 +927,7 @@ int recurrent_forward(cudaStream_t s, const RecFwdArgs& r) {
     p.dbg = dbg_buf;
     p.dbg_t = r.T / 2;
   }
-  CUDA_TRY(cudaMemsetAsync(r.flags, 0, FLAG_COUNT * sizeof(unsigned int), s));
+  CUDA_TRY(cudaMemsetAsync(r.flags, 0, RF_FLAG_WORDS * sizeof(unsigned int), s));
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(2 * NP); cfg.blockDim = dim3(RF_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = s;
   cudaLaunchAttribute attr[1];
