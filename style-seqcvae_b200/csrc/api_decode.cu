@@ -43,6 +43,10 @@ static void plan_decode(const Dims& d, int B, int N, int S, int K, int J, Plan& 
   p.add("alpha", R * N * f);
   if (d.tied) p.add("ob", R * d.Ep * b);
   p.add("logits", R * d.V * f);
+  const size_t nst = gemm_rowstats_tiles(d.V);            // greedy: softmax statistics of the head GEMM instead of logits
+  p.add("rs_max", R * nst * f);
+  p.add("rs_sum", R * nst * f);
+  p.add("rs_arg", R * nst * 4);
   p.add("fsm_bits", Bv * S * d.V * 4);
   p.add("cand_val", R * S * Pmax * f);
   p.add("cand_tok", R * S * Pmax * 4);
@@ -115,6 +119,13 @@ static int decode_impl(Handle* h, int B, int J, int N, int S, int K, int P, cons
   float* c1[2] = {Wf("c1a"), Wf("c1b")};
   float* cd[2] = {Wf("cda"), Wf("cdb")};
 
+  // Unconstrained K = 1 search (greedy decode, diverse sampling): arg max and log-sum-exp come out of the head GEMM's
+  // epilogue (RowStatsEpi) and the (rows, V) fp32 logits are never written: -2 x rows x V x 4 bytes per step.
+  static const bool no_fused_head = [] { const char* e = getenv("SSCVAE_DECODE_FUSED_HEAD"); return e && e[0] == '0'; }();
+  const bool greedy = S == 1 && K == 1 && fsm == nullptr && !no_fused_head;
+  RowStatsEpi rs;
+  rs.mode = 1; rs.st_max = Wf("rs_max"); rs.st_sum = Wf("rs_sum"); rs.st_arg = Wi("rs_arg");
+  const int nst = gemm_rowstats_tiles(d.V);
   auto cell = [&](int rows, const int* tokens, const int* rowmap, bool first, const float* eps_t, int eps_stride,
                   int step) -> int {
     // in = index 0, out = index 1
@@ -132,9 +143,10 @@ static int decode_impl(Handle* h, int B, int J, int N, int S, int K, int P, cons
       GemmSeg sg = seg(Wb("XE") + Fp, KXe, Pb("wq"), Hp, Hp);
       GemmEpi e; e.tag = "gemm.decode"; e.C32 = Wf("q"); e.ldc32 = d.A;
       TRY(gemm_bf16_tn(s, rows, d.A, 1, &sg, e));
-      AttnArgs aa; aa.R = rows; aa.N = N; aa.A = d.A; aa.Ap = d.Ap; aa.F = d.F; aa.Fp = Fp; aa.rowmap = rowmap;
+      AttnArgs aa = {}; aa.R = rows; aa.N = N; aa.A = d.A; aa.Ap = d.Ap; aa.F = d.F; aa.Fp = Fp; aa.rowmap = rowmap;
       aa.q = Wf("q"); aa.ld_q = d.A; aa.proj = Wb("projb"); aa.feats = Wb("featsb"); aa.mask = Wf("mask");
       aa.w_a = W(SSCVAE_W_ATT_VEC);
+      aa.rows_per_image = first ? J : SK * J;                  // rowmap0: r / J ; rowmap: r / (SK * J)
       TRY(attention_forward(s, aa, Wf("alpha"), nullptr, Wb("XE"), KXe));
     }
     {  // eval: z ~ N(prior_mean, prior_var) (updown_cell.py:200-208); no encoder LSTM
@@ -159,11 +171,13 @@ static int decode_impl(Handle* h, int B, int J, int N, int S, int K, int P, cons
       GemmEpi e; e.tag = "gemm.decode"; e.bias = W(SSCVAE_W_OUT_PROJ_B); e.act = 1; e.C16 = Wb("ob"); e.ldc16 = d.Ep;
       TRY(gemm_bf16_tn(s, rows, d.E, 1, &sg, e));
       GemmSeg sv = seg(Wb("ob"), d.Ep, Pb("embb"), d.Ep, d.E);
-      GemmEpi ev; ev.tag = "gemm.decode"; ev.C32 = Wf("logits"); ev.ldc32 = d.V;
+      GemmEpi ev; ev.tag = "gemm.decode";
+      if (greedy) ev.rs = &rs; else { ev.C32 = Wf("logits"); ev.ldc32 = d.V; }
       TRY(gemm_bf16_tn(s, rows, d.V, 1, &sv, ev));
     } else {
       GemmSeg sg = seg(XA[1] + Hp, 2 * Hp, Pb("w_out"), Hp, Hp);
-      GemmEpi e; e.tag = "gemm.decode"; e.bias = W(SSCVAE_W_OUT_PROJ_B); e.C32 = Wf("logits"); e.ldc32 = d.V;
+      GemmEpi e; e.tag = "gemm.decode"; e.bias = W(SSCVAE_W_OUT_PROJ_B);
+      if (greedy) e.rs = &rs; else { e.C32 = Wf("logits"); e.ldc32 = d.V; }
       TRY(gemm_bf16_tn(s, rows, d.V, 1, &sg, e));
     }
     return 0;
@@ -171,7 +185,9 @@ static int decode_impl(Handle* h, int B, int J, int N, int S, int K, int P, cons
 
   // ---- step 0: one row per image, zero states (cbs.py:127-155)
   TRY(cell(Bv, Wi("start_tok"), Wi("rowmap0"), true, eps, SK, 0));
-  {
+  if (greedy) {
+    TRY(greedy_merge(s, rs.st_max, rs.st_sum, rs.st_arg, nst, Bv, nullptr, nullptr, d.boundary, tok_hist, nullptr, score_hist));
+  } else {
     SearchRowsArgs a = {};
     a.logp = Wf("logits"); a.ld = d.V; a.V = d.V; a.normalized = 0; a.fsm_bits = fsm_bits; a.R = Bv; a.S = S; a.K = K;
     a.rows_per_image = 1; a.P = K; a.end_index = d.boundary; a.neg_value = -INFINITY;
@@ -184,6 +200,12 @@ static int decode_impl(Handle* h, int B, int J, int N, int S, int K, int P, cons
   // ---- steps 1..L-1 on all R rows (cbs.py:161-250); the early exit is resolved at the end
   for (int t = 1; t < L; ++t) {
     TRY(cell(R, tok_hist + (size_t)(t - 1) * R, Wi("rowmap"), false, eps ? eps + (size_t)t * R * d.Z : nullptr, 1, t));
+    if (greedy) {
+      TRY(greedy_merge(s, rs.st_max, rs.st_sum, rs.st_arg, nst, R, tok_hist + (size_t)(t - 1) * R, score_hist + (size_t)(t - 1) * R,
+                       d.boundary, tok_hist + (size_t)t * R, bp_hist + (size_t)t * R, score_hist + (size_t)t * R));
+      TRY(state_gather(s, bp_hist + (size_t)t * R, R, SK, XA[1], XA[0], 2 * Hp, c1[1], c1[0], cd[1], cd[0], H));
+      continue;
+    }
     SearchRowsArgs a = {};
     a.logp = Wf("logits"); a.ld = d.V; a.V = d.V; a.normalized = 0; a.fsm_bits = fsm_bits; a.R = R; a.S = S; a.K = K;
     a.rows_per_image = SK; a.P = P; a.end_index = d.boundary; a.neg_value = -1e20f;

@@ -20,6 +20,7 @@ struct Dims {
   int sv, simple, tied, pad, boundary, cond;
   float prior_std, mult;
   int Fp, Ep, Hp, Ap, Zp, Vp, G, Gp, Z2, Z2p, KX;
+  int debug_logits;                    // SSCVAE_DEBUG_LOGITS=1 at create: the training forward also stores the fp32 logits (tests)
   int GP;                              // rows of a packed forward LSTM weight block: gate-interleaved, lstm_gate_rows(H)
 };
 int init_dims(const SscvaeDims* in, Dims& d);

@@ -48,6 +48,7 @@ int init_dims(const SscvaeDims* in, Dims& d) {
   d.G = 4 * d.H; d.Gp = round_up(d.G, kPad); d.Z2 = 2 * d.Z; d.Z2p = round_up(d.Z2, kPad);
   d.KX = d.Fp + 2 * d.Hp;
   d.GP = lstm_gate_rows(d.H);
+  { const char* e = getenv("SSCVAE_DEBUG_LOGITS"); d.debug_logits = (e && e[0] == '1') ? 1 : 0; }
   return 0;
 }
 
@@ -145,7 +146,17 @@ static void plan_train(const Dims& d, int B, int N, Plan& p) {
     p.add("ob", TB * d.Ep * b);
     p.add("o32", TB * d.E * f);
   }
-  p.add("logits", TB * d.V * f);
+  // The fp32 logits (T*B, V) are NOT materialised: the head GEMM's epilogue keeps per-tile softmax statistics
+  // (gemm.cuh: RowStatsEpi) and the backward recomputes the tile to emit the bf16 CE gradient. SSCVAE_DEBUG_LOGITS=1
+  // (read at sscvae_create) additionally stores them for the parity tests.
+  if (d.debug_logits) p.add("logits", TB * d.V * f);
+  const size_t nst = gemm_rowstats_tiles(d.V);
+  p.add("rs_max", TB * nst * f);
+  p.add("rs_sum", TB * nst * f);
+  p.add("rs_arg", TB * nst * 4);
+  p.add("rs_tgt", TB * f);
+  p.add("tgt_row", TB * 4);
+  p.add("gcoef", TB * f);
   p.add("lse", TB * f);
   p.add("nll", TB * f);
   // ---- backward
@@ -406,7 +417,7 @@ static int train_forward_impl(Handle* h, int B, int N, const char* pk, const voi
   }
   LatentArgs la; la.R = B; la.Z = d.Z; la.Zp = d.Zp; la.sentiment_vae = d.sv; la.prior_var = d.prior_std * d.prior_std;
   la.prior_mean_row = Wf("pm_row"); la.rowmap = nullptr;
-  AttnArgs aa; aa.R = B; aa.N = N; aa.A = d.A; aa.Ap = d.Ap; aa.F = d.F; aa.Fp = Fp; aa.rowmap = nullptr;
+  AttnArgs aa = {}; aa.R = B; aa.N = N; aa.A = d.A; aa.Ap = d.Ap; aa.F = d.F; aa.Fp = Fp; aa.rowmap = nullptr;
   aa.proj = Wb("projb"); aa.feats = Wb("featsb"); aa.mask = Wf("mask"); aa.w_a = W(SSCVAE_W_ATT_VEC); aa.ld_q = d.A;
   // ---- the T-step recurrence: one persistent cooperative kernel (recurrent_fwd.cu) when the shape allows it,
   //      otherwise ~10 launches per timestep
@@ -484,22 +495,28 @@ static int train_forward_impl(Handle* h, int B, int N, const char* pk, const voi
       }
     }
   }
-  // output head over all T*B rows at once (updown_captioner.py:444-445)
+  // output head over all T*B rows at once (updown_captioner.py:444-445) with the masked cross entropy
+  // (updown_captioner.py:457-466) fused: per-row max / sum-exp / target logit come out of the vocabulary GEMM's epilogue
   const bf16* hdec_all = Wb("XA") + (size_t)B * 2 * Hp + Hp;
+  TRY(ce_prepare(s, tok, B, d.L, tmask, Wf("lengths"), nullptr, Wi("tgt_row"), nullptr));
+  RowStatsEpi rs;
+  rs.mode = 1; rs.st_max = Wf("rs_max"); rs.st_sum = Wf("rs_sum"); rs.st_arg = Wi("rs_arg");
+  rs.target = Wi("tgt_row"); rs.tgt_logit = Wf("rs_tgt");
   if (d.tied) {
     GemmSeg sg = seg(hdec_all, 2 * Hp, Pb("w_out"), Hp, Hp);
     GemmEpi e; e.tag = "gemm.head"; e.bias = W(SSCVAE_W_OUT_PROJ_B); e.act = 1; e.C32 = Wf("o32"); e.ldc32 = d.E; e.C16 = Wb("ob"); e.ldc16 = d.Ep;
     TRY(gemm_bf16_tn(s, TB, d.E, 1, &sg, e));
     GemmSeg sv = seg(Wb("ob"), d.Ep, Pb("embb"), d.Ep, d.E);
-    GemmEpi ev; ev.tag = "gemm.head"; ev.C32 = Wf("logits"); ev.ldc32 = d.V;
+    GemmEpi ev; ev.tag = "gemm.head"; ev.rs = &rs;
+    if (d.debug_logits) { ev.C32 = Wf("logits"); ev.ldc32 = d.V; }
     TRY(gemm_bf16_tn(s, TB, d.V, 1, &sv, ev));
   } else {
     GemmSeg sg = seg(hdec_all, 2 * Hp, Pb("w_out"), Hp, Hp);
-    GemmEpi e; e.tag = "gemm.head"; e.bias = W(SSCVAE_W_OUT_PROJ_B); e.C32 = Wf("logits"); e.ldc32 = d.V;
+    GemmEpi e; e.tag = "gemm.head"; e.bias = W(SSCVAE_W_OUT_PROJ_B); e.rs = &rs;
+    if (d.debug_logits) { e.C32 = Wf("logits"); e.ldc32 = d.V; }
     TRY(gemm_bf16_tn(s, TB, d.V, 1, &sg, e));
   }
-  // masked cross entropy and KL sums (updown_captioner.py:315-322, 457-466)
-  TRY(ce_forward(s, Wf("logits"), d.V, TB, d.V, tok, B, d.L, tmask, Wf("lse"), Wf("nll")));
+  TRY(ce_merge(s, rs.st_max, rs.st_sum, rs.st_arg, gemm_rowstats_tiles(d.V), TB, Wf("rs_tgt"), Wf("lse"), Wf("nll")));
   TRY(loss_reduce(s, Wf("nll"), Wf("kl"), tmask, Wf("lengths"), T, B, loss, kld));
   TRY(set_l2_window(s, nullptr, 0));
   return 0;
@@ -543,8 +560,24 @@ static int train_backward_impl(Handle* h, int B, int N, const char* pk, const vo
   if (d.tied) CUDA_TRY(zero("dpreo"));
 
   // ---- head: d logits, d h_dec from the vocabulary projection
-  TRY(ce_backward(s, Wf("logits"), V, TB, V, tok, B, d.L, tmask, Wf("lengths"), Wf("lse"), gloss, Wb("dlogits"), d.Vp));
+  // d logits = g_b (softmax - onehot) (allennlp sequence_cross_entropy_with_logits, average=None, x len_b): the vocabulary
+  // GEMM is recomputed and its epilogue writes the bf16 gradient operand directly (the forward kept only lse per row)
   const bf16* hdec_all = Wb("XA") + (size_t)B * 2 * Hp + Hp;     // h_dec_t, t = 0..T-1, ld 2Hp
+  TRY(ce_prepare(s, tok, B, d.L, tmask, Wf("lengths"), gloss, Wi("tgt_row"), Wf("gcoef")));
+  if (d.Vp > V) CUDA_TRY(cudaMemset2DAsync(Wb("dlogits") + V, (size_t)d.Vp * 2, 0, (size_t)(d.Vp - V) * 2, (size_t)TB, s));
+  {
+    RowStatsEpi rs;
+    rs.mode = 2; rs.target = Wi("tgt_row"); rs.lse = Wf("lse"); rs.gcoef = Wf("gcoef");
+    GemmEpi e; e.tag = "gemm.head_bwd"; e.rs = &rs; e.C16 = Wb("dlogits"); e.ldc16 = d.Vp;
+    if (d.tied) {
+      GemmSeg sv = seg(Wb("ob"), d.Ep, Pb("embb"), d.Ep, E);
+      TRY(gemm_bf16_tn(s, TB, V, 1, &sv, e));
+    } else {
+      GemmSeg sg = seg(hdec_all, 2 * Hp, Pb("w_out"), Hp, Hp);
+      e.bias = W(SSCVAE_W_OUT_PROJ_B);
+      TRY(gemm_bf16_tn(s, TB, V, 1, &sg, e));
+    }
+  }
   if (d.tied) {
     GemmSeg sg = seg(Wb("dlogits"), d.Vp, Pb("embT"), d.Vp, V);
     GemmEpi e; e.tag = "gemm.head_bwd"; e.dtanh = Wf("o32"); e.ldd = E; e.C16 = Wb("dpreo"); e.ldc16 = d.Ep;
@@ -581,7 +614,7 @@ static int train_backward_impl(Handle* h, int B, int N, const char* pk, const vo
   // ---- reverse time loop
   LatentArgs la; la.R = B; la.Z = Z; la.Zp = d.Zp; la.sentiment_vae = d.sv; la.prior_var = d.prior_std * d.prior_std;
   la.prior_mean_row = Wf("pm_row"); la.rowmap = nullptr;
-  AttnArgs aa; aa.R = B; aa.N = N; aa.A = A; aa.Ap = d.Ap; aa.F = F; aa.Fp = Fp; aa.rowmap = nullptr;
+  AttnArgs aa = {}; aa.R = B; aa.N = N; aa.A = A; aa.Ap = d.Ap; aa.F = F; aa.Fp = Fp; aa.rowmap = nullptr;
   aa.proj = Wb("projb"); aa.feats = Wb("featsb"); aa.mask = Wf("mask"); aa.w_a = W(SSCVAE_W_ATT_VEC); aa.ld_q = A;
   float* dXE[2] = {Wf("dXEH0"), Wf("dXEH1")};             // [d xhat | d h1 | d h_dec_{t-1} | d h_enc_{t-1}]
   const int KXH = KX + Hp, KXZ = KX + d.Zp;

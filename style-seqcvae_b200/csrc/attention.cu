@@ -71,6 +71,207 @@ attention_fwd_kernel(AttnArgs a, AttnPlan pl, float* __restrict__ alpha, float* 
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Decode form: the rows of an image share its features (rows r = img * rows_per_image + i are contiguous:
+// (state, beam) rows of CBS, latent samples of the diverse-sampling call). attention_fwd_kernel streams the image's
+// N*(Ap+Fp) bf16 (203 KB) once per ROW: at 100 rows per image that is 1.3 GB of L2 -> SM traffic per decode step
+// (313 us per step of the batched sampling call, 0.6 % of the per-image HBM roofline, profiles/decode_profile_r01c.txt).
+// Here a CTA owns GR = 8 rows of ONE image: the projections P are copied to shared memory once and every consumer
+// warp scores its own row against all N boxes (q and w_a stay in registers; MUFU.TANH is the bound: N*A per row);
+// then the features stream through a small ring ONCE for all 8 rows and a thread accumulates 8 rows x 8 feature
+// columns in registers (64 FMAs per 16-byte shared-memory load).
+// ---------------------------------------------------------------------------------------------------------------
+namespace {
+constexpr int GR = 8;                               // rows per CTA = consumer warps
+constexpr int G_XSTAGES = 3;
+constexpr int G_XSTAGE_BYTES = 16384;
+constexpr int G_PVMAX = 4;                          // 16-byte projection vectors per lane: Ap <= 1024
+}  // namespace
+
+static size_t grouped_smem_bytes(const AttnArgs& a) {
+  const int N4 = (a.N + 3) & ~3;
+  return 128 + (size_t)a.N * a.Ap * 2 + (size_t)G_XSTAGES * G_XSTAGE_BYTES + (1 + 2 * G_XSTAGES) * 8 + 16 + (size_t)N4 * GR * 4 + (size_t)N4 * 4 + 64;
+}
+
+__global__ void __launch_bounds__(ATT_THREADS, 2)
+attention_fwd_grouped_kernel(AttnArgs a, int rows_per_image, int chunks_per_image, int bF, int nF, float* __restrict__ alpha,
+                             bf16* __restrict__ xhat, int ld_x) {
+  extern __shared__ __align__(128) uint8_t att_smem_raw[];
+  const int N = a.N, N4 = (N + 3) & ~3;
+  uint8_t* sp = att_smem_raw;
+  bf16* P_s = reinterpret_cast<bf16*>(sp); sp += (size_t)N * a.Ap * 2;
+  uint8_t* x_ring = sp; sp += (size_t)G_XSTAGES * G_XSTAGE_BYTES;
+  uint64_t* p_full = reinterpret_cast<uint64_t*>(sp); sp += 8;
+  uint64_t* x_full = reinterpret_cast<uint64_t*>(sp); sp += G_XSTAGES * 8;
+  uint64_t* x_empty = reinterpret_cast<uint64_t*>(sp); sp += G_XSTAGES * 8;
+  sp += (16 - ((1 + 2 * G_XSTAGES) * 8) % 16) % 16;                          // float4 reads of al_s
+  float* al_s = reinterpret_cast<float*>(sp); sp += (size_t)N4 * GR * 4;      // [box][row]
+  float* mask_s = reinterpret_cast<float*>(sp);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int img = blockIdx.x / chunks_per_image, chunk = blockIdx.x - img * chunks_per_image;
+  const int i0 = chunk * GR;
+  const int nrows = min(GR, rows_per_image - i0);
+  const int r0 = img * rows_per_image + i0;
+  if (threadIdx.x == 0) {
+    ptx::mbar_init(p_full, 1);
+    for (int s = 0; s < G_XSTAGES; ++s) { ptx::mbar_init(&x_full[s], 1); ptx::mbar_init(&x_empty[s], ATT_CWARPS); }
+    ptx::mbar_fence_init();
+  }
+  for (int i = threadIdx.x; i < N4 * GR; i += blockDim.x) al_s[i] = 0.f;
+  __syncthreads();
+  pdl_wait();
+  pdl_launch_dependents(2);
+  for (int i = threadIdx.x; i < N4; i += blockDim.x) mask_s[i] = i < N ? a.mask[(size_t)img * N + i] : 0.f;
+
+  if (warp == ATT_CWARPS) {                          // ---- producer: P in one go, then the feature chunks through the ring
+    if (lane == 0) {
+      const uint64_t pol = a.l2_policy == 1 ? ptx::l2_policy_evict_first() : a.l2_policy == 2 ? ptx::l2_policy_evict_last() : 0;
+      const uint8_t* pbase = reinterpret_cast<const uint8_t*>(a.proj + (size_t)img * N * a.Ap);
+      const uint32_t pbytes = (uint32_t)N * a.Ap * 2;
+      ptx::mbar_expect_tx(p_full, pbytes);
+      for (uint32_t off = 0; off < pbytes; off += 32768) {
+        const uint32_t nb = min(32768u, pbytes - off);
+        ptx::bulk_g2s(reinterpret_cast<uint8_t*>(P_s) + off, pbase + off, nb, p_full);
+      }
+      const uint8_t* fbase = reinterpret_cast<const uint8_t*>(a.feats + (size_t)img * N * a.Fp);
+      int stage = 0; uint32_t phase = 0;
+      for (int c = 0; c < nF; ++c) {
+        const int n0 = c * bF, nb = min(bF, N - n0);
+        const uint32_t bytes = (uint32_t)nb * a.Fp * 2;
+        ptx::mbar_wait(&x_empty[stage], phase ^ 1);
+        ptx::mbar_expect_tx(&x_full[stage], bytes);
+        if (pol) ptx::bulk_g2s_hint(x_ring + (size_t)stage * G_XSTAGE_BYTES, fbase + (size_t)n0 * a.Fp * 2, bytes, &x_full[stage], pol);
+        else ptx::bulk_g2s(x_ring + (size_t)stage * G_XSTAGE_BYTES, fbase + (size_t)n0 * a.Fp * 2, bytes, &x_full[stage]);
+        if (++stage == G_XSTAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+    return;
+  }
+  // ---- consumers: warp w scores row i0 + w
+  ptx::bar_sync(1, ATT_CONSUMERS);                   // mask_s visible
+  const int nvec = a.Ap >> 3;
+  if (warp < nrows) {
+    const int r = r0 + warp;
+    float qv[G_PVMAX][8], wv[G_PVMAX][8];
+#pragma unroll
+    for (int v = 0; v < G_PVMAX; ++v) {
+      const int i = lane + 32 * v;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int col = i * 8 + k;
+        const bool ok = i < nvec && col < a.A;
+        qv[v][k] = ok ? a.q[(size_t)r * a.ld_q + col] : 0.f;
+        wv[v][k] = ok ? a.w_a[col] : 0.f;
+      }
+    }
+    ptx::mbar_wait(p_full, 0);
+    float u[ATT_NREG];
+#pragma unroll
+    for (int k = 0; k < ATT_NREG; ++k) u[k] = 0.f;
+    for (int n = 0; n < N; ++n) {
+      float s = 0.f;
+      if (mask_s[n] != 0.f) {                        // masked boxes enter the softmax as u*m = 0
+        const bf16x8* prow = reinterpret_cast<const bf16x8*>(P_s + (size_t)n * a.Ap);
+#pragma unroll
+        for (int v = 0; v < G_PVMAX; ++v) {
+          const int i = lane + 32 * v;
+          if (i < nvec) {
+            const bf16x8 pv = prow[i];
+            const float2 f0 = __bfloat1622float2(pv.v[0]), f1 = __bfloat1622float2(pv.v[1]);
+            const float2 f2 = __bfloat1622float2(pv.v[2]), f3 = __bfloat1622float2(pv.v[3]);
+            s += wv[v][0] * tanh_approx(qv[v][0] + f0.x) + wv[v][1] * tanh_approx(qv[v][1] + f0.y);
+            s += wv[v][2] * tanh_approx(qv[v][2] + f1.x) + wv[v][3] * tanh_approx(qv[v][3] + f1.y);
+            s += wv[v][4] * tanh_approx(qv[v][4] + f2.x) + wv[v][5] * tanh_approx(qv[v][5] + f2.y);
+            s += wv[v][6] * tanh_approx(qv[v][6] + f3.x) + wv[v][7] * tanh_approx(qv[v][7] + f3.y);
+          }
+        }
+        s = warp_sum(s);
+      }
+#pragma unroll
+      for (int k = 0; k < ATT_NREG; ++k)
+        if (n == lane + 32 * k) u[k] = s;
+    }
+    // masked softmax (allennlp: softmax(u*m)*m / (sum + 1e-13)); lane holds boxes lane, lane+32, ...
+    float m[ATT_NREG], x[ATT_NREG];
+    float mx = -INFINITY;
+#pragma unroll
+    for (int k = 0; k < ATT_NREG; ++k) {
+      const int n = lane + 32 * k;
+      m[k] = n < N ? mask_s[n] : 0.f;
+      x[k] = n < N ? u[k] * m[k] : -INFINITY;
+      mx = fmaxf(mx, x[k]);
+    }
+    mx = warp_max(mx);
+    float se = 0.f;
+#pragma unroll
+    for (int k = 0; k < ATT_NREG; ++k) {
+      x[k] = (lane + 32 * k < N) ? __expf(x[k] - mx) : 0.f;
+      se += x[k];
+    }
+    se = warp_sum(se);
+    float sr = 0.f;
+#pragma unroll
+    for (int k = 0; k < ATT_NREG; ++k) { x[k] = x[k] / se; sr += x[k] * m[k]; }
+    sr = warp_sum(sr);
+    const float Rn = sr + 1e-13f;
+#pragma unroll
+    for (int k = 0; k < ATT_NREG; ++k) {
+      const int n = lane + 32 * k;
+      if (n < N) {
+        const float al = x[k] * m[k] / Rn;
+        alpha[(size_t)r * N + n] = al;
+        al_s[n * GR + warp] = al;
+      }
+    }
+  }
+  ptx::bar_sync(1, ATT_CONSUMERS);                   // alpha of all rows of the chunk is in shared memory
+  // ---- weighted sum: thread = 8 feature columns x 8 rows
+  const int nfv = a.Fp >> 3;
+  float acc[GR][8];
+#pragma unroll
+  for (int i = 0; i < GR; ++i)
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc[i][k] = 0.f;
+  int stage = 0; uint32_t phase = 0;
+  for (int c = 0; c < nF; ++c) {
+    const int n0 = c * bF, nb = min(bF, N - n0);
+    ptx::mbar_wait(&x_full[stage], phase);
+    const uint4* buf = reinterpret_cast<const uint4*>(x_ring + (size_t)stage * G_XSTAGE_BYTES);
+    if ((int)threadIdx.x < nfv) {
+      for (int j = 0; j < nb; ++j) {
+        const uint4 xq = buf[(size_t)j * nfv + threadIdx.x];
+        float xf[8];
+        xf[0] = __uint_as_float(xq.x << 16); xf[1] = __uint_as_float(xq.x & 0xffff0000u);
+        xf[2] = __uint_as_float(xq.y << 16); xf[3] = __uint_as_float(xq.y & 0xffff0000u);
+        xf[4] = __uint_as_float(xq.z << 16); xf[5] = __uint_as_float(xq.z & 0xffff0000u);
+        xf[6] = __uint_as_float(xq.w << 16); xf[7] = __uint_as_float(xq.w & 0xffff0000u);
+        const float4 w0 = *reinterpret_cast<const float4*>(al_s + (n0 + j) * GR);
+        const float4 w1 = *reinterpret_cast<const float4*>(al_s + (n0 + j) * GR + 4);
+        const float w[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+        for (int i = 0; i < GR; ++i)
+#pragma unroll
+          for (int k = 0; k < 8; ++k) acc[i][k] = fmaf(w[i], xf[k], acc[i][k]);
+      }
+    }
+    __syncwarp();
+    if (lane == 0) ptx::mbar_arrive(&x_empty[stage]);
+    if (++stage == G_XSTAGES) { stage = 0; phase ^= 1; }
+  }
+  if ((int)threadIdx.x < nfv) {
+#pragma unroll
+    for (int i = 0; i < GR; ++i) {
+      if (i < nrows) {
+        bf16x8 o;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) o.v[k] = __floats2bfloat162_rn(acc[i][2 * k], acc[i][2 * k + 1]);
+        st_bf16x8(xhat + (size_t)(r0 + i) * ld_x + threadIdx.x * 8, o);
+      }
+    }
+  }
+}
+
 static int make_plan(const AttnArgs& a, AttnPlan& pl) {
   if (a.N > 32 * ATT_NREG || a.Fp > 8 * ATT_CONSUMERS * ATT_FV || a.Ap > 2 * ATT_CONSUMERS * ATT_PV ||
       a.Ap * 2 > ATT_STAGE_BYTES || a.Fp * 2 > ATT_STAGE_BYTES || attn_smem_bytes(a, true) > 112 * 1024) {
@@ -110,6 +311,23 @@ int attention_forward(cudaStream_t s, const AttnArgs& a_in, float* alpha, float*
   REQUIRE(a.R > 0 && (ld_x % 8) == 0 && (reinterpret_cast<uintptr_t>(xhat) & 15) == 0, "attention_forward: bad xhat layout");
   AttnPlan pl;
   TRY(make_plan(a, pl));
+  // decode: rows of an image are contiguous and share its features -> one CTA per 8 rows of an image
+  static const bool no_grouped = [] { const char* e = getenv("SSCVAE_ATT_GROUPED"); return e && e[0] == '0'; }();
+  if (!no_grouped && a.rows_per_image >= 4 && smx == nullptr && a.Fp <= 8 * ATT_CONSUMERS && a.Ap <= 256 * G_PVMAX &&
+      (a.R % a.rows_per_image) == 0 && grouped_smem_bytes(a) <= 113 * 1024 && pl.bF * a.Fp * 2 <= G_XSTAGE_BYTES) {
+    const size_t gsmem = grouped_smem_bytes(a);
+    static bool gconf = false;
+    if (!gconf) {
+      CUDA_TRY(cudaFuncSetAttribute(attention_fwd_grouped_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024));
+      gconf = true;
+    }
+    const int cpi = ceil_div(a.rows_per_image, GR);
+    const int images = a.R / a.rows_per_image;
+    CUDA_TRY(launch_pdl(attention_fwd_grouped_kernel, dim3(images * cpi), dim3(ATT_THREADS), gsmem, s, a, a.rows_per_image, cpi, pl.bF,
+                        pl.nF, alpha, xhat, ld_x));
+    LAUNCHED();
+    return 0;
+  }
   const size_t smem = attn_smem_bytes(a, false);
   static bool configured = false;
   if (!configured) {

@@ -15,6 +15,21 @@ struct GemmSeg {
   int K;
 };
 
+// Row-wise softmax statistics / cross-entropy gradient in the epilogue of the vocabulary head GEMM, so that the (rows, V)
+// fp32 logits are never written (north_star kernel #3; updown_captioner.py:450, 457-466). The GEMM runs on the 128 x 128
+// tile kernel; a thread owns one output row and sees the tile's 128 logits of that row.
+//   mode 1: per (row, 128-column tile tn) partial  max / sum exp(x - max) / arg max (lowest index wins)  at
+//           [tn * M + row]; if `target` is given, the target's logit goes to tgt_logit[row]. gemm_rowstats_tiles(N) tiles.
+//   mode 2: the logit x is replaced by  gcoef[row] * (exp(x - lse[row]) - [n == target[row]])  before the normal store
+//           (the bf16 d logits operand of the BPTT head GEMMs).
+struct RowStatsEpi {
+  int mode = 0;
+  float* st_max = nullptr; float* st_sum = nullptr; int* st_arg = nullptr;
+  const int* target = nullptr; float* tgt_logit = nullptr;
+  const float* lse = nullptr; const float* gcoef = nullptr;
+};
+inline int gemm_rowstats_tiles(int N) { return (N + 127) / 128; }
+
 struct GemmEpi {
   float alpha = 1.0f;                                  // v = alpha * acc
   const float* bias = nullptr;                         // v += bias[n]
@@ -36,6 +51,7 @@ struct GemmEpi {
   // GEMM epilogue and the pre-activations never leave the SM; otherwise the GEMM writes C32 (required, ldc32 >= N)
   // and lstm_forward runs behind it.
   const LstmFwdArgs* lstm = nullptr;
+  const RowStatsEpi* rs = nullptr;                     // see RowStatsEpi (forces the 128 x 128 tile kernel)
 };
 
 // K-split (cluster size 1, 2 or 4) the swapped-operand kernel uses for a skinny GEMM (M <= 256)

@@ -47,6 +47,7 @@ struct GemmParams {
   long long* dbg;                                 // SSCVAE_GEMM_DBG=1: per-CTA clock64 stamps of the pair kernel's phases
   LstmFwdArgs lstm;
   CUtensorMap tl[7];                              // gates i,f,g,o (fp32), c (fp32), h -> h1_dst, h2_dst (bf16); box 32 units x 32 rows
+  RowStatsEpi rs;                                 // vocabulary head: softmax statistics / CE gradient in the epilogue
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -336,18 +337,96 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_tcgen05_kernel(const __g
     mbar_wait(accum_bar, 0);
     tc_fence_after();
     const int row = m0 + q * 32 + lane;
+    // vocabulary head (RowStatsEpi): running softmax statistics of this thread's row over the tile's columns
+    const RowStatsEpi rs = p.rs;
+    float rs_m = -INFINITY, rs_s = 0.f, rs_t = 0.f; int rs_a = 0x7fffffff;
+    int rs_target = -1; float rs_lse = 0.f, rs_g = 0.f;
+    if (rs.mode && row < p.M) {
+      if (rs.target) rs_target = rs.target[row];
+      if (rs.mode == 2) { rs_lse = rs.lse[row]; rs_g = rs.gcoef[row]; }
+    }
 #pragma unroll 1
     for (int c0 = 0; c0 < BN; c0 += 32) {
       if (n0 + c0 >= p.N) break;                 // warp-uniform
       uint32_t acc[32];
       tmem_ld_32x32(tmem_acc + (static_cast<uint32_t>(q * 32) << 16) + c0, acc);
       tmem_ld_wait();
+      if (rs.mode) {
+        // One warp per SM sub-partition runs this with nothing to hide latency behind: everything is written as
+        // independent operations + tree reductions (a running  s += exp(..)  chain cost ~120 cycles per element).
+        const int nb = n0 + c0;
+        const bool full = nb + 32 <= p.N;                     // warp-uniform: only the last tile has a ragged edge
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[j]) * p.epi.alpha;
+        if (p.epi.bias) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (full || nb + j < p.N) v[j] += p.epi.bias[nb + j];
+        }
+        if (!full) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (nb + j >= p.N) v[j] = -INFINITY;              // exp -> 0, never the max
+        }
+        if (rs.mode == 1) {
+          float t[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) t[j] = fmaxf(v[j], v[j + 16]);
+#pragma unroll
+          for (int w = 8; w > 0; w >>= 1)
+#pragma unroll
+            for (int j = 0; j < w; ++j) t[j] = fmaxf(t[j], t[j + w]);
+          const float cm = t[0];
+          if (cm > rs_m) {                       // strict: an earlier column / tile keeps the arg max on ties
+#pragma unroll
+            for (int j = 31; j >= 0; --j)
+              if (v[j] == cm) rs_a = nb + j;
+            rs_s *= exp2f((rs_m - cm) * 1.4426950408889634f);
+            rs_m = cm;
+          }
+          const float mb = rs_m * 1.4426950408889634f;
+          float e[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) e[j] = exp2f(fmaf(v[j], 1.4426950408889634f, -mb));
+#pragma unroll
+          for (int w = 16; w > 0; w >>= 1)
+#pragma unroll
+            for (int j = 0; j < w; ++j) e[j] += e[j + w];
+          rs_s += e[0];
+          if (rs_target >= nb && rs_target < nb + 32) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (nb + j == rs_target) rs_t = v[j];
+          }
+          if (!p.epi.C32 && !p.epi.C16) continue;      // statistics only: the logits are never written
+        } else {
+          const float lb = rs_lse * 1.4426950408889634f;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) acc[j] = __float_as_uint(rs_g * exp2f(fmaf(v[j], 1.4426950408889634f, -lb)));
+          if (rs_target >= nb && rs_target < nb + 32) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (nb + j == rs_target) acc[j] = __float_as_uint(__uint_as_float(acc[j]) - rs_g);
+          }
+          GemmEpi e2 = p.epi;
+          e2.alpha = 1.f; e2.bias = nullptr;
+          epilogue_row32(e2, p.vec, p.M, p.N, m0 + q * 32, n0 + c0, BN - c0 < 32 ? BN - c0 : 32, acc,
+                         smem_u32(smem_a) + (warp - 2) * 32 * 36 * 4, 0, 1);
+          continue;
+        }
+      }
       if (BN >= 32 && p.tma_store) {
         epilogue_tma_row32(p.epi, &p.tc, p.N, m0 + q * 32, n0 + c0, acc, smem_u32(smem_a) + (warp - 2) * 4096);
       } else {
         epilogue_row32(p.epi, p.vec, p.M, p.N, m0 + q * 32, n0 + c0, BN - c0 < 32 ? BN - c0 : 32, acc,
                        smem_u32(smem_a) + (warp - 2) * 32 * 36 * 4, gridDim.z > 1, blockIdx.z == 0);
       }
+    }
+    if (rs.mode == 1 && row < p.M) {             // partial statistics of (row, this 128-column tile): lanes = consecutive rows
+      const size_t o = (size_t)blockIdx.x * p.M + row;
+      rs.st_max[o] = rs_m; rs.st_sum[o] = rs_s; rs.st_arg[o] = rs_a;
+      if (rs.tgt_logit && rs_target >= n0 && rs_target < n0 + BN) rs.tgt_logit[row] = rs_t;
     }
   }
   if (p.tma_store && warp >= 2 && (threadIdx.x & 31) == 0) tma_store_wait_all();
@@ -1380,7 +1459,7 @@ static bool pair_kernel_disabled() {
 
 int gemm_bf16_tn(cudaStream_t stream, int M, int N, int nseg, const GemmSeg* segs, const GemmEpi& epi) {
   REQUIRE(M > 0 && N > 0 && nseg >= 1 && nseg <= MAX_SEG, "gemm: bad shape M=%d N=%d nseg=%d", M, N, nseg);
-  REQUIRE(epi.C32 || epi.C16, "gemm: no output");
+  REQUIRE(epi.C32 || epi.C16 || (epi.rs && epi.rs->mode == 1), "gemm: no output");
   if (epi.lstm) {
     REQUIRE(N == lstm_gate_rows(epi.lstm->H) && epi.lstm->R == M, "gemm: fused LSTM shape mismatch (N=%d H=%d M=%d R=%d)", N,
             epi.lstm->H, M, epi.lstm->R);
@@ -1425,6 +1504,7 @@ int gemm_bf16_tn(cudaStream_t stream, int M, int N, int nseg, const GemmSeg* seg
   GemmParams prm;
   memset(&prm, 0, sizeof(prm));
   prm.nseg = nseg; prm.M = M; prm.N = N; prm.epi = epi;
+  if (epi.rs) prm.rs = *epi.rs;
   for (int s = 0; s < nseg; ++s) {
     REQUIRE(segs[s].K > 0, "gemm: empty K segment %d", s);
     prm.kblocks[s] = ceil_div(segs[s].K, BK);
@@ -1452,6 +1532,27 @@ int gemm_bf16_tn(cudaStream_t stream, int M, int N, int nseg, const GemmSeg* seg
       CUDA_TRY(cudaMemset2DAsync(epi.C32, (size_t)epi.ldc32 * 4, 0, (size_t)N * 4, (size_t)M, stream));
     return 0;
   };
+  if (epi.rs && epi.rs->mode) {                           // vocabulary head with softmax statistics / CE gradient in the epilogue
+    REQUIRE(!epi.add1 && !epi.add2 && !epi.act && !epi.dtanh && !epi.accumulate && !epi.lstm, "gemm: row statistics take a plain (alpha, bias) epilogue");
+    REQUIRE(epi.rs->mode != 1 || (epi.rs->st_max && epi.rs->st_sum && epi.rs->st_arg), "gemm: row statistics need their partial buffers");
+    REQUIRE(epi.rs->mode != 2 || (epi.rs->lse && epi.rs->gcoef && epi.rs->target && epi.C16), "gemm: CE gradient needs lse, gcoef, target and a bf16 output");
+    prm.tma_store = 0;
+    GemmParams& q = prm;
+    for (int s2 = 0; s2 < q.nseg; ++s2) {
+      TRY(encode_tmap(&q.ta[s2], segs[s2].A, q.M, segs[s2].K, segs[s2].lda, BM));
+      TRY(encode_tmap(&q.tb[s2], segs[s2].B, q.N, segs[s2].K, segs[s2].ldb, 128));
+    }
+    constexpr int smem_rs = 1024 + 3 * (A_STAGE_BYTES + 128 * BK * 2) + 256;
+    static bool configured_rs = false;
+    if (!configured_rs) {
+      CUDA_TRY(cudaFuncSetAttribute(gemm_tcgen05_kernel<128, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_rs));
+      configured_rs = true;
+    }
+    dim3 grid(ceil_div(q.N, 128), ceil_div(q.M, BM), 1);
+    CUDA_TRY(launch_pdl(gemm_tcgen05_kernel<128, 3>, grid, dim3(GEMM_THREADS), smem_rs, stream, q));
+    ++g_launch_count;
+    return 0;
+  }
   if (const char* e = getenv("SSCVAE_GEMM_SPLITK")) TRY(use_splits(atoi(e)));
   static const bool no_swapped = [] { const char* e = getenv("SSCVAE_GEMM_NO_SWAPPED"); return e && e[0] == '1'; }();
   // skinny and long-K (the per-timestep LSTM and BPTT GEMMs): swapped-operand cluster split-K. Measured on B200

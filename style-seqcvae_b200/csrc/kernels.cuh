@@ -85,6 +85,14 @@ int ce_backward(cudaStream_t s, const float* logits, int ld, int TB, int V, cons
                 const float* tmask, const float* lengths, const float* lse, const float* gloss, bf16* dlogits,
                 int ld_d);
 
+// vocabulary head with the softmax statistics in the GEMM epilogue (gemm.cuh: RowStatsEpi): the logits are never written
+int ce_prepare(cudaStream_t s, const int* tok, int B, int L, const float* tmask, const float* lengths, const float* gloss /*or null*/,
+               int* target /*(T*B)*/, float* gcoef /*(T*B) or null*/);
+int ce_merge(cudaStream_t s, const float* st_max, const float* st_sum, const int* st_arg, int ntiles, int TB,
+             const float* tgt_logit, float* lse, float* nll);
+int greedy_merge(cudaStream_t s, const float* st_max, const float* st_sum, const int* st_arg, int ntiles, int R,
+                 const int* last_tokens, const float* last_scores, int end_index, int* tok, int* bp, float* score);
+
 // ---- layout helpers -------------------------------------------------------------------------------
 int transpose_bf16(cudaStream_t s, const bf16* in, int rows, int cols, int ld_in, bf16* out, int ld_out);
 int transpose_f32_to_bf16(cudaStream_t s, const float* in, int rows, int cols, int ld_in, bf16* out, int ld_out);
@@ -140,6 +148,8 @@ struct AttnArgs {
   const bf16* feats;                   // (images, N, Fp)
   const float* mask;                   // (images, N)
   const float* w_a;                    // (A)
+  int rows_per_image;                  // > 0: rows img*rows_per_image + i, i < rows_per_image, belong to image img (decode: the rows of
+                                       // an image share its features; 0 = use rowmap / one image per row)
   int l2_policy;                       // set by the launchers (SSCVAE_ATT_POLICY): 0 none, 1 evict_first, 2 evict_last
 };
 // smx (R,N): softmax(u*m) before the mask renormalisation, saved for the backward (null in decode)

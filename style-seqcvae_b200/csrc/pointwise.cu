@@ -531,6 +531,97 @@ int ce_backward(cudaStream_t s, const float* logits, int ld, int TB, int V, cons
   return 0;
 }
 
+// ---- vocabulary head with the softmax statistics in the GEMM epilogue (gemm.cuh: RowStatsEpi) ----------------------
+// row r = t*B + b: target token and (backward) the coefficient of its CE gradient; masked rows get coefficient 0
+__global__ void ce_prep_kernel(const int* __restrict__ tok, int B, int L, int TB, const float* __restrict__ tmask,
+                               const float* __restrict__ lengths, const float* __restrict__ gloss, int* __restrict__ target,
+                               float* __restrict__ gcoef) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= TB) return;
+  const int t = r / B, b = r - t * B;
+  target[r] = tok[(size_t)b * (L + 2) + t + 1];
+  if (gcoef) {
+    const float len = lengths[b];
+    gcoef[r] = tmask[r] != 0.f ? gloss[b] * (len / (len + 1e-13f)) : 0.f;
+  }
+}
+int ce_prepare(cudaStream_t s, const int* tok, int B, int L, const float* tmask, const float* lengths, const float* gloss,
+               int* target, float* gcoef) {
+  const int TB = (L + 1) * B;
+  ce_prep_kernel<<<ceil_div(TB, 256), 256, 0, s>>>(tok, B, L, TB, tmask, lengths, gloss, target, gcoef);
+  LAUNCHED();
+  return 0;
+}
+
+// merges the per-tile partial (max, sum exp, arg max) of row r; partials at [tile * R + r]. One WARP per row: lanes take
+// tiles lane, lane + 32, ...; (value desc, index asc) order as everywhere in the search.
+__device__ __forceinline__ void merge_row_stats(const float* __restrict__ st_max, const float* __restrict__ st_sum,
+                                                const int* __restrict__ st_arg, int ntiles, int R, int r, float& M, float& S,
+                                                int& arg) {
+  const int lane = threadIdx.x & 31;
+  float m = -INFINITY; int a = 0x7fffffff;
+  for (int i = lane; i < ntiles; i += 32) {
+    const float v = st_max[(size_t)i * R + r];
+    if (v > m) { m = v; a = st_arg[(size_t)i * R + r]; }            // strict: the lowest tile wins ties
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float om = __shfl_xor_sync(0xffffffffu, m, o);
+    const int oa = __shfl_xor_sync(0xffffffffu, a, o);
+    if (om > m || (om == m && oa < a)) { m = om; a = oa; }
+  }
+  float s = 0.f;
+  for (int i = lane; i < ntiles; i += 32) s += st_sum[(size_t)i * R + r] * __expf(st_max[(size_t)i * R + r] - m);
+  S = warp_sum(s); M = m; arg = a;
+}
+
+__global__ void ce_merge_kernel(const float* __restrict__ st_max, const float* __restrict__ st_sum, const int* __restrict__ st_arg,
+                                int ntiles, int TB, const float* __restrict__ tgt_logit, float* __restrict__ lse,
+                                float* __restrict__ nll) {
+  const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (r >= TB) return;
+  float M, S; int arg;
+  merge_row_stats(st_max, st_sum, st_arg, ntiles, TB, r, M, S, arg);
+  if ((threadIdx.x & 31) == 0) {
+    const float l = M + logf(S);
+    lse[r] = l;
+    nll[r] = l - tgt_logit[r];
+  }
+}
+int ce_merge(cudaStream_t s, const float* st_max, const float* st_sum, const int* st_arg, int ntiles, int TB,
+             const float* tgt_logit, float* lse, float* nll) {
+  PROF_SCOPE(s, "ce_fwd", 0, (double)TB * ntiles * 12.0);
+  ce_merge_kernel<<<ceil_div(TB, 8), 256, 0, s>>>(st_max, st_sum, st_arg, ntiles, TB, tgt_logit, lse, nll);
+  LAUNCHED();
+  return 0;
+}
+
+// greedy step of the unconstrained K = 1 search (cbs.py:161-250 with S = K = P = 1): token = arg max, score = parent score
+// + log-softmax of the max = -log(sum exp(x - max)); a sequence that has ended keeps emitting the boundary (cbs.py:177-181)
+__global__ void greedy_merge_kernel(const float* __restrict__ st_max, const float* __restrict__ st_sum, const int* __restrict__ st_arg,
+                                    int ntiles, int R, const int* __restrict__ last_tokens, const float* __restrict__ last_scores,
+                                    int end_index, int* __restrict__ tok, int* __restrict__ bp, float* __restrict__ score) {
+  const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (r >= R) return;
+  float M, S; int arg;
+  merge_row_stats(st_max, st_sum, st_arg, ntiles, R, r, M, S, arg);
+  if ((threadIdx.x & 31) == 0) {
+    const bool forced = last_tokens != nullptr && last_tokens[r] == end_index;
+    const float lp = forced ? 0.f : -logf(S);
+    tok[r] = forced ? end_index : arg;
+    score[r] = last_scores ? last_scores[r] + lp : lp;
+    if (bp) bp[r] = 0;
+  }
+}
+int greedy_merge(cudaStream_t s, const float* st_max, const float* st_sum, const int* st_arg, int ntiles, int R,
+                 const int* last_tokens, const float* last_scores, int end_index, int* tok, int* bp, float* score) {
+  PROF_SCOPE(s, "search_rows", 0, (double)R * ntiles * 12.0);
+  greedy_merge_kernel<<<ceil_div(R, 8), 256, 0, s>>>(st_max, st_sum, st_arg, ntiles, R, last_tokens, last_scores, end_index, tok,
+                                                    bp, score);
+  LAUNCHED();
+  return 0;
+}
+
 // ---------------------------------------------------------------------------------------------
 // layout helpers
 // ---------------------------------------------------------------------------------------------

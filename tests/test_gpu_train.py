@@ -37,7 +37,10 @@ def _run_cuda(name, train=True):
 
 
 @pytest.mark.parametrize("name", TRAIN)
-def test_forward_matches_oracle_and_reference(name):
+def test_forward_matches_oracle_and_reference(name, monkeypatch):
+    # the product path never writes the (T*B, V) logits (the head GEMM's epilogue keeps softmax statistics only);
+    # this debug switch, read when the module is created, makes the forward store them as well
+    monkeypatch.setenv("SSCVAE_DEBUG_LOGITS", "1")
     g, cfg, m, out = _run_cuda(name)
     ocfg = uo.OracleConfig(**cfg)
     B, N, _ = g["image_features"].shape
