@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define SSCVAE_ABI_VERSION 3
+#define SSCVAE_ABI_VERSION 4
 
 #define SSCVAE_ERR_BAD_ARG (-1)
 #define SSCVAE_ERR_WORKSPACE (-2)
@@ -214,10 +214,12 @@ int sscvae_sgd_step(float* params, const float* grads, float* momentum_buf, size
 
 /* The same for ALL parameter tensors in three launches (squared-norm partials, final sum, update). Host arrays of
  * `count` (<= 32) device pointers / sizes; scratch: device floats, at least sum(ceil(size_i / 16384)) + 1. The global
- * norm is reduced with a fixed chunking and ordered sums (bit-reproducible). */
+ * norm is reduced with a fixed chunking and ordered sums (bit-reproducible). grads[i] == NULL = a zero gradient (torch 1.1's
+ * zero_grad() semantics for a frozen parameter). `grad_scale` multiplies every gradient before the norm and the update:
+ * data-parallel ranks pass 1 / world_size and all-reduce SUMS (no separate averaging pass over the buckets). */
 int sscvae_sgd_step_multi(int count, void* const* params, const void* const* grads, void* const* momentum_bufs,
                           const uint64_t* sizes, const int32_t* first_step, float max_norm, float lr, float momentum,
-                          float weight_decay, float* scratch, size_t scratch_floats, void* stream);
+                          float weight_decay, float grad_scale, float* scratch, size_t scratch_floats, void* stream);
 
 /* Optional instrumentation (off by default): CUDA events around every kernel launch of the library,
  * aggregated per kernel class. report() synchronises the device and writes a JSON object

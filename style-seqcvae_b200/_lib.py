@@ -101,7 +101,7 @@ def lib():
     L.sscvae_decode_samples.argtypes = [vp, i32, i32, i32, vp, C.POINTER(vp), vp, vp, vp, u64, vp, sz, vp, vp, vp, vp]
     L.sscvae_test_gemm_splitk.argtypes = [vp, i32, vp, i32, i32, i32, i32, vp, i32, i32, vp, vp]
     L.sscvae_sgd_step_multi.argtypes = [i32, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(u64), C.POINTER(i32),
-                                        C.c_float, C.c_float, C.c_float, C.c_float, vp, sz, vp]
+                                        C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, vp, sz, vp]
     L.sscvae_grad_sqnorm.argtypes = [vp, sz, vp, vp, vp]
     L.sscvae_sgd_step.argtypes = [vp, vp, vp, sz, vp, f32, f32, f32, f32, i32, vp]
     L.sscvae_test_gemm.argtypes = [vp, i32, vp, i32, i32, i32, i32, vp, i32, vp, i32, i32, vp]
@@ -111,7 +111,7 @@ def lib():
         fn = getattr(L, name)
         if fn.restype is C.c_int and name not in ("sscvae_abi_version",):
             fn.restype = C.c_int
-    if L.sscvae_abi_version() != 3:
+    if L.sscvae_abi_version() != 4:
         raise ImportError("libsscvae_b200.so ABI version mismatch")
     _lib = L
     return L

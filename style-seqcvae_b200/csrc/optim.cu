@@ -78,7 +78,7 @@ __device__ __forceinline__ int mt_find(const MultiTensorTable& t, unsigned block
   return i;
 }
 
-__global__ void __launch_bounds__(256) mt_sqnorm_kernel(const __grid_constant__ MultiTensorTable t, float* __restrict__ partial) {
+__global__ void __launch_bounds__(256) mt_sqnorm_kernel(const __grid_constant__ MultiTensorTable t, float gscale, float* __restrict__ partial) {
   __shared__ float red[8];
   const int ti = mt_find(t, blockIdx.x);
   const size_t lo = (size_t)(blockIdx.x - t.chunk0[ti]) * MT_CHUNK;
@@ -86,7 +86,7 @@ __global__ void __launch_bounds__(256) mt_sqnorm_kernel(const __grid_constant__ 
   const float* g = t.g[ti];
   float s = 0.f;
   if (g)                                               // NULL gradient = all zeros (see sscvae_sgd_step_multi)
-    for (size_t i = lo + threadIdx.x; i < hi; i += 256) { const float v = g[i]; s += v * v; }
+    for (size_t i = lo + threadIdx.x; i < hi; i += 256) { const float v = g[i] * gscale; s += v * v; }
   s = warp_sum(s);
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
   __syncthreads();
@@ -98,12 +98,13 @@ __global__ void __launch_bounds__(256) mt_sqnorm_kernel(const __grid_constant__ 
 }
 
 __global__ void __launch_bounds__(256) mt_sgd_kernel(const __grid_constant__ MultiTensorTable t, const float* __restrict__ sqnorm,
-                                                     float max_norm, float lr, float momentum, float wd) {
+                                                     float max_norm, float lr, float momentum, float wd, float gscale) {
   const int ti = mt_find(t, blockIdx.x);
   const size_t lo = (size_t)(blockIdx.x - t.chunk0[ti]) * MT_CHUNK;
   const size_t hi = min((size_t)t.n[ti], lo + MT_CHUNK);
   float coef = 1.f;
   if (max_norm > 0.f) coef = fminf(1.f, max_norm / (sqrtf(*sqnorm) + 1e-6f));   // torch clip_grad_norm_
+  coef *= gscale;                                      // gradients arrive as a SUM over ranks: the mean is taken here
   float* p = t.p[ti]; const float* g = t.g[ti]; float* m = t.m[ti];
   const bool first = t.first[ti] != 0;
   for (size_t i = lo + threadIdx.x; i < hi; i += 256) {
@@ -123,7 +124,7 @@ using namespace sscvae;
 extern "C" {
 int sscvae_sgd_step_multi(int count, void* const* params, const void* const* grads, void* const* momentum_bufs,
                           const uint64_t* sizes, const int32_t* first_step, float max_norm, float lr, float momentum,
-                          float weight_decay, float* scratch, size_t scratch_floats, void* stream) {
+                          float weight_decay, float grad_scale, float* scratch, size_t scratch_floats, void* stream) {
   REQUIRE(count > 0 && count <= MT_MAX && params && grads && sizes && first_step && scratch, "bad argument (at most %d tensors)", MT_MAX);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   MultiTensorTable t;
@@ -139,11 +140,11 @@ int sscvae_sgd_step_multi(int count, void* const* params, const void* const* gra
   }
   t.chunk0[count] = chunks; t.count = count;
   REQUIRE(scratch_floats >= (size_t)chunks + 1, "scratch too small: need %u floats", chunks + 1);
-  mt_sqnorm_kernel<<<chunks, 256, 0, st>>>(t, scratch);
+  mt_sqnorm_kernel<<<chunks, 256, 0, st>>>(t, grad_scale, scratch);
   LAUNCHED();
   sqnorm_final_kernel<<<1, 1024, 0, st>>>(scratch, (int)chunks, scratch + chunks);
   LAUNCHED();
-  mt_sgd_kernel<<<chunks, 256, 0, st>>>(t, scratch + chunks, max_norm, lr, momentum, weight_decay);
+  mt_sgd_kernel<<<chunks, 256, 0, st>>>(t, scratch + chunks, max_norm, lr, momentum, weight_decay, grad_scale);
   LAUNCHED();
   return 0;
 }

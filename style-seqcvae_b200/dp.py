@@ -60,13 +60,16 @@ class BucketedGradReducer:
     def world(self) -> int:
         return dist.get_world_size(self.pg) if dist.is_initialized() else 1
 
-    def reduce(self, events: Optional[Sequence] = None, buckets: Optional[Dict] = None):
+    def reduce(self, events: Optional[Sequence] = None, buckets: Optional[Dict] = None, average: bool = True):
         """`buckets` = UpDownCaptioner.grad_buckets(): when every gradient of a bucket is the captioner's own view into
-        the bucket's flat buffer (the normal case) the bucket is all-reduced IN PLACE: no flatten / copy-back."""
+        the bucket's flat buffer (the normal case) the bucket is all-reduced IN PLACE: no flatten / copy-back.
+        `average=False` leaves the SUM over ranks (FusedClipSGD.step(grad_scale=1/world) takes the mean on the fly and
+        saves one pass over every bucket)."""
         world = self.world()
         if world == 1:
             return
-        if buckets and self._reduce_in_place(buckets, world, events):
+        self.last_comm_done = None
+        if buckets and self._reduce_in_place(buckets, world, events, average):
             return
         cuda = any(p.is_cuda for g in self.groups for p in g)
         if cuda and self._side_stream is None:
@@ -95,7 +98,8 @@ class BucketedGradReducer:
             h.wait()
             ctx = torch.cuda.stream(self._side_stream) if cuda else _NullCtx()
             with ctx:
-                flat.div_(world)
+                if average:
+                    flat.div_(world)
                 off = 0
                 for p in ps:
                     p.grad.copy_(flat[off:off + p.grad.numel()].view_as(p.grad))
@@ -112,7 +116,7 @@ class BucketedGradReducer:
         else:
             self._side_stream.wait_stream(torch.cuda.current_stream())
 
-    def _reduce_in_place(self, buckets: Dict, world: int, events) -> bool:
+    def _reduce_in_place(self, buckets: Dict, world: int, events, average: bool = True) -> bool:
         for g, (flat, pairs) in buckets.items():
             for p, v in pairs:
                 if p.grad is not None and p.grad.data_ptr() != v.data_ptr():
@@ -132,7 +136,11 @@ class BucketedGradReducer:
                 handles.append((dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.pg, async_op=True), flat))
             for h, flat in handles:
                 h.wait()
-                flat.div_(world)
+                if average:
+                    flat.div_(world)
+            if cuda:                                       # when the last collective finished (bench.py: comm_exposed_ms)
+                self.last_comm_done = torch.cuda.Event(enable_timing=True)
+                self.last_comm_done.record(self._side_stream)
         if cuda:
             torch.cuda.current_stream().wait_stream(self._side_stream)
         return True

@@ -39,7 +39,10 @@ class FusedClipSGD:
             p.grad = None
 
     @torch.no_grad()
-    def step(self):
+    def step(self, grad_scale: float = 1.0):
+        """`grad_scale` multiplies every gradient before clipping and the update. Data-parallel training passes
+        1 / world_size together with `BucketedGradReducer.reduce(..., average=False)`: the all-reduce leaves the SUM in
+        the buckets and no extra pass divides them."""
         L = _lib.lib()
         ps = [p for p in self.params if p.grad is not None or (self.legacy_zero_grad and id(p) in self._mom)]
         if not ps:
@@ -67,6 +70,7 @@ class FusedClipSGD:
             n, (vp * n)(*[p.data_ptr() for p in ps]), (vp * n)(*[None if g is None else g.data_ptr() for g in grads]),
             (vp * n)(*[self._mom[id(p)].data_ptr() for p in ps]), (C.c_uint64 * n)(*[p.numel() for p in ps]),
             (C.c_int32 * n)(*firsts), float(self.max_norm), float(self.lr), float(self.momentum), float(self.weight_decay),
+            float(grad_scale),
             _lib.ptr(self._partial), self._partial.numel(), stream))
         for p in ps:
             # the kernel wrote through raw pointers: tell autograd (and the captioner's packed-weight cache, which is
