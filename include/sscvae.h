@@ -221,6 +221,15 @@ int sscvae_sgd_step_multi(int count, void* const* params, const void* const* gra
                           const uint64_t* sizes, const int32_t* first_step, float max_norm, float lr, float momentum,
                           float weight_decay, float grad_scale, float* scratch, size_t scratch_floats, void* stream);
 
+/* Per-handle options consumed by the following calls (0 = default):
+ *   "features_bf16"     1: every `image_features` pointer is bf16 (B,N,F) instead of fp32 - the bf16 feature cache of SURVEY
+ *                       8(f)-3 (updown-baseline/updown/data/readers.py:21-139 reads fp32 from HDF5). Results are bit-identical
+ *                       to the fp32 input rounded to bf16: the kernels round the features to bf16 first either way.
+ *   "reuse_image_state" 1: the decode workspace already holds the per-image state of THIS batch (bf16 features, mask, mean
+ *                       features, W_v projection): sscvae_decode / sscvae_decode_samples skip recomputing it. The analogue
+ *                       of the reference's lru_cache on the projected features (updown-baseline/updown/modules/attention.py:99). */
+int sscvae_set_option(SscvaeHandle* h, const char* name, int value);
+
 /* Optional instrumentation (off by default): CUDA events around every kernel launch of the library,
  * aggregated per kernel class. report() synchronises the device and writes a JSON object
  * {"class": {"count", "ms", "flops", "bytes"}} (algorithmic FLOPs / bytes as declared at the call site). */

@@ -10,7 +10,8 @@ from .captioner import UpDownCaptioner
 from .search import (BeamSearch, ConstrainedBeamSearch, select_best_beam, select_best_beam_with_constraints, pad_fsm_batch)
 from .dp import BucketedGradReducer, shard_batch, global_grad_norm
 from .optim import FusedClipSGD
+from .ingest import FeatureCache, collate_features, pack_features
 
-__all__ = ["UpDownCaptioner", "ConstrainedBeamSearch", "BeamSearch", "select_best_beam",
+__all__ = ["FeatureCache", "collate_features", "pack_features", "UpDownCaptioner", "ConstrainedBeamSearch", "BeamSearch", "select_best_beam",
            "select_best_beam_with_constraints", "pad_fsm_batch", "BucketedGradReducer", "shard_batch", "global_grad_norm",
            "FusedClipSGD"]

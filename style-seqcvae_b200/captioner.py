@@ -285,6 +285,30 @@ class UpDownCaptioner(nn.Module):
             if p.device != t.device or p.dtype != torch.float32 or not p.is_contiguous():
                 raise RuntimeError("sscvae: parameters must be contiguous fp32 tensors on the input's device")
 
+    def _features(self, image_features: torch.Tensor) -> torch.Tensor:
+        """fp32 (the reference's format) or bf16 region features (the bf16 feature cache, `sscvae.pack_features`): bf16
+        inputs are consumed as they are - half the host->device bytes, bit-identical results - anything else is
+        converted to fp32. Tells the library which of the two the following call gets."""
+        if image_features.dtype == torch.bfloat16:
+            image_features = image_features.contiguous()
+        else:
+            image_features = image_features.contiguous().float()
+        _lib.check(_lib.lib().sscvae_set_option(self._handle, b"features_bf16", int(image_features.dtype == torch.bfloat16)))
+        return image_features
+
+    def _reuse_image_state(self, ws_key, image_features) -> None:
+        """Decode calls on the SAME feature tensor (the reference's loop over latent samples) reuse the per-image state
+        left in the decode workspace by the previous call: the analogue of the reference's lru_cache on the projected
+        features (attention.py:99), keyed like it on tensor identity. The previous tensor is kept alive here, so a new
+        tensor can never alias its storage; an in-place update bumps the version counter; new weights or another
+        workspace invalidate the state as well."""
+        key = (ws_key, image_features._version, tuple(image_features.shape), image_features.dtype,
+               tuple((p.data_ptr(), p._version) for p in self._weight_tensors()))
+        last = getattr(self, "_image_state", None)
+        reuse = last is not None and last[0] is image_features and last[1] == key
+        self._image_state = (image_features, key)
+        _lib.check(_lib.lib().sscvae_set_option(self._handle, b"reuse_image_state", int(reuse)))
+
     def _packed_weights(self) -> torch.Tensor:
         ws = self._weight_tensors()
         # one key per weight: a weight is re-packed when its storage or its version counter changed (torch's own
@@ -405,7 +429,7 @@ class UpDownCaptioner(nn.Module):
         constraint2states=None,
     ):
         self._require_cuda(image_features)
-        image_features = image_features.contiguous().float()
+        image_features = self._features(image_features)
         B, N, F = image_features.shape
         if F != self.image_feature_size:
             raise ValueError(f"image_features last dim {F} != image_feature_size {self.image_feature_size}")
@@ -452,7 +476,7 @@ class UpDownCaptioner(nn.Module):
         if self._use_cbs:
             raise ValueError("sample() is the unconstrained beam-1 path; use forward() for constrained beam search")
         L = _lib.lib()
-        image_features = image_features.contiguous().float()
+        image_features = self._features(image_features)
         dev = image_features.device
         B, N, F = image_features.shape
         if F != self.image_feature_size:
@@ -485,6 +509,7 @@ class UpDownCaptioner(nn.Module):
             self._ws_cache[okey] = outs
         preds, scores, n_steps = outs
         stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        self._reuse_image_state(key, image_features)
         _lib.check(L.sscvae_decode_samples(
             self._handle, B, J, N, _lib.ptr(self._packed_weights()), _lib.ptr_array(self._weight_tensors()),
             _lib.ptr(image_features), _lib.ptr(sentiment), _lib.ptr(eps), C.c_uint64(self._next_seed()), _lib.ptr(ws), nbytes,
@@ -536,6 +561,7 @@ class UpDownCaptioner(nn.Module):
             self._ws_cache[okey] = outs
         preds, scores, best, n_steps = outs
         stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        self._reuse_image_state(key, image_features)
         _lib.check(L.sscvae_decode(
             self._handle, B, N, S, K, P, _lib.ptr(self._packed_weights()), _lib.ptr_array(self._weight_tensors()),
             _lib.ptr(image_features), _lib.ptr(sentiment), _lib.ptr(fsm), _lib.ptr(nc),

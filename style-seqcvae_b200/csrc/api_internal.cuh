@@ -40,6 +40,9 @@ struct Handle {
   Plan tp; int tp_B = -1, tp_N = -1;   // training workspace for the last (B,N)
   Plan dp; int dp_B = -1, dp_N = -1, dp_S = -1, dp_K = -1, dp_J = -1;   // decode workspace
   GraphCache fwd_graphs, bwd_graphs, dec_graphs;
+  // per-handle options (sscvae_set_option), consumed by the following calls
+  int opt_features_bf16 = 0;           // image_features pointers are bf16 (B,N,F) instead of fp32
+  int opt_reuse_image_state = 0;       // decode: the workspace already holds this batch's featsb / projb / mask / avg state
   const Plan& train_plan(int B, int N);
   const Plan& decode_plan(int B, int N, int S, int K, int J);
 };

@@ -395,7 +395,7 @@ static int train_forward_impl(Handle* h, int B, int N, const char* pk, const voi
   int* tok = Wi("tok");
   float* tmask = Wf("tmask");
   TRY(boundary_tokens(s, cap, B, d.L, d.pad, d.boundary, tok, tmask, Wf("lengths")));
-  TRY(image_prep(s, feats, B, N, d.F, Wb("featsb"), Fp, Wf("mask"), Wb("avgb")));
+  TRY(image_prep(s, feats, h->opt_features_bf16, B, N, d.F, Wb("featsb"), Fp, Wf("mask"), Wb("avgb")));
   TRY(scale_rows_f32(s, d.cond ? sent : nullptr, d.mult, Wf("pm_row"), B));    // prior mean (updown_captioner.py:253)
   TRY(scale_rows_f32(s, d.cond ? sent : nullptr, 1.0f, Wf("sent"), B));
   {  // P = W_v x  (attention.py:125), once per image, kept in bf16
@@ -813,6 +813,15 @@ int sscvae_abi_version(void) { return SSCVAE_ABI_VERSION; }
 const char* sscvae_last_error(void) { return get_error(); }
 uint64_t sscvae_launch_count(void) { return g_launch_count + g_launch_count_pw; }
 
+int sscvae_set_option(SscvaeHandle* hh, const char* name, int value) {
+  Handle* h = reinterpret_cast<Handle*>(hh);
+  REQUIRE(h && name, "NULL argument");
+  if (strcmp(name, "features_bf16") == 0) { h->opt_features_bf16 = value ? 1 : 0; return 0; }
+  if (strcmp(name, "reuse_image_state") == 0) { h->opt_reuse_image_state = value ? 1 : 0; return 0; }
+  set_error("unknown option '%s'", name);
+  return SSCVAE_ERR_BAD_ARG;
+}
+
 int sscvae_create(const SscvaeDims* dims, SscvaeHandle** out) {
   REQUIRE(out != nullptr, "out is NULL");
   Handle* h = new Handle();
@@ -865,6 +874,7 @@ int sscvae_train_forward(SscvaeHandle* hh, int batch, int num_boxes, const void*
                            cudaMemcpyHostToDevice, st));
   std::vector<uint64_t> key;
   key_add(key, (uint64_t)batch); key_add(key, (uint64_t)num_boxes); key_add(key, packed); key_add(key, image_features);
+  key_add(key, (uint64_t)h->opt_features_bf16);
   key_add(key, caption_tokens); key_add(key, sentiment); key_add(key, eps); key_add(key, workspace);
   key_add(key, (uint64_t)workspace_bytes); key_add(key, loss); key_add(key, kld);
   for (int i = 0; i < SSCVAE_W_COUNT; ++i) key_add(key, weights[i]);

@@ -8,7 +8,8 @@ namespace sscvae {
 
 // ---- pre-loop -----------------------------------------------------------------------------------
 // a6 (updown_cell.py:233-270): mask = sum_f |x| > 0 ; avg = masked mean ; bf16 copy of the features.
-int image_prep(cudaStream_t s, const float* feats, int B, int N, int F, bf16* featsb, int Fp, float* mask,
+// feats: fp32 (B,N,F), or bf16 when feats_bf16 != 0 (the bf16 feature cache)
+int image_prep(cudaStream_t s, const void* feats, int feats_bf16, int B, int N, int F, bf16* featsb, int Fp, float* mask,
                bf16* avgb);
 // a16 (allennlp add_sentence_boundary_token_ids) + mask/lengths of the targets (updown_captioner.py:265-278)
 int boundary_tokens(cudaStream_t s, const long long* caption_tokens, int B, int L, int pad, int boundary,

@@ -13,17 +13,20 @@ unsigned long long g_launch_count_pw = 0;
 // ---------------------------------------------------------------------------------------------
 // image_prep: one CTA per image. Pass 1: bf16 copy + per-box |x| sum -> mask. Pass 2: masked mean.
 // ---------------------------------------------------------------------------------------------
-__global__ void image_prep_kernel(const float* __restrict__ feats, int N, int F, bf16* __restrict__ featsb, int Fp,
+// TIn = float (the reference's region features) or bf16 (the bf16 feature cache of SURVEY 8(f)-3: the masked mean is taken
+// over the bf16-rounded values either way, so both inputs give bit-identical featsb / avgb).
+template <typename TIn>
+__global__ void image_prep_kernel(const TIn* __restrict__ feats, int N, int F, bf16* __restrict__ featsb, int Fp,
                                   float* __restrict__ mask, bf16* __restrict__ avgb) {
   extern __shared__ float s_mask[];                 // N
   const int b = blockIdx.x;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
-  const float* x = feats + (size_t)b * N * F;
+  const TIn* x = feats + (size_t)b * N * F;
   bf16* xb = featsb + (size_t)b * N * Fp;
   for (int n = warp; n < N; n += nwarp) {
     float s = 0.f;
     for (int f = lane; f < Fp; f += 32) {
-      float v = (f < F) ? x[(size_t)n * F + f] : 0.f;
+      float v = (f < F) ? (float)x[(size_t)n * F + f] : 0.f;
       s += fabsf(v);
       xb[(size_t)n * Fp + f] = __float2bfloat16_rn(v);
     }
@@ -43,9 +46,10 @@ __global__ void image_prep_kernel(const float* __restrict__ feats, int N, int F,
   }
 }
 
-int image_prep(cudaStream_t s, const float* feats, int B, int N, int F, bf16* featsb, int Fp, float* mask, bf16* avgb) {
-  PROF_SCOPE(s, "image_prep", 0, (double)B*N*(F*4.0+Fp*2.0));
-  image_prep_kernel<<<B, 256, N * sizeof(float), s>>>(feats, N, F, featsb, Fp, mask, avgb);
+int image_prep(cudaStream_t s, const void* feats, int feats_bf16, int B, int N, int F, bf16* featsb, int Fp, float* mask, bf16* avgb) {
+  PROF_SCOPE(s, "image_prep", 0, (double)B*N*(F*(feats_bf16 ? 2.0 : 4.0)+Fp*2.0));
+  if (feats_bf16) image_prep_kernel<bf16><<<B, 256, N * sizeof(float), s>>>(reinterpret_cast<const bf16*>(feats), N, F, featsb, Fp, mask, avgb);
+  else image_prep_kernel<float><<<B, 256, N * sizeof(float), s>>>(reinterpret_cast<const float*>(feats), N, F, featsb, Fp, mask, avgb);
   LAUNCHED();
   return 0;
 }
@@ -247,8 +251,21 @@ __global__ void __launch_bounds__(128) lstm_bwd_v4_kernel(LstmBwdArgs a) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   pdl_wait();
   pdl_launch_dependents(8);
-  if (idx >= a.R * H4) return;
-  const int r = idx / H4, j = (idx - r * H4) * 4;
+  int r, j;
+  if (a.tiled) {
+    // row-tiled state: a warp covers 8 rows x 4 unit-quads, so the tiled reads (8 consecutive rows = 128 contiguous
+    // bytes) and the row-major accesses (4 consecutive quads = 64 contiguous bytes of a row) both use whole sectors
+    const int lane = idx & 31, wg = idx >> 5;
+    const int tr = (a.R + 7) >> 3, tq = (H4 + 3) >> 2;
+    if (wg >= tr * tq) return;
+    r = (wg % tr) * 8 + (lane & 7);
+    const int jq = (wg / tr) * 4 + (lane >> 3);
+    if (r >= a.R || jq >= H4) return;
+    j = jq * 4;
+  } else {
+    if (idx >= a.R * H4) return;
+    r = idx / H4; j = (idx - r * H4) * 4;
+  }
   float4 dh = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
   for (int k = 0; k < 3; ++k)
@@ -295,7 +312,8 @@ int lstm_backward(cudaStream_t s, const LstmBwdArgs& a) {
   for (int k = 0; k < 3; ++k) v4 = v4 && (!a.dh[k] || (al16(a.dh[k]) && (a.ld_dh[k] % 4) == 0));
   REQUIRE(!a.tiled || v4, "lstm_backward: the row-tiled state layout needs H %% 4 == 0 and 16-byte aligned buffers");
   if (v4) {
-    CUDA_TRY(launch_pdl(lstm_bwd_v4_kernel, dim3(ceil_div(a.R * (a.H / 4), 128)), dim3(128), 0, s, a));
+    const int items = a.tiled ? ceil_div(a.R, 8) * ceil_div(a.H / 4, 4) * 32 : a.R * (a.H / 4);
+    CUDA_TRY(launch_pdl(lstm_bwd_v4_kernel, dim3(ceil_div(items, 128)), dim3(128), 0, s, a));
   } else {
     dim3 grid(ceil_div(a.H, 128), a.R);
     CUDA_TRY(launch_pdl(lstm_bwd_kernel, grid, dim3(128), 0, s, a));
