@@ -298,7 +298,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_tcgen05_kernel(const __g
   pdl_launch_dependents(1);
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one_sync()) {
       int stage = 0; uint32_t phase = 0;
       int s = 0, base = 0;                              // segment of the current k-block, its first global index
       for (int g = kb_begin; g < kb_end; ++g) {
@@ -312,7 +312,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_tcgen05_kernel(const __g
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (elect_one_sync()) {
       int stage = 0; uint32_t phase = 0;
       for (int kb = kb_begin; kb < kb_end; ++kb) {
         mbar_wait(&full_bar[stage], phase);
@@ -489,7 +489,7 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ GemmParams p) {
   pdl_launch_dependents(1);
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one_sync()) {
       int stage = 0; uint32_t phase = 0;
       int s = 0, base = 0;
       for (int g = kb_begin; g < kb_end; ++g) {
@@ -503,7 +503,7 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ GemmParams p) {
       }
     }
   } else if (warp == 1) {
-    if (rank == 0 && lane == 0) {
+    if (rank == 0 && elect_one_sync()) {
       int stage = 0; uint32_t phase = 0;
       for (int kb = kb_begin; kb < kb_end; ++kb) {
         mbar_wait(&full_bar[stage], phase);
@@ -654,7 +654,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_swapped_kernel(c
   pdl_launch_dependents(1);
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one_sync()) {
       int stage = 0; uint32_t phase = 0;
       int s = 0, base = 0;
       for (int g = kb_begin; g < kb_end; ++g) {
@@ -669,7 +669,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_swapped_kernel(c
     }
     __syncwarp();
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (elect_one_sync()) {
       int stage = 0; uint32_t phase = 0;
       for (int kb = kb_begin; kb < kb_end; ++kb) {
         mbar_wait(&full_bar[stage], phase);
@@ -928,7 +928,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_swapped_pair_ker
   const LstmFwdArgs lstm = p.lstm;                      // registers (see the note at epilogue_block_vec)
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one_sync()) {
       int stage = 0; uint32_t phase = 0;
       int s = 0, base = 0;
       uint64_t w_pol = 0;
@@ -946,7 +946,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_swapped_pair_ker
     }
     __syncwarp();
   } else if (warp == 1) {
-    if (xr == 0 && lane == 0) {
+    if (xr == 0 && elect_one_sync()) {
       const uint16_t pair_mask = static_cast<uint16_t>(3u << (2 * rank));
       int stage = 0; uint32_t phase = 0;
       for (int kb = kb_begin; kb < kb_end; ++kb) {

@@ -603,7 +603,7 @@ recurrent_fwd_kernel(const __grid_constant__ RfParams p) {
 
   if (warp == 0) {
     // ================= TMA producer of the GEMM operand ring (both CTAs of the pair) =================
-    if (lane == 0) {
+    if (elect_one_sync()) {
       int stage = 0; uint32_t phase = 0;
       uint64_t w_pol = 0;
       if (p.w_policy) asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(w_pol));
@@ -657,7 +657,7 @@ recurrent_fwd_kernel(const __grid_constant__ RfParams p) {
     __syncwarp();
   } else if (warp == 1) {
     // ================= MMA issuer (leader CTA of the pair) =================
-    if (rank == 0 && lane == 0) {
+    if (rank == 0 && elect_one_sync()) {
       int stage = 0; uint32_t phase = 0;
       for (int t = 0; t < T; ++t) {
         for (int j = 0; j < njobs; ++j) {

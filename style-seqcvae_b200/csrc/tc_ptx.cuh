@@ -13,6 +13,16 @@ namespace sscvae {
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
+// One lane of a CONVERGED warp. Unlike `lane == 0`, the compiler knows that exactly one thread runs the guarded code, so the
+// operands of the uniform-datapath instructions (UTMALDG, UTCHMMA, UTCBAR, SYNCS) are moved to uniform registers once
+// instead of through a per-instruction R2UR "waterfall" loop. Measured with tools/mc_probe.cu: a k-block of four
+// tcgen05.mma.cta_group::2 takes 0.38 us when issued under `lane == 0` and 0.24 us under elect.sync
+// (profiles/mc_probe_r02.md).
+__device__ __forceinline__ bool elect_one_sync() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
 }

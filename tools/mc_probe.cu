@@ -94,14 +94,45 @@ __global__ void __launch_bounds__(64, 1) probe2_kernel(const __grid_constant__ P
         tma_load(dst + TILE_BYTES, &p.wtile, &full[stage], k, wrow);
       } else {
         if (rank == 0) mbar_expect_tx(&full[stage], 2 * SB);
-        if (p.mode == 4) tma_load_2sm(dst, &p.full_tile, &full[stage], k, (int)rank * 128);
+        if (p.mode == 4 || p.mode == 7) tma_load_2sm(dst, &p.full_tile, &full[stage], k, (int)rank * 128);
         else tma_load_3d_2sm(dst, &p.x3d, &full[stage], k, (int)rank * 128, i & 7);
         if (p.mode == 6) tma_load_2sm_hint(dst + TILE_BYTES, &p.wtile, &full[stage], k, wrow, pol);
         else tma_load_2sm(dst + TILE_BYTES, &p.wtile, &full[stage], k, wrow);
       }
       if (++stage == STAGES) { stage = 0; phase ^= 1; }
     }
-  } else if (threadIdx.x == 32 && rank == 0) {
+  } else if (p.mode == 7 && threadIdx.x >= 32 && rank == 0) {
+    // converged warp: every lane runs the loop, one elected lane issues; loop state is warp-uniform (uniform registers)
+    int stage = 0; uint32_t phase = 0;
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.mma_n >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+    const uint32_t tm = tmem_slot;
+    const uint32_t base = smem_u32(smem);
+    for (int i = 0; i < p.iters; ++i) {
+      mbar_wait(&full[stage], phase);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      uint32_t elected;
+      asm volatile("{\n.reg .pred P;\nelect.sync _|P, 0xffffffff;\nselp.u32 %0, 1, 0, P;\n}" : "=r"(elected));
+      if (elected) {
+        const uint32_t xb = base + stage * SB, wb = xb + TILE_BYTES;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          if (k < p.nmma) {
+            uint64_t ad = ((uint64_t)(((xb + k * 32) & 0x3FFFF) >> 4)) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+            uint64_t bd = ((uint64_t)(((wb + k * 32) & 0x3FFFF) >> 4)) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+            asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n}" ::"r"(tm), "l"(ad), "l"(bd), "r"(idesc), "r"(1u) : "memory");
+          }
+        }
+        asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(&empty[stage])), "h"((uint16_t)3) : "memory");
+      }
+      __syncwarp();
+      if (++stage == STAGES) { stage = 0; phase ^= 1; }
+    }
+    if (threadIdx.x == 32) {
+      unsigned long long t1;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+      p.out[blockIdx.x * 2 + 1] = t1;
+    }
+  } else if (p.mode != 7 && threadIdx.x == 32 && rank == 0) {
     int stage = 0; uint32_t phase = 0;
     for (int i = 0; i < p.iters; ++i) {
       mbar_wait(&full[stage], phase);
@@ -206,7 +237,8 @@ int main(int argc, char** argv) {
                       {3, 1, 148, "X same + W own, plain, 148 CTAs"}, {3, 1, 116, "X same + W own, plain, 116 CTAs"},
                       {4, 2, 148, "X+W, CTA pair 2sm loads, 148"}, {5, 2, 148, "X+W, pair, 3-D X map, 148"}, {6, 2, 148, "X+W, pair, 3-D X, W hint, 148"},
                       {6, 2, 116, "X+W, pair, 3-D X, W hint, 116"}, {4, 2, 32, "X+W, CTA pair 2sm loads, 32"}, {4, 2, 148, "pair + 1 MMA N=128 per k-block", 1, 128}, {4, 2, 148, "pair + 4 MMA N=128 per k-block", 4, 128},
-                      {4, 2, 148, "pair + 4 MMA N=48 per k-block", 4, 48}, {4, 2, 32, "pair + 4 MMA N=48, 32 CTAs", 4, 48}};
+                      {4, 2, 148, "pair + 4 MMA N=48 per k-block", 4, 48}, {4, 2, 32, "pair + 4 MMA N=48, 32 CTAs", 4, 48},
+                      {7, 2, 148, "elect-warp + 4 MMA N=128", 4, 128}, {7, 2, 148, "elect-warp + 4 MMA N=256(fake)", 4, 256}, {7, 2, 148, "elect-warp + 0 MMA", 0, 128}, {7, 2, 148, "elect-warp + 2 MMA N=128", 2, 128}};
   for (const Cfg& c : cfgs) {
     Params p; p.mode = c.mode; p.nmma = c.nmma; p.mma_n = c.mma_n; p.iters = 4000; p.csize = c.csize; p.kmax = K; p.rows_total = ROWS; p.out = out;
     make(&p.full_tile, TILE_ROWS); make(&p.slice, c.mode == 2 ? TILE_ROWS / c.csize : TILE_ROWS); make(&p.wtile, 64);
