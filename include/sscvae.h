@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define SSCVAE_ABI_VERSION 4
+#define SSCVAE_ABI_VERSION 5
 
 #define SSCVAE_ERR_BAD_ARG (-1)
 #define SSCVAE_ERR_WORKSPACE (-2)
@@ -44,13 +44,17 @@ typedef struct SscvaeDims {
   int32_t z_space;                   /* Z */
   int32_t vocab_size;                /* V */
   int32_t max_caption_length;        /* L; teacher-forced steps T = L + 1 */
-  int32_t sentiment_vae;             /* 0 | 1   (2 = attribute-grounded prior: unsupported) */
+  int32_t sentiment_vae;             /* 0 | 1 | 2 (2 = attribute-grounded prior, updown_cell.py:160-174: per-step prior mean
+                                        sum_n alpha_n * obj_means_n, also fed to the encoder / decoder LSTMs) */
   int32_t simple_vae;                /* 0 | 1 */
   int32_t tied_embedding;            /* 1: frozen embedding tied to the output layer + tanh projection (E in {300,600}) */
   int32_t pad_index;                 /* "@@UNKNOWN@@"  */
   int32_t boundary_index;            /* "@@BOUNDARY@@" */
   float prior_std;
   float senti_prior_multip;
+  int32_t latent_embedding;          /* sentiment_vae == 2 only: 0 = "glove": the LSTM conditioning block is the whole prior mean
+                                        (Z columns; the reference hard-codes 150 = its Z, updown_cell.py:63-70); 1 = "senti_word_net":
+                                        its first column only (updown_cell.py:55-61, 168-171) */
 } SscvaeDims;
 
 /* Order of the weight / gradient pointer arrays = the reference state_dict. */
@@ -111,7 +115,10 @@ int sscvae_train_forward(SscvaeHandle* h, int batch, int num_boxes,
                          const void* const* weights_f32,  /* host array; biases / w_a are read in fp32 */
                          const float* image_features,     /* (B,N,F) zero rows = padding boxes */
                          const int64_t* caption_tokens,   /* (B,L) pad = pad_index */
-                         const float* sentiment,          /* (B,1) or NULL when sentiment_vae == 0 */
+                         const float* sentiment,          /* (B,1) or NULL when sentiment_vae != 1 */
+                         const float* obj_means,          /* (B,N,Z) per-box attribute means = the result of the reference's
+                                                             translate_obj_atts2obj_means (updown_captioner.py:509-532);
+                                                             required when sentiment_vae == 2, else NULL */
                          const float* eps,                /* (T,B,Z) N(0,1) draws, or NULL -> Philox(seed) */
                          uint64_t seed,
                          void* workspace, size_t workspace_bytes,
@@ -176,6 +183,7 @@ size_t sscvae_decode_workspace_bytes(const SscvaeHandle* h, int batch, int num_b
 int sscvae_decode(SscvaeHandle* h, int batch, int num_boxes, int states, int beam, int per_node,
                   const void* packed, const void* const* weights_f32,
                   const float* image_features, const float* sentiment,
+                  const float* obj_means,             /* (B,N,Z) when sentiment_vae == 2 (rows of an image share them), else NULL */
                   const uint8_t* fsm,                 /* (B,S,S,V) uint8 as the reference passes it, or NULL */
                   const int64_t* num_constraints,     /* (B) or NULL */
                   int min_constraints_to_satisfy,
@@ -194,7 +202,7 @@ int sscvae_decode(SscvaeHandle* h, int batch, int num_boxes, int states, int bea
 size_t sscvae_decode_samples_workspace_bytes(const SscvaeHandle* h, int batch, int samples, int num_boxes);
 int sscvae_decode_samples(SscvaeHandle* h, int batch, int samples, int num_boxes,
                           const void* packed, const void* const* weights_f32,
-                          const float* image_features, const float* sentiment,
+                          const float* image_features, const float* sentiment, const float* obj_means,
                           const float* eps, uint64_t seed,
                           void* workspace, size_t workspace_bytes,
                           int64_t* predictions,               /* out (B,samples,L) */

@@ -91,6 +91,137 @@ def gen_train(name, *, E, sv, simple=False, V=120, F=64, H=32, A=24, Z=16, N=7, 
     print("wrote", name, "loss", out["loss"].detach().numpy().round(3))
 
 
+ATT_WORDS = ["red", "old", "shiny", "happy", "broken", "wet"]
+
+
+def make_mean_choice(Z, latent_embedding, seed):
+    """{attribute word: (Z,) vector} like the tables the reference loads (updown_captioner.py:79-86): "senti_word_net"
+    repeats one score over all Z components, "glove" has a free vector per word."""
+    g = torch.Generator().manual_seed(seed)
+    out = {}
+    for w in ATT_WORDS:
+        if latent_embedding == "senti_word_net":
+            out[w] = np.repeat(float(torch.rand(1, generator=g)) * 2 - 1, Z)
+        else:
+            out[w] = (torch.randn(Z, generator=g) * 0.5).numpy().astype(np.float64)
+    return out
+
+
+def make_obj_atts(B, N, seed):
+    """per image N `(object, [attribute strings])` entries in the reference's format (updown_captioner.py:509-520):
+    the first word of an attribute string is looked up; unknown words and boxes without attributes occur."""
+    g = torch.Generator().manual_seed(seed)
+    words = ATT_WORDS + ["unknownword"]
+    out = []
+    for b in range(B):
+        boxes = []
+        for n in range(N):
+            k = int(torch.randint(0, 4, (1,), generator=g))
+            atts = [words[int(torch.randint(0, len(words), (1,), generator=g))] + " thing" for _ in range(k)]
+            boxes.append(("obj%d" % n, atts))
+        out.append(boxes)
+    return out
+
+
+def gen_train_sv2(name, *, E, le, Z, V=120, F=64, H=32, A=24, N=7, B=5, L=20, prior_std=1.0, multip=2.0, seed=0):
+    """SENTIMENT_VAE = 2 training forward + backward of the reference (attribute-grounded prior, updown_cell.py:160-190)."""
+    vocab = rh.make_vocabulary(V)
+    mc = make_mean_choice(Z, le, seed + 5)
+    m = rh.build_reference_model(vocab, image_feature_size=F, embedding_size=E, hidden_size=H,
+                                 attention_projection_size=A, z_space=Z, sentiment_vae=2, latent_embedding=le,
+                                 max_caption_length=L, prior_std=prior_std, seed=seed, latent_embedding_multip=multip,
+                                 mean_choice=mc)
+    cfg = dict(vocab_size=V, image_feature_size=F, embedding_size=E, hidden_size=H,
+               attention_projection_size=A, z_space=Z, sentiment_vae=2, simple_vae=False, latent_embedding=le,
+               max_caption_length=L, prior_std=prior_std, senti_prior_multip=0.5)
+    feats, toks, sentiment = synthetic_batch(B, N, F, V, L, seed + 1)
+    obj_atts = make_obj_atts(B, N, seed + 2)
+    obj_means = m.translate_obj_atts2obj_means(obj_atts)
+    m.train()
+    logits_rec = []
+    hk = m._output_layer.register_forward_hook(lambda mod, i, o: logits_rec.append(o.detach().clone()))
+    torch.manual_seed(EPS_SEED)
+    out = m(feats.clone(), obj_atts, None, toks, sentiment)
+    hk.remove()
+    (out["loss"].mean() + out["kld"].mean() / 750.0).backward()
+    torch.manual_seed(EPS_SEED)
+    eps = torch.stack([torch.randn(B, Z) for _ in range(L + 1)])
+    sd = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    grads = {k: p.grad.detach().clone() for k, p in m.named_parameters() if p.grad is not None}
+    ocfg = uo.OracleConfig(**cfg)
+    p = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    if ocfg.tied:
+        p["_output_layer.weight"] = p["_embedding_layer.weight"]
+    o = uo.train_forward(p, ocfg, feats, toks, sentiment, eps, record=True, obj_means=obj_means)
+    assert torch.allclose(o["loss"], out["loss"], rtol=1e-5, atol=1e-4), name
+    assert torch.allclose(o["kld"], out["kld"], rtol=1e-5, atol=1e-4), name
+    assert torch.allclose(o["logits"], torch.stack(logits_rec, 1), rtol=1e-4, atol=1e-4), name
+    uo.train_objective(o).backward()
+    for k, gref in grads.items():
+        assert torch.allclose(p[k].grad, gref, rtol=1e-3, atol=1e-5), (name, k)
+    np.savez_compressed(
+        os.path.join(OUT, name + ".npz"),
+        cfg=json.dumps(cfg), image_features=feats.numpy(), caption_tokens=toks.numpy(),
+        sentiment=sentiment.numpy(), eps=eps.numpy(), loss=out["loss"].detach().numpy(),
+        kld=out["kld"].detach().numpy(), logits=torch.stack(logits_rec, 1).numpy(),
+        obj_means=obj_means.numpy(), obj_atts=json.dumps(obj_atts), latent_embedding_multip=multip,
+        mean_choice=json.dumps({k: np.asarray(v).tolist() for k, v in mc.items()}),
+        **{"param:" + k: v.numpy() for k, v in sd.items()},
+        **{"grad:" + k: v.numpy() for k, v in grads.items()})
+    print("wrote", name, "loss", out["loss"].detach().numpy().round(3), "kld", out["kld"].detach().numpy().round(3))
+
+
+def gen_decode_sv2(name, *, le, Z, E=600, V0=40, F=64, H=32, A=24, N=7, seed=21):
+    """SENTIMENT_VAE = 2 eval forward of the reference at B = 1, beam 1 (the reference does not replicate obj_atts per
+    beam, updown_captioner.py:405-424, so wider beams do not run): z ~ N(sum_n alpha_n obj_n, prior_std^2) per step."""
+    ref = rh.load_reference()
+    with tempfile.TemporaryDirectory() as d:             # the unconstrained one-state FSM, built by the reference
+        tsv = os.path.join(d, "wf.tsv")
+        with open(tsv, "w") as f:
+            f.write("dog\tdog,dogs\n")
+        vocab = rh.make_vocabulary(V0)
+        vocab = ref.add_constraint_words_to_vocabulary(vocab, tsv)
+        V = vocab.get_vocab_size()
+        builder = ref.FiniteStateMachineBuilder(vocab, tsv, None, max_given_constraints=0)
+        fsm, nstates, _ = builder.build([])
+        fsm = fsm[None, :nstates, :nstates]
+    assert fsm.shape[1] == 1
+    mc = make_mean_choice(Z, le, seed + 5)
+    m = rh.build_reference_model(vocab, image_feature_size=F, embedding_size=E, hidden_size=H,
+                                 attention_projection_size=A, z_space=Z, sentiment_vae=2, latent_embedding=le,
+                                 beam_size=1, seed=seed, latent_embedding_multip=1.5, mean_choice=mc, prior_std=0.7)
+    cfg = dict(vocab_size=V, image_feature_size=F, embedding_size=E, hidden_size=H,
+               attention_projection_size=A, z_space=Z, sentiment_vae=2, simple_vae=False, latent_embedding=le,
+               max_caption_length=20, prior_std=0.7, senti_prior_multip=0.5)
+    m.eval()
+    feats, _, _ = synthetic_batch(1, N, F, V, 20, seed + 1, ragged=False)
+    obj_atts = make_obj_atts(1, N, seed + 2)
+    obj_means = m.translate_obj_atts2obj_means(obj_atts)
+    torch.manual_seed(EPS_SEED)
+    with torch.no_grad():
+        out = m(feats.clone(), obj_atts, None, fsm=fsm, num_constraints=torch.tensor([0]), constraints=None,
+                constraint2states=None, sentiment=torch.zeros(1, 1))
+    pred = out["predictions"]
+    torch.manual_seed(EPS_SEED)
+    eps = torch.stack([torch.randn(1, Z) for _ in range(20)])
+    sd = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    ocfg = uo.OracleConfig(**cfg)
+    stepper = uo.DecodeStepper(sd, ocfg, feats, None, obj_means=obj_means)
+    ctr = {"t": 0}
+
+    def step(last, state):
+        t = ctr["t"]
+        ctr["t"] += 1
+        return stepper(last, state, eps[t])
+    p2, s2 = so.cbs_search(torch.ones(1, dtype=torch.long), step, fsm, 1, None, 1, 20)
+    b2, _ = so.select_best_beam_with_constraints(p2, s2, torch.tensor([0]), 2)
+    assert torch.equal(b2, pred), (b2, pred)
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), cfg=json.dumps(cfg), image_features=feats.numpy(),
+                        obj_means=obj_means.numpy(), eps=eps.numpy(), predictions=pred.numpy(),
+                        **{"param:" + k: v.numpy() for k, v in sd.items()})
+    print("wrote", name, "pred", pred.tolist())
+
+
 def gen_decode_step(name, *, E=600, V=120, F=64, H=32, A=24, Z=16, N=7, B=3, nb=4, seed=3):
     """Reference eval-mode `_decode_step` with replicated rows (updown_captioner.py:405-424),
     uniform sentiment so the reference's tiled repeat equals the aligned one."""
@@ -284,6 +415,10 @@ def gen_decode_e2e(name, *, K, constraints, mg, E=600, V0=40, F=64, H=32, A=24, 
 
 def main():
     os.makedirs(OUT, exist_ok=True)
+    import sys
+    if len(sys.argv) > 1 and sys.argv[1] == "sv2":       # only the SENTIMENT_VAE = 2 fixtures (added in round 2)
+        return main_sv2()
+    main_sv2()
     gen_train("train_tied_sv1", E=600, sv=1)
     gen_train("train_tied300_sv0", E=300, sv=0, seed=7)
     gen_train("train_untied_sv1", E=40, sv=1, seed=11)
@@ -301,6 +436,13 @@ def main():
     gen_beam("beam_k1_greedy", K=1, P=None, B=4, seed=12, end_bias_from=8)
     gen_decode_e2e("decode_e2e_cbs_k5", K=5, constraints=["pos", "dog"], mg=3)
     gen_decode_e2e("decode_e2e_greedy", K=1, constraints=[], mg=0, seed=6)
+
+
+def main_sv2():
+    gen_train_sv2("train_tied_sv2_glove", E=600, le="glove", Z=150, seed=17)
+    gen_train_sv2("train_untied_sv2_swn", E=40, le="senti_word_net", Z=16, seed=19, prior_std=0.9)
+    gen_decode_sv2("decode_greedy_sv2_swn", le="senti_word_net", Z=16)
+    gen_decode_sv2("decode_greedy_sv2_glove", le="glove", Z=150, seed=29)
 
 
 if __name__ == "__main__":

@@ -11,6 +11,13 @@ yacs, overrides, anytree) are replaced by the stubs in `oracle/ref_shims/` (SURV
 Nothing from /root/reference is copied into the repo: the modules are imported in place, and the
 three torch>=1.2 incompatibilities of `updown-baseline/updown/modules/cbs.py` (:135, :205 `1 - uint8
 mask`; :231 `/` on int64) are patched on the source text in memory.
+
+SENTIMENT_VAE = 2: with a frozen-GloVe embedding size the reference's ctor opens hard-coded
+`/path/to/*.pkl|json` files and reads an attribute that is never set (`self.senti_glove_5`,
+updown_captioner.py:76-93), so it cannot be constructed as shipped. `build_reference_model` therefore constructs the
+captioner with sentiment_vae=1 and then swaps in the reference's own `UpDownCell(..., sentiment_vae=2, ...)`, sets
+`model.sentiment_vae = 2` and installs a caller-supplied `mean_choice` table: every line of the forward pass that runs
+is the reference's.
 """
 import importlib
 import os
@@ -84,7 +91,8 @@ def build_reference_model(vocab, *, image_feature_size, embedding_size, hidden_s
                           attention_projection_size, max_caption_length=20, beam_size=1,
                           use_cbs=None, min_constraints_to_satisfy=2, z_space=150, prior_std=1.0,
                           simple_vae=False, latent_embedding="glove", sentiment_vae=1,
-                          senti_prior_multip=0.5, cbs_simple=True, seed=0):
+                          senti_prior_multip=0.5, cbs_simple=True, seed=0, latent_embedding_multip=1,
+                          mean_choice=None):
     """Constructs the reference captioner on CPU with `torch.manual_seed(seed)` default init
     (SURVEY Appendix C)."""
     import torch
@@ -97,8 +105,16 @@ def build_reference_model(vocab, *, image_feature_size, embedding_size, hidden_s
         max_caption_length=max_caption_length, beam_size=beam_size, use_cbs=use_cbs,
         min_constraints_to_satisfy=min_constraints_to_satisfy, z_space=z_space,
         prior_std=prior_std, simple_vae=simple_vae, latent_embedding=latent_embedding,
-        sentiment_vae=sentiment_vae, senti_prior_multip=senti_prior_multip,
+        latent_embedding_multip=latent_embedding_multip,
+        sentiment_vae=1 if sentiment_vae == 2 else sentiment_vae, senti_prior_multip=senti_prior_multip,
         cbs_simple=cbs_simple, device=torch.device("cpu"))
+    if sentiment_vae == 2:                               # see the module docstring
+        cell_mod = importlib.import_module("var_updown.modules.updown_cell")
+        model._updown_cell = cell_mod.UpDownCell(
+            image_feature_size, embedding_size, hidden_size, attention_projection_size, z_space, 2, simple_vae,
+            torch.device("cpu"), latent_embedding)
+        model.sentiment_vae = 2
+        model.mean_choice = mean_choice
     if use_cbs:
         model._beam_search = ref.ConstrainedBeamSearch(
             model._boundary_index, max_steps=max_caption_length, beam_size=beam_size,

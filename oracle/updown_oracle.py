@@ -56,9 +56,11 @@ class OracleConfig:
         # (var_updown/var_updown/modules/updown_cell.py:47-81)
         if self.simple_vae or self.sentiment_vae == 0:
             return 0
-        if self.sentiment_vae == 1:
-            return 1
-        raise NotImplementedError("SENTIMENT_VAE=2 (attribute-grounded prior) is SURVEY §8(f)-4")
+        if self.sentiment_vae == 1 or self.latent_embedding == "senti_word_net":
+            return 1                                     # cell:55-61 (the elif order of the reference)
+        if self.sentiment_vae == 2:
+            return self.z_space                          # cell:63-70 writes the literal 150 = its Z_SPACE
+        raise NotImplementedError
 
 
 class Rounding:
@@ -226,6 +228,8 @@ def prior(cfg: OracleConfig, sentiment: Optional[torch.Tensor], batch: int):
         prior_mean = torch.zeros(batch, Z)
     elif cfg.sentiment_vae == 1:
         prior_mean = sentiment.repeat(1, Z) * cfg.senti_prior_multip
+    elif cfg.sentiment_vae == 2:
+        prior_mean = torch.zeros(batch, Z)               # capt:254-256; replaced per step by the cell (cell:160-163)
     else:
         raise NotImplementedError
     prior_var = (torch.ones(batch, Z) * cfg.prior_std).pow(2)
@@ -239,10 +243,11 @@ def zero_states(rows: int, H: int) -> Dict[str, torch.Tensor]:
 
 
 def decoder_step(p, cfg: OracleConfig, feats, mask, avg, proj, tokens, states, sentiment,
-                 prior_mean, prior_var, eps, training: bool, q: Rounding = FP32):
+                 prior_mean, prior_var, eps, training: bool, q: Rounding = FP32, obj_means=None):
     """One timestep: embedding -> UpDownCell -> output head.
     updown_captioner.py:430-450, updown_cell.py:143-231, attention.py:68-97.
-    Returns (logits, new_states, aux) with aux = {alpha, attended, mean, log_var, z, h_dec}."""
+    obj_means: (rows, N, Z) per-box attribute means, sentiment_vae == 2 only.
+    Returns (logits, new_states, aux) with aux = {alpha, attended, mean, log_var, z, h_dec, prior_mean}."""
     c = "_updown_cell."
     E, F, H = cfg.embedding_size, cfg.image_feature_size, cfg.hidden_size
     emb = p["_embedding_layer.weight"][tokens]                       # capt:430
@@ -259,8 +264,20 @@ def decoder_step(p, cfg: OracleConfig, feats, mask, avg, proj, tokens, states, s
                      p[c + "_butd_attention._attention_layer.weight"].t()).squeeze(-1)
     alpha = masked_softmax(u, mask)
     attended = (alpha.unsqueeze(-1) * feats).sum(dim=1)              # cell:156-158
-    # --- conditioning column (cell:176-190, 211-224)
-    cond = [sentiment] if cfg.cond_size == 1 else []
+    # --- attribute-grounded prior (cell:160-174): the prior mean of THIS step follows the attention
+    if cfg.sentiment_vae == 2:
+        prior_mean = (alpha.unsqueeze(-1) * obj_means).sum(dim=1)    # cell:160-163
+    if cfg.simple_vae:
+        prior_mean = torch.zeros_like(prior_mean)                    # cell:165-166
+    # --- conditioning column (cell:168-190, 211-224)
+    if cfg.cond_size == 0:
+        cond = []
+    elif cfg.sentiment_vae == 1:
+        cond = [sentiment]
+    elif cfg.latent_embedding == "glove":
+        cond = [prior_mean]                                          # cell:168-169
+    else:
+        cond = [prior_mean[:, 0].unsqueeze(1)]                       # cell:170-171
     h_dec_prev = states["h_decoder"]
     if training:
         x_enc = torch.cat([attended, h1, h_dec_prev] + cond, dim=1)  # cell:178-190
@@ -293,7 +310,7 @@ def decoder_step(p, cfg: OracleConfig, feats, mask, avg, proj, tokens, states, s
     new_states = {"h1": h1, "c1": c1, "h_encoder": h_enc, "c_encoder": c_enc,
                   "h_decoder": h_dec, "c_decoder": c_dec}
     aux = {"alpha": alpha, "attended": attended, "mean": mean, "log_var": log_var, "z": z,
-           "h_dec": h_dec, "h1": h1}
+           "h_dec": h_dec, "h1": h1, "prior_mean": prior_mean}
     return logits, new_states, aux
 
 
@@ -310,7 +327,7 @@ def kl_step(cfg: OracleConfig, mean, log_var, prior_mean, prior_var):
 # training forward (teacher forced) — updown_captioner.py:263-323
 # ----------------------------------------------------------------------------------------------
 def train_forward(p, cfg: OracleConfig, image_features, caption_tokens, sentiment, eps,
-                  q: Rounding = FP32, record: bool = False):
+                  q: Rounding = FP32, record: bool = False, obj_means=None):
     """image_features (B,N,F) f32; caption_tokens (B,L) i64 pad=0; sentiment (B,1) f32 or None;
     eps (T,B,Z) with T=L+1 (the reference draws one (B,Z) normal per step, cell:206).
     Returns {"loss": (B,), "kld": (B,)} (+ per-step records)."""
@@ -324,7 +341,8 @@ def train_forward(p, cfg: OracleConfig, image_features, caption_tokens, sentimen
     step_logits, step_klds, rec = [], [], []
     for t in range(T):                                                                # capt:282
         logits, states, aux = decoder_step(p, cfg, feats, mask, avg, proj, tokens[:, t], states,
-                                           sentiment, prior_mean, prior_var, eps[t], True, q)
+                                           sentiment, prior_mean, prior_var, eps[t], True, q, obj_means)
+        prior_mean = aux["prior_mean"]                   # capt:285 reassigns it from the step's return value
         step_klds.append(kl_step(cfg, aux["mean"], aux["log_var"], prior_mean, prior_var))
         step_logits.append(logits)
         if record:
@@ -359,11 +377,12 @@ class DecodeStepper:
     over one batch of images; R = B * net_beam with rows of an image contiguous
     (row r belongs to image r // net_beam), as updown_captioner.py:405-416 lays them out."""
 
-    def __init__(self, p, cfg: OracleConfig, image_features, sentiment, q: Rounding = FP32):
+    def __init__(self, p, cfg: OracleConfig, image_features, sentiment, q: Rounding = FP32, obj_means=None):
         self.p, self.cfg, self.q = p, cfg, q
         self.B = image_features.shape[0]
         self.feats, self.mask, self.avg, self.proj = image_precompute(p, cfg, image_features, q)
         self.sentiment = sentiment
+        self.obj_means = obj_means
         self.prior_mean, self.prior_var = prior(cfg, sentiment, self.B)
 
     def __call__(self, last_predictions, states, eps):
@@ -375,5 +394,5 @@ class DecodeStepper:
         logits, states, aux = decoder_step(
             self.p, self.cfg, rep(self.feats), rep(self.mask), rep(self.avg), rep(self.proj),
             last_predictions, states, rep(self.sentiment), rep(self.prior_mean), rep(self.prior_var),
-            eps, False, self.q)
+            eps, False, self.q, rep(self.obj_means))
         return torch.log_softmax(logits, dim=1), states                               # capt:450

@@ -54,7 +54,7 @@ class SscvaeDims(C.Structure):
         ("attention_projection_size", C.c_int32), ("z_space", C.c_int32), ("vocab_size", C.c_int32),
         ("max_caption_length", C.c_int32), ("sentiment_vae", C.c_int32), ("simple_vae", C.c_int32),
         ("tied_embedding", C.c_int32), ("pad_index", C.c_int32), ("boundary_index", C.c_int32),
-        ("prior_std", C.c_float), ("senti_prior_multip", C.c_float),
+        ("prior_std", C.c_float), ("senti_prior_multip", C.c_float), ("latent_embedding", C.c_int32),
     ]
 
 
@@ -82,7 +82,7 @@ def lib():
     L.sscvae_pack_weights.argtypes = [vp, C.POINTER(vp), vp, sz, C.POINTER(C.c_uint8), vp]
     L.sscvae_train_workspace_bytes.argtypes = [vp, i32, i32]
     L.sscvae_train_workspace_bytes.restype = sz
-    L.sscvae_train_forward.argtypes = [vp, i32, i32, vp, C.POINTER(vp), vp, vp, vp, vp, u64, vp, sz, vp, vp, vp]
+    L.sscvae_train_forward.argtypes = [vp, i32, i32, vp, C.POINTER(vp), vp, vp, vp, vp, vp, u64, vp, sz, vp, vp, vp]
     L.sscvae_train_backward.argtypes = [vp, i32, i32, vp, C.POINTER(vp), vp, sz, vp, vp, C.POINTER(vp), C.POINTER(vp), vp]
     L.sscvae_train_region.argtypes = [vp, i32, i32, C.c_char_p, C.POINTER(sz), C.POINTER(sz)]
     L.sscvae_fsm_pack.argtypes = [vp, i32, i32, i32, vp, vp]
@@ -94,11 +94,11 @@ def lib():
     L.sscvae_decode_workspace_bytes.argtypes = [vp, i32, i32, i32, i32]
     L.sscvae_decode_workspace_bytes.restype = sz
     L.sscvae_decode_region.argtypes = [vp, i32, i32, i32, i32, C.c_char_p, C.POINTER(sz), C.POINTER(sz)]
-    L.sscvae_decode.argtypes = [vp, i32, i32, i32, i32, i32, vp, C.POINTER(vp), vp, vp, vp, vp, i32, vp, u64, vp, sz,
+    L.sscvae_decode.argtypes = [vp, i32, i32, i32, i32, i32, vp, C.POINTER(vp), vp, vp, vp, vp, vp, i32, vp, u64, vp, sz,
                                 vp, vp, vp, vp, vp]
     L.sscvae_decode_samples_workspace_bytes.argtypes = [vp, i32, i32, i32]
     L.sscvae_decode_samples_workspace_bytes.restype = sz
-    L.sscvae_decode_samples.argtypes = [vp, i32, i32, i32, vp, C.POINTER(vp), vp, vp, vp, u64, vp, sz, vp, vp, vp, vp]
+    L.sscvae_decode_samples.argtypes = [vp, i32, i32, i32, vp, C.POINTER(vp), vp, vp, vp, vp, u64, vp, sz, vp, vp, vp, vp]
     L.sscvae_test_gemm_splitk.argtypes = [vp, i32, vp, i32, i32, i32, i32, vp, i32, i32, vp, vp]
     L.sscvae_sgd_step_multi.argtypes = [i32, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(u64), C.POINTER(i32),
                                         C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, vp, sz, vp]
@@ -112,7 +112,7 @@ def lib():
         fn = getattr(L, name)
         if fn.restype is C.c_int and name not in ("sscvae_abi_version",):
             fn.restype = C.c_int
-    if L.sscvae_abi_version() != 4:
+    if L.sscvae_abi_version() != 5:
         raise ImportError("libsscvae_b200.so ABI version mismatch")
     _lib = L
     return L

@@ -47,7 +47,7 @@ class _TrainStep(torch.autograd.Function):
     """forward = sscvae_train_forward, backward = sscvae_train_backward (BPTT kernels)."""
 
     @staticmethod
-    def forward(ctx, module, image_features, caption_tokens, sentiment, eps, seed, *params):
+    def forward(ctx, module, image_features, caption_tokens, sentiment, obj_means, eps, seed, *params):
         L = _lib.lib()
         B, N, _ = image_features.shape
         packed = module._packed_weights()
@@ -61,11 +61,11 @@ class _TrainStep(torch.autograd.Function):
         wptr = _lib.ptr_array(module._weight_tensors())
         _lib.check(L.sscvae_train_forward(
             module._handle, B, N, _lib.ptr(packed), wptr, _lib.ptr(image_features), _lib.ptr(caption_tokens),
-            _lib.ptr(sentiment), _lib.ptr(eps), C.c_uint64(seed), _lib.ptr(ws), ws.numel(), _lib.ptr(loss_buf),
+            _lib.ptr(sentiment), _lib.ptr(obj_means), _lib.ptr(eps), C.c_uint64(seed), _lib.ptr(ws), ws.numel(), _lib.ptr(loss_buf),
             _lib.ptr(kld_buf), stream))
         module._ws_generation += 1
         ctx.module, ctx.B, ctx.N, ctx.generation = module, B, N, module._ws_generation
-        ctx.keep = (image_features, caption_tokens, sentiment, eps)
+        ctx.keep = (image_features, caption_tokens, sentiment, obj_means, eps)
         return loss_buf.clone(), kld_buf.clone()
 
     @staticmethod
@@ -76,7 +76,7 @@ class _TrainStep(torch.autograd.Function):
                                "call backward before the next forward")
         L = _lib.lib()
         params = module._weight_tensors()
-        needs = ctx.needs_input_grad[6:]
+        needs = ctx.needs_input_grad[7:]
         # Gradients are written into persistent per-bucket flat buffers (stable pointers: the backward graph is replayed,
         # and the data-parallel all-reduce runs in place on the buckets). If a parameter still holds the previous
         # gradient in that very storage (gradient accumulation without zero_grad), a fresh tensor is used instead.
@@ -127,7 +127,7 @@ class _TrainStep(torch.autograd.Function):
                 out.append(None)
             else:
                 out.append(g)
-        return (None, None, None, None, None, None) + tuple(out)
+        return (None, None, None, None, None, None, None) + tuple(out)
 
 
 class UpDownCaptioner(nn.Module):
@@ -152,6 +152,7 @@ class UpDownCaptioner(nn.Module):
         cbs_simple=False,
         device=None,
         glove_vectors: Optional[torch.Tensor] = None,
+        mean_choice: Optional[dict] = None,
     ):
         super().__init__()
         self._vocabulary = vocabulary
@@ -177,10 +178,14 @@ class UpDownCaptioner(nn.Module):
         self.per_node_beam_size = (beam_size // 2) or beam_size     # updown_captioner.py:134, cbs.py:57
         self.device = device
         self.cbs_simple = cbs_simple
-        if self.sentiment_vae not in (0, 1):
-            raise NotImplementedError("SENTIMENT_VAE=2 (attribute-grounded prior) is not on this path yet (SURVEY §8(f)-4)")
+        if self.sentiment_vae not in (0, 1, 2):
+            raise NotImplementedError()                              # updown_cell.py:72-73
         if latent_embedding not in ("glove", "senti_word_net"):
             raise NotImplementedError()                              # updown_cell.py:169-174
+        # sentiment_vae == 2: {attribute word: (Z,) vector} the per-box attribute means are built from. The reference loads
+        # it from hard-coded pickle / json paths in its ctor (updown_captioner.py:76-93); here it is an argument (and forward()
+        # also accepts the already translated (B, N, Z) tensor).
+        self.mean_choice = mean_choice
         if use_cbs and not cbs_simple:
             raise NotImplementedError("only cbs_simple best-beam selection is implemented (SURVEY §8(f)-2)")
 
@@ -195,7 +200,14 @@ class UpDownCaptioner(nn.Module):
             self._embedding_layer = nn.Embedding(_vocab_size, embedding_size, padding_idx=self._pad_index)
             assert not use_cbs, "CBS is not supported without Frozen GloVe embeddings (300d / 600d)"
 
-        cond = 0 if (self.simple_vae or self.sentiment_vae == 0) else 1
+        # width of the conditioning block of the encoder / decoder LSTM inputs (updown_cell.py:47-81; the reference writes
+        # the "glove" width of sentiment_vae == 2 as the literal 150 = its Z_SPACE)
+        if self.simple_vae or self.sentiment_vae == 0:
+            cond = 0
+        elif self.sentiment_vae == 1 or latent_embedding == "senti_word_net":
+            cond = 1
+        else:
+            cond = z_space
         self._updown_cell = _UpDownCellParams(image_feature_size, embedding_size, hidden_size,
                                               attention_projection_size, z_space, cond)
         if self._tied:
@@ -210,7 +222,8 @@ class UpDownCaptioner(nn.Module):
         dims = _lib.SscvaeDims(
             image_feature_size, embedding_size, hidden_size, attention_projection_size, z_space, _vocab_size,
             max_caption_length, self.sentiment_vae, int(self.simple_vae), int(self._tied), self._pad_index,
-            self._boundary_index, float(self.prior_std), float(senti_prior_multip))
+            self._boundary_index, float(self.prior_std), float(senti_prior_multip),
+            int(latent_embedding == "senti_word_net"))
         self._dims = dims
         self._handle = C.c_void_p()
         _lib.check(_lib.lib().sscvae_create(C.byref(dims), C.byref(self._handle)))
@@ -440,6 +453,7 @@ class UpDownCaptioner(nn.Module):
             sentiment = sentiment.to(image_features.device).contiguous().float().view(B, 1)
         else:
             sentiment = None
+        obj_means = self._obj_means(obj_atts, B, N, image_features.device)
 
         if self.training and caption_tokens is not None:
             caption_tokens = caption_tokens.to(image_features.device).contiguous().long()
@@ -457,14 +471,50 @@ class UpDownCaptioner(nn.Module):
             if eps is not None:
                 eps = eps.to(image_features.device).contiguous().float()
                 assert eps.shape == (T, B, self.z_space)
-            loss, kld = _TrainStep.apply(self, image_features, caption_tokens, sentiment, eps, self._next_seed(),
+            loss, kld = _TrainStep.apply(self, image_features, caption_tokens, sentiment, obj_means, eps, self._next_seed(),
                                          *self._weight_tensors())
             return {"loss": loss, "kld": kld}
 
-        return {"predictions": self._decode(image_features, sentiment, fsm, num_constraints)}
+        return {"predictions": self._decode(image_features, sentiment, fsm, num_constraints, obj_means)}
+
+    # ------------------------------------------------------------------------------------------
+    def translate_obj_atts2obj_means(self, obj_atts) -> torch.Tensor:
+        """Per-box attribute means of sentiment_vae == 2 (updown_captioner.py:509-532): `obj_atts` holds, per image, one
+        `(object, [attribute strings])` entry per box; a box's mean is the average of `mean_choice[first word]` over its
+        attributes that have an entry (zeros when none has), boxes are zero-padded to the longest image and the result is
+        scaled by `latent_embedding_multip`. Returns (B, max boxes, Z) fp32 on the CPU."""
+        if self.mean_choice is None:
+            raise ValueError("sentiment_vae == 2 with attribute lists needs `mean_choice` ({word: (Z,) vector})")
+        Z = self.z_space
+        per_image = []
+        for boxes in obj_atts:
+            rows = torch.zeros(len(boxes), Z, dtype=torch.float64)
+            for i, box in enumerate(boxes):
+                hits = [self.mean_choice[a.split(" ")[0]] for a in box[1] if a.split(" ")[0] in self.mean_choice]
+                if hits:
+                    rows[i] = torch.stack([torch.as_tensor(h, dtype=torch.float64).reshape(-1) for h in hits]).mean(dim=0)
+            per_image.append(rows)
+        out = torch.zeros(len(per_image), max(len(r) for r in per_image), Z, dtype=torch.float64)
+        for i, rows in enumerate(per_image):
+            out[i, :len(rows)] = rows
+        return (out * self.latent_embedding_multip).float()
+
+    def _obj_means(self, obj_atts, B, N, device):
+        """(B, N, Z) fp32 device tensor for sentiment_vae == 2 (a tensor is taken as already translated), else None."""
+        if self.sentiment_vae != 2 or self.simple_vae:
+            return None
+        if obj_atts is None:
+            raise ValueError("obj_atts is required when sentiment_vae == 2")
+        if not torch.is_tensor(obj_atts):
+            obj_atts = self.translate_obj_atts2obj_means(obj_atts)
+        obj_atts = obj_atts.to(device).contiguous().float()
+        if obj_atts.shape != (B, N, self.z_space):
+            # the reference multiplies (B, N) attention weights with it (updown_cell.py:161-163): one row per box
+            raise ValueError(f"obj_atts must be (B, num_boxes, z_space) = {(B, N, self.z_space)}, got {tuple(obj_atts.shape)}")
+        return obj_atts
 
     @torch.no_grad()
-    def sample(self, image_features: torch.Tensor, sentiment=None, n_samples: int = 100):
+    def sample(self, image_features: torch.Tensor, sentiment=None, n_samples: int = 100, obj_atts=None):
         """Diverse sampling: `n_samples` greedy captions per image with independent latent draws, in one call.
 
         Replaces the reference's inference loop `for k in range(N_Z_SAMPLES): model(image_features, ...)`
@@ -490,6 +540,7 @@ class UpDownCaptioner(nn.Module):
             sentiment = sentiment.to(dev).contiguous().float().view(B, 1)
         else:
             sentiment = None
+        obj_means = self._obj_means(obj_atts, B, N, dev)
         eps = self._eps_override
         if eps is not None:
             eps = eps.to(dev).contiguous().float()
@@ -512,13 +563,13 @@ class UpDownCaptioner(nn.Module):
         self._reuse_image_state(key, image_features)
         _lib.check(L.sscvae_decode_samples(
             self._handle, B, J, N, _lib.ptr(self._packed_weights()), _lib.ptr_array(self._weight_tensors()),
-            _lib.ptr(image_features), _lib.ptr(sentiment), _lib.ptr(eps), C.c_uint64(self._next_seed()), _lib.ptr(ws), nbytes,
-            _lib.ptr(preds), _lib.ptr(scores), _lib.ptr(n_steps), stream))
+            _lib.ptr(image_features), _lib.ptr(sentiment), _lib.ptr(obj_means), _lib.ptr(eps), C.c_uint64(self._next_seed()),
+            _lib.ptr(ws), nbytes, _lib.ptr(preds), _lib.ptr(scores), _lib.ptr(n_steps), stream))
         n = int(n_steps.item())
         return {"predictions": preds[..., :n].clone(), "log_probs": scores.clone()}
 
     @torch.no_grad()
-    def _decode(self, image_features, sentiment, fsm, num_constraints):
+    def _decode(self, image_features, sentiment, fsm, num_constraints, obj_means=None):
         L = _lib.lib()
         dev = image_features.device
         B, N, _ = image_features.shape
@@ -564,7 +615,7 @@ class UpDownCaptioner(nn.Module):
         self._reuse_image_state(key, image_features)
         _lib.check(L.sscvae_decode(
             self._handle, B, N, S, K, P, _lib.ptr(self._packed_weights()), _lib.ptr_array(self._weight_tensors()),
-            _lib.ptr(image_features), _lib.ptr(sentiment), _lib.ptr(fsm), _lib.ptr(nc),
+            _lib.ptr(image_features), _lib.ptr(sentiment), _lib.ptr(obj_means), _lib.ptr(fsm), _lib.ptr(nc),
             int(self._min_constraints_to_satisfy), _lib.ptr(eps), C.c_uint64(self._next_seed()), _lib.ptr(ws), nbytes,
             _lib.ptr(preds), _lib.ptr(scores), _lib.ptr(best), _lib.ptr(n_steps), stream))
         n = int(n_steps.item())                                     # the reference's data-dependent early exit (cbs.py:167)

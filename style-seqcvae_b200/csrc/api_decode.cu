@@ -37,7 +37,8 @@ static void plan_decode(const Dims& d, int B, int N, int S, int K, int J, Plan& 
   p.add("cdb", R * d.H * f);
   p.add("XE", R * (d.Fp + d.Hp) * b);
   p.add("embb_r", R * d.Ep * b);
-  p.add("ZB", R * d.Zp * b);
+  p.add("ZB", R * d.ZC * b);                 // [z | c]: c = the conditioning block of sentiment_vae == 2
+  if (d.cvar) p.add("pm", R * d.Z * f);      // per-row prior mean of the current step (updown_cell.py:160-163)
   p.add("acc", R * d.GP * f);
   p.add("q", R * d.A * f);
   p.add("alpha", R * N * f);
@@ -70,12 +71,14 @@ static inline GemmSeg seg(const bf16* A, int lda, const bf16* B, int ldb, int K)
 }
 
 static int decode_impl(Handle* h, int B, int J, int N, int S, int K, int P, const char* pk, const void* const* wv,
-                       const void* feats, const float* sent, const uint8_t* fsm, const long long* num_constraints,
+                       const void* feats, const float* sent, const float* obj, const uint8_t* fsm, const long long* num_constraints,
                        int min_sat, const float* eps, unsigned long long seed, char* ws, size_t ws_bytes,
                        long long* predictions, float* log_probs, long long* best, int32_t* n_steps, cudaStream_t s) {
   const Dims& d = h->d;
   REQUIRE(B > 0 && N > 0 && S >= 1 && S <= 32 && K >= 1 && K <= 8 && P >= 1 && P <= K, "bad decode shape B=%d N=%d S=%d K=%d P=%d", B, N, S, K, P);
-  REQUIRE(d.cond == 0 || sent != nullptr, "sentiment is required when sentiment_vae == 1");
+  const bool csent = d.cond && !d.cvar;
+  REQUIRE(!csent || sent != nullptr, "sentiment is required when sentiment_vae == 1");
+  REQUIRE(!d.cvar || obj != nullptr, "obj_means is required when sentiment_vae == 2");
   REQUIRE(S == 1 || fsm != nullptr, "an FSM is required for more than one state");
   REQUIRE(J >= 1 && (J == 1 || (S == 1 && fsm == nullptr)), "samples per image > 1 needs the unconstrained search (S == 1)");
   const Plan& dp = h->decode_plan(B, N, S, K, J);
@@ -96,6 +99,7 @@ static int decode_impl(Handle* h, int B, int J, int N, int S, int K, int P, cons
   (void)seed;
 
   CUDA_TRY(zero("XA0")); CUDA_TRY(zero("XA1")); CUDA_TRY(zero("XE")); CUDA_TRY(zero("bp_hist"));
+  if (d.cvar) CUDA_TRY(zero("ZB"));                    // the padding columns behind c
   if (!h->opt_reuse_image_state) CUDA_TRY(zero("projb"));
   if (d.tied) CUDA_TRY(zero("ob"));
   // The per-image state (bf16 features, mask, mean, W_v projection, mean-feature gate block) depends on the images only:
@@ -103,8 +107,8 @@ static int decode_impl(Handle* h, int B, int J, int N, int S, int K, int P, cons
   // lru_cache on the projected features, attention.py:99) sets the option and the state in the workspace is reused.
   const bool reuse = h->opt_reuse_image_state != 0;
   if (!reuse) TRY(image_prep(s, feats, h->opt_features_bf16, B, N, d.F, Wb("featsb"), Fp, Wf("mask"), Wb("avgb")));
-  TRY(scale_rows_f32(s, d.cond ? sent : nullptr, d.mult, Wf("pm_row"), B));
-  TRY(scale_rows_f32(s, d.cond ? sent : nullptr, 1.0f, Wf("sent"), B));
+  TRY(scale_rows_f32(s, csent ? sent : nullptr, d.mult, Wf("pm_row"), B));
+  TRY(scale_rows_f32(s, csent ? sent : nullptr, 1.0f, Wf("sent"), B));
   TRY(iota_div_i32(s, Wi("rowmap"), R, SK * J));
   TRY(iota_div_i32(s, Wi("rowmap_exp"), R, SK));
   TRY(iota_div_i32(s, Wi("rowmap0"), Bv, J));
@@ -155,17 +159,21 @@ static int decode_impl(Handle* h, int B, int J, int N, int S, int K, int P, cons
       TRY(attention_forward(s, aa, Wf("alpha"), nullptr, Wb("XE"), KXe));
     }
     {  // eval: z ~ N(prior_mean, prior_var) (updown_cell.py:200-208); no encoder LSTM
-      LatentArgs la; la.R = rows; la.Z = d.Z; la.Zp = d.Zp; la.sentiment_vae = d.sv; la.prior_var = d.prior_std * d.prior_std;
+      LatentArgs la = {}; la.R = rows; la.Z = d.Z; la.Zp = d.Zp; la.sentiment_vae = d.sv; la.prior_var = d.prior_std * d.prior_std;
       la.prior_mean_row = Wf("pm_row"); la.rowmap = rowmap;
-      TRY(latent_forward_eval(s, la, eps_t, eps_stride, seed_dev, (unsigned long long)step, Wb("ZB"), d.Zp));
+      if (d.cvar) {  // attribute-grounded prior: mean of this step from the row's attention weights; also the block c
+        TRY(prior_mean_forward(s, Wf("alpha"), obj, rowmap, rows, N, d.Z, Wf("pm"), Wb("ZB") + d.Zp, d.ZC, d.cond));
+        la.prior_mean_full = Wf("pm");
+      }
+      TRY(latent_forward_eval(s, la, eps_t, eps_stride, seed_dev, (unsigned long long)step, Wb("ZB"), d.ZC));
     }
     {
       GemmSeg sg[3] = {seg(Wb("XE"), KXe, Pb("w_dec_x"), KX, KXe),
-                       seg(Wb("ZB"), d.Zp, Pb("w_dec_z"), d.Zp, d.Zp),
+                       seg(Wb("ZB"), d.ZC, Pb("w_dec_z"), d.ZC, d.ZC),
                        seg(XA[0] + Hp, 2 * Hp, Pb("w_dec_x") + KXe, KX, Hp)};
       LstmFwdArgs l = {};
       l.R = rows; l.H = H; l.bias = Pf("b_dec"); l.rowmap = rowmap;
-      if (d.cond) { l.sent = Wf("sent"); l.scol = Pf("scol_dec"); }
+      if (csent) { l.sent = Wf("sent"); l.scol = Pf("scol_dec"); }
       l.c_prev = first ? nullptr : cd[0]; l.c_out = cd[1];
       l.h1_dst = XA[1] + Hp; l.ld_h1 = 2 * Hp;
       GemmEpi e; e.tag = "gemm.decode"; e.C32 = Wf("acc"); e.ldc32 = GP; e.lstm = &l;
@@ -304,8 +312,8 @@ int sscvae_decode_region(const SscvaeHandle* hh, int batch, int num_boxes, int s
 }
 
 int sscvae_decode(SscvaeHandle* hh, int batch, int num_boxes, int states, int beam, int per_node, const void* packed,
-                  const void* const* weights, const float* image_features, const float* sentiment, const uint8_t* fsm,
-                  const int64_t* num_constraints, int min_constraints_to_satisfy, const float* eps, uint64_t seed,
+                  const void* const* weights, const float* image_features, const float* sentiment, const float* obj_means,
+                  const uint8_t* fsm, const int64_t* num_constraints, int min_constraints_to_satisfy, const float* eps, uint64_t seed,
                   void* workspace, size_t workspace_bytes, int64_t* predictions, float* log_probs, int64_t* best,
                   int32_t* n_steps, void* stream) {
   Handle* h = reinterpret_cast<Handle*>(hh);
@@ -322,22 +330,22 @@ int sscvae_decode(SscvaeHandle* hh, int batch, int num_boxes, int states, int be
                      (uint64_t)min_constraints_to_satisfy, (uint64_t)workspace_bytes,
                      (uint64_t)(h->opt_features_bf16 * 2 + h->opt_reuse_image_state)})
     key_add(key, v);
-  for (const void* q : {packed, (const void*)image_features, (const void*)sentiment, (const void*)fsm,
+  for (const void* q : {packed, (const void*)image_features, (const void*)sentiment, (const void*)obj_means, (const void*)fsm,
                         (const void*)num_constraints, (const void*)eps, (const void*)workspace, (const void*)predictions,
                         (const void*)log_probs, (const void*)best, (const void*)n_steps})
     key_add(key, q);
   for (int i = 0; i < SSCVAE_W_COUNT; ++i) key_add(key, weights[i]);
   return run_with_graph(h->dec_graphs, key, st, true, [&](cudaStream_t s) {
     return decode_impl(h, batch, 1, num_boxes, states, beam, per_node, reinterpret_cast<const char*>(packed), weights,
-                       image_features, sentiment, fsm, reinterpret_cast<const long long*>(num_constraints),
+                       image_features, sentiment, obj_means, fsm, reinterpret_cast<const long long*>(num_constraints),
                        min_constraints_to_satisfy, eps, seed, reinterpret_cast<char*>(workspace), workspace_bytes,
                        reinterpret_cast<long long*>(predictions), log_probs, reinterpret_cast<long long*>(best), n_steps, s);
   });
 }
 
 int sscvae_decode_samples(SscvaeHandle* hh, int batch, int samples, int num_boxes, const void* packed,
-                          const void* const* weights, const float* image_features, const float* sentiment, const float* eps,
-                          uint64_t seed, void* workspace, size_t workspace_bytes, int64_t* predictions, float* log_probs,
+                          const void* const* weights, const float* image_features, const float* sentiment,
+                          const float* obj_means, const float* eps, uint64_t seed, void* workspace, size_t workspace_bytes, int64_t* predictions, float* log_probs,
                           int32_t* n_steps, void* stream) {
   Handle* h = reinterpret_cast<Handle*>(hh);
   REQUIRE(h && packed && weights && image_features && workspace && predictions && log_probs && n_steps, "NULL argument");
@@ -352,15 +360,15 @@ int sscvae_decode_samples(SscvaeHandle* hh, int batch, int samples, int num_boxe
   for (uint64_t v : {(uint64_t)batch, (uint64_t)num_boxes, (uint64_t)samples, (uint64_t)0x5a5a, (uint64_t)workspace_bytes,
                      (uint64_t)(h->opt_features_bf16 * 2 + h->opt_reuse_image_state)})
     key_add(key, v);
-  for (const void* q : {packed, (const void*)image_features, (const void*)sentiment, (const void*)eps, (const void*)workspace,
-                        (const void*)predictions, (const void*)log_probs, (const void*)n_steps})
+  for (const void* q : {packed, (const void*)image_features, (const void*)sentiment, (const void*)obj_means, (const void*)eps,
+                        (const void*)workspace, (const void*)predictions, (const void*)log_probs, (const void*)n_steps})
     key_add(key, q);
   for (int i = 0; i < SSCVAE_W_COUNT; ++i) key_add(key, weights[i]);
   char* wsb = reinterpret_cast<char*>(workspace);
   long long* best = reinterpret_cast<long long*>(wsb + dp.find("best_samples")->off);
   return run_with_graph(h->dec_graphs, key, st, true, [&](cudaStream_t s) {
     return decode_impl(h, batch, samples, num_boxes, 1, 1, 1, reinterpret_cast<const char*>(packed), weights, image_features,
-                       sentiment, nullptr, nullptr, 0, eps, seed, wsb, workspace_bytes, reinterpret_cast<long long*>(predictions),
+                       sentiment, obj_means, nullptr, nullptr, 0, eps, seed, wsb, workspace_bytes, reinterpret_cast<long long*>(predictions),
                        log_probs, best, n_steps, s);
   });
 }

@@ -18,6 +18,10 @@ constexpr int kPad = 64;   // elements: operand row strides / column blocks are 
 struct Dims {
   int F, E, H, A, Z, V, L, T;
   int sv, simple, tied, pad, boundary, cond;
+  // sentiment_vae == 2 (updown_cell.py:160-190): the conditioning block of the encoder / decoder LSTM inputs is the per-step
+  // prior mean (cond = Z columns, or 1 with latent_embedding "senti_word_net"), a time-varying bf16 operand kept next to z:
+  // rows of ZB are [z (Zp) | c (Cp)], ZC = Zp + Cp. cvar = 0: Cp = 0 and ZC = Zp.
+  int le, cvar, Cp, ZC;
   float prior_std, mult;
   int Fp, Ep, Hp, Ap, Zp, Vp, G, Gp, Z2, Z2p, KX;
   int debug_logits;                    // SSCVAE_DEBUG_LOGITS=1 at create: the training forward also stores the fp32 logits (tests)

@@ -31,14 +31,18 @@ int init_dims(const SscvaeDims* in, Dims& d) {
   d.sv = in->sentiment_vae; d.simple = in->simple_vae; d.tied = in->tied_embedding;
   d.pad = in->pad_index; d.boundary = in->boundary_index; d.prior_std = in->prior_std; d.mult = in->senti_prior_multip;
   REQUIRE(d.F > 0 && d.E > 0 && d.H > 0 && d.A > 0 && d.Z > 0 && d.V > 1 && d.L > 0, "non-positive dimension");
-  if (d.sv != 0 && d.sv != 1) {
-    set_error("sentiment_vae=%d unsupported (only 0 and 1; 2 is SURVEY §8(f)-4)", d.sv);
+  if (d.sv < 0 || d.sv > 2) {
+    set_error("sentiment_vae=%d unsupported (0, 1 or 2)", d.sv);
     return SSCVAE_ERR_UNSUPPORTED;
   }
+  d.le = in->latent_embedding;
+  REQUIRE(d.sv != 2 || d.le == 0 || d.le == 1, "latent_embedding must be 0 (glove) or 1 (senti_word_net)");
   REQUIRE(d.pad >= 0 && d.pad < d.V && d.boundary >= 0 && d.boundary < d.V, "pad/boundary index out of range");
   REQUIRE(d.prior_std > 0.f, "prior_std must be positive");
   d.T = d.L + 1;
-  d.cond = (d.simple || d.sv == 0) ? 0 : 1;
+  // width of the conditioning column block of the encoder / decoder LSTM inputs (updown_cell.py:47-81); simple_vae drops it
+  d.cvar = (d.sv == 2 && !d.simple) ? 1 : 0;
+  d.cond = (d.simple || d.sv == 0) ? 0 : d.sv == 1 ? 1 : (d.le == 1 ? 1 : d.Z);
   // Every bf16 operand row stride and column-block offset is a multiple of 64 elements = 128 bytes, so that each
   // 128-byte row segment of a TMA box is exactly ONE cache line. With 16-byte granularity (the TMA minimum) a
   // segment straddles two lines and the TMA unit pulls both whole lines into the SM: ncu showed 2.0x the operand
@@ -47,6 +51,8 @@ int init_dims(const SscvaeDims* in, Dims& d) {
   d.Zp = round_up(d.Z, kPad); d.Vp = round_up(d.V, kPad);
   d.G = 4 * d.H; d.Gp = round_up(d.G, kPad); d.Z2 = 2 * d.Z; d.Z2p = round_up(d.Z2, kPad);
   d.KX = d.Fp + 2 * d.Hp;
+  d.Cp = d.cvar ? round_up(d.cond, kPad) : 0;
+  d.ZC = d.Zp + d.Cp;
   d.GP = lstm_gate_rows(d.H);
   { const char* e = getenv("SSCVAE_DEBUG_LOGITS"); d.debug_logits = (e && e[0] == '1') ? 1 : 0; }
   return 0;
@@ -74,14 +80,15 @@ static void plan_packed(const Dims& d, Plan& p) {
   p.add("wq", (size_t)d.A * d.Hp * b);
   p.add("w_enc_x", (size_t)d.GP * d.KX * b);
   p.add("w_enc_hh", (size_t)d.GP * d.Hp * b);
+  if (d.cvar) p.add("w_enc_c", (size_t)d.GP * d.Cp * b);
   p.add("w_fc", (size_t)d.Z2 * d.Hp * b);
   p.add("w_dec_x", (size_t)d.GP * d.KX * b);
-  p.add("w_dec_z", (size_t)d.GP * d.Zp * b);
+  p.add("w_dec_z", (size_t)d.GP * d.ZC * b);               // [W_z | W_c] against the [z | c] rows of ZB
   p.add("fwd_end", 0);
   // --- transposed twins streamed at every backward timestep
-  p.add("w_dec_xzT", (size_t)(d.KX + d.Zp) * d.Gp * b);   // rows [0,KX): W_dec_x^T ; rows [KX,KX+Zp): W_dec_z^T
+  p.add("w_dec_xzT", (size_t)(d.KX + d.ZC) * d.Gp * b);   // rows [0,KX): W_dec_x^T ; [KX,KX+Zp): W_dec_z^T ; then Cp rows W_dec_c^T
   p.add("w_fcT", (size_t)d.Hp * d.Z2p * b);
-  p.add("w_enc_xhT", (size_t)(d.KX + d.Hp) * d.Gp * b);   // rows [0,KX): W_enc_x^T ; rows [KX,KX+Hp): W_enc_hh^T
+  p.add("w_enc_xhT", (size_t)(d.KX + d.Hp + d.Cp) * d.Gp * b);   // rows [0,KX): W_enc_x^T ; [KX,KX+Hp): W_enc_hh^T ; then Cp rows W_enc_c^T
   p.add("wqT", (size_t)d.Hp * d.Ap * b);
   p.add("w_att_recT", (size_t)2 * d.Hp * d.Gp * b);
   p.add("bwd_end", 0);
@@ -123,7 +130,13 @@ static void plan_train(const Dims& d, int B, int N, Plan& p) {
   p.add("XA", (T + 1) * B * 2 * d.Hp * b);
   p.add("XE", TB * d.KX * b);
   p.add("HE", (T + 1) * B * d.Hp * b);
-  p.add("ZB", TB * d.Zp * b);
+  p.add("ZB", TB * d.ZC * b);
+  if (d.cvar) {
+    p.add("objm", BN * d.Z * f);                        // per-box attribute means (kept for the backward)
+    p.add("pm", TB * d.Z * f);                          // per-step prior mean sum_n alpha_n objm_n
+    p.add("dpm", (size_t)B * d.Z * f);
+    p.add("dalpha_x", (size_t)B * N * f);
+  }
   p.add("acc", (size_t)B * d.GP * f);
   p.add("gates_att", TB * d.G * f);
   p.add("gates_enc", TB * d.G * f);
@@ -168,9 +181,9 @@ static void plan_train(const Dims& d, int B, int N, Plan& p) {
   p.add("dG_dec", TB * d.Gp * b);
   p.add("dml", TB * d.Z2p * b);
   p.add("dqb", TB * d.Ap * b);
-  p.add("dXEZ", (size_t)B * (d.KX + d.Zp) * f);          // decoder part of d[xhat|h1|h_dec] and d z
-  p.add("dXEH0", (size_t)B * (d.KX + d.Hp) * f);         // total d[xhat|h1|h_dec] and d h_enc_{t-1} (ping-pong)
-  p.add("dXEH1", (size_t)B * (d.KX + d.Hp) * f);
+  p.add("dXEZ", (size_t)B * (d.KX + d.ZC) * f);          // decoder part of d[xhat|h1|h_dec], d z (and d c)
+  p.add("dXEH0", (size_t)B * (d.KX + d.Hp + d.Cp) * f);  // total d[xhat|h1|h_dec], d h_enc_{t-1} (and the encoder's d c) (ping-pong)
+  p.add("dXEH1", (size_t)B * (d.KX + d.Hp + d.Cp) * f);
   p.add("dXA0", (size_t)B * 2 * d.Hp * f);
   p.add("dXA1", (size_t)B * 2 * d.Hp * f);
   p.add("dhenc_fc", (size_t)B * d.H * f);
@@ -187,7 +200,7 @@ static void plan_train(const Dims& d, int B, int N, Plan& p) {
   p.add("HETp", (size_t)d.Hp * TBp * b);
   p.add("HETc", (size_t)d.Hp * TBp * b);
   p.add("hdecTc", (size_t)d.Hp * TBp * b);
-  p.add("ZBT", (size_t)d.Zp * TBp * b);
+  p.add("ZBT", (size_t)d.ZC * TBp * b);
   p.add("embT_t", (size_t)d.Ep * TBp * b);
   p.add("dmlT", (size_t)d.Z2p * TBp * b);
   p.add("dqT", (size_t)d.Ap * TBp * b);
@@ -269,7 +282,11 @@ static int pack_weights_impl(Handle* h, const void* const* wv, char* pk, const u
       TRY(jobs.add(wex + offs_dst[k], d.KX, 0, we + offs_src[k], lde, G, widths[k], nullptr, 0, H));
       TRY(jobs.add(wexT + (size_t)offs_dst[k] * d.Gp, d.Gp, 1, we + offs_src[k], lde, G, widths[k], nullptr, 0));
     }
-    if (c) TRY(copy_block_f32(s, we + F + 2 * H, lde, Pf("scol_enc"), 1, G, 1));
+    if (c && !d.cvar) TRY(copy_block_f32(s, we + F + 2 * H, lde, Pf("scol_enc"), 1, G, 1));
+    if (d.cvar) {
+      TRY(jobs.add(Pb("w_enc_c"), d.Cp, 0, we + F + 2 * H, lde, G, c, nullptr, 0, H));
+      TRY(jobs.add(wexT + (size_t)(d.KX + d.Hp) * d.Gp, d.Gp, 1, we + F + 2 * H, lde, G, c, nullptr, 0));
+    }
   }
   if (need({SSCVAE_W_ENC_HH})) {
     TRY(jobs.add(Pb("w_enc_hh"), d.Hp, 0, W(SSCVAE_W_ENC_HH), H, G, H, nullptr, 0, H));
@@ -289,9 +306,13 @@ static int pack_weights_impl(Handle* h, const void* const* wv, char* pk, const u
     }
   }
   if (need({SSCVAE_W_DEC_IH})) {
-    TRY(jobs.add(Pb("w_dec_z"), d.Zp, 0, wd + F + 2 * H + c, ldd, G, Z, nullptr, 0, H));
+    TRY(jobs.add(Pb("w_dec_z"), d.ZC, 0, wd + F + 2 * H + c, ldd, G, Z, nullptr, 0, H));
     TRY(jobs.add(Pb("w_dec_xzT") + (size_t)d.KX * d.Gp, d.Gp, 1, wd + F + 2 * H + c, ldd, G, Z, nullptr, 0));
-    if (c) TRY(copy_block_f32(s, wd + F + 2 * H, ldd, Pf("scol_dec"), 1, G, 1));
+    if (c && !d.cvar) TRY(copy_block_f32(s, wd + F + 2 * H, ldd, Pf("scol_dec"), 1, G, 1));
+    if (d.cvar) {
+      TRY(jobs.add(Pb("w_dec_z") + d.Zp, d.ZC, 0, wd + F + 2 * H, ldd, G, c, nullptr, 0, H));
+      TRY(jobs.add(Pb("w_dec_xzT") + (size_t)(d.KX + d.Zp) * d.Gp, d.Gp, 1, wd + F + 2 * H, ldd, G, c, nullptr, 0));
+    }
   }
   if (need({SSCVAE_W_DEC_BIH, SSCVAE_W_DEC_BHH})) TRY(vec_add_f32(s, W(SSCVAE_W_DEC_BIH), W(SSCVAE_W_DEC_BHH), Pf("b_dec"), G));
   // latent heads stacked [fc_mean ; fc_log_var]
@@ -356,6 +377,7 @@ static inline GemmSeg seg(const bf16* A, int lda, const bf16* B, int ldb, int K)
 // Does the training forward of this shape run as the persistent recurrent kernel (recurrent_fwd.cu)? The backward asks
 // the same question: the persistent kernel saves the LSTM state in the row-tiled layout.
 static bool persistent_forward(const Dims& d, int B, int N) {
+  if (d.cvar) return false;                            // the time-varying conditioning operand runs on the per-launch path
   RecFwdArgs rf = {};
   rf.B = B; rf.T = d.T; rf.H = d.H; rf.Hp = d.Hp; rf.Fp = d.Fp; rf.Zp = d.Zp; rf.Z = d.Z; rf.A = d.A; rf.KX = d.KX; rf.GP = d.GP;
   rf.Ep = d.Ep;
@@ -365,11 +387,13 @@ static bool persistent_forward(const Dims& d, int B, int N) {
 
 // ---- training forward --------------------------------------------------------------------------
 static int train_forward_impl(Handle* h, int B, int N, const char* pk, const void* const* wv, const float* feats,
-                              const long long* cap, const float* sent, const float* eps, unsigned long long seed,
-                              char* ws, size_t ws_bytes, float* loss, float* kld, cudaStream_t s) {
+                              const long long* cap, const float* sent, const float* obj, const float* eps,
+                              unsigned long long seed, char* ws, size_t ws_bytes, float* loss, float* kld, cudaStream_t s) {
   const Dims& d = h->d;
   REQUIRE(B > 0 && N > 0, "batch/num_boxes must be positive");
-  REQUIRE(d.cond == 0 || sent != nullptr, "sentiment is required when sentiment_vae == 1");
+  const bool csent = d.cond && !d.cvar;                // sentiment_vae == 1: the time-invariant sentiment column
+  REQUIRE(!csent || sent != nullptr, "sentiment is required when sentiment_vae == 1");
+  REQUIRE(!d.cvar || obj != nullptr, "obj_means is required when sentiment_vae == 2");
   const Plan& tp = h->train_plan(B, N);
   if (ws_bytes < tp.total) { set_error("workspace too small: %zu < %zu", ws_bytes, tp.total); return SSCVAE_ERR_WORKSPACE; }
   REQUIRE((reinterpret_cast<uintptr_t>(ws) & 255) == 0 && (reinterpret_cast<uintptr_t>(pk) & 255) == 0,
@@ -396,8 +420,9 @@ static int train_forward_impl(Handle* h, int B, int N, const char* pk, const voi
   float* tmask = Wf("tmask");
   TRY(boundary_tokens(s, cap, B, d.L, d.pad, d.boundary, tok, tmask, Wf("lengths")));
   TRY(image_prep(s, feats, h->opt_features_bf16, B, N, d.F, Wb("featsb"), Fp, Wf("mask"), Wb("avgb")));
-  TRY(scale_rows_f32(s, d.cond ? sent : nullptr, d.mult, Wf("pm_row"), B));    // prior mean (updown_captioner.py:253)
-  TRY(scale_rows_f32(s, d.cond ? sent : nullptr, 1.0f, Wf("sent"), B));
+  TRY(scale_rows_f32(s, csent ? sent : nullptr, d.mult, Wf("pm_row"), B));    // prior mean (updown_captioner.py:253)
+  TRY(scale_rows_f32(s, csent ? sent : nullptr, 1.0f, Wf("sent"), B));
+  if (d.cvar) CUDA_TRY(cudaMemcpyAsync(Wf("objm"), obj, (size_t)B * N * d.Z * sizeof(float), cudaMemcpyDeviceToDevice, s));
   {  // P = W_v x  (attention.py:125), once per image, kept in bf16
     GemmSeg sg = seg(Wb("featsb"), Fp, Pb("wv"), Fp, d.F);
     GemmEpi e; e.tag = "gemm.pre"; e.C16 = Wb("projb"); e.ldc16 = d.Ap;
@@ -415,7 +440,7 @@ static int train_forward_impl(Handle* h, int B, int N, const char* pk, const voi
     GemmEpi e; e.tag = "gemm.pre"; e.C32 = Wf("gavg"); e.ldc32 = GP;
     TRY(gemm_bf16_tn(s, B, GP, 1, &sg, e));
   }
-  LatentArgs la; la.R = B; la.Z = d.Z; la.Zp = d.Zp; la.sentiment_vae = d.sv; la.prior_var = d.prior_std * d.prior_std;
+  LatentArgs la = {}; la.R = B; la.Z = d.Z; la.Zp = d.Zp; la.sentiment_vae = d.sv; la.prior_var = d.prior_std * d.prior_std;
   la.prior_mean_row = Wf("pm_row"); la.rowmap = nullptr;
   AttnArgs aa = {}; aa.R = B; aa.N = N; aa.A = d.A; aa.Ap = d.Ap; aa.F = d.F; aa.Fp = Fp; aa.rowmap = nullptr;
   aa.proj = Wb("projb"); aa.feats = Wb("featsb"); aa.mask = Wf("mask"); aa.w_a = W(SSCVAE_W_ATT_VEC); aa.ld_q = d.A;
@@ -428,7 +453,7 @@ static int train_forward_impl(Handle* h, int B, int N, const char* pk, const voi
   rf.w_att_rec = Pb("w_att_rec"); rf.wq = Pb("wq"); rf.w_enc_x = Pb("w_enc_x"); rf.w_enc_hh = Pb("w_enc_hh");
   rf.w_fc = Pb("w_fc"); rf.w_dec_x = Pb("w_dec_x"); rf.w_dec_z = Pb("w_dec_z");
   rf.gavg = Wf("gavg"); rf.b_att = Pf("b_att"); rf.b_enc = Pf("b_enc"); rf.b_dec = Pf("b_dec");
-  rf.sent = d.cond ? sent : nullptr; rf.scol_enc = Pf("scol_enc"); rf.scol_dec = Pf("scol_dec");
+  rf.sent = csent ? sent : nullptr; rf.scol_enc = Pf("scol_enc"); rf.scol_dec = Pf("scol_dec");
   rf.c1 = Wf("c1"); rf.c_enc = Wf("c_enc"); rf.c_dec = Wf("c_dec");
   rf.gates_att = Wf("gates_att"); rf.gates_enc = Wf("gates_enc"); rf.gates_dec = Wf("gates_dec");
   rf.XA = Wb("XA"); rf.XE = Wb("XE"); rf.HE = Wb("HE"); rf.ZB = Wb("ZB");
@@ -447,8 +472,8 @@ static int train_forward_impl(Handle* h, int B, int N, const char* pk, const voi
       bf16* XE_n = (t + 1 < T) ? XE_t + (size_t)B * KX : nullptr;
       bf16* HE_t = Wb("HE") + (size_t)t * B * Hp;
       bf16* HE_n = HE_t + (size_t)B * Hp;
-      bf16* ZB_t = Wb("ZB") + (size_t)t * B * d.Zp;
-      const size_t rG = (size_t)t * B * d.G, rH = (size_t)t * B * H;
+      bf16* ZB_t = Wb("ZB") + (size_t)t * B * d.ZC;
+      const size_t rG = (size_t)t * B * d.G, rH = (size_t)t * B * H, rZ = (size_t)t * B * d.Z;
       {  // attention LSTM (updown_cell.py:143-148): gate GEMM with the cell fused into its epilogue
         LstmFwdArgs l = {};
         l.R = B; l.H = H; l.add1 = Wf("gx_att") + (size_t)t * B * GP; l.ld1 = GP; l.add2 = Wf("gavg"); l.ld2 = GP;
@@ -465,31 +490,38 @@ static int train_forward_impl(Handle* h, int B, int N, const char* pk, const voi
         TRY(gemm_bf16_tn(s, B, d.A, 1, &sg, e));
         aa.q = Wf("q") + (size_t)t * B * d.A;
         TRY(attention_forward(s, aa, Wf("alpha") + (size_t)t * B * N, Wf("smx") + (size_t)t * B * N, XE_t, KX));
+        // attribute-grounded prior (updown_cell.py:160-174): prior mean of this step from the attention weights; it is
+        // also the conditioning block c of the two LSTM inputs below, stored next to z
+        if (d.cvar) {
+          TRY(prior_mean_forward(s, Wf("alpha") + (size_t)t * B * N, Wf("objm"), nullptr, B, N, d.Z, Wf("pm") + rZ,
+                                 ZB_t + d.Zp, d.ZC, d.cond));
+          la.prior_mean_full = Wf("pm") + rZ;
+        }
       }
       {  // posterior (encoder) LSTM + latent heads + reparameterised sample (updown_cell.py:176-208)
         LstmFwdArgs l = {};
         l.R = B; l.H = H; l.bias = Pf("b_enc");
-        if (d.cond) { l.sent = sent; l.scol = Pf("scol_enc"); }
+        if (csent) { l.sent = sent; l.scol = Pf("scol_enc"); }
         l.c_prev = t ? Wf("c_enc") + rH - (size_t)B * H : nullptr; l.c_out = Wf("c_enc") + rH;
         l.gates_out = Wf("gates_enc") + rG; l.h1_dst = HE_n; l.ld_h1 = Hp;
-        GemmSeg sg[2] = {seg(XE_t, KX, Pb("w_enc_x"), KX, KX), seg(HE_t, Hp, Pb("w_enc_hh"), Hp, Hp)};
+        GemmSeg sg[3] = {seg(XE_t, KX, Pb("w_enc_x"), KX, KX), seg(HE_t, Hp, Pb("w_enc_hh"), Hp, Hp), GemmSeg()};
+        if (d.cvar) sg[2] = seg(ZB_t + d.Zp, d.ZC, Pb("w_enc_c"), d.Cp, d.Cp);
         GemmEpi e; e.tag = "gemm.step"; e.C32 = acc; e.ldc32 = GP; e.lstm = &l;
-        TRY(gemm_bf16_tn(s, B, GP, 2, sg, e));
+        TRY(gemm_bf16_tn(s, B, GP, d.cvar ? 3 : 2, sg, e));
         GemmSeg sf = seg(HE_n, Hp, Pb("w_fc"), Hp, Hp);
         GemmEpi ef; ef.tag = "gemm.step"; ef.C32 = Wf("ml"); ef.ldc32 = d.Z2;
         TRY(gemm_bf16_tn(s, B, d.Z2, 1, &sf, ef));
-        const size_t rZ = (size_t)t * B * d.Z;
         TRY(latent_forward_train(s, la, Wf("ml"), d.Z2, Pf("b_fc"), eps ? eps + rZ : nullptr, seed_dev, (unsigned long long)t,
-                                 Wf("mean") + rZ, Wf("logvar") + rZ, Wf("eps") + rZ, ZB_t, d.Zp, Wf("kl") + (size_t)t * B));
+                                 Wf("mean") + rZ, Wf("logvar") + rZ, Wf("eps") + rZ, ZB_t, d.ZC, Wf("kl") + (size_t)t * B));
       }
       {  // language (decoder) LSTM (updown_cell.py:211-229)
         LstmFwdArgs l = {};
         l.R = B; l.H = H; l.bias = Pf("b_dec");
-        if (d.cond) { l.sent = sent; l.scol = Pf("scol_dec"); }
+        if (csent) { l.sent = sent; l.scol = Pf("scol_dec"); }
         l.c_prev = t ? Wf("c_dec") + rH - (size_t)B * H : nullptr; l.c_out = Wf("c_dec") + rH;
         l.gates_out = Wf("gates_dec") + rG; l.h1_dst = XA_n + Hp; l.ld_h1 = 2 * Hp;
         if (XE_n) { l.h2_dst = XE_n + Fp + Hp; l.ld_h2 = KX; }
-        GemmSeg sg[2] = {seg(XE_t, KX, Pb("w_dec_x"), KX, KX), seg(ZB_t, d.Zp, Pb("w_dec_z"), d.Zp, d.Zp)};
+        GemmSeg sg[2] = {seg(XE_t, KX, Pb("w_dec_x"), KX, KX), seg(ZB_t, d.ZC, Pb("w_dec_z"), d.ZC, d.ZC)};
         GemmEpi e; e.tag = "gemm.step"; e.C32 = acc; e.ldc32 = GP; e.lstm = &l;
         TRY(gemm_bf16_tn(s, B, GP, 2, sg, e));
       }
@@ -612,12 +644,12 @@ static int train_backward_impl(Handle* h, int B, int N, const char* pk, const vo
   TRY(event(0));
 
   // ---- reverse time loop
-  LatentArgs la; la.R = B; la.Z = Z; la.Zp = d.Zp; la.sentiment_vae = d.sv; la.prior_var = d.prior_std * d.prior_std;
+  LatentArgs la = {}; la.R = B; la.Z = Z; la.Zp = d.Zp; la.sentiment_vae = d.sv; la.prior_var = d.prior_std * d.prior_std;
   la.prior_mean_row = Wf("pm_row"); la.rowmap = nullptr;
   AttnArgs aa = {}; aa.R = B; aa.N = N; aa.A = A; aa.Ap = d.Ap; aa.F = F; aa.Fp = Fp; aa.rowmap = nullptr;
   aa.proj = Wb("projb"); aa.feats = Wb("featsb"); aa.mask = Wf("mask"); aa.w_a = W(SSCVAE_W_ATT_VEC); aa.ld_q = A;
   float* dXE[2] = {Wf("dXEH0"), Wf("dXEH1")};             // [d xhat | d h1 | d h_dec_{t-1} | d h_enc_{t-1}]
-  const int KXH = KX + Hp, KXZ = KX + d.Zp;
+  const int KXH = KX + Hp + d.Cp, KXZ = KX + d.ZC;      // [.. | d h_enc_{t-1} | d c (encoder)] and [.. | d z | d c (decoder)]
   float* dXA[2] = {Wf("dXA0"), Wf("dXA1")};
   for (int t = T - 1; t >= 0; --t) {
     const int cur = t & 1, nxt = cur ^ 1;
@@ -640,6 +672,7 @@ static int train_backward_impl(Handle* h, int B, int N, const char* pk, const vo
       GemmEpi e; e.tag = "gemm.step_bwd"; e.C32 = Wf("dXEZ"); e.ldc32 = KXZ;
       TRY(gemm_bf16_tn(s, B, KXZ, 1, &sg, e));
       bf16* dml_t = Wb("dml") + (size_t)t * B * d.Z2p;
+      if (d.cvar) { la.prior_mean_full = Wf("pm") + rZ; la.dpm_out = Wf("dpm"); }
       TRY(latent_backward(s, la, Wf("dXEZ") + KX, KXZ, Wf("eps") + rZ, Wf("mean") + rZ, Wf("logvar") + rZ, gkld,
                           tmask + (size_t)t * B, dml_t, d.Z2p));
       GemmSeg s2 = seg(dml_t, d.Z2p, Pb("w_fcT"), d.Z2p, d.Z2);
@@ -665,6 +698,11 @@ static int train_backward_impl(Handle* h, int B, int N, const char* pk, const vo
     {  // fused attention backward, then d h1 through the query projection
       aa.q = Wf("q") + (size_t)t * B * A;
       bf16* dq_t = Wb("dqb") + (size_t)t * B * d.Ap;
+      if (d.cvar) {  // d prior_mean = KL term + the two LSTMs' d c  ->  extra d alpha_n = objm_n . d prior_mean
+        TRY(prior_mean_backward(s, B, N, Z, c, Wf("dpm"), Wf("dXEZ") + KX + d.Zp, KXZ, dXE[cur] + KX + Hp, KXH, Wf("objm"),
+                                Wf("dalpha_x")));
+        aa.dalpha_extra = Wf("dalpha_x");
+      }
       TRY(attention_backward(s, aa, Wf("smx") + (size_t)t * B * N, dXE[cur], KXH, dq_t, d.Ap, Wf("du") + (size_t)t * B * N));
       GemmSeg sg = seg(dq_t, d.Ap, Pb("wqT"), d.Ap, A);
       GemmEpi e; e.tag = "gemm.step_bwd"; e.C32 = Wf("dh1_q"); e.ldc32 = H;
@@ -703,17 +741,20 @@ static int train_backward_impl(Handle* h, int B, int N, const char* pk, const vo
   const float* sentv = Wf("sent");
   const int ldE = F + 2 * H + c, ldD = F + 2 * H + c + Z, ldA = E + F + 2 * H;
 
+  // z_t (and, sentiment_vae == 2, the conditioning block c_t behind it) transposed
+  if (Gr(SSCVAE_W_DEC_IH) || (d.cvar && Gr(SSCVAE_W_ENC_IH))) TRY(transpose_bf16(s, Wb("ZB"), TB, d.ZC, d.ZC, Wb("ZBT"), TBp));
+  const bf16* condT = Wb("ZBT") + (size_t)d.Zp * TBp;
   // group 1: decoder LSTM. W_ih column blocks [xhat | h1 | h_dec | cond | z]; W_hh shares the h_dec operand.
   if (any({SSCVAE_W_DEC_IH, SSCVAE_W_DEC_HH, SSCVAE_W_DEC_BIH, SSCVAE_W_DEC_BHH})) {
     TRY(transpose_bf16(s, Wb("dG_dec"), TB, G, Gp, dGT, TBp));
     float* g = Gr(SSCVAE_W_DEC_IH);
     if (g) {
-      TRY(transpose_bf16(s, Wb("ZB"), TB, d.Zp, d.Zp, Wb("ZBT"), TBp));
       TRY(wgrad(dGT, G, xhatT, F, TB, TBp, g, ldD));
       TRY(wgrad(dGT, G, h1T, H, TB, TBp, g + F, ldD));
       TRY(wgrad(dGT, G, hdecpT, H, TB, TBp, g + F + H, ldD));
       TRY(wgrad(dGT, G, Wb("ZBT"), Z, TB, TBp, g + F + 2 * H + c, ldD));
-      if (c) TRY(rowdot_bf16(s, dGT, G, TB, TBp, sentv, B, g + F + 2 * H, ldD));
+      if (c && !d.cvar) TRY(rowdot_bf16(s, dGT, G, TB, TBp, sentv, B, g + F + 2 * H, ldD));
+      if (d.cvar) TRY(wgrad(dGT, G, condT, c, TB, TBp, g + F + 2 * H, ldD));
     }
     TRY(wgrad(dGT, G, hdecpT, H, TB, TBp, Gr(SSCVAE_W_DEC_HH), H));
     if (Gr(SSCVAE_W_DEC_BIH)) TRY(rowsum_bf16(s, dGT, G, TB, TBp, Gr(SSCVAE_W_DEC_BIH), 0));
@@ -729,7 +770,8 @@ static int train_backward_impl(Handle* h, int B, int N, const char* pk, const vo
       TRY(wgrad(dGT, G, xhatT, F, TB, TBp, g, ldE));
       TRY(wgrad(dGT, G, h1T, H, TB, TBp, g + F, ldE));
       TRY(wgrad(dGT, G, hdecpT, H, TB, TBp, g + F + H, ldE));
-      if (c) TRY(rowdot_bf16(s, dGT, G, TB, TBp, sentv, B, g + F + 2 * H, ldE));
+      if (c && !d.cvar) TRY(rowdot_bf16(s, dGT, G, TB, TBp, sentv, B, g + F + 2 * H, ldE));
+      if (d.cvar) TRY(wgrad(dGT, G, condT, c, TB, TBp, g + F + 2 * H, ldE));
     }
     if (Gr(SSCVAE_W_ENC_HH)) {
       TRY(transpose_bf16(s, Wb("HE"), TB, Hp, Hp, Wb("HETp"), TBp));               // h_enc_{t-1}
@@ -861,8 +903,8 @@ int sscvae_train_region(const SscvaeHandle* hh, int batch, int num_boxes, const 
 
 int sscvae_train_forward(SscvaeHandle* hh, int batch, int num_boxes, const void* packed, const void* const* weights,
                          const float* image_features, const int64_t* caption_tokens, const float* sentiment,
-                         const float* eps, uint64_t seed, void* workspace, size_t workspace_bytes, float* loss, float* kld,
-                         void* stream) {
+                         const float* obj_means, const float* eps, uint64_t seed, void* workspace, size_t workspace_bytes,
+                         float* loss, float* kld, void* stream) {
   Handle* h = reinterpret_cast<Handle*>(hh);
   REQUIRE(h && packed && weights && image_features && caption_tokens && workspace && loss && kld, "NULL argument");
   REQUIRE(batch > 0 && num_boxes > 0, "batch/num_boxes must be positive");
@@ -875,12 +917,12 @@ int sscvae_train_forward(SscvaeHandle* hh, int batch, int num_boxes, const void*
   std::vector<uint64_t> key;
   key_add(key, (uint64_t)batch); key_add(key, (uint64_t)num_boxes); key_add(key, packed); key_add(key, image_features);
   key_add(key, (uint64_t)h->opt_features_bf16);
-  key_add(key, caption_tokens); key_add(key, sentiment); key_add(key, eps); key_add(key, workspace);
+  key_add(key, caption_tokens); key_add(key, sentiment); key_add(key, obj_means); key_add(key, eps); key_add(key, workspace);
   key_add(key, (uint64_t)workspace_bytes); key_add(key, loss); key_add(key, kld);
   for (int i = 0; i < SSCVAE_W_COUNT; ++i) key_add(key, weights[i]);
   return run_with_graph(h->fwd_graphs, key, st, true, [&](cudaStream_t s) {
     return train_forward_impl(h, batch, num_boxes, reinterpret_cast<const char*>(packed), weights, image_features,
-                              reinterpret_cast<const long long*>(caption_tokens), sentiment, eps, seed,
+                              reinterpret_cast<const long long*>(caption_tokens), sentiment, obj_means, eps, seed,
                               reinterpret_cast<char*>(workspace), workspace_bytes, loss, kld, s);
   });
 }

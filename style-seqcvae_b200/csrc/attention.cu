@@ -423,7 +423,7 @@ attention_bwd_kernel(AttnArgs a, AttnPlan pl, const float* __restrict__ smx, con
         const bool ok = n < a.N;
         m[k] = ok ? mask_img[n] : 0.f;
         sv[k] = ok ? sm.sv(cur)[n] : 0.f;
-        da[k] = ok ? gather_partial(sm.u, sm.N4, a.N, pl.bF, n) : 0.f;
+        da[k] = ok ? gather_partial(sm.u, sm.N4, a.N, pl.bF, n) + (a.dalpha_extra ? a.dalpha_extra[(size_t)r * a.N + n] : 0.f) : 0.f;
         sr += sv[k] * m[k];
       }
       const float Rn = warp_sum(sr) + 1e-13f;

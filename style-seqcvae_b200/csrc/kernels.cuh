@@ -61,7 +61,17 @@ struct LatentArgs {
   float prior_var;                     // prior_std^2
   const float* prior_mean_row;         // (R) per-row prior mean value (broadcast over Z) or null (0)
   const int* rowmap;                   // optional row -> prior_mean_row index
+  const float* prior_mean_full;        // sentiment_vae == 2: (R,Z) per-row, per-component prior mean of this step (replaces prior_mean_row)
+  float* dpm_out;                      // backward, with prior_mean_full: (R,Z) gradient of the KL term w.r.t. the prior mean
 };
+// sentiment_vae == 2 (updown_cell.py:160-174): pm[r,:] = sum_n alpha[r,n] * obj[img(r),n,:]; the first `cond` components
+// are also written as the bf16 conditioning block c of the encoder / decoder LSTM inputs (cond = Z: "glove", 1: "senti_word_net")
+int prior_mean_forward(cudaStream_t s, const float* alpha, const float* obj, const int* rowmap, int R, int N, int Z,
+                       float* pm /*(R,Z)*/, bf16* c_dst, int ld_c, int cond);
+// d pm = dpm_kl + [d c of the decoder LSTM + d c of the encoder LSTM on the first `cond` components];
+// dalpha[r,n] = obj[r,n,:] . d pm[r,:]   (training layout: image r)
+int prior_mean_backward(cudaStream_t s, int R, int N, int Z, int cond, const float* dpm_kl, const float* dc_dec, int ld_dec,
+                        const float* dc_enc, int ld_enc, const float* obj, float* dalpha /*(R,N)*/);
 // training: ml (R,2Z) = [mean|log_var] pre-bias GEMM output
 int latent_forward_train(cudaStream_t s, const LatentArgs& a, const float* ml, int ld_ml, const float* bias_ml,
                          const float* eps_in /*(R,Z) or null*/, const unsigned long long* seed_dev, unsigned long long step,
@@ -152,6 +162,7 @@ struct AttnArgs {
   int rows_per_image;                  // > 0: rows img*rows_per_image + i, i < rows_per_image, belong to image img (decode: the rows of
                                        // an image share its features; 0 = use rowmap / one image per row)
   int l2_policy;                       // set by the launchers (SSCVAE_ATT_POLICY): 0 none, 1 evict_first, 2 evict_last
+  const float* dalpha_extra;           // backward only: optional (R,N) added to d alpha (the attribute-grounded prior's path)
 };
 // smx (R,N): softmax(u*m) before the mask renormalisation, saved for the backward (null in decode)
 int attention_forward(cudaStream_t s, const AttnArgs& a, float* alpha /*(R,N)*/, float* smx /*(R,N) or null*/, bf16* xhat,

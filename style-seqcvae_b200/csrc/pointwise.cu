@@ -341,11 +341,12 @@ __global__ void latent_fwd_train_kernel(LatentArgs a, const float* __restrict__ 
   const int Z = a.Z;
   pdl_wait();
   pdl_launch_dependents(8);
-  const float pm = a.prior_mean_row ? a.prior_mean_row[a.rowmap ? a.rowmap[r] : r] : 0.f;
+  const float pm_row = a.prior_mean_row ? a.prior_mean_row[a.rowmap ? a.rowmap[r] : r] : 0.f;
   const float log_pv = logf(a.prior_var);
   float part = 0.f;
   for (int z = threadIdx.x; z < a.Zp; z += blockDim.x) {
     if (z < Z) {
+      const float pm = a.prior_mean_full ? a.prior_mean_full[(size_t)r * Z + z] : pm_row;
       const float mu = ml[(size_t)r * ld_ml + z] + bias_ml[z];
       const float lv = ml[(size_t)r * ld_ml + Z + z] + bias_ml[Z + z];
       const float var = __expf(lv);
@@ -388,12 +389,13 @@ __global__ void latent_fwd_eval_kernel(LatentArgs a, const float* __restrict__ e
   const int r = blockIdx.x;
   pdl_wait();
   pdl_launch_dependents(8);
-  const float pm = a.prior_mean_row ? a.prior_mean_row[a.rowmap ? a.rowmap[r] : r] : 0.f;
+  const float pm_row = a.prior_mean_row ? a.prior_mean_row[a.rowmap ? a.rowmap[r] : r] : 0.f;
   const float sd = sqrtf(a.prior_var);
   for (int z = threadIdx.x; z < a.Zp; z += blockDim.x) {
     float v = 0.f;
     if (z < a.Z) {
       const float e = eps_in ? eps_in[(size_t)r * eps_row_stride * a.Z + z] : philox_normal(*seed_dev, step, r, z, a.Z);
+      const float pm = a.prior_mean_full ? a.prior_mean_full[(size_t)r * a.Z + z] : pm_row;
       v = e * sd + pm;
     }
     zb[(size_t)r * ld_z + z] = __float2bfloat16_rn(v);
@@ -417,7 +419,7 @@ __global__ void latent_bwd_kernel(LatentArgs a, const float* __restrict__ dz, in
   const int Z = a.Z;
   pdl_wait();
   pdl_launch_dependents(8);
-  const float pm = a.prior_mean_row ? a.prior_mean_row[a.rowmap ? a.rowmap[r] : r] : 0.f;
+  const float pm_row = a.prior_mean_row ? a.prior_mean_row[a.rowmap ? a.rowmap[r] : r] : 0.f;
   const float w = gkld[r] * tmask_t[r];
   const float inv_pv = 1.0f / (a.prior_var + 0.00001f);
   for (int z = threadIdx.x; z < ld_dml; z += blockDim.x) {
@@ -428,8 +430,10 @@ __global__ void latent_bwd_kernel(LatentArgs a, const float* __restrict__ dz, in
       const float var = __expf(lv);
       const float g = dz[(size_t)r * ld_dz + zi];
       if (z < Z) {
+        const float pm = a.prior_mean_full ? a.prior_mean_full[(size_t)r * Z + zi] : pm_row;
         const float dkl = (a.sentiment_vae == 0) ? mu : (mu - pm) * inv_pv;
         out = g + w * dkl;
+        if (a.dpm_out) a.dpm_out[(size_t)r * Z + zi] = -w * dkl;      // d kld / d prior_mean = -d kld / d mean
       } else {
         const float dkl = (a.sentiment_vae == 0) ? -0.5f * (1.f - var) : -0.5f * (1.f - var * inv_pv);
         out = g * eps[(size_t)r * Z + zi] * 0.5f * sqrtf(var) + w * dkl;
@@ -444,6 +448,68 @@ int latent_backward(cudaStream_t s, const LatentArgs& a, const float* dz, int ld
   PROF_SCOPE(s, "latent_bwd", 0, (double)a.R*a.Z*24.0);
   CUDA_TRY(launch_pdl(latent_bwd_kernel, dim3(a.R), dim3(min(256, round_up(ld_dml, 32))), 0, s, a, dz, ld_dz, eps, mean, logvar,
                       gkld, tmask_t, dml, ld_dml));
+  LAUNCHED();
+  return 0;
+}
+
+// ---- attribute-grounded prior (sentiment_vae == 2, updown_cell.py:160-174) ----
+__global__ void prior_mean_fwd_kernel(const float* __restrict__ alpha, const float* __restrict__ obj,
+                                      const int* __restrict__ rowmap, int N, int Z, float* __restrict__ pm,
+                                      bf16* __restrict__ c_dst, int ld_c, int cond) {
+  extern __shared__ float al_s[];
+  const int r = blockIdx.x;
+  pdl_wait();
+  pdl_launch_dependents(8);
+  const int img = rowmap ? rowmap[r] : r;
+  for (int n = threadIdx.x; n < N; n += blockDim.x) al_s[n] = alpha[(size_t)r * N + n];
+  __syncthreads();
+  const float* o = obj + (size_t)img * N * Z;
+  for (int z = threadIdx.x; z < Z; z += blockDim.x) {
+    float acc = 0.f;
+    for (int n = 0; n < N; ++n) acc += al_s[n] * o[(size_t)n * Z + z];
+    pm[(size_t)r * Z + z] = acc;
+    if (z < cond) c_dst[(size_t)r * ld_c + z] = __float2bfloat16_rn(acc);
+  }
+}
+
+int prior_mean_forward(cudaStream_t s, const float* alpha, const float* obj, const int* rowmap, int R, int N, int Z,
+                       float* pm, bf16* c_dst, int ld_c, int cond) {
+  PROF_SCOPE(s, "prior_mean", 0, (double)R * N * Z * 4.0);
+  REQUIRE(cond >= 0 && cond <= Z, "prior_mean_forward: cond=%d out of range", cond);
+  CUDA_TRY(launch_pdl(prior_mean_fwd_kernel, dim3(R), dim3(min(256, round_up(Z, 32))), (size_t)N * sizeof(float), s, alpha, obj,
+                      rowmap, N, Z, pm, c_dst, ld_c, cond));
+  LAUNCHED();
+  return 0;
+}
+
+__global__ void prior_mean_bwd_kernel(int N, int Z, int cond, const float* __restrict__ dpm_kl, const float* __restrict__ dc_dec,
+                                      int ld_dec, const float* __restrict__ dc_enc, int ld_enc, const float* __restrict__ obj,
+                                      float* __restrict__ dalpha) {
+  extern __shared__ float dpm_s[];
+  const int r = blockIdx.x;
+  pdl_wait();
+  pdl_launch_dependents(8);
+  for (int z = threadIdx.x; z < Z; z += blockDim.x) {
+    float v = dpm_kl[(size_t)r * Z + z];
+    if (z < cond) v += dc_dec[(size_t)r * ld_dec + z] + dc_enc[(size_t)r * ld_enc + z];
+    dpm_s[z] = v;
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  const float* o = obj + (size_t)r * N * Z;
+  for (int n = warp; n < N; n += nw) {
+    float acc = 0.f;
+    for (int z = lane; z < Z; z += 32) acc += o[(size_t)n * Z + z] * dpm_s[z];
+    acc = warp_sum(acc);
+    if (lane == 0) dalpha[(size_t)r * N + n] = acc;
+  }
+}
+
+int prior_mean_backward(cudaStream_t s, int R, int N, int Z, int cond, const float* dpm_kl, const float* dc_dec, int ld_dec,
+                        const float* dc_enc, int ld_enc, const float* obj, float* dalpha) {
+  PROF_SCOPE(s, "prior_mean", 0, (double)R * N * Z * 4.0);
+  CUDA_TRY(launch_pdl(prior_mean_bwd_kernel, dim3(R), dim3(256), (size_t)Z * sizeof(float), s, N, Z, cond, dpm_kl, dc_dec, ld_dec,
+                      dc_enc, ld_enc, obj, dalpha));
   LAUNCHED();
   return 0;
 }

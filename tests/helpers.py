@@ -24,7 +24,7 @@ class StubVocabulary:
         return d
 
 
-def module_from_cfg(cfg: dict, params=None, beam_size=1, use_cbs=None, device="cuda", min_sat=2):
+def module_from_cfg(cfg: dict, params=None, beam_size=1, use_cbs=None, device="cuda", min_sat=2, **extra):
     tied = cfg["embedding_size"] in (300, 600)
     if use_cbs is None:
         use_cbs = tied
@@ -32,8 +32,9 @@ def module_from_cfg(cfg: dict, params=None, beam_size=1, use_cbs=None, device="c
         StubVocabulary(cfg["vocab_size"]), cfg["image_feature_size"], cfg["embedding_size"], cfg["hidden_size"],
         cfg["attention_projection_size"], max_caption_length=cfg["max_caption_length"], beam_size=beam_size,
         use_cbs=use_cbs, min_constraints_to_satisfy=min_sat, z_space=cfg["z_space"], prior_std=cfg["prior_std"],
-        simple_vae=cfg["simple_vae"], latent_embedding="glove", sentiment_vae=cfg["sentiment_vae"],
-        senti_prior_multip=cfg["senti_prior_multip"], cbs_simple=True, device=torch.device(device))
+        simple_vae=cfg["simple_vae"], latent_embedding=cfg.get("latent_embedding", "glove"),
+        sentiment_vae=cfg["sentiment_vae"], senti_prior_multip=cfg["senti_prior_multip"], cbs_simple=True,
+        device=torch.device(device), **extra)
     if params is not None:
         missing, unexpected = m.load_state_dict(params, strict=True)
     return m.to(device)

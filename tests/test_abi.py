@@ -28,12 +28,19 @@ def test_library_exports_every_declared_symbol():
 
 def test_abi_version_and_error_string():
     L = _lib.lib()
-    assert L.sscvae_abi_version() == 4
+    assert L.sscvae_abi_version() == 5
     h = ctypes.c_void_p()
-    bad = _lib.SscvaeDims(64, 600, 32, 24, 16, 100, 20, 2, 0, 1, 0, 1, 1.0, 0.5)   # sentiment_vae=2 unsupported
+    bad = _lib.SscvaeDims(64, 600, 32, 24, 16, 100, 20, 3, 0, 1, 0, 1, 1.0, 0.5, 0)   # sentiment_vae is 0, 1 or 2
     rc = L.sscvae_create(ctypes.byref(bad), ctypes.byref(h))
     assert rc == -3
     assert b"sentiment_vae" in L.sscvae_last_error()
+    ok = _lib.SscvaeDims(64, 600, 32, 24, 16, 100, 20, 2, 0, 1, 0, 1, 1.0, 0.5, 1)    # attribute-grounded prior
+    _lib.check(L.sscvae_create(ctypes.byref(ok), ctypes.byref(h)))
+    off, nb = ctypes.c_size_t(), ctypes.c_size_t()
+    _lib.check(L.sscvae_train_region(h, 4, 7, b"pm", ctypes.byref(off), ctypes.byref(nb)))
+    assert nb.value == 21 * 4 * 16 * 4
+    L.sscvae_destroy(h)
+    h = ctypes.c_void_p()
     with pytest.raises(RuntimeError):
         _lib.check(rc)
 

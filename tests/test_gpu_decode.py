@@ -18,7 +18,7 @@ def _eps(g, S, K, Z, steps=20):
     return e
 
 
-def _replay_path_check(m, g, cfg, S, K, eps, feats, sent, fsm, tol=6e-3):
+def _replay_path_check(m, g, cfg, S, K, eps, feats, sent, fsm, tol=6e-3, obj_means=None):
     """Search amplifies bf16-level logit noise into different (equally valid) beams, so beams are not
     compared token by token with an independent oracle search. Instead the oracle cell is replayed ALONG
     THE PATH THE CUDA SEARCH TOOK (its tokens and back-pointers): every finite beam score the device
@@ -31,7 +31,7 @@ def _replay_path_check(m, g, cfg, S, K, eps, feats, sent, fsm, tol=6e-3):
     sc = m.decode_region(B, N, S, K, "score_hist", torch.float32, (L, R)).cpu()
     ocfg = uo.OracleConfig(**cfg)
     stepper = uo.DecodeStepper({k: v.detach().cpu() for k, v in m.state_dict().items()}, ocfg, feats, sent,
-                               q=uo.Rounding("bf16"))
+                               q=uo.Rounding("bf16"), obj_means=obj_means)
     base = (torch.arange(R) // SK) * SK
     logp0, state = stepper(torch.ones(B, dtype=torch.long), None, eps[0, ::SK])
     exp0 = logp0[torch.arange(R) // SK, tok[0]]
