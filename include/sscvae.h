@@ -158,6 +158,26 @@ int sscvae_train_region(const SscvaeHandle* h, int batch, int num_boxes, const c
  * fsm_bits: (B,S,V) uint32, bit i of fsm_bits[b,s,w] = reference fsm[b,s,i,w]; NULL = all allowed (plain beam).
  * normalized = 1: `logp` already holds log-softmax values; 0: raw logits, log-softmax is fused. */
 int sscvae_fsm_pack(const uint8_t* fsm /*(B,S,S,V)*/, int batch, int states, int vocab, uint32_t* fsm_bits, void* stream);
+/* The same bit table built ON THE DEVICE from the constraint word ids, replacing the dense tensors of
+ * FiniteStateMachineBuilder.build (updown-baseline/updown/utils/constraints.py:329-478; 0.64 MB per image at S = 8,
+ * V = 10 000) by a few dozen ints per image. The host lists the builder's _connect calls (:427-478) in call order:
+ *   connections        (n,5) int32 rows {from_state, to_state, reset_state, first word-form, number of word-forms}
+ *   connection_offsets (B+1) int32: image b owns rows [off[b], off[b+1])
+ *   wordform_ids       int32 token ids the rows index into
+ *   state_counts       (B,2) int32: {2**max_given_constraints = the states that start with a self loop on every word,
+ *                      the number of states the image uses = the builder's next free sub-state}. The reference trims its
+ *                      24-state tensor to that count (updown-baseline/updown/data/datasets.py:611-613): connections from or
+ *                      to a state beyond it (a repeated constraint produces them) are dropped the same way.
+ * `states` = the largest state count of the batch (states an image does not use stay without transitions, as in a
+ * zero-padded batch). */
+int sscvae_fsm_build(const int32_t* connections, const int32_t* connection_offsets, const int32_t* wordform_ids,
+                     const int32_t* state_counts, int batch, int states, int vocab, uint32_t* fsm_bits, void* stream);
+/* Best beam among an explicit set of valid states per image: the non-`cbs_simple` rule of select_best_beam_with_constraints
+ * (updown-baseline/updown/utils/decoding.py:87-135), whose object / attribute state sets are host-side bookkeeping.
+ * predictions (B,S,K,steps) int64, log_probs (B,S,K), valid_states (B,S) uint8 -> best (B,steps) = beam 0 of the valid
+ * state with the highest beam-0 log-probability (first one on ties). */
+int sscvae_select_best_beam(const int64_t* predictions, const float* log_probs, const uint8_t* valid_states, int batch,
+                            int states, int beam, int steps, int64_t* best, void* stream);
 int sscvae_search_first_step(const float* logp, int batch, int states, int beam, int vocab, const uint32_t* fsm_bits,
                              int normalized, int32_t* tokens, float* scores, void* stream);
 int sscvae_search_step(const float* logp, int batch, int states, int beam, int per_node, int vocab,
@@ -233,6 +253,8 @@ int sscvae_sgd_step_multi(int count, void* const* params, const void* const* gra
  *   "features_bf16"     1: every `image_features` pointer is bf16 (B,N,F) instead of fp32 - the bf16 feature cache of SURVEY
  *                       8(f)-3 (updown-baseline/updown/data/readers.py:21-139 reads fp32 from HDF5). Results are bit-identical
  *                       to the fp32 input rounded to bf16: the kernels round the features to bf16 first either way.
+ *   "fsm_packed"        1: the `fsm` pointer of sscvae_decode is the (B,S,V) uint32 bit table (sscvae_fsm_build / sscvae_fsm_pack)
+ *                       instead of the reference's (B,S,S,V) uint8 tensor.
  *   "reuse_image_state" 1: the decode workspace already holds the per-image state of THIS batch (bf16 features, mask, mean
  *                       features, W_v projection): sscvae_decode / sscvae_decode_samples skip recomputing it. The analogue
  *                       of the reference's lru_cache on the projected features (updown-baseline/updown/modules/attention.py:99). */

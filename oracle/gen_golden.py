@@ -413,12 +413,91 @@ def gen_decode_e2e(name, *, K, constraints, mg, E=600, V0=40, F=64, H=32, A=24, 
     print("wrote", name, "pred", pred.tolist())
 
 
+WF_TABLE = {"pos": ["good", "nice", "great"], "neg": ["bad", "ugly"], "dog": ["dog", "dogs"], "fire": ["fire"],
+            "hydrant": ["hydrant", "hydrants"], "cat": ["cat"], "red": ["red", "reddish"], "old": ["old"]}
+
+
+def _reference_builder(mg, mw=3):
+    ref = rh.load_reference()
+    d = tempfile.mkdtemp()
+    tsv = os.path.join(d, "wf.tsv")
+    with open(tsv, "w") as f:
+        for k, v in WF_TABLE.items():
+            f.write(k + "\t" + ",".join(v) + "\n")
+    vocab = rh.make_vocabulary(40)
+    vocab = ref.add_constraint_words_to_vocabulary(vocab, tsv)
+    return vocab, ref.FiniteStateMachineBuilder(vocab, tsv, None, max_given_constraints=mg, max_words_per_constraint=mw)
+
+
+def gen_fsm_build(name):
+    """FiniteStateMachineBuilder.build of the reference (constraints.py:329-478) on single-word, multi-word, repeated and
+    fewer-than-maximum constraint lists: trimmed dense tensors, state counts and constraint2states."""
+    cases = [(3, ["pos", "neg", "dog"]), (3, ["dog", "pos", "fire hydrant"]), (3, ["pos", "pos", "pos"]),
+             (3, ["fire hydrant", "fire hydrant"]), (3, ["cat"]), (3, []), (2, ["neg", "dog"]), (1, ["cat"]),
+             (3, ["red", "dog", "old"])]
+    vocab, _ = _reference_builder(3)
+    word_ids = {w: vocab.get_token_index(w) for ws in WF_TABLE.values() for w in ws}
+    out = {"wordforms": json.dumps(WF_TABLE), "word_ids": json.dumps(word_ids), "vocab_size": vocab.get_vocab_size(),
+           "cases": json.dumps(cases)}
+    for i, (mg, cons) in enumerate(cases):
+        _, builder = _reference_builder(mg)
+        fsm, nstates, c2s = builder.build(cons)
+        out[f"fsm{i}"] = fsm[:nstates, :nstates].numpy()
+        out[f"nstates{i}"] = nstates
+        out[f"c2s{i}"] = json.dumps(c2s)
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **out)
+    print("wrote", name, [int(out[f"nstates{i}"]) for i in range(len(cases))])
+
+
+def gen_select_attributes(name, seed=31):
+    """select_best_beam_with_constraints with cbs_simple=False (decoding.py:87-138): object / attribute candidates as the
+    evaluation dataset hands them over (datasets.py:528-580), constraint2states from the reference's FSM builder."""
+    ref = rh.load_reference()
+    _, builder = _reference_builder(3)
+    cases = [
+        ([["dog", ["red"]], ["cat", []]], ["dog", "red", "cat"]),
+        ([["dog", ["red", "old"]]], ["dog", "red", "old"]),
+        ([["dog", []], ["cat", []]], ["dog", "cat"]),
+        ([["cat", ["old"]], ["dog", ["red"]]], ["cat", "old", "dog"]),      # "red" is not among the FSM constraints of this image
+        ([["dog", []]], ["dog"]),
+    ]
+    g = torch.Generator().manual_seed(seed)
+    out = {"cases": json.dumps([c for c, _ in cases]), "fsm_inputs": json.dumps([f for _, f in cases])}
+    for i, (cands, fsm_input) in enumerate(cases):
+        _, nstates, c2s = builder.build(fsm_input)
+        for o in cands:                              # the selection indexes constraint2states by every listed name
+            for a in [o[0]] + o[1]:
+                c2s.setdefault(a, [])
+        S, K, steps = nstates, 3, 9
+        beams = torch.randint(2, 40, (1, S, K, steps), generator=g)
+        logp = -torch.rand(1, S, K, generator=g) * 10
+        logp, _ = logp.sort(dim=2, descending=True)
+        for min_sat in (1, 2):
+            try:
+                best, _ = ref.select_best_beam_with_constraints(beams, logp, torch.tensor([len(fsm_input)]), [cands], [c2s],
+                                                                min_sat, False)
+                out[f"best{i}_{min_sat}"] = best.numpy()
+            except (RuntimeError, IndexError, ValueError):       # no valid state: the reference fails on the empty arg max
+                out[f"best{i}_{min_sat}"] = np.zeros((0,), dtype=np.int64)
+        out[f"beams{i}"] = beams.numpy()
+        out[f"logp{i}"] = logp.numpy()
+        out[f"c2s{i}"] = json.dumps(c2s)
+        out[f"nc{i}"] = len(fsm_input)
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **out)
+    print("wrote", name, {k: v.shape for k, v in out.items() if k.startswith("best")})
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     import sys
+    if len(sys.argv) > 1 and sys.argv[1] == "f2":        # only the FSM-builder / attribute-selection fixtures (round 2)
+        gen_fsm_build("fsm_build")
+        return gen_select_attributes("select_attributes")
     if len(sys.argv) > 1 and sys.argv[1] == "sv2":       # only the SENTIMENT_VAE = 2 fixtures (added in round 2)
         return main_sv2()
     main_sv2()
+    gen_fsm_build("fsm_build")
+    gen_select_attributes("select_attributes")
     gen_train("train_tied_sv1", E=600, sv=1)
     gen_train("train_tied300_sv0", E=300, sv=0, seed=7)
     gen_train("train_untied_sv1", E=40, sv=1, seed=11)

@@ -11,7 +11,8 @@ from .search import (BeamSearch, ConstrainedBeamSearch, select_best_beam, select
 from .dp import BucketedGradReducer, shard_batch, global_grad_norm
 from .optim import FusedClipSGD
 from .ingest import FeatureCache, collate_features, pack_features
+from .fsm import FiniteStateMachineBuilder, FsmProgram, FsmBits, build_fsm_bits, valid_states_with_attributes
 
 __all__ = ["FeatureCache", "collate_features", "pack_features", "UpDownCaptioner", "ConstrainedBeamSearch", "BeamSearch", "select_best_beam",
            "select_best_beam_with_constraints", "pad_fsm_batch", "BucketedGradReducer", "shard_batch", "global_grad_norm",
-           "FusedClipSGD"]
+           "FusedClipSGD", "FiniteStateMachineBuilder", "FsmProgram", "FsmBits", "build_fsm_bits", "valid_states_with_attributes"]

@@ -40,7 +40,7 @@ GRAD_GROUPS = 5
 SYMBOLS = [
     "sscvae_abi_version", "sscvae_last_error", "sscvae_launch_count", "sscvae_create", "sscvae_destroy", "sscvae_set_option",
     "sscvae_packed_bytes", "sscvae_pack_weights", "sscvae_test_gemm_splitk", "sscvae_sgd_step_multi", "sscvae_train_workspace_bytes", "sscvae_train_forward",
-    "sscvae_train_backward", "sscvae_train_region", "sscvae_fsm_pack", "sscvae_search_first_step",
+    "sscvae_train_backward", "sscvae_train_region", "sscvae_fsm_pack", "sscvae_fsm_build", "sscvae_select_best_beam", "sscvae_search_first_step",
     "sscvae_search_step", "sscvae_search_scratch_bytes", "sscvae_search_finish",
     "sscvae_decode_workspace_bytes", "sscvae_decode", "sscvae_decode_region", "sscvae_decode_samples_workspace_bytes",
     "sscvae_decode_samples", "sscvae_grad_sqnorm", "sscvae_sgd_step", "sscvae_test_gemm",
@@ -86,6 +86,8 @@ def lib():
     L.sscvae_train_backward.argtypes = [vp, i32, i32, vp, C.POINTER(vp), vp, sz, vp, vp, C.POINTER(vp), C.POINTER(vp), vp]
     L.sscvae_train_region.argtypes = [vp, i32, i32, C.c_char_p, C.POINTER(sz), C.POINTER(sz)]
     L.sscvae_fsm_pack.argtypes = [vp, i32, i32, i32, vp, vp]
+    L.sscvae_fsm_build.argtypes = [vp, vp, vp, vp, i32, i32, i32, vp, vp]
+    L.sscvae_select_best_beam.argtypes = [vp, vp, vp, i32, i32, i32, i32, vp, vp]
     L.sscvae_search_first_step.argtypes = [vp, i32, i32, i32, i32, vp, i32, vp, vp, vp]
     L.sscvae_search_scratch_bytes.argtypes = [i32, i32, i32, i32]
     L.sscvae_search_scratch_bytes.restype = sz

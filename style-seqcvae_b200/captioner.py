@@ -186,8 +186,6 @@ class UpDownCaptioner(nn.Module):
         # it from hard-coded pickle / json paths in its ctor (updown_captioner.py:76-93); here it is an argument (and forward()
         # also accepts the already translated (B, N, Z) tensor).
         self.mean_choice = mean_choice
-        if use_cbs and not cbs_simple:
-            raise NotImplementedError("only cbs_simple best-beam selection is implemented (SURVEY §8(f)-2)")
 
         self._tied = embedding_size in (300, 600)                    # updown_captioner.py:75
         if self._tied:
@@ -475,7 +473,8 @@ class UpDownCaptioner(nn.Module):
                                          *self._weight_tensors())
             return {"loss": loss, "kld": kld}
 
-        return {"predictions": self._decode(image_features, sentiment, fsm, num_constraints, obj_means)}
+        return {"predictions": self._decode(image_features, sentiment, fsm, num_constraints, obj_means, constraints,
+                                            constraint2states)}
 
     # ------------------------------------------------------------------------------------------
     def translate_obj_atts2obj_means(self, obj_atts) -> torch.Tensor:
@@ -569,7 +568,8 @@ class UpDownCaptioner(nn.Module):
         return {"predictions": preds[..., :n].clone(), "log_probs": scores.clone()}
 
     @torch.no_grad()
-    def _decode(self, image_features, sentiment, fsm, num_constraints, obj_means=None):
+    def _decode(self, image_features, sentiment, fsm, num_constraints, obj_means=None, constraints=None,
+                constraint2states=None):
         L = _lib.lib()
         dev = image_features.device
         B, N, _ = image_features.shape
@@ -577,15 +577,37 @@ class UpDownCaptioner(nn.Module):
         if self._use_cbs:
             if fsm is None:
                 raise ValueError("fsm is required when use_cbs=True")
-            fsm = fsm.to(dev).to(torch.uint8).contiguous()
-            S = fsm.shape[1]
-            if fsm.shape != (B, S, S, self._vocab_size):
-                raise ValueError(f"fsm must be (B,S,S,V), got {tuple(fsm.shape)}")
+            from .fsm import FsmBits, valid_states_with_attributes
+            fsm_packed = isinstance(fsm, FsmBits)
+            if fsm_packed:                                           # bit table built on the device (fsm.build_fsm_bits)
+                fsm = fsm.bits
+                S = fsm.shape[1]
+                if fsm.shape != (B, S, self._vocab_size) or fsm.device != dev or not fsm.is_contiguous():
+                    raise ValueError(f"FsmBits must be a contiguous (B,S,V) table on {dev}, got {tuple(fsm.shape)}")
+            else:
+                fsm = fsm.to(dev).to(torch.uint8).contiguous()
+                S = fsm.shape[1]
+                if fsm.shape != (B, S, S, self._vocab_size):
+                    raise ValueError(f"fsm must be (B,S,S,V), got {tuple(fsm.shape)}")
             nc = None if num_constraints is None else num_constraints.to(dev).long().contiguous()
             if nc is None:
                 nc = torch.zeros(B, dtype=torch.long, device=dev)
+            valid = None
+            if not self.cbs_simple:
+                # object / attribute rule (decoding.py:87-123): the valid end states come from host-side bookkeeping
+                if constraints is None or constraint2states is None:
+                    raise ValueError("cbs_simple=False needs `constraints` and `constraint2states`")
+                counts = [int(n) for n in (num_constraints if num_constraints is not None else [0] * B)]
+                mask = torch.zeros(B, S, dtype=torch.uint8)
+                for i in range(B):
+                    states = valid_states_with_attributes(counts[i], constraints[i], constraint2states[i],
+                                                          self._min_constraints_to_satisfy)
+                    if not states:
+                        raise ValueError(f"image {i}: no state satisfies the constraints")
+                    mask[i, states] = 1
+                valid = mask.to(dev)
         else:
-            S, fsm, nc = 1, None, None
+            S, fsm, nc, valid, fsm_packed = 1, None, None, None, False
         R = B * S * K
         eps = self._eps_override
         if eps is None and self.rng_mode == "reference":
@@ -613,11 +635,15 @@ class UpDownCaptioner(nn.Module):
         preds, scores, best, n_steps = outs
         stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
         self._reuse_image_state(key, image_features)
+        _lib.check(L.sscvae_set_option(self._handle, b"fsm_packed", int(fsm_packed)))
         _lib.check(L.sscvae_decode(
             self._handle, B, N, S, K, P, _lib.ptr(self._packed_weights()), _lib.ptr_array(self._weight_tensors()),
             _lib.ptr(image_features), _lib.ptr(sentiment), _lib.ptr(obj_means), _lib.ptr(fsm), _lib.ptr(nc),
             int(self._min_constraints_to_satisfy), _lib.ptr(eps), C.c_uint64(self._next_seed()), _lib.ptr(ws), nbytes,
             _lib.ptr(preds), _lib.ptr(scores), _lib.ptr(best), _lib.ptr(n_steps), stream))
+        if valid is not None:
+            _lib.check(L.sscvae_select_best_beam(_lib.ptr(preds), _lib.ptr(scores), _lib.ptr(valid), B, S, K, steps,
+                                                 _lib.ptr(best), stream))
         n = int(n_steps.item())                                     # the reference's data-dependent early exit (cbs.py:167)
         self.last_search = {"predictions": preds[..., :n].clone(), "log_probs": scores.clone(), "n_steps": n}
         return best[:, :n].clone()

@@ -114,7 +114,12 @@ static int decode_impl(Handle* h, int B, int J, int N, int S, int K, int P, cons
   TRY(iota_div_i32(s, Wi("rowmap0"), Bv, J));
   TRY(fill_i32(s, Wi("start_tok"), d.boundary, Bv));                       // updown_captioner.py:326
   const uint32_t* fsm_bits = nullptr;
-  if (fsm) { TRY(fsm_pack(s, fsm, Bv, S, d.V, reinterpret_cast<uint32_t*>(Wi("fsm_bits")))); fsm_bits = reinterpret_cast<uint32_t*>(Wi("fsm_bits")); }
+  if (fsm && h->opt_fsm_packed) {                      // already the (B,S,V) uint32 bit table (sscvae_fsm_build / sscvae_fsm_pack)
+    fsm_bits = reinterpret_cast<const uint32_t*>(fsm);
+  } else if (fsm) {
+    TRY(fsm_pack(s, fsm, Bv, S, d.V, reinterpret_cast<uint32_t*>(Wi("fsm_bits"))));
+    fsm_bits = reinterpret_cast<uint32_t*>(Wi("fsm_bits"));
+  }
   if (!reuse) {  // once per image (the reference recomputes both every step in decode)
     GemmSeg sg = seg(Wb("featsb"), Fp, Pb("wv"), Fp, d.F);
     GemmEpi e; e.tag = "gemm.decode"; e.C16 = Wb("projb"); e.ldc16 = d.Ap;
@@ -245,6 +250,20 @@ int sscvae_fsm_pack(const uint8_t* fsm, int batch, int states, int vocab, uint32
   return fsm_pack(reinterpret_cast<cudaStream_t>(stream), fsm, batch, states, vocab, fsm_bits);
 }
 
+int sscvae_fsm_build(const int32_t* connections, const int32_t* connection_offsets, const int32_t* wordform_ids,
+                     const int32_t* state_counts, int batch, int states, int vocab, uint32_t* fsm_bits, void* stream) {
+  REQUIRE(connections && connection_offsets && wordform_ids && state_counts && fsm_bits && batch > 0 && vocab > 0, "bad argument");
+  return fsm_build(reinterpret_cast<cudaStream_t>(stream), connections, connection_offsets, wordform_ids, state_counts, batch,
+                   states, vocab, fsm_bits);
+}
+
+int sscvae_select_best_beam(const int64_t* predictions, const float* log_probs, const uint8_t* valid_states, int batch,
+                            int states, int beam, int steps, int64_t* best, void* stream) {
+  REQUIRE(predictions && log_probs && valid_states && best && batch > 0 && states > 0 && beam > 0 && steps > 0, "bad argument");
+  return select_best_masked(reinterpret_cast<cudaStream_t>(stream), reinterpret_cast<const long long*>(predictions), log_probs,
+                            valid_states, batch, states, beam, steps, reinterpret_cast<long long*>(best));
+}
+
 int sscvae_search_first_step(const float* logp, int batch, int states, int beam, int vocab, const uint32_t* fsm_bits,
                              int normalized, int32_t* tokens, float* scores, void* stream) {
   REQUIRE(logp && tokens && scores, "NULL argument");
@@ -328,7 +347,7 @@ int sscvae_decode(SscvaeHandle* hh, int batch, int num_boxes, int states, int be
   std::vector<uint64_t> key;
   for (uint64_t v : {(uint64_t)batch, (uint64_t)num_boxes, (uint64_t)states, (uint64_t)beam, (uint64_t)per_node,
                      (uint64_t)min_constraints_to_satisfy, (uint64_t)workspace_bytes,
-                     (uint64_t)(h->opt_features_bf16 * 2 + h->opt_reuse_image_state)})
+                     (uint64_t)(h->opt_fsm_packed * 4 + h->opt_features_bf16 * 2 + h->opt_reuse_image_state)})
     key_add(key, v);
   for (const void* q : {packed, (const void*)image_features, (const void*)sentiment, (const void*)obj_means, (const void*)fsm,
                         (const void*)num_constraints, (const void*)eps, (const void*)workspace, (const void*)predictions,

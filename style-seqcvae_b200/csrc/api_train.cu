@@ -860,6 +860,7 @@ int sscvae_set_option(SscvaeHandle* hh, const char* name, int value) {
   REQUIRE(h && name, "NULL argument");
   if (strcmp(name, "features_bf16") == 0) { h->opt_features_bf16 = value ? 1 : 0; return 0; }
   if (strcmp(name, "reuse_image_state") == 0) { h->opt_reuse_image_state = value ? 1 : 0; return 0; }
+  if (strcmp(name, "fsm_packed") == 0) { h->opt_fsm_packed = value ? 1 : 0; return 0; }
   set_error("unknown option '%s'", name);
   return SSCVAE_ERR_BAD_ARG;
 }

@@ -35,6 +35,66 @@ int fsm_pack(cudaStream_t st, const uint8_t* fsm, int B, int S, int V, uint32_t*
   return 0;
 }
 
+// ---- FSM construction on the device (constraints.py:329-478) ----
+// The host turns the constraints of an image into a short list of CONNECTIONS (from, to, reset, word-form ids), in the
+// order the reference's builder makes them; a thread owns one (image, from-state, word) entry of the bit table and replays
+// the connections of its from-state: its word-forms move to `to`, every other word goes (back) to `reset`
+// (constraints.py:427-478: reset_state is always given, so the second half of _connect always runs). The reference builds in
+// a 24-state tensor and trims it to the states in use afterwards (datasets.py:611-613): a repeated constraint makes it connect
+// states beyond that count, so connections from / to a state >= the image's count are dropped here the same way.
+__global__ void fsm_build_kernel(const int32_t* __restrict__ rec, const int32_t* __restrict__ rec_off,
+                                 const int32_t* __restrict__ wf, const int32_t* __restrict__ counts, int S, int V,
+                                 uint32_t* __restrict__ bits) {
+  const int w = blockIdx.x * blockDim.x + threadIdx.x, s = blockIdx.y, b = blockIdx.z;
+  if (w >= V) return;
+  const int n_main = counts[2 * b], n_used = counts[2 * b + 1];
+  auto bit = [&](int x) { return (x >= 0 && x < n_used) ? 1u << x : 0u; };
+  uint32_t m = s < n_main ? bit(s) : 0u;              // self loops for all words on the main states
+  for (int i = rec_off[b]; i < rec_off[b + 1] && s < n_used; ++i) {
+    const int32_t* r = rec + (size_t)i * 5;            // from, to, reset, first word-form, number of word-forms
+    if (r[0] != s) continue;
+    bool is_wf = false;
+    for (int k = 0; k < r[4]; ++k) is_wf = is_wf || wf[r[3] + k] == w;
+    if (is_wf) m |= bit(r[1]);
+    m &= ~bit(s);
+    if (is_wf) m &= ~bit(r[2]); else m |= bit(r[2]);
+  }
+  bits[((size_t)b * S + s) * V + w] = m;
+}
+int fsm_build(cudaStream_t st, const int32_t* rec, const int32_t* rec_off, const int32_t* wf, const int32_t* counts, int B,
+              int S, int V, uint32_t* bits) {
+  REQUIRE(S >= 1 && S <= 32, "CBS supports 1..32 FSM states (got %d)", S);
+  fsm_build_kernel<<<dim3((V + 255) / 256, S, B), 256, 0, st>>>(rec, rec_off, wf, counts, S, V, bits);
+  LAUNCHED();
+  return 0;
+}
+
+// ---- best beam among an explicit set of valid states (decoding.py:125-135 with the caller's valid_states) ----
+__global__ void select_best_masked_kernel(const long long* __restrict__ predictions, const float* __restrict__ scores,
+                                          const uint8_t* __restrict__ valid, int S, int K, int steps,
+                                          long long* __restrict__ best) {
+  const int b = blockIdx.x;
+  __shared__ int s_best;
+  if (threadIdx.x == 0) {
+    int arg = -1; float v = 0.f;
+    for (int s = 0; s < S; ++s) {                     // first maximum, like torch.argmax over the listed states
+      if (!valid[(size_t)b * S + s]) continue;
+      const float x = scores[((size_t)b * S + s) * K];
+      if (arg < 0 || x > v) { arg = s; v = x; }
+    }
+    s_best = arg < 0 ? 0 : arg;
+  }
+  __syncthreads();
+  const long long* src = predictions + (((size_t)b * S + s_best) * K) * steps;
+  for (int t = threadIdx.x; t < steps; t += blockDim.x) best[(size_t)b * steps + t] = src[t];
+}
+int select_best_masked(cudaStream_t st, const long long* predictions, const float* scores, const uint8_t* valid, int B, int S,
+                       int K, int steps, long long* best) {
+  select_best_masked_kernel<<<B, 32, 0, st>>>(predictions, scores, valid, S, K, steps, best);
+  LAUNCHED();
+  return 0;
+}
+
 template <int P>
 __device__ __forceinline__ void list_insert(float (&val)[P], int (&idx)[P], float v, int w) {
   if (!better(v, w, val[P - 1], idx[P - 1])) return;

@@ -6,6 +6,12 @@ namespace sscvae {
 
 // bits[b,s,w] bit i = fsm[b,s,i,w] != 0   (fsm is the reference's (B,S,S,V) uint8 adjacency tensor)
 int fsm_pack(cudaStream_t st, const uint8_t* fsm, int B, int S, int V, uint32_t* bits);
+// the same table built on the device from the builder's connection list (include/sscvae.h: sscvae_fsm_build)
+int fsm_build(cudaStream_t st, const int32_t* rec, const int32_t* rec_off, const int32_t* wf, const int32_t* counts, int B,
+              int S, int V, uint32_t* bits);
+// best[b,:] = predictions[b, argmax_{s: valid[b,s]} scores[b,s,0], 0, :]
+int select_best_masked(cudaStream_t st, const long long* predictions, const float* scores, const uint8_t* valid, int B, int S,
+                       int K, int steps, long long* best);
 
 // Per row r and to-state i: the P best words by (value desc, word index asc), where
 //   value(w) = allowed(from_state(r), i, w) ? logp[r,w] : neg_value        (+ last_scores[r] afterwards)

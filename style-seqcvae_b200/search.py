@@ -113,21 +113,27 @@ def select_best_beam(beams: torch.Tensor, beam_log_probabilities: torch.Tensor) 
 
 def select_best_beam_with_constraints(beams, beam_log_probabilities, given_constraints, constraints=None,
                                       constraint2states=None, min_constraints_to_satisfy: int = 2, cbs_simple=True):
-    """cbs_simple selection (decoding.py:82-86,128-138): best first-beam among the states whose bit
-    count satisfies min(#constraints, min_constraints_to_satisfy)."""
-    if not cbs_simple:
-        raise NotImplementedError("constraint2states-based selection is SURVEY §8(f)-2")
+    """Best first-beam among the valid end states (decoding.py:82-138). cbs_simple: the states whose bit count
+    satisfies min(#constraints, min_constraints_to_satisfy); otherwise the object / attribute rule
+    (`fsm.valid_states_with_attributes`, decoding.py:87-123) over `constraints[i]` and `constraint2states[i]`."""
+    from .fsm import valid_states_with_attributes
     B = beams.shape[0]
     best, valid = [], []
     for i in range(B):
         nc = int(given_constraints[i])
-        need = min(nc, min_constraints_to_satisfy)
-        states = [s for s in range(2 ** nc) if bin(s).count("1") >= need]
+        if cbs_simple:
+            need = min(nc, min_constraints_to_satisfy)
+            states = [s for s in range(2 ** nc) if bin(s).count("1") >= need]
+        else:
+            states = valid_states_with_attributes(nc, constraints[i], constraint2states[i], min_constraints_to_satisfy)
         vb = beams[i, states, 0, :]
         vl = beam_log_probabilities[i, states, 0]
         best.append(vb[torch.argmax(vl)])
         valid.append(vb)
-    return torch.stack(best).long(), torch.stack(valid)
+    # the reference stacks the per-image valid beams (it decodes one image at a time); images of a batch can have
+    # different numbers of valid states, then the list is returned as it is
+    same = all(v.shape == valid[0].shape for v in valid)
+    return torch.stack(best).long(), (torch.stack(valid) if same else valid)
 
 
 def pad_fsm_batch(fsms, num_constraints=None):
