@@ -260,6 +260,11 @@ int sscvae_sgd_step_multi(int count, void* const* params, const void* const* gra
  *                       of the reference's lru_cache on the projected features (updown-baseline/updown/modules/attention.py:99). */
 int sscvae_set_option(SscvaeHandle* h, const char* name, int value);
 
+/* 1 if sscvae_train_backward runs the BPTT loop of this shape as the persistent kernel (csrc/recurrent_bwd.cu), 0 if it
+ * runs the per-launch path, < 0 on error. Option "persistent_bwd" (default 1) = 0 forces the per-launch path (tests compare
+ * the two). Replaces nothing in the reference: autograd owns its backward (var_updown/scripts/train.py:172). */
+int sscvae_train_backward_is_persistent(const SscvaeHandle* h, int batch, int num_boxes);
+
 /* Optional instrumentation (off by default): CUDA events around every kernel launch of the library,
  * aggregated per kernel class. report() synchronises the device and writes a JSON object
  * {"class": {"count", "ms", "flops", "bytes"}} (algorithmic FLOPs / bytes as declared at the call site). */

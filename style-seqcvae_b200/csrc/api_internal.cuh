@@ -47,6 +47,7 @@ struct Handle {
   // per-handle options (sscvae_set_option), consumed by the following calls
   int opt_features_bf16 = 0;           // image_features pointers are bf16 (B,N,F) instead of fp32
   int opt_reuse_image_state = 0;       // decode: the workspace already holds this batch's featsb / projb / mask / avg state
+  int opt_persistent_bwd = 1;          // training: run the BPTT loop as the persistent kernel (recurrent_bwd.cu) when the shape fits
   int opt_fsm_packed = 0;              // decode: `fsm` is the (B,S,V) uint32 bit table, not the (B,S,S,V) uint8 tensor
   const Plan& train_plan(int B, int N);
   const Plan& decode_plan(int B, int N, int S, int K, int J);

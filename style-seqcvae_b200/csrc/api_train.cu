@@ -191,6 +191,12 @@ static void plan_train(const Dims& d, int B, int N, Plan& p) {
   p.add("dc1", (size_t)B * d.H * f);
   p.add("dc_enc", (size_t)B * d.H * f);
   p.add("dc_dec", (size_t)B * d.H * f);
+  // persistent BPTT kernel (recurrent_bwd.cu): dataflow counters and the split-K slots of its data-gradient GEMMs
+  p.add("rb_flags", 1024);
+  p.add("rb_dXEA", (size_t)RB_MAX_SPLIT_A * B * d.KX * f);
+  p.add("rb_dXEB", (size_t)RB_MAX_SPLIT_B * B * d.Hp * f);
+  p.add("rb_dXA", (size_t)RB_MAX_SPLIT_X * B * 2 * d.Hp * f);
+  p.add("rb_dzp", (size_t)RB_MAX_SPLIT_Z * B * d.Zp * f);
   p.add("dproj_acc", BN * d.A * f);
   p.add("dwa_acc", (size_t)B * d.A * f);
   // ---- transposed operands of the batched-over-time weight-gradient GEMMs
@@ -383,6 +389,21 @@ static bool persistent_forward(const Dims& d, int B, int N) {
   rf.Ep = d.Ep;
   rf.att.R = B; rf.att.N = N; rf.att.A = d.A; rf.att.Ap = d.Ap; rf.att.F = d.F; rf.att.Fp = d.Fp;
   return recurrent_forward_supported(rf);
+}
+
+// The BPTT loop runs as the persistent kernel of recurrent_bwd.cu (it reads either the
+// row-tiled or row-major saved state) and the shape fits.
+static void fill_rec_bwd_args(const Dims& d, int B, int N, RecBwdArgs& rb) {
+  rb = RecBwdArgs();
+  rb.B = B; rb.T = d.T; rb.H = d.H; rb.Hp = d.Hp; rb.Fp = d.Fp; rb.Zp = d.Zp; rb.Z = d.Z; rb.Z2p = d.Z2p; rb.A = d.A; rb.Ap = d.Ap;
+  rb.KX = d.KX; rb.Gp = d.Gp;
+  rb.att.R = B; rb.att.N = N; rb.att.A = d.A; rb.att.Ap = d.Ap; rb.att.F = d.F; rb.att.Fp = d.Fp;
+}
+static bool persistent_backward(const Dims& d, int B, int N) {
+  if (d.cvar) return false;                            // the attribute-grounded prior's d alpha path runs on the per-launch path
+  RecBwdArgs rb;
+  fill_rec_bwd_args(d, B, N, rb);
+  return recurrent_backward_supported(rb);
 }
 
 // ---- training forward --------------------------------------------------------------------------
@@ -585,10 +606,16 @@ static int train_backward_impl(Handle* h, int B, int N, const char* pk, const vo
   const float* tmask = Wf("tmask");
 
   const int tiled = persistent_forward(d, B, N) ? 1 : 0;
+  const bool pbwd = h->opt_persistent_bwd && persistent_backward(d, B, N);
   TRY(set_l2_window(s, pk + pp.find("w_dec_xzT")->off, pp.find("bwd_end")->off - pp.find("w_dec_xzT")->off));
-  const char* zl[] = {"dc1", "dc_enc", "dc_dec", "dXEH0", "dXEH1", "dXA0", "dXA1",
-                      "dG_att", "dG_enc", "dG_dec", "dqb"};
-  for (const char* n : zl) CUDA_TRY(zero(n));
+  if (pbwd) {
+    const char* zl[] = {"dc1", "dc_enc", "dc_dec", "dG_att", "dG_enc", "dG_dec", "dqb", "dml"};
+    for (const char* n : zl) CUDA_TRY(zero(n));
+  } else {
+    const char* zl[] = {"dc1", "dc_enc", "dc_dec", "dXEH0", "dXEH1", "dXA0", "dXA1",
+                        "dG_att", "dG_enc", "dG_dec", "dqb"};
+    for (const char* n : zl) CUDA_TRY(zero(n));
+  }
   if (d.tied) CUDA_TRY(zero("dpreo"));
 
   // ---- head: d logits, d h_dec from the vocabulary projection
@@ -651,7 +678,24 @@ static int train_backward_impl(Handle* h, int B, int N, const char* pk, const vo
   float* dXE[2] = {Wf("dXEH0"), Wf("dXEH1")};             // [d xhat | d h1 | d h_dec_{t-1} | d h_enc_{t-1}]
   const int KXH = KX + Hp + d.Cp, KXZ = KX + d.ZC;      // [.. | d h_enc_{t-1} | d c (encoder)] and [.. | d z | d c (decoder)]
   float* dXA[2] = {Wf("dXA0"), Wf("dXA1")};
-  for (int t = T - 1; t >= 0; --t) {
+  if (pbwd) {  // the whole reverse time loop in one persistent cooperative kernel (recurrent_bwd.cu)
+    RecBwdArgs rb;
+    fill_rec_bwd_args(d, B, N, rb);
+    rb.sentiment_vae = d.sv; rb.prior_var = d.prior_std * d.prior_std; rb.tiled = tiled;
+    rb.w_dec_xzT = Pb("w_dec_xzT"); rb.w_enc_xhT = Pb("w_enc_xhT"); rb.w_att_recT = Pb("w_att_recT"); rb.w_fcT = Pb("w_fcT"); rb.wqT = Pb("wqT");
+    rb.gates_att = Wf("gates_att"); rb.gates_enc = Wf("gates_enc"); rb.gates_dec = Wf("gates_dec");
+    rb.c1 = Wf("c1"); rb.c_enc = Wf("c_enc"); rb.c_dec = Wf("c_dec");
+    rb.mean = Wf("mean"); rb.logvar = Wf("logvar"); rb.eps = Wf("eps"); rb.pm_row = Wf("pm_row");
+    rb.q = Wf("q"); rb.smx = Wf("smx"); rb.dhead = Wf("dhead"); rb.gkld = gkld; rb.tmask = tmask;
+    rb.dc1 = Wf("dc1"); rb.dc_enc = Wf("dc_enc"); rb.dc_dec = Wf("dc_dec");
+    rb.dG_att = Wb("dG_att"); rb.dG_enc = Wb("dG_enc"); rb.dG_dec = Wb("dG_dec"); rb.dml = Wb("dml"); rb.dqb = Wb("dqb"); rb.du = Wf("du");
+    rb.dXEA = Wf("rb_dXEA"); rb.dXEB = Wf("rb_dXEB"); rb.dXA = Wf("rb_dXA"); rb.dzp = Wf("rb_dzp");
+    rb.dhe_fc = Wf("dhenc_fc"); rb.dh1q = Wf("dh1_q");
+    rb.att = aa;
+    rb.flags = reinterpret_cast<unsigned int*>(ws + tp.find("rb_flags")->off);
+    TRY(recurrent_backward(s, rb));
+  }
+  for (int t = T - 1; t >= 0 && !pbwd; --t) {
     const int cur = t & 1, nxt = cur ^ 1;
     const size_t rG = (size_t)t * B * G, rH = (size_t)t * B * H, rGp = (size_t)t * B * Gp, rZ = (size_t)t * B * Z;
     bf16* dGd = Wb("dG_dec") + rGp; bf16* dGe = Wb("dG_enc") + rGp; bf16* dGa = Wb("dG_att") + rGp;
@@ -861,8 +905,15 @@ int sscvae_set_option(SscvaeHandle* hh, const char* name, int value) {
   if (strcmp(name, "features_bf16") == 0) { h->opt_features_bf16 = value ? 1 : 0; return 0; }
   if (strcmp(name, "reuse_image_state") == 0) { h->opt_reuse_image_state = value ? 1 : 0; return 0; }
   if (strcmp(name, "fsm_packed") == 0) { h->opt_fsm_packed = value ? 1 : 0; return 0; }
+  if (strcmp(name, "persistent_bwd") == 0) { h->opt_persistent_bwd = value ? 1 : 0; return 0; }
   set_error("unknown option '%s'", name);
   return SSCVAE_ERR_BAD_ARG;
+}
+
+int sscvae_train_backward_is_persistent(const SscvaeHandle* hh, int batch, int num_boxes) {
+  const Handle* h = reinterpret_cast<const Handle*>(hh);
+  REQUIRE(h && batch > 0 && num_boxes > 0, "bad argument");
+  return h->opt_persistent_bwd && persistent_backward(h->d, batch, num_boxes) ? 1 : 0;
 }
 
 int sscvae_create(const SscvaeDims* dims, SscvaeHandle** out) {
@@ -938,6 +989,7 @@ int sscvae_train_backward(SscvaeHandle* hh, int batch, int num_boxes, const void
   std::vector<uint64_t> key;
   key_add(key, (uint64_t)batch); key_add(key, (uint64_t)num_boxes); key_add(key, packed); key_add(key, workspace);
   key_add(key, (uint64_t)workspace_bytes); key_add(key, grad_loss); key_add(key, grad_kld);
+  key_add(key, (uint64_t)h->opt_persistent_bwd);
   for (int i = 0; i < SSCVAE_W_COUNT; ++i) { key_add(key, weights[i]); key_add(key, grads[i]); }
   for (int g = 0; g < SSCVAE_GRAD_GROUPS; ++g) key_add(key, group_events ? group_events[g] : nullptr);
   return run_with_graph(h->bwd_graphs, key, reinterpret_cast<cudaStream_t>(stream), true, [&](cudaStream_t s) {

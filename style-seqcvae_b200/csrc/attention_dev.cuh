@@ -47,15 +47,15 @@ struct AttnSmem {
   float* q0;             // 2 x Ap (double buffer, prefetched one row ahead)
   float* u;              // ATT_CWARPS x N4 partial scores (d alpha in backward): [sub-warp][box]
   float* alw;            // ATT_CWARPS x N4: every consumer warp's own copy of alpha (broadcast reads in the weighted sum)
-  float* dx0;            // 2 x Fp (backward only)
+  float* dx0;            // 2 x ndx x Fp (backward only; ndx = split-K slots of d xhat, summed in place before use)
   float* sv0;            // 2 x N4 (backward only: saved softmax)
-  int Ap, Fp, N4;
+  int Ap, Fp, N4, ndx;
   __device__ __forceinline__ float* q(int slot) const { return q0 + slot * Ap; }
-  __device__ __forceinline__ float* dx(int slot) const { return dx0 + slot * Fp; }
+  __device__ __forceinline__ float* dx(int slot, int k = 0) const { return dx0 + (slot * ndx + k) * Fp; }
   __device__ __forceinline__ float* sv(int slot) const { return sv0 + slot * N4; }
 };
 
-__device__ __forceinline__ AttnSmem carve(uint8_t* raw, const AttnArgs& a, bool bwd) {
+__device__ __forceinline__ AttnSmem carve(uint8_t* raw, const AttnArgs& a, bool bwd, int ndx = 1) {
   AttnSmem s;
   // no integer round trip on the pointer: it would lose the shared address space and turn every access below into a
   // generic LD/ST with 64-bit address arithmetic (a third of the instructions of the first version of these kernels)
@@ -64,22 +64,22 @@ __device__ __forceinline__ AttnSmem carve(uint8_t* raw, const AttnArgs& a, bool 
   s.full = reinterpret_cast<uint64_t*>(p); p += ATT_STAGES * 8;
   s.empty = reinterpret_cast<uint64_t*>(p); p += ATT_STAGES * 8;
   float* f = reinterpret_cast<float*>(p);
-  s.Ap = a.Ap; s.Fp = a.Fp; s.N4 = (a.N + 3) & ~3;
+  s.Ap = a.Ap; s.Fp = a.Fp; s.N4 = (a.N + 3) & ~3; s.ndx = ndx;
   s.wa = f; f += a.Ap;
   s.q0 = f; f += 2 * a.Ap;
   s.u = f; f += ATT_CWARPS * s.N4;
   s.alw = f; f += ATT_CWARPS * s.N4;
   s.dx0 = s.sv0 = nullptr;
   if (bwd) {
-    s.dx0 = f; f += 2 * a.Fp;
+    s.dx0 = f; f += 2 * ndx * a.Fp;
     s.sv0 = f; f += 2 * s.N4;
   }
   return s;
 }
-__host__ __device__ inline size_t attn_smem_bytes(const AttnArgs& a, bool bwd) {
+__host__ __device__ inline size_t attn_smem_bytes(const AttnArgs& a, bool bwd, int ndx = 1) {
   size_t n = 128 + (size_t)ATT_STAGES * ATT_STAGE_BYTES + 2 * ATT_STAGES * 8;
   n += (size_t)(3 * a.Ap + 2 * ATT_CWARPS * ((a.N + 3) & ~3)) * 4;
-  if (bwd) n += (size_t)(2 * a.Fp + 2 * ((a.N + 3) & ~3)) * 4;
+  if (bwd) n += (size_t)(2 * ndx * a.Fp + 2 * ((a.N + 3) & ~3)) * 4;
   return n;
 }
 
@@ -212,7 +212,7 @@ __device__ __forceinline__ void attn_prologue(const AttnSmem& sm, const AttnArgs
     sm.q0[a.Ap + i] = 0.f;
   }
   if (bwd)
-    for (int i = threadIdx.x; i < 2 * a.Fp; i += blockDim.x) sm.dx0[i] = 0.f;
+    for (int i = threadIdx.x; i < 2 * sm.ndx * a.Fp; i += blockDim.x) sm.dx0[i] = 0.f;
   __syncthreads();
 }
 
@@ -318,6 +318,137 @@ __device__ __forceinline__ void attn_fwd_row(const AttnArgs& a, const AttnPlan& 
       for (int k = 0; k < 4; ++k) o.v[k] = __floats2bfloat162_rn(acc[v][2 * k], acc[v][2 * k + 1]);
       st_bf16x8(xhat_row + vec * 8, o);
     }
+  }
+}
+
+// One row of the per-step backward (d u saved for the deferred part, d q as the bf16 operand of the query-projection
+// GEMM), executed by the ATT_CONSUMERS consumer threads of the persistent BPTT kernel (recurrent_bwd.cu). Same math as
+// attention.cu: attention_bwd_kernel. The caller has issued (and committed) the cp.async prefetch of this row's q,
+// saved softmax and d xhat (sm.ndx split-K slots) into buffer `cur`; `prefetch_next()` issues the next row's.
+// The producer warp streams, per row, the feature chunks then the P chunks.
+template <typename PrefetchNext>
+__device__ __forceinline__ void attn_bwd_row(const AttnArgs& a, const AttnPlan& pl, const AttnSmem& sm, Ring& ring, int cur,
+                                             const float* mask_img, PrefetchNext prefetch_next, bf16* __restrict__ dq_row,
+                                             int ld_dq, float* __restrict__ du_row) {
+  const int tid = attn_tid();
+  const int warp = tid >> 5, lane = tid & 31;
+  const int nfv = a.Fp >> 3, npair = a.Ap >> 1;
+  ptx::cp_async_wait_all();
+  ptx::bar_sync(1, ATT_CONSUMERS);
+  prefetch_next();
+  float* dx_s = sm.dx(cur, 0);
+  if (sm.ndx > 1) {                                  // sum the split-K slots of d xhat in place
+    for (int k = 1; k < sm.ndx; ++k) {
+      const float4* o = reinterpret_cast<const float4*>(sm.dx(cur, k));
+      for (int i = tid; i < (a.Fp >> 2); i += ATT_CONSUMERS) {
+        float4 v = reinterpret_cast<float4*>(dx_s)[i];
+        const float4 w = o[i];
+        v.x += w.x; v.y += w.y; v.z += w.z; v.w += w.w;
+        reinterpret_cast<float4*>(dx_s)[i] = v;
+      }
+    }
+    ptx::bar_sync(1, ATT_CONSUMERS);
+  }
+  // d alpha_n = d xhat . x_n : warp per box
+  for (int c = 0; c < pl.nF; ++c) {
+    const int n0 = c * pl.bF, nb = min(pl.bF, a.N - n0);
+    ptx::mbar_wait(&sm.full[ring.stage], ring.phase);
+    const bf16x8* buf = reinterpret_cast<const bf16x8*>(sm.stage + (size_t)ring.stage * ATT_STAGE_BYTES);
+    const int wpb = warps_per_box(nb);
+    const int j = warp / wpb, sub = warp % wpb;
+    if (j < nb) {
+      const int n = n0 + j;
+      float s = 0.f;
+      if (mask_img[n] != 0.f) {
+        const bf16x8* p = buf + (size_t)j * nfv;
+        for (int i = sub * 32 + lane; i < nfv; i += 32 * wpb) {
+          const bf16x8 v = p[i];
+          const float4 da = *reinterpret_cast<const float4*>(dx_s + i * 8);
+          const float4 db = *reinterpret_cast<const float4*>(dx_s + i * 8 + 4);
+          const float2 f0 = __bfloat1622float2(v.v[0]), f1 = __bfloat1622float2(v.v[1]);
+          const float2 f2 = __bfloat1622float2(v.v[2]), f3 = __bfloat1622float2(v.v[3]);
+          s += da.x * f0.x + da.y * f0.y + da.z * f1.x + da.w * f1.y;
+          s += db.x * f2.x + db.y * f2.y + db.z * f3.x + db.w * f3.y;
+        }
+        s = warp_sum(s);
+      }
+      if (lane == 0) sm.u[sub * sm.N4 + n] = s;
+    }
+    __syncwarp();
+    if (lane == 0) ptx::mbar_arrive(&sm.empty[ring.stage]);
+    ring.advance();
+  }
+  ptx::bar_sync(1, ATT_CONSUMERS);
+  // softmax backward, redundantly per warp (see attention_bwd_kernel)
+  float duv[ATT_NREG];
+  {
+    float m[ATT_NREG], sv[ATT_NREG], da[ATT_NREG];
+    float sr = 0.f;
+#pragma unroll
+    for (int k = 0; k < ATT_NREG; ++k) {
+      const int n = lane + 32 * k;
+      const bool ok = n < a.N;
+      m[k] = ok ? mask_img[n] : 0.f;
+      sv[k] = ok ? sm.sv(cur)[n] : 0.f;
+      da[k] = ok ? gather_partial(sm.u, sm.N4, a.N, pl.bF, n) : 0.f;
+      sr += sv[k] * m[k];
+    }
+    const float Rn = warp_sum(sr) + 1e-13f;
+    float dot = 0.f;
+#pragma unroll
+    for (int k = 0; k < ATT_NREG; ++k) dot += da[k] * (sv[k] * m[k] / Rn);
+    dot = warp_sum(dot);
+    float dss = 0.f;
+#pragma unroll
+    for (int k = 0; k < ATT_NREG; ++k) {
+      da[k] = (da[k] - dot) / Rn * m[k];
+      dss += da[k] * sv[k];
+    }
+    dss = warp_sum(dss);
+#pragma unroll
+    for (int k = 0; k < ATT_NREG; ++k) duv[k] = sv[k] * (da[k] - dss) * m[k];
+  }
+  if (warp == 0) {
+#pragma unroll
+    for (int k = 0; k < ATT_NREG; ++k) {
+      const int n = lane + 32 * k;
+      if (n < a.N) du_row[n] = duv[k];
+    }
+  }
+  // d q_a = w_a sum_n du_n (1 - tanh^2(q_a + P_na)): a thread owns pairs of projection columns
+  const float* q_s = sm.q(cur);
+  float g[ATT_PV][2];
+#pragma unroll
+  for (int v = 0; v < ATT_PV; ++v) g[v][0] = g[v][1] = 0.f;
+  for (int c = 0; c < pl.nP; ++c) {
+    const int n0 = c * pl.bP, nb = min(pl.bP, a.N - n0);
+    ptx::mbar_wait(&sm.full[ring.stage], ring.phase);
+    const __nv_bfloat162* buf = reinterpret_cast<const __nv_bfloat162*>(sm.stage + (size_t)ring.stage * ATT_STAGE_BYTES);
+    for (int j = 0; j < nb; ++j) {
+      const int n = n0 + j;
+      const float d = __shfl_sync(0xffffffffu, pick(duv, n >> 5), n & 31);
+      if (d != 0.f) {                                // warp-uniform (masked boxes, padded timesteps)
+#pragma unroll
+        for (int v = 0; v < ATT_PV; ++v) {
+          const int cp = tid + ATT_CONSUMERS * v;
+          if (cp < npair) {
+            const float2 f = __bfloat1622float2(buf[(size_t)j * npair + cp]);
+            const float t0 = tanh_approx(q_s[2 * cp] + f.x), t1 = tanh_approx(q_s[2 * cp + 1] + f.y);
+            g[v][0] += d * (1.f - t0 * t0);
+            g[v][1] += d * (1.f - t1 * t1);
+          }
+        }
+      }
+    }
+    __syncwarp();
+    if (lane == 0) ptx::mbar_arrive(&sm.empty[ring.stage]);
+    ring.advance();
+  }
+#pragma unroll
+  for (int v = 0; v < ATT_PV; ++v) {
+    const int cp = tid + ATT_CONSUMERS * v;
+    if (cp < npair && 2 * cp < ld_dq)
+      *reinterpret_cast<__nv_bfloat162*>(dq_row + 2 * cp) = __floats2bfloat162_rn(sm.wa[2 * cp] * g[v][0], sm.wa[2 * cp + 1] * g[v][1]);
   }
 }
 

@@ -208,5 +208,35 @@ bool recurrent_forward_supported(const RecFwdArgs& r);
 size_t recurrent_forward_kl_parts(int Z);   // number of per-row KL partial sums per timestep
 int recurrent_forward(cudaStream_t s, const RecFwdArgs& r);
 
+// ---- persistent kernel of the backward-through-time loop (recurrent_bwd.cu) -----------------------
+// One cooperative launch runs the T reverse timesteps that api_train.cu otherwise issues as ten kernels per step. It
+// reads the state the persistent forward kernel saved (row-tiled gates / cell states) and writes what the
+// weight-gradient GEMMs behind the loop consume: dG_att / dG_enc / dG_dec (T*B, Gp), dml (T*B, Z2p), dqb (T*B, Ap) in
+// bf16 (padding columns must be zero at entry) and du (T*B, N). dc1 / dc_enc / dc_dec (B, H) must be zero at entry.
+constexpr int RB_MAX_SPLIT_A = 2, RB_MAX_SPLIT_B = 4, RB_MAX_SPLIT_X = 4, RB_MAX_SPLIT_Z = 16;   // K splits (slots) per GEMM
+struct RecBwdArgs {
+  int B, T, H, Hp, Fp, Zp, Z, Z2p, A, Ap, KX, Gp;
+  int sentiment_vae; float prior_var;
+  int tiled;                           // layout of the saved gates / cell states: 1 row-tiled (lstm_tiled_*_offset), 0 row-major
+  const bf16* w_dec_xzT; const bf16* w_enc_xhT; const bf16* w_att_recT; const bf16* w_fcT; const bf16* wqT;
+  const float* gates_att; const float* gates_enc; const float* gates_dec;
+  const float* c1; const float* c_enc; const float* c_dec;
+  const float* mean; const float* logvar; const float* eps; const float* pm_row;
+  const float* q; const float* smx;
+  const float* dhead;                  // (T*B, H) fp32 row-major
+  const float* gkld; const float* tmask;
+  float* dc1; float* dc_enc; float* dc_dec;
+  bf16* dG_att; bf16* dG_enc; bf16* dG_dec; bf16* dml; bf16* dqb; float* du;
+  float* dXEA;                         // RB_MAX_SPLIT_A x B x KX fp32 scratch
+  float* dXEB;                         // RB_MAX_SPLIT_B x B x Hp
+  float* dXA;                          // RB_MAX_SPLIT_X x B x 2Hp
+  float* dzp;                          // RB_MAX_SPLIT_Z x B x Zp
+  float* dhe_fc; float* dh1q;          // B x H each
+  AttnArgs att;                        // R = B, rowmap = null; q / ld_q unused
+  unsigned int* flags;                 // >= 256 B of scratch for the dataflow counters
+};
+bool recurrent_backward_supported(const RecBwdArgs& r);
+int recurrent_backward(cudaStream_t s, const RecBwdArgs& r);
+
 extern unsigned long long g_launch_count_pw;   // launches from the non-GEMM kernels
 }  // namespace sscvae
