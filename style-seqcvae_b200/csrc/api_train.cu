@@ -193,6 +193,7 @@ static void plan_train(const Dims& d, int B, int N, Plan& p) {
   p.add("dc_dec", (size_t)B * d.H * f);
   // persistent BPTT kernel (recurrent_bwd.cu): dataflow counters and the split-K slots of its data-gradient GEMMs
   p.add("rb_flags", 1024);
+  p.add("rb_rows", (TB + T) * 4);
   p.add("rb_dXEA", (size_t)RB_MAX_SPLIT_A * B * d.KX * f);
   p.add("rb_dXEB", (size_t)RB_MAX_SPLIT_B * B * d.Hp * f);
   p.add("rb_dXA", (size_t)RB_MAX_SPLIT_X * B * 2 * d.Hp * f);
@@ -609,7 +610,7 @@ static int train_backward_impl(Handle* h, int B, int N, const char* pk, const vo
   const bool pbwd = h->opt_persistent_bwd && persistent_backward(d, B, N);
   TRY(set_l2_window(s, pk + pp.find("w_dec_xzT")->off, pp.find("bwd_end")->off - pp.find("w_dec_xzT")->off));
   if (pbwd) {
-    const char* zl[] = {"dc1", "dc_enc", "dc_dec", "dG_att", "dG_enc", "dG_dec", "dqb", "dml"};
+    const char* zl[] = {"dc1", "dc_enc", "dc_dec", "dG_att", "dG_enc", "dG_dec", "dqb", "dml", "du"};
     for (const char* n : zl) CUDA_TRY(zero(n));
   } else {
     const char* zl[] = {"dc1", "dc_enc", "dc_dec", "dXEH0", "dXEH1", "dXA0", "dXA1",
@@ -693,6 +694,7 @@ static int train_backward_impl(Handle* h, int B, int N, const char* pk, const vo
     rb.dhe_fc = Wf("dhenc_fc"); rb.dh1q = Wf("dh1_q");
     rb.att = aa;
     rb.flags = reinterpret_cast<unsigned int*>(ws + tp.find("rb_flags")->off);
+    rb.rows = Wi("rb_rows");
     TRY(recurrent_backward(s, rb));
   }
   for (int t = T - 1; t >= 0 && !pbwd; --t) {

@@ -26,7 +26,10 @@ __device__ __forceinline__ float tanh_approx(float x) {
 constexpr int ATT_CONSUMERS = 256;                 // 8 consumer warps
 constexpr int ATT_CWARPS = ATT_CONSUMERS / 32;
 constexpr int ATT_THREADS = ATT_CONSUMERS + 32;    // + 1 producer warp
-constexpr int ATT_STAGES = 4;
+#ifndef ATT_STAGES_N
+#define ATT_STAGES_N 4
+#endif
+constexpr int ATT_STAGES = ATT_STAGES_N;           // ring depth (per translation unit, like ATT_TID0)
 constexpr int ATT_STAGE_BYTES = 16384;             // two CTAs per SM: their phases overlap
 constexpr int ATT_MAXB = 8;                        // boxes per chunk (<= consumer warps: one box per warp and chunk)
 constexpr int ATT_NREG = 4;                        // boxes per lane in the softmax: N <= 128
@@ -87,8 +90,9 @@ __host__ __device__ inline size_t attn_smem_bytes(const AttnArgs& a, bool bwd, i
 struct Ring {
   int stage = 0;
   uint32_t phase = 0;
+  int n = ATT_STAGES;                              // stages in use (<= ATT_STAGES; tuning knob of the persistent kernels)
   __device__ __forceinline__ void advance() {
-    if (++stage == ATT_STAGES) { stage = 0; phase ^= 1; }
+    if (++stage == n) { stage = 0; phase ^= 1; }
   }
 };
 
@@ -326,15 +330,17 @@ __device__ __forceinline__ void attn_fwd_row(const AttnArgs& a, const AttnPlan& 
 // attention.cu: attention_bwd_kernel. The caller has issued (and committed) the cp.async prefetch of this row's q,
 // saved softmax and d xhat (sm.ndx split-K slots) into buffer `cur`; `prefetch_next()` issues the next row's.
 // The producer warp streams, per row, the feature chunks then the P chunks.
-template <typename PrefetchNext>
+struct NoStamp { __device__ __forceinline__ void operator()(int) const {} };
+template <typename PrefetchNext, typename Stamp = NoStamp>
 __device__ __forceinline__ void attn_bwd_row(const AttnArgs& a, const AttnPlan& pl, const AttnSmem& sm, Ring& ring, int cur,
                                              const float* mask_img, PrefetchNext prefetch_next, bf16* __restrict__ dq_row,
-                                             int ld_dq, float* __restrict__ du_row) {
+                                             int ld_dq, float* __restrict__ du_row, Stamp stamp = Stamp()) {
   const int tid = attn_tid();
   const int warp = tid >> 5, lane = tid & 31;
   const int nfv = a.Fp >> 3, npair = a.Ap >> 1;
   ptx::cp_async_wait_all();
   ptx::bar_sync(1, ATT_CONSUMERS);
+  stamp(0);
   prefetch_next();
   float* dx_s = sm.dx(cur, 0);
   if (sm.ndx > 1) {                                  // sum the split-K slots of d xhat in place
@@ -349,7 +355,9 @@ __device__ __forceinline__ void attn_bwd_row(const AttnArgs& a, const AttnPlan& 
     }
     ptx::bar_sync(1, ATT_CONSUMERS);
   }
-  // d alpha_n = d xhat . x_n : warp per box
+  stamp(1);
+  // d alpha_n = d xhat . x_n : warp per box. Independent accumulators and an unrolled vector loop: the loop is a chain of
+  // shared-memory round trips otherwise (a warp has no other work to hide them behind).
   for (int c = 0; c < pl.nF; ++c) {
     const int n0 = c * pl.bF, nb = min(pl.bF, a.N - n0);
     ptx::mbar_wait(&sm.full[ring.stage], ring.phase);
@@ -361,16 +369,20 @@ __device__ __forceinline__ void attn_bwd_row(const AttnArgs& a, const AttnPlan& 
       float s = 0.f;
       if (mask_img[n] != 0.f) {
         const bf16x8* p = buf + (size_t)j * nfv;
+        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll 4
         for (int i = sub * 32 + lane; i < nfv; i += 32 * wpb) {
           const bf16x8 v = p[i];
           const float4 da = *reinterpret_cast<const float4*>(dx_s + i * 8);
           const float4 db = *reinterpret_cast<const float4*>(dx_s + i * 8 + 4);
           const float2 f0 = __bfloat1622float2(v.v[0]), f1 = __bfloat1622float2(v.v[1]);
           const float2 f2 = __bfloat1622float2(v.v[2]), f3 = __bfloat1622float2(v.v[3]);
-          s += da.x * f0.x + da.y * f0.y + da.z * f1.x + da.w * f1.y;
-          s += db.x * f2.x + db.y * f2.y + db.z * f3.x + db.w * f3.y;
+          s0 = fmaf(da.x, f0.x, fmaf(da.y, f0.y, s0));
+          s1 = fmaf(da.z, f1.x, fmaf(da.w, f1.y, s1));
+          s2 = fmaf(db.x, f2.x, fmaf(db.y, f2.y, s2));
+          s3 = fmaf(db.z, f3.x, fmaf(db.w, f3.y, s3));
         }
-        s = warp_sum(s);
+        s = warp_sum((s0 + s1) + (s2 + s3));
       }
       if (lane == 0) sm.u[sub * sm.N4 + n] = s;
     }
@@ -379,6 +391,7 @@ __device__ __forceinline__ void attn_bwd_row(const AttnArgs& a, const AttnPlan& 
     ring.advance();
   }
   ptx::bar_sync(1, ATT_CONSUMERS);
+  stamp(2);
   // softmax backward, redundantly per warp (see attention_bwd_kernel)
   float duv[ATT_NREG];
   {
@@ -415,27 +428,47 @@ __device__ __forceinline__ void attn_bwd_row(const AttnArgs& a, const AttnPlan& 
       if (n < a.N) du_row[n] = duv[k];
     }
   }
-  // d q_a = w_a sum_n du_n (1 - tanh^2(q_a + P_na)): a thread owns pairs of projection columns
+  stamp(3);
+  // d q_a = w_a sum_n du_n (1 - tanh^2(q_a + P_na)): a thread owns pairs of projection columns. Four boxes per iteration
+  // without a branch on d u (a masked box contributes d = 0): 8 - 16 independent tanh chains per thread instead of one.
   const float* q_s = sm.q(cur);
-  float g[ATT_PV][2];
+  float g[ATT_PV][2], qv[ATT_PV][2];
 #pragma unroll
-  for (int v = 0; v < ATT_PV; ++v) g[v][0] = g[v][1] = 0.f;
+  for (int v = 0; v < ATT_PV; ++v) {
+    g[v][0] = g[v][1] = 0.f;
+    const int cp = tid + ATT_CONSUMERS * v;
+    qv[v][0] = cp < npair ? q_s[2 * cp] : 0.f;
+    qv[v][1] = cp < npair ? q_s[2 * cp + 1] : 0.f;
+  }
+  bool any = false;                                  // padded timesteps: every d u is zero, nothing to add
+#pragma unroll
+  for (int k = 0; k < ATT_NREG; ++k) any = any || duv[k] != 0.f;
+  any = __any_sync(0xffffffffu, any);
   for (int c = 0; c < pl.nP; ++c) {
     const int n0 = c * pl.bP, nb = min(pl.bP, a.N - n0);
     ptx::mbar_wait(&sm.full[ring.stage], ring.phase);
     const __nv_bfloat162* buf = reinterpret_cast<const __nv_bfloat162*>(sm.stage + (size_t)ring.stage * ATT_STAGE_BYTES);
-    for (int j = 0; j < nb; ++j) {
-      const int n = n0 + j;
-      const float d = __shfl_sync(0xffffffffu, pick(duv, n >> 5), n & 31);
-      if (d != 0.f) {                                // warp-uniform (masked boxes, padded timesteps)
+    if (any) {
+      for (int j0 = 0; j0 < nb; j0 += 4) {
+        float d[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int n = min(n0 + j0 + u, a.N - 1);
+          const float dv = __shfl_sync(0xffffffffu, pick(duv, n >> 5), n & 31);
+          d[u] = (j0 + u < nb) ? dv : 0.f;
+        }
 #pragma unroll
         for (int v = 0; v < ATT_PV; ++v) {
           const int cp = tid + ATT_CONSUMERS * v;
           if (cp < npair) {
-            const float2 f = __bfloat1622float2(buf[(size_t)j * npair + cp]);
-            const float t0 = tanh_approx(q_s[2 * cp] + f.x), t1 = tanh_approx(q_s[2 * cp + 1] + f.y);
-            g[v][0] += d * (1.f - t0 * t0);
-            g[v][1] += d * (1.f - t1 * t1);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const int jj = min(j0 + u, nb - 1);    // clamped: the box exists, its weight d[u] is zero
+              const float2 f = __bfloat1622float2(buf[(size_t)jj * npair + cp]);
+              const float t0 = tanh_approx(qv[v][0] + f.x), t1 = tanh_approx(qv[v][1] + f.y);
+              g[v][0] = fmaf(d[u], 1.f - t0 * t0, g[v][0]);
+              g[v][1] = fmaf(d[u], 1.f - t1 * t1, g[v][1]);
+            }
           }
         }
       }
@@ -444,6 +477,7 @@ __device__ __forceinline__ void attn_bwd_row(const AttnArgs& a, const AttnPlan& 
     if (lane == 0) ptx::mbar_arrive(&sm.empty[ring.stage]);
     ring.advance();
   }
+  stamp(4);
 #pragma unroll
   for (int v = 0; v < ATT_PV; ++v) {
     const int cp = tid + ATT_CONSUMERS * v;

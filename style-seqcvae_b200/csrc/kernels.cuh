@@ -212,7 +212,8 @@ int recurrent_forward(cudaStream_t s, const RecFwdArgs& r);
 // One cooperative launch runs the T reverse timesteps that api_train.cu otherwise issues as ten kernels per step. It
 // reads the state the persistent forward kernel saved (row-tiled gates / cell states) and writes what the
 // weight-gradient GEMMs behind the loop consume: dG_att / dG_enc / dG_dec (T*B, Gp), dml (T*B, Z2p), dqb (T*B, Ap) in
-// bf16 (padding columns must be zero at entry) and du (T*B, N). dc1 / dc_enc / dc_dec (B, H) must be zero at entry.
+// bf16 (padding columns must be zero at entry) and du (T*B, N) (zero at entry: rows past the end of their caption are
+// not visited). dc1 / dc_enc / dc_dec (B, H) must be zero at entry.
 constexpr int RB_MAX_SPLIT_A = 2, RB_MAX_SPLIT_B = 4, RB_MAX_SPLIT_X = 4, RB_MAX_SPLIT_Z = 16;   // K splits (slots) per GEMM
 struct RecBwdArgs {
   int B, T, H, Hp, Fp, Zp, Z, Z2p, A, Ap, KX, Gp;
@@ -225,6 +226,7 @@ struct RecBwdArgs {
   const float* q; const float* smx;
   const float* dhead;                  // (T*B, H) fp32 row-major
   const float* gkld; const float* tmask;
+  int* rows;                           // (T*B + T) ints of scratch: per-step list of the rows that still carry gradient
   float* dc1; float* dc_enc; float* dc_dec;
   bf16* dG_att; bf16* dG_enc; bf16* dG_dec; bf16* dml; bf16* dqb; float* du;
   float* dXEA;                         // RB_MAX_SPLIT_A x B x KX fp32 scratch

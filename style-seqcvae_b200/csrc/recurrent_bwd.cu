@@ -22,6 +22,7 @@
 // The pointwise stages (the three LSTM cell backwards, the latent backward) and the attention rows are spread over the
 // compute warps of ALL CTAs. Saved forward state is read in the row-tiled layout the persistent forward kernel wrote.
 #define ATT_TID0 64
+#define ATT_STAGES_N 3
 #include "kernels.cuh"
 #include "gemm.cuh"
 #include "prof.cuh"
@@ -41,7 +42,7 @@ namespace {
 constexpr int RB_CWARPS = 8;                                   // compute warps (epilogues, pointwise stages, attention consumers)
 constexpr int RB_THREADS = 32 * (2 + RB_CWARPS + 1);           // + TMA producer, MMA issuer, attention producer
 constexpr int RB_CTHREADS = 32 * RB_CWARPS;
-constexpr int RB_STAGES = 4;
+constexpr int RB_STAGES = 5;
 constexpr int RB_X_BYTES = 128 * 64 * 2;                       // activation tile: 128 batch rows x 64 k (bf16)
 constexpr int RB_W_BYTES = 64 * 64 * 2;                        // weight tile half: <= 64 rows x 64 k
 constexpr int RB_STAGE_BYTES = RB_X_BYTES + RB_W_BYTES;
@@ -93,6 +94,7 @@ struct RbParams {
   const float* q; const float* smx;
   const float* dhead;              // (T*B, H) row-major: d h_dec_t from the output head
   const float* gkld; const float* tmask;
+  const int* rows; const int* nrows;   // rows[t*B + i] = i-th batch row that still carries gradient at step t; nrows[t] of them
   // carried cell-state gradients (row-tiled, B x H, zero at entry)
   float* dc1; float* dc_enc; float* dc_dec;
   // outputs kept for the weight-gradient GEMMs
@@ -102,6 +104,9 @@ struct RbParams {
   AttnArgs att; AttnPlan plan;
   unsigned int* flags;
   int w_policy;
+  int sig_mode;
+  int att_stages;                  // attention ring stages in use (<= ATT_STAGES)
+  int att_prefetch;                // 1: bulk L2 prefetch of this CTA's attention rows ahead of the attention stage
   int stages;
   unsigned long long timeout_ns;
   unsigned long long* dbg;         // SSCVAE_RB_DBG=1: globaltimer stamps of step dbg_s, 32 per CTA
@@ -206,6 +211,7 @@ struct RbSmem {
 // row-tiled fp32 matrix with B rows: element (b, col)
 __device__ __forceinline__ size_t tl_off(int B, int b, int col) { return ((size_t)(col >> 2) * B + b) * 4 + (col & 3); }
 __device__ __forceinline__ float4 ld4g(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __device__ __forceinline__ void add4(float4& a, const float4& b) { a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w; }
 __device__ __forceinline__ void st_bf16x4_rb(bf16* p, float a, float b, float c, float d) {
   __nv_bfloat162 lo = __floats2bfloat162_rn(a, b), hi = __floats2bfloat162_rn(c, d);
@@ -216,9 +222,12 @@ __device__ __forceinline__ void st_bf16x4_rb(bf16* p, float a, float b, float c,
 }
 
 // The compute warps signal "my part of tensor X of this step is in global memory" (every CTA, every step).
-__device__ __forceinline__ void signal_done(const RbParams& p, int flag, int ctid) {
-  fence_proxy_async_global();                          // generic-proxy stores -> later TMA (async proxy) reads
-  __threadfence();
+// `tma`: the tensor is read through TMA (async proxy) by its consumers.
+// sig_mode 1: no per-thread membar.gl: the CTA barrier orders the threads' stores before thread 0's gpu-scope release
+// (cumulativity; the pattern of cooperative-groups grid sync).
+__device__ __forceinline__ void signal_done(const RbParams& p, int flag, int ctid, bool tma = true) {
+  if (tma || p.sig_mode == 0) fence_proxy_async_global();   // generic-proxy stores -> later TMA (async proxy) reads
+  if (p.sig_mode == 0) __threadfence();
   ptx::bar_sync(2, RB_CTHREADS);
   if (ctid == 0) red_release_add(p.flags + flag, 1u);
 }
@@ -230,47 +239,70 @@ __device__ __forceinline__ void wait_all(const RbParams& p, int flag, unsigned i
 // ---- pointwise stages (all CTAs) ---------------------------------------------------------------------------------
 // LSTM cell backward (torch.nn.LSTMCell, gate order i,f,g,o; the math of pointwise.cu: lstm_bwd_v4_kernel) of timestep t.
 // WHICH: 0 attention LSTM, 1 encoder, 2 decoder. A warp covers 8 rows x 4 unit-quads.
+// Inputs of one cell item (a lane = one row x 4 units) that do NOT depend on a dataflow counter: the saved gates and
+// cell states, this thread's own carried d c, and (decoder) the head gradient.
+struct CellPre { float4 gi, gf, gg, go, c, cp, dci, dh0; int r, j; bool ok; };
+
 template <int WHICH>
-__device__ __forceinline__ void cell_stage(const RbParams& p, int t, int s, int gw, int GW, int lane) {
+__device__ __forceinline__ void cell_preload(const RbParams& p, int t, int wi, int lane, CellPre& in) {
   const int B = p.B, H = p.H, H4 = H >> 2;
   const int tr = (B + 7) >> 3, tq = (H4 + 3) >> 2;
+  const int r = (wi % tr) * 8 + (lane & 7);
+  const int jq = (wi / tr) * 4 + (lane >> 3);
+  in.ok = wi < tr * tq && r < B && jq < H4;
+  in.r = r; in.j = jq * 4;
+  if (!in.ok) return;
+  const int j = in.j;
   const float* gates = (WHICH == 0 ? p.gates_att : WHICH == 1 ? p.gates_enc : p.gates_dec) + (size_t)t * B * 4 * H;
   const float* cbuf = (WHICH == 0 ? p.c1 : WHICH == 1 ? p.c_enc : p.c_dec) + (size_t)t * B * H;
-  float* dcb = WHICH == 0 ? p.dc1 : WHICH == 1 ? p.dc_enc : p.dc_dec;
-  bf16* dG = (WHICH == 0 ? p.dG_att : WHICH == 1 ? p.dG_enc : p.dG_dec) + (size_t)t * B * p.Gp;
-  const bool prev = s > 0;                             // contributions of step t + 1 exist
-  for (int wi = gw; wi < tr * tq; wi += GW) {
-    const int r = (wi % tr) * 8 + (lane & 7);
-    const int jq = (wi / tr) * 4 + (lane >> 3);
-    if (r >= B || jq >= H4) continue;
-    const int j = jq * 4;
-    float4 dh = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (WHICH == 2) {                                  // d h_dec_t: output head + LSTM inputs of step t+1 (S6A, S10)
-      dh = ld4g(p.dhead + ((size_t)t * B + r) * H + j);
-      if (prev) {
-        for (int k = 0; k < p.splitA; ++k) add4(dh, ld4g(p.dXEA + (size_t)k * B * p.KX + tl_off(B, r, p.Fp + p.Hp + j)));
-        for (int k = 0; k < p.splitX; ++k) add4(dh, ld4g(p.dXA + (size_t)k * B * 2 * p.Hp + tl_off(B, r, p.Hp + j)));
-      }
-    } else if (WHICH == 1) {                           // d h_enc_t: latent heads + recurrence (S6B of step t+1)
-      dh = ld4g(p.dhe_fc + tl_off(B, r, j));
-      if (prev)
-        for (int k = 0; k < p.splitB; ++k) add4(dh, ld4g(p.dXEB + (size_t)k * B * p.Hp + tl_off(B, r, j)));
-    } else {                                           // d h1_t: enc/dec inputs of this step + query + recurrence (S10 of t+1)
-      dh = ld4g(p.dh1q + tl_off(B, r, j));
-      for (int k = 0; k < p.splitA; ++k) add4(dh, ld4g(p.dXEA + (size_t)k * B * p.KX + tl_off(B, r, p.Fp + j)));
-      if (prev)
-        for (int k = 0; k < p.splitX; ++k) add4(dh, ld4g(p.dXA + (size_t)k * B * 2 * p.Hp + tl_off(B, r, j)));
-    }
-    const float* g = gates + (p.tiled ? lstm_tiled_gate_offset(B, r, 0, j) : (size_t)r * 4 * H + j);
-    const size_t gs = p.tiled ? (size_t)B * 4 : (size_t)H;
-    const size_t co = p.tiled ? lstm_tiled_c_offset(B, r, j) : (size_t)r * H + j;
-    const float4 gi = ld4g(g), gf = ld4g(g + gs), gg = ld4g(g + 2 * gs), go = ld4g(g + 3 * gs);
-    const float4 c = ld4g(cbuf + co);
-    float4 cp = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (t > 0) cp = ld4g(cbuf - (size_t)B * H + co);
-    float* dcp_ptr = dcb + tl_off(B, r, j);
-    const float4 dci = ld4g(dcp_ptr);
-    float4 di, df, dg, d_o, dcp;
+  const float* dcb = WHICH == 0 ? p.dc1 : WHICH == 1 ? p.dc_enc : p.dc_dec;
+  const float* g = gates + (p.tiled ? lstm_tiled_gate_offset(B, r, 0, j) : (size_t)r * 4 * H + j);
+  const size_t gs = p.tiled ? (size_t)B * 4 : (size_t)H;
+  const size_t co = p.tiled ? lstm_tiled_c_offset(B, r, j) : (size_t)r * H + j;
+  in.gi = ld4g(g); in.gf = ld4g(g + gs); in.gg = ld4g(g + 2 * gs); in.go = ld4g(g + 3 * gs);
+  in.c = ld4g(cbuf + co);
+  in.cp = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (t > 0) in.cp = ld4g(cbuf - (size_t)B * H + co);
+  in.dci = ld4g(dcb + tl_off(B, r, j));
+  in.dh0 = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (WHICH == 2) in.dh0 = ld4g(p.dhead + ((size_t)t * B + r) * H + j);
+}
+
+// The counter-dependent part: sum of the split-K slots that feed d h of this cell, then the LSTM cell backward
+// (torch.nn.LSTMCell, gate order i,f,g,o; the math of pointwise.cu: lstm_bwd_v4_kernel).
+template <int WHICH>
+__device__ __forceinline__ void cell_finish(const RbParams& p, int t, bool prev, const CellPre& in) {
+  if (!in.ok) return;
+  const int B = p.B, H = p.H, r = in.r, j = in.j;
+  // all slot loads are issued before the first add (a runtime-trip-count loop of load + add serialises the L2 round trips)
+  const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  float4 va[RB_MAX_SPLIT_A], vx[RB_MAX_SPLIT_X], v0 = z4;
+  if (WHICH == 2) {                                    // d h_dec_t: output head + LSTM inputs of step t+1 (S6A, S10)
+#pragma unroll
+    for (int k = 0; k < RB_MAX_SPLIT_A; ++k) va[k] = (prev && k < p.splitA) ? ld4g(p.dXEA + (size_t)k * B * p.KX + tl_off(B, r, p.Fp + p.Hp + j)) : z4;
+#pragma unroll
+    for (int k = 0; k < RB_MAX_SPLIT_X; ++k) vx[k] = (prev && k < p.splitX) ? ld4g(p.dXA + (size_t)k * B * 2 * p.Hp + tl_off(B, r, p.Hp + j)) : z4;
+  } else if (WHICH == 1) {                             // d h_enc_t: latent heads + recurrence (S6B of step t+1)
+    v0 = ld4g(p.dhe_fc + tl_off(B, r, j));
+#pragma unroll
+    for (int k = 0; k < RB_MAX_SPLIT_A; ++k) va[k] = z4;
+#pragma unroll
+    for (int k = 0; k < RB_MAX_SPLIT_B; ++k) vx[k] = (prev && k < p.splitB) ? ld4g(p.dXEB + (size_t)k * B * p.Hp + tl_off(B, r, j)) : z4;
+  } else {                                             // d h1_t: enc/dec inputs of this step + query + recurrence (S10 of t+1)
+    v0 = ld4g(p.dh1q + tl_off(B, r, j));
+#pragma unroll
+    for (int k = 0; k < RB_MAX_SPLIT_A; ++k) va[k] = (k < p.splitA) ? ld4g(p.dXEA + (size_t)k * B * p.KX + tl_off(B, r, p.Fp + j)) : z4;
+#pragma unroll
+    for (int k = 0; k < RB_MAX_SPLIT_X; ++k) vx[k] = (prev && k < p.splitX) ? ld4g(p.dXA + (size_t)k * B * 2 * p.Hp + tl_off(B, r, j)) : z4;
+  }
+  float4 dh = in.dh0;
+  add4(dh, v0);
+#pragma unroll
+  for (int k = 0; k < RB_MAX_SPLIT_A; ++k) add4(dh, va[k]);
+#pragma unroll
+  for (int k = 0; k < RB_MAX_SPLIT_X; ++k) add4(dh, vx[k]);
+  const float4 gi = in.gi, gf = in.gf, gg = in.gg, go = in.go, c = in.c, cp = in.cp, dci = in.dci;
+  float4 di, df, dg, d_o, dcp;
 #define RB_LSTM_LANE(X)                                                                  \
   {                                                                                      \
     const float tc = tanhf(c.X);                                                         \
@@ -281,14 +313,61 @@ __device__ __forceinline__ void cell_stage(const RbParams& p, int t, int s, int 
     d_o.X = dh.X * tc * go.X * (1.f - go.X);                                             \
     dcp.X = dc * gf.X;                                                                   \
   }
-    RB_LSTM_LANE(x) RB_LSTM_LANE(y) RB_LSTM_LANE(z) RB_LSTM_LANE(w)
+  RB_LSTM_LANE(x) RB_LSTM_LANE(y) RB_LSTM_LANE(z) RB_LSTM_LANE(w)
 #undef RB_LSTM_LANE
-    bf16* o = dG + (size_t)r * p.Gp + j;
-    st_bf16x4_rb(o, di.x, di.y, di.z, di.w);
-    st_bf16x4_rb(o + H, df.x, df.y, df.z, df.w);
-    st_bf16x4_rb(o + 2 * H, dg.x, dg.y, dg.z, dg.w);
-    st_bf16x4_rb(o + 3 * H, d_o.x, d_o.y, d_o.z, d_o.w);
-    *reinterpret_cast<float4*>(dcp_ptr) = dcp;
+  float* dcb = WHICH == 0 ? p.dc1 : WHICH == 1 ? p.dc_enc : p.dc_dec;
+  bf16* o = (WHICH == 0 ? p.dG_att : WHICH == 1 ? p.dG_enc : p.dG_dec) + ((size_t)t * B + r) * p.Gp + j;
+  st_bf16x4_rb(o, di.x, di.y, di.z, di.w);
+  st_bf16x4_rb(o + H, df.x, df.y, df.z, df.w);
+  st_bf16x4_rb(o + 2 * H, dg.x, dg.y, dg.z, dg.w);
+  st_bf16x4_rb(o + 3 * H, d_o.x, d_o.y, d_o.z, d_o.w);
+  *reinterpret_cast<float4*>(dcb + tl_off(B, r, j)) = dcp;
+}
+
+// Cell stage of timestep t (WHICH: 0 attention LSTM, 1 encoder, 2 decoder). A warp item covers 8 rows x 4 unit-quads and
+// the item -> warp map is the same at every step. The stage is split around the wait for the counters its slot sums
+// depend on: the saved state of the warp's first item is loaded BEFORE the wait (cell_stage_pre), so that after it only
+// one L2 round trip (the slots) separates the warp from its stores (two such items per thread spill registers).
+template <int WHICH>
+__device__ __forceinline__ void cell_stage_pre(const RbParams& p, int t, int gw, int GW, int lane, CellPre& pre) {
+  cell_preload<WHICH>(p, t, gw, lane, pre);
+}
+template <int WHICH>
+__device__ __forceinline__ void cell_stage_post(const RbParams& p, int t, int s, int gw, int GW, int lane, const CellPre& pre) {
+  const int B = p.B, H4 = p.H >> 2;
+  const int total = ((B + 7) >> 3) * ((H4 + 3) >> 2);
+  const bool prev = s > 0;                             // contributions of step t + 1 exist
+  cell_finish<WHICH>(p, t, prev, pre);
+  for (int wi = gw + GW; wi < total; wi += GW) {       // further items of this warp
+    CellPre x;
+    cell_preload<WHICH>(p, t, wi, lane, x);
+    cell_finish<WHICH>(p, t, prev, x);
+  }
+}
+
+// The saved state a cell stage reads was written milliseconds earlier (forward pass, head backward): pull the lines of
+// timestep t (the NEXT step of this loop) into L2 while the current step's GEMMs run.
+template <int WHICH>
+__device__ __forceinline__ void cell_prefetch(const RbParams& p, int t, int gw, int GW, int lane) {
+  if (t < 0) return;
+  const int B = p.B, H = p.H, H4 = H >> 2;
+  const int tr = (B + 7) >> 3, tq = (H4 + 3) >> 2;
+  const float* gates = (WHICH == 0 ? p.gates_att : WHICH == 1 ? p.gates_enc : p.gates_dec) + (size_t)t * B * 4 * H;
+  const float* cbuf = (WHICH == 0 ? p.c1 : WHICH == 1 ? p.c_enc : p.c_dec) + (size_t)t * B * H;
+  for (int wi = gw; wi < tr * tq; wi += GW) {
+    const int r = (wi % tr) * 8 + (lane & 7);
+    const int jq = (wi / tr) * 4 + (lane >> 3);
+    if (r >= B || jq >= H4) continue;
+    const int j = jq * 4;
+    const float* g = gates + (p.tiled ? lstm_tiled_gate_offset(B, r, 0, j) : (size_t)r * 4 * H + j);
+    const size_t gs = p.tiled ? (size_t)B * 4 : (size_t)H;
+    const size_t co = p.tiled ? lstm_tiled_c_offset(B, r, j) : (size_t)r * H + j;
+    // tiled: 8 consecutive rows share a 128-byte line (lanes 0..7 of a quad): one prefetch per line
+    if (!p.tiled || (lane & 7) == 0) {
+      prefetch_l2(g); prefetch_l2(g + gs); prefetch_l2(g + 2 * gs); prefetch_l2(g + 3 * gs);
+      if (t > 0) prefetch_l2(cbuf - (size_t)B * H + co);
+    }
+    if (WHICH == 2 && (lane >> 3) == 0) prefetch_l2(p.dhead + ((size_t)t * B + r) * H + j);   // 4 quads = 64 B of a row
   }
 }
 
@@ -300,24 +379,56 @@ __device__ __forceinline__ void latent_stage(const RbParams& p, int t, int gtid,
   for (int idx = gtid; idx < B * ZQ; idx += GT) {
     const int r = idx % B, zq = idx / B;
     const size_t row = (size_t)t * B + r;
-    float4 g4 = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int k = 0; k < p.splitZ; ++k) add4(g4, ld4g(p.dzp + (size_t)k * B * p.Zp + tl_off(B, r, zq * 4)));
-    const float gz[4] = {g4.x, g4.y, g4.z, g4.w};
+    // every load first (Z is even and z0 a multiple of 4: 8-byte aligned pairs)
+    float4 gs[RB_MAX_SPLIT_Z];
+#pragma unroll
+    for (int k = 0; k < RB_MAX_SPLIT_Z; ++k)
+      gs[k] = k < p.splitZ ? ld4g(p.dzp + (size_t)k * B * p.Zp + tl_off(B, r, zq * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    const int z0 = zq * 4;
+    const bool hi = z0 + 2 < Z;
+    const float2 zero2 = make_float2(0.f, 0.f);
+    const float2 mu0 = *reinterpret_cast<const float2*>(p.mean + row * Z + z0);
+    const float2 lv0 = *reinterpret_cast<const float2*>(p.logvar + row * Z + z0);
+    const float2 ep0 = *reinterpret_cast<const float2*>(p.eps + row * Z + z0);
+    const float2 mu1 = hi ? *reinterpret_cast<const float2*>(p.mean + row * Z + z0 + 2) : zero2;
+    const float2 lv1 = hi ? *reinterpret_cast<const float2*>(p.logvar + row * Z + z0 + 2) : zero2;
+    const float2 ep1 = hi ? *reinterpret_cast<const float2*>(p.eps + row * Z + z0 + 2) : zero2;
     const float w = p.gkld[r] * p.tmask[row];
     const float pm = p.pm_row ? p.pm_row[r] : 0.f;
+    float4 g4 = gs[0];
+#pragma unroll
+    for (int k = 1; k < RB_MAX_SPLIT_Z; ++k) add4(g4, gs[k]);
+    const float gz[4] = {g4.x, g4.y, g4.z, g4.w};
+    const float mu[4] = {mu0.x, mu0.y, mu1.x, mu1.y}, lv[4] = {lv0.x, lv0.y, lv1.x, lv1.y}, ep[4] = {ep0.x, ep0.y, ep1.x, ep1.y};
     bf16* out = p.dml + row * p.Z2p;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int z = zq * 4 + i;
+    for (int i = 0; i < 4; i += 2) {
+      const int z = z0 + i;
       if (z < Z) {
-        const float mu = p.mean[row * Z + z], lv = p.logvar[row * Z + z];
-        const float var = __expf(lv);
-        const float dkl_m = (p.sentiment_vae == 0) ? mu : (mu - pm) * inv_pv;
-        const float dkl_l = (p.sentiment_vae == 0) ? -0.5f * (1.f - var) : -0.5f * (1.f - var * inv_pv);
-        out[z] = __float2bfloat16_rn(gz[i] + w * dkl_m);
-        out[Z + z] = __float2bfloat16_rn(gz[i] * p.eps[row * Z + z] * 0.5f * sqrtf(var) + w * dkl_l);
+        float om[2], ol[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          const float var = __expf(lv[i + u]);
+          const float dkl_m = (p.sentiment_vae == 0) ? mu[i + u] : (mu[i + u] - pm) * inv_pv;
+          const float dkl_l = (p.sentiment_vae == 0) ? -0.5f * (1.f - var) : -0.5f * (1.f - var * inv_pv);
+          om[u] = gz[i + u] + w * dkl_m;
+          ol[u] = gz[i + u] * ep[i + u] * 0.5f * sqrtf(var) + w * dkl_l;
+        }
+        *reinterpret_cast<__nv_bfloat162*>(out + z) = __floats2bfloat162_rn(om[0], om[1]);
+        *reinterpret_cast<__nv_bfloat162*>(out + Z + z) = __floats2bfloat162_rn(ol[0], ol[1]);
       }
     }
+  }
+}
+// next step's mean / log_var / eps rows into L2
+__device__ __forceinline__ void latent_prefetch(const RbParams& p, int t, int gtid, int GT) {
+  if (t < 0) return;
+  const int B = p.B, Z = p.Z, ZQ = (Z + 3) >> 2;
+  for (int idx = gtid; idx < B * ZQ; idx += GT) {
+    const int r = idx % B, zq = idx / B;
+    if (zq & 7) continue;                              // one prefetch per 128 bytes of a row
+    const size_t o = ((size_t)t * B + r) * Z + zq * 4;
+    prefetch_l2(p.mean + o); prefetch_l2(p.logvar + o); prefetch_l2(p.eps + o);
   }
 }
 
@@ -480,7 +591,7 @@ recurrent_bwd_kernel(const __grid_constant__ RbParams p) {
             for (int kb = 0; kb < sg.kblocks; ++kb) tma_prefetch_2d(&p.wmap[sg.wmap], sg.k0 + kb * 64, job.w_row[rank]);
             wait_flag(p, sg.flag, (unsigned int)((s + 1) * sg.count), 100 + job.kind * 10 + g, s);
             fence_proxy_async_global();
-            RB_STAMP(true, 16 + j * 2 + g);
+            RB_STAMP(true, 20 + j * 2 + g);
             for (int kb = 0; kb < sg.kblocks; ++kb) {
               mbar_wait_bounded(p, &sm.empty[stage], phase ^ 1, 1, s);
               if (rank == 0) mbar_expect_tx(&sm.full[stage], tx);
@@ -525,7 +636,7 @@ recurrent_bwd_kernel(const __grid_constant__ RbParams p) {
             }
           }
           umma_commit_2sm(&sm.tfull[slot]);
-          RB_STAMP(true, 24 + j);
+          RB_STAMP(true, 28 + j);
         }
       }
     }
@@ -538,6 +649,7 @@ recurrent_bwd_kernel(const __grid_constant__ RbParams p) {
     // spread the (few) latent items over all CTAs: consecutive global thread ids alternate between CTAs
     const int gtid = ctid * G + cta, GT = G * RB_CTHREADS;
     Ring ring;
+    ring.n = p.att_stages;
     const RbJob* jk[NUM_KINDS];
     for (int k = 0; k < NUM_KINDS; ++k) jk[k] = nullptr;
     for (int j = 0; j < njobs; ++j) jk[sm.jobs[j].kind] = &sm.jobs[j];
@@ -545,82 +657,133 @@ recurrent_bwd_kernel(const __grid_constant__ RbParams p) {
     auto epilogue = [&](int kind, int s) {
       if (jk[kind]) {
         epi_store(p, sm, *jk[kind], s, tmem_base, cw, lane, rank);
-        signal_done(p, jk[kind]->sig, ctid);
+        signal_done(p, jk[kind]->sig, ctid, false);
+      }
+    };
+    auto prefetch_qs = [&](int t, int b, int slot) {
+      const size_t r = (size_t)t * B + b;
+      prefetch_vec(asm_.q(slot), p.q + r * p.A, a.A);
+      prefetch_vec(asm_.sv(slot), p.smx + r * a.N, a.N);
+    };
+    auto prefetch_dx = [&](int b, int slot) {
+      for (int k = 0; k < ndx; ++k) {
+        const float* src = p.dXEA + (size_t)k * B * p.KX;
+        float* dst = asm_.dx(slot, k);
+        for (int i = ctid; i < (a.Fp >> 2); i += RB_CTHREADS) ptx::cp_async16(dst + i * 4, src + ((size_t)i * B + b) * 4);
+      }
+    };
+    cell_prefetch<2>(p, T - 1, gw, GW, lane);
+    cell_prefetch<1>(p, T - 1, gw, GW, lane);
+    cell_prefetch<0>(p, T - 1, gw, GW, lane);
+    latent_prefetch(p, T - 1, gtid, GT);
+    // bulk L2 prefetch of the attention stream of this CTA's rows (features + projections are evict_first: they come from
+    // HBM at every step, and the 4 x 16 KB ring then runs at HBM latency)
+    auto att_prefetch = [&](int t) {
+      if (!p.att_prefetch) return;
+      const int nact = p.nrows[t];
+      for (int i = cta; i < nact; i += G) {
+        const int b = p.rows[(size_t)t * B + i];
+        const uint8_t* f = reinterpret_cast<const uint8_t*>(a.feats + (size_t)b * a.N * a.Fp);
+        const uint8_t* pj = reinterpret_cast<const uint8_t*>(a.proj + (size_t)b * a.N * a.Ap);
+        const int nf = a.N * a.Fp * 2, np = a.N * a.Ap * 2;          // multiples of 16
+        for (int o = ctid * 8192; o < nf; o += RB_CTHREADS * 8192)
+          asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(f + o), "r"(min(8192, nf - o)) : "memory");
+        for (int o = ctid * 8192; o < np; o += RB_CTHREADS * 8192)
+          asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(pj + o), "r"(min(8192, np - o)) : "memory");
       }
     };
     for (int s = 0; s < T; ++s) {
       const int t = T - 1 - s;
       RB_STAMP(ctid == 0, 0);
       // ---- decoder cell: needs S10 (and S6A) of step t + 1
+      CellPre pre;
+      cell_stage_pre<2>(p, t, gw, GW, lane, pre);
       wait_all(p, F_DXA, (unsigned int)(s * p.cnt[F_DXA]), 20, s, ctid);
       RB_STAMP(ctid == 0, 1);
-      cell_stage<2>(p, t, s, gw, GW, lane);
-      signal_done(p, F_DGDEC, ctid);
+      cell_stage_post<2>(p, t, s, gw, GW, lane, pre);
       RB_STAMP(ctid == 0, 2);
+      signal_done(p, F_DGDEC, ctid);
+      cell_prefetch<2>(p, t - 1, gw, GW, lane);
+      RB_STAMP(ctid == 0, 3);
       epilogue(K_S2, s);
+      RB_STAMP(ctid == 0, 4);
       // ---- latent heads
       wait_all(p, F_DZP, (unsigned int)((s + 1) * p.cnt[F_DZP]), 21, s, ctid);
-      RB_STAMP(ctid == 0, 3);
+      RB_STAMP(ctid == 0, 5);
       latent_stage(p, t, gtid, GT);
       signal_done(p, F_DML, ctid);
+      latent_prefetch(p, t - 1, gtid, GT);
+      RB_STAMP(ctid == 0, 6);
       epilogue(K_S4, s);
+      RB_STAMP(ctid == 0, 7);
       // ---- encoder cell: needs S4 of this step and S6B of step t + 1
+      cell_stage_pre<1>(p, t, gw, GW, lane, pre);
       wait_all(p, F_DHE, (unsigned int)((s + 1) * p.cnt[F_DHE]), 22, s, ctid);
       if (s > 0) wait_all(p, F_DXEB, (unsigned int)(s * p.cnt[F_DXEB]), 23, s, ctid);
-      RB_STAMP(ctid == 0, 4);
-      cell_stage<1>(p, t, s, gw, GW, lane);
+      RB_STAMP(ctid == 0, 8);
+      cell_stage_post<1>(p, t, s, gw, GW, lane, pre);
+      RB_STAMP(ctid == 0, 9);
       signal_done(p, F_DGENC, ctid);
-      RB_STAMP(ctid == 0, 5);
+      cell_prefetch<1>(p, t - 1, gw, GW, lane);
+      att_prefetch(t);
+      RB_STAMP(ctid == 0, 10);
       epilogue(K_S6A, s);
-      RB_STAMP(ctid == 0, 6);
-      // ---- region attention backward of this CTA's rows
+      RB_STAMP(ctid == 0, 11);
+      // ---- region attention backward of this CTA's share of the rows that still carry gradient (a row past the end of
+      //      its caption has d x_hat = 0: its d q / d u stay at the zeros they were initialised with); q and the saved
+      //      softmax of the first row do not depend on S6A
+      const int nact = p.nrows[t];
+      const int* act = p.rows + (size_t)t * B;
+      if (cta < nact) prefetch_qs(t, act[cta], 0);
       wait_all(p, F_DXEA, (unsigned int)((s + 1) * p.cnt[F_DXEA]), 24, s, ctid);
-      RB_STAMP(ctid == 0, 7);
-      if (cta < B) {
-        auto prefetch_row = [&](int b, int slot) {
-          const size_t r = (size_t)t * B + b;
-          prefetch_vec(asm_.q(slot), p.q + r * p.A, a.A);
-          prefetch_vec(asm_.sv(slot), p.smx + r * a.N, a.N);
-          for (int k = 0; k < ndx; ++k) {
-            const float* src = p.dXEA + (size_t)k * B * p.KX;
-            float* dst = asm_.dx(slot, k);
-            for (int i = ctid; i < (a.Fp >> 2); i += RB_CTHREADS) ptx::cp_async16(dst + i * 4, src + ((size_t)i * B + b) * 4);
-          }
-          ptx::cp_async_commit();
-        };
-        prefetch_row(cta, 0);
+      RB_STAMP(ctid == 0, 12);
+      if (cta < nact) {
+        prefetch_dx(act[cta], 0);
+        ptx::cp_async_commit();
         int cur = 0;
-        for (int b = cta; b < B; b += G, cur ^= 1) {
+        for (int i = cta; i < nact; i += G, cur ^= 1) {
+          const int b = act[i];
           const size_t r = (size_t)t * B + b;
-          const int bn = b + G;
+          const int bn = i + G < nact ? act[i + G] : -1;
           attn_bwd_row(a, p.plan, asm_, ring, cur, a.mask + (size_t)b * a.N,
-                       [&] { if (bn < B) prefetch_row(bn, cur ^ 1); },
-                       p.dqb + r * p.Ap, p.Ap, p.du + r * a.N);
+                       [&] { if (bn >= 0) { prefetch_qs(t, bn, cur ^ 1); prefetch_dx(bn, cur ^ 1); ptx::cp_async_commit(); } },
+                       p.dqb + r * p.Ap, p.Ap, p.du + r * a.N,
+                       [&](int k) { RB_STAMP(ctid == 0 && i == cta, k == 0 ? 19 : k == 1 ? 23 : k == 2 ? 25 : k == 3 ? 26 : 27); });
         }
       }
-      RB_STAMP(ctid == 0, 8);
+      RB_STAMP(ctid == 0, 13);
       signal_done(p, F_DQ, ctid);
       epilogue(K_S6B, s);
       epilogue(K_S8, s);
+      RB_STAMP(ctid == 0, 14);
       // ---- attention-LSTM cell: needs S8, S6A of this step, S10 of step t + 1
+      cell_stage_pre<0>(p, t, gw, GW, lane, pre);
       wait_all(p, F_DH1Q, (unsigned int)((s + 1) * p.cnt[F_DH1Q]), 25, s, ctid);
-      RB_STAMP(ctid == 0, 9);
-      cell_stage<0>(p, t, s, gw, GW, lane);
+      RB_STAMP(ctid == 0, 15);
+      cell_stage_post<0>(p, t, s, gw, GW, lane, pre);
+      RB_STAMP(ctid == 0, 16);
       signal_done(p, F_DGATT, ctid);
-      RB_STAMP(ctid == 0, 10);
+      cell_prefetch<0>(p, t - 1, gw, GW, lane);
+      RB_STAMP(ctid == 0, 17);
       epilogue(K_S10, s);
-      RB_STAMP(ctid == 0, 11);
+      RB_STAMP(ctid == 0, 18);
     }
   } else {
     // ================= attention producer: streams the region features and P of this CTA's rows =================
-    if (lane == 0 && cta < p.B) {
+    if (lane == 0) {
       Ring ring;
+      ring.n = p.att_stages;
       const uint64_t pol = a.l2_policy == 1 ? ptx::l2_policy_evict_first() : a.l2_policy == 2 ? ptx::l2_policy_evict_last() : 0;
-      for (int s = 0; s < T; ++s)
-        for (int b = cta; b < p.B; b += G) {
+      for (int s = 0; s < T; ++s) {
+        const int t = T - 1 - s;
+        const int nact = p.nrows[t];
+        const int* act = p.rows + (size_t)t * p.B;
+        for (int i = cta; i < nact; i += G) {
+          const int b = act[i];
           produce_block(asm_, ring, reinterpret_cast<const uint8_t*>(a.feats + (size_t)b * a.N * a.Fp), a.N, a.Fp * 2, p.plan.nF, p.plan.bF, pol);
           produce_block(asm_, ring, reinterpret_cast<const uint8_t*>(a.proj + (size_t)b * a.N * a.Ap), a.N, a.Ap * 2, p.plan.nP, p.plan.bP, pol);
         }
+      }
     }
     __syncwarp();
   }
@@ -629,6 +792,26 @@ recurrent_bwd_kernel(const __grid_constant__ RbParams p) {
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc_2sm<RB_TMEM_COLS>(tmem_base);
+  }
+}
+
+// rows[t*B + i] = i-th batch row (ascending) that still carries gradient at step t, nrows[t] = how many: a row is live at t
+// if any target at a step >= t is unmasked (the loss and KL of masked steps have zero weight, updown_captioner.py:295-323,
+// and nothing flows into a row from later steps once all of them are masked). One block of >= B threads.
+__global__ void rb_active_rows_kernel(const float* __restrict__ tmask, int T, int B, int* __restrict__ rows, int* __restrict__ nrows) {
+  __shared__ int wsum[32];
+  const int b = threadIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  bool live = false;
+  for (int t = T - 1; t >= 0; --t) {
+    if (b < B && tmask[(size_t)t * B + b] != 0.f) live = true;
+    const unsigned m = __ballot_sync(0xffffffffu, live);
+    if (lane == 0) wsum[warp] = __popc(m);
+    __syncthreads();
+    int base = 0, total = 0;
+    for (int w = 0; w < nw; ++w) { if (w < warp) base += wsum[w]; total += wsum[w]; }
+    if (live) rows[(size_t)t * B + base + __popc(m & ((1u << lane) - 1u))] = b;
+    if (threadIdx.x == 0) nrows[t] = total;
+    __syncthreads();
   }
 }
 
@@ -733,7 +916,7 @@ int recurrent_backward(cudaStream_t s, const RecBwdArgs& r) {
   RbParams p;
   memset(&p, 0, sizeof(p));
   AttnArgs a = r.att;
-  static const int att_pol = [] { const char* e = getenv("SSCVAE_ATT_POLICY"); return e ? atoi(e) : 1; }();
+  static const int att_pol = [] { const char* e = getenv("SSCVAE_RB_ATT_POLICY"); return e ? atoi(e) : 1; }();
   static const int w_pol = [] { const char* e = getenv("SSCVAE_RB_W_POLICY"); return e ? atoi(e) : 1; }();
   a.l2_policy = att_pol;
   REQUIRE(rb_shape_ok(r), "recurrent_bwd: unsupported shape");
@@ -766,12 +949,18 @@ int recurrent_backward(cudaStream_t s, const RecBwdArgs& r) {
   p.c1 = r.c1; p.c_enc = r.c_enc; p.c_dec = r.c_dec;
   p.mean = r.mean; p.logvar = r.logvar; p.eps = r.eps; p.pm_row = r.pm_row;
   p.q = r.q; p.smx = r.smx; p.dhead = r.dhead; p.gkld = r.gkld; p.tmask = r.tmask;
+  p.rows = r.rows; p.nrows = r.rows + (size_t)r.T * r.B;
   p.dc1 = r.dc1; p.dc_enc = r.dc_enc; p.dc_dec = r.dc_dec;
   p.dG_att = r.dG_att; p.dG_enc = r.dG_enc; p.dG_dec = r.dG_dec; p.dml = r.dml; p.dqb = r.dqb; p.du = r.du;
   p.dXEA = r.dXEA; p.dXEB = r.dXEB; p.dXA = r.dXA; p.dzp = r.dzp; p.dhe_fc = r.dhe_fc; p.dh1q = r.dh1q;
   p.att = a;
   p.flags = r.flags;
   p.w_policy = w_pol;
+  static const int sig_mode = [] { const char* e = getenv("SSCVAE_RB_SIG_MODE"); return e ? atoi(e) : 1; }();
+  static const int att_pf = [] { const char* e = getenv("SSCVAE_RB_ATT_PREFETCH"); return e ? atoi(e) : 0; }();
+  p.sig_mode = sig_mode; p.att_prefetch = att_pf;
+  static const int att_stages = [] { const char* e = getenv("SSCVAE_RB_ATT_STAGES"); return e ? std::min(ATT_STAGES, std::max(2, atoi(e))) : ATT_STAGES; }();
+  p.att_stages = att_stages;
   static const int n_stages = [] { const char* e = getenv("SSCVAE_RB_STAGES"); return e ? std::min(RB_STAGES, std::max(2, atoi(e))) : RB_STAGES; }();
   p.stages = n_stages;
   static const unsigned long long timeout_ms = [] { const char* e = getenv("SSCVAE_RF_TIMEOUT_MS"); return e ? (unsigned long long)atoll(e) : 4000ull; }();
@@ -799,6 +988,9 @@ int recurrent_backward(cudaStream_t s, const RecBwdArgs& r) {
     p.dbg_s = r.T / 2;
   }
   CUDA_TRY(cudaMemsetAsync(r.flags, 0, 64 * sizeof(unsigned int), s));
+  rb_active_rows_kernel<<<1, round_up(r.B, 32), 0, s>>>(r.tmask, r.T, r.B, r.rows, r.rows + (size_t)r.T * r.B);
+  CUDA_TRY(cudaGetLastError());
+  ++g_launch_count;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(2 * NP); cfg.blockDim = dim3(RB_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = s;
   cudaLaunchAttribute attr[1];
@@ -819,7 +1011,7 @@ int recurrent_backward(cudaStream_t s, const RecBwdArgs& r) {
       for (int c : show) {
         if (c < 0 || c >= 2 * NP) continue;
         fprintf(stderr, "[rbdbg] B=%d s=%d cta=%3d:", r.B, p.dbg_s, c);
-        for (int i = 0; i < 28; ++i) fprintf(stderr, " %d:%.1f", i, h[c * 32 + i] ? (double)(h[c * 32 + i] - t0) / 1e3 : -1.0);
+        for (int i = 0; i < 32; ++i) fprintf(stderr, " %d:%.1f", i, h[c * 32 + i] ? (double)(h[c * 32 + i] - t0) / 1e3 : -1.0);
         fprintf(stderr, "\n");
       }
     }
