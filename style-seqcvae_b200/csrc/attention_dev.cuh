@@ -30,7 +30,11 @@ constexpr int ATT_THREADS = ATT_CONSUMERS + 32;    // + 1 producer warp
 #define ATT_STAGES_N 4
 #endif
 constexpr int ATT_STAGES = ATT_STAGES_N;           // ring depth (per translation unit, like ATT_TID0)
-constexpr int ATT_STAGE_BYTES = 16384;             // two CTAs per SM: their phases overlap
+#ifndef ATT_STAGE_BYTES_N
+#define ATT_STAGE_BYTES_N 16384                    // stand-alone kernels: two CTAs per SM, their phases overlap
+#endif
+constexpr int ATT_STAGE_BYTES = ATT_STAGE_BYTES_N; // per translation unit: the persistent kernels use 2 x 32 KB (8 feature rows per
+                                                   // chunk = one box per consumer warp: half the per-chunk handshakes)
 constexpr int ATT_MAXB = 8;                        // boxes per chunk (<= consumer warps: one box per warp and chunk)
 constexpr int ATT_NREG = 4;                        // boxes per lane in the softmax: N <= 128
 constexpr int ATT_FV = 2;                          // 16-byte feature vectors per thread: Fp <= 4096
@@ -50,15 +54,20 @@ struct AttnSmem {
   float* q0;             // 2 x Ap (double buffer, prefetched one row ahead)
   float* u;              // ATT_CWARPS x N4 partial scores (d alpha in backward): [sub-warp][box]
   float* alw;            // ATT_CWARPS x N4: every consumer warp's own copy of alpha (broadcast reads in the weighted sum)
+  float* msk0;           // 2 x N4: the box mask of the row (a global-memory read per chunk put an L2 round trip, ~0.7 us,
+                         // in front of every chunk of the score / d alpha loops)
   float* dx0;            // 2 x ndx x Fp (backward only; ndx = split-K slots of d xhat, summed in place before use)
   float* sv0;            // 2 x N4 (backward only: saved softmax)
-  int Ap, Fp, N4, ndx;
+  int Ap, Fp, N4, ndx, dxb;
   __device__ __forceinline__ float* q(int slot) const { return q0 + slot * Ap; }
-  __device__ __forceinline__ float* dx(int slot, int k = 0) const { return dx0 + (slot * ndx + k) * Fp; }
+  __device__ __forceinline__ float* msk(int slot) const { return msk0 + slot * N4; }
+  __device__ __forceinline__ float* dx(int slot, int k = 0) const { return dx0 + ((dxb == 1 ? 0 : slot) * ndx + k) * Fp; }
   __device__ __forceinline__ float* sv(int slot) const { return sv0 + slot * N4; }
 };
 
-__device__ __forceinline__ AttnSmem carve(uint8_t* raw, const AttnArgs& a, bool bwd, int ndx = 1) {
+// ndx: split-K slots of d xhat; dxb: d xhat buffers (2: the next row is prefetched while this one runs, 1: the caller
+// prefetches the next row's d xhat only after the d alpha phase of the current one)
+__device__ __forceinline__ AttnSmem carve(uint8_t* raw, const AttnArgs& a, bool bwd, int ndx = 1, int dxb = 2) {
   AttnSmem s;
   // no integer round trip on the pointer: it would lose the shared address space and turn every access below into a
   // generic LD/ST with 64-bit address arithmetic (a third of the instructions of the first version of these kernels)
@@ -67,22 +76,23 @@ __device__ __forceinline__ AttnSmem carve(uint8_t* raw, const AttnArgs& a, bool 
   s.full = reinterpret_cast<uint64_t*>(p); p += ATT_STAGES * 8;
   s.empty = reinterpret_cast<uint64_t*>(p); p += ATT_STAGES * 8;
   float* f = reinterpret_cast<float*>(p);
-  s.Ap = a.Ap; s.Fp = a.Fp; s.N4 = (a.N + 3) & ~3; s.ndx = ndx;
+  s.Ap = a.Ap; s.Fp = a.Fp; s.N4 = (a.N + 3) & ~3; s.ndx = ndx; s.dxb = dxb;
   s.wa = f; f += a.Ap;
   s.q0 = f; f += 2 * a.Ap;
   s.u = f; f += ATT_CWARPS * s.N4;
   s.alw = f; f += ATT_CWARPS * s.N4;
+  s.msk0 = f; f += 2 * s.N4;
   s.dx0 = s.sv0 = nullptr;
   if (bwd) {
-    s.dx0 = f; f += 2 * ndx * a.Fp;
+    s.dx0 = f; f += dxb * ndx * a.Fp;
     s.sv0 = f; f += 2 * s.N4;
   }
   return s;
 }
-__host__ __device__ inline size_t attn_smem_bytes(const AttnArgs& a, bool bwd, int ndx = 1) {
+__host__ __device__ inline size_t attn_smem_bytes(const AttnArgs& a, bool bwd, int ndx = 1, int dxb = 2) {
   size_t n = 128 + (size_t)ATT_STAGES * ATT_STAGE_BYTES + 2 * ATT_STAGES * 8;
-  n += (size_t)(3 * a.Ap + 2 * ATT_CWARPS * ((a.N + 3) & ~3)) * 4;
-  if (bwd) n += (size_t)(2 * ndx * a.Fp + 2 * ((a.N + 3) & ~3)) * 4;
+  n += (size_t)(3 * a.Ap + (2 * ATT_CWARPS + 2) * ((a.N + 3) & ~3)) * 4;
+  if (bwd) n += (size_t)(dxb * ndx * a.Fp + 2 * ((a.N + 3) & ~3)) * 4;
   return n;
 }
 
@@ -129,9 +139,12 @@ __device__ __forceinline__ float pick(const float (&v)[K], int k) {
 // A chunk holds nb <= ATT_MAXB boxes; 8/pow2ceil(nb) warps share one box (each a slice of the vectors), so all
 // consumer warps stay busy whatever the chunk size. Partial sums land in part[sub][n] and are added by the readers.
 __device__ __forceinline__ int warps_per_box(int nb) { return nb > 4 ? 1 : nb > 2 ? 2 : nb > 1 ? 4 : 8; }
-__device__ __forceinline__ float gather_partial(const float* part, int N4, int N, int bper, int n) {
+__device__ __forceinline__ int wpb_log2(int wpb) { return wpb == 1 ? 0 : wpb == 2 ? 1 : wpb == 4 ? 2 : 3; }
+// pair: full chunks (ATT_CWARPS boxes) were reduced in "pair mode" (attn_bwd_row): two partials per box
+__device__ __forceinline__ float gather_partial(const float* part, int N4, int N, int bper, int n, bool pair = false) {
   const int n0 = (n / bper) * bper;
-  const int wpb = warps_per_box(min(bper, N - n0));
+  const int nbk = min(bper, N - n0);
+  const int wpb = (pair && nbk == ATT_CWARPS) ? 2 : warps_per_box(nbk);
   float s = 0.f;
   for (int k = 0; k < wpb; ++k) s += part[k * N4 + n];
   return s;
@@ -143,7 +156,7 @@ __device__ __forceinline__ void chunk_scores(const AttnArgs& a, const bf16* buf,
   const int warp = attn_tid() >> 5, lane = threadIdx.x & 31;
   const int nvec = a.Ap >> 3;
   const int wpb = warps_per_box(nb);
-  const int j = warp / wpb, sub = warp % wpb;
+  const int j = warp >> wpb_log2(wpb), sub = warp & (wpb - 1);
   if (j >= nb) return;
   const int n = n0 + j;
   float s = 0.f;
@@ -216,7 +229,7 @@ __device__ __forceinline__ void attn_prologue(const AttnSmem& sm, const AttnArgs
     sm.q0[a.Ap + i] = 0.f;
   }
   if (bwd)
-    for (int i = threadIdx.x; i < 2 * sm.ndx * a.Fp; i += blockDim.x) sm.dx0[i] = 0.f;
+    for (int i = threadIdx.x; i < sm.dxb * sm.ndx * a.Fp; i += blockDim.x) sm.dx0[i] = 0.f;
   __syncthreads();
 }
 
@@ -224,14 +237,17 @@ __device__ __forceinline__ void attn_prologue(const AttnSmem& sm, const AttnArgs
 // One row of the forward pass, executed by the ATT_CONSUMERS consumer threads (named barrier 1). The caller has issued
 // (and committed) the cp.async prefetch of this row's q into sm.q(cur); `q_next` (or null) is prefetched into the other
 // buffer while this row is processed. The producer warp streams, per row, the P chunks then the feature chunks.
+// `mask_g`: the row's box mask in global memory, copied to sm.msk(cur) here; null = the caller already placed it there.
 __device__ __forceinline__ void attn_fwd_row(const AttnArgs& a, const AttnPlan& pl, const AttnSmem& sm, Ring& ring, int cur,
-                                             const float* mask_img, const float* q_next, float* __restrict__ alpha_row,
+                                             const float* mask_g, const float* q_next, float* __restrict__ alpha_row,
                                              float* __restrict__ smx_row, bf16* __restrict__ xhat_row) {
   const int tid = attn_tid();
   const int warp = tid >> 5, lane = tid & 31;
   const int nfv = a.Fp >> 3;
+  const float* mask_img = sm.msk(cur);
+  if (mask_g && tid < a.N) sm.msk(cur)[tid] = mask_g[tid];      // buffer `cur` was last read two rows ago
   ptx::cp_async_wait_all();
-  ptx::bar_sync(1, ATT_CONSUMERS);                 // q[cur] landed; everybody is done with the previous row
+  ptx::bar_sync(1, ATT_CONSUMERS);                 // q[cur] (and the mask) landed; everybody is done with the previous row
   if (q_next) {
     prefetch_vec(sm.q(cur ^ 1), q_next, a.A);
     ptx::cp_async_commit();
@@ -328,16 +344,23 @@ __device__ __forceinline__ void attn_fwd_row(const AttnArgs& a, const AttnPlan& 
 // One row of the per-step backward (d u saved for the deferred part, d q as the bf16 operand of the query-projection
 // GEMM), executed by the ATT_CONSUMERS consumer threads of the persistent BPTT kernel (recurrent_bwd.cu). Same math as
 // attention.cu: attention_bwd_kernel. The caller has issued (and committed) the cp.async prefetch of this row's q,
-// saved softmax and d xhat (sm.ndx split-K slots) into buffer `cur`; `prefetch_next()` issues the next row's.
+// saved softmax and d xhat (sm.ndx split-K slots, each in the two-plane layout: quad q of the row at float offset
+// (q & 1) * Fp/2 + (q >> 1) * 4) into buffer `cur`; `prefetch_next()` issues the next row's.
 // The producer warp streams, per row, the feature chunks then the P chunks.
 struct NoStamp { __device__ __forceinline__ void operator()(int) const {} };
-template <typename PrefetchNext, typename Stamp = NoStamp>
+// `after_dalpha()` runs once the d xhat buffer of this row is no longer needed (single-buffered d xhat: the caller issues the
+// next row's d xhat prefetch there).
+struct NoCall { __device__ __forceinline__ void operator()() const {} };
+template <typename PrefetchNext, typename AfterDalpha = NoCall, typename Stamp = NoStamp>
 __device__ __forceinline__ void attn_bwd_row(const AttnArgs& a, const AttnPlan& pl, const AttnSmem& sm, Ring& ring, int cur,
-                                             const float* mask_img, PrefetchNext prefetch_next, bf16* __restrict__ dq_row,
-                                             int ld_dq, float* __restrict__ du_row, Stamp stamp = Stamp()) {
+                                             const float* mask_g, PrefetchNext prefetch_next, bf16* __restrict__ dq_row,
+                                             int ld_dq, float* __restrict__ du_row, AfterDalpha after_dalpha = AfterDalpha(),
+                                             Stamp stamp = Stamp(), int probe = 0) {
   const int tid = attn_tid();
   const int warp = tid >> 5, lane = tid & 31;
   const int nfv = a.Fp >> 3, npair = a.Ap >> 1;
+  const float* mask_img = sm.msk(cur);               // mask_g: as for attn_fwd_row
+  if (mask_g && tid < a.N) sm.msk(cur)[tid] = mask_g[tid];
   ptx::cp_async_wait_all();
   ptx::bar_sync(1, ATT_CONSUMERS);
   stamp(0);
@@ -356,41 +379,87 @@ __device__ __forceinline__ void attn_bwd_row(const AttnArgs& a, const AttnPlan& 
     ptx::bar_sync(1, ATT_CONSUMERS);
   }
   stamp(1);
-  // d alpha_n = d xhat . x_n : warp per box. Independent accumulators and an unrolled vector loop: the loop is a chain of
-  // shared-memory round trips otherwise (a warp has no other work to hide them behind).
+  // d alpha_n = d xhat . x_n. d xhat sits in shared memory as two planes (floats 0-3 / 4-7 of every group of 8: both
+  // 16-byte reads of a lane are then conflict-free). A full chunk (8 boxes) runs in pair mode: a warp owns one half of
+  // the vectors of TWO boxes, so that every d xhat vector it reads serves two boxes (the per-box form re-reads the
+  // 8 KB of d xhat for each of the 36 boxes: 2/3 of the phase's shared-memory traffic); partials are added by the readers.
+  const float4* dx_lo = reinterpret_cast<const float4*>(dx_s);
+  const float4* dx_hi = reinterpret_cast<const float4*>(dx_s + (a.Fp >> 1));
   for (int c = 0; c < pl.nF; ++c) {
     const int n0 = c * pl.bF, nb = min(pl.bF, a.N - n0);
     ptx::mbar_wait(&sm.full[ring.stage], ring.phase);
     const bf16x8* buf = reinterpret_cast<const bf16x8*>(sm.stage + (size_t)ring.stage * ATT_STAGE_BYTES);
-    const int wpb = warps_per_box(nb);
-    const int j = warp / wpb, sub = warp % wpb;
-    if (j < nb) {
-      const int n = n0 + j;
-      float s = 0.f;
-      if (mask_img[n] != 0.f) {
-        const bf16x8* p = buf + (size_t)j * nfv;
-        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-#pragma unroll 4
-        for (int i = sub * 32 + lane; i < nfv; i += 32 * wpb) {
-          const bf16x8 v = p[i];
-          const float4 da = *reinterpret_cast<const float4*>(dx_s + i * 8);
-          const float4 db = *reinterpret_cast<const float4*>(dx_s + i * 8 + 4);
-          const float2 f0 = __bfloat1622float2(v.v[0]), f1 = __bfloat1622float2(v.v[1]);
-          const float2 f2 = __bfloat1622float2(v.v[2]), f3 = __bfloat1622float2(v.v[3]);
-          s0 = fmaf(da.x, f0.x, fmaf(da.y, f0.y, s0));
-          s1 = fmaf(da.z, f1.x, fmaf(da.w, f1.y, s1));
-          s2 = fmaf(db.x, f2.x, fmaf(db.y, f2.y, s2));
-          s3 = fmaf(db.z, f3.x, fmaf(db.w, f3.y, s3));
+    if (probe == 1) {
+      // timing experiments only: consume the chunk without computing
+    } else if (nb == ATT_CWARPS) {
+      const int pr = warp >> 1, half = warp & 1, hv = nfv >> 1;
+      const int na = n0 + 2 * pr;
+      const bool ma = mask_img[na] != 0.f, mb = mask_img[na + 1] != 0.f;
+      float sa = 0.f, sb = 0.f;
+      if (ma || mb) {
+        const bf16x8* pa = buf + (size_t)(2 * pr) * nfv;
+        const bf16x8* pb = pa + nfv;
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f, b0 = 0.f, b1 = 0.f, b2 = 0.f, b3 = 0.f;
+#pragma unroll 2
+        for (int i = half * hv + lane; i < (half + 1) * hv; i += 32) {
+          const float4 da = dx_lo[i], db = dx_hi[i];
+          const bf16x8 va = pa[i], vb = pb[i];
+          float2 f0 = __bfloat1622float2(va.v[0]), f1 = __bfloat1622float2(va.v[1]);
+          float2 f2 = __bfloat1622float2(va.v[2]), f3 = __bfloat1622float2(va.v[3]);
+          a0 = fmaf(da.x, f0.x, fmaf(da.y, f0.y, a0));
+          a1 = fmaf(da.z, f1.x, fmaf(da.w, f1.y, a1));
+          a2 = fmaf(db.x, f2.x, fmaf(db.y, f2.y, a2));
+          a3 = fmaf(db.z, f3.x, fmaf(db.w, f3.y, a3));
+          f0 = __bfloat1622float2(vb.v[0]); f1 = __bfloat1622float2(vb.v[1]);
+          f2 = __bfloat1622float2(vb.v[2]); f3 = __bfloat1622float2(vb.v[3]);
+          b0 = fmaf(da.x, f0.x, fmaf(da.y, f0.y, b0));
+          b1 = fmaf(da.z, f1.x, fmaf(da.w, f1.y, b1));
+          b2 = fmaf(db.x, f2.x, fmaf(db.y, f2.y, b2));
+          b3 = fmaf(db.z, f3.x, fmaf(db.w, f3.y, b3));
         }
-        s = warp_sum((s0 + s1) + (s2 + s3));
+        sa = (a0 + a1) + (a2 + a3);
+        sb = (b0 + b1) + (b2 + b3);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {             // two interleaved butterfly sums
+          sa += __shfl_xor_sync(0xffffffffu, sa, o);
+          sb += __shfl_xor_sync(0xffffffffu, sb, o);
+        }
       }
-      if (lane == 0) sm.u[sub * sm.N4 + n] = s;
+      if (lane == 0) {
+        sm.u[half * sm.N4 + na] = ma ? sa : 0.f;
+        sm.u[half * sm.N4 + na + 1] = mb ? sb : 0.f;
+      }
+    } else {
+      const int wpb = warps_per_box(nb);
+      const int j = warp >> wpb_log2(wpb), sub = warp & (wpb - 1);
+      if (j < nb) {
+        const int n = n0 + j;
+        float s = 0.f;
+        if (mask_img[n] != 0.f) {
+          const bf16x8* p = buf + (size_t)j * nfv;
+          float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll 2
+          for (int i = sub * 32 + lane; i < nfv; i += 32 * wpb) {
+            const bf16x8 v = p[i];
+            const float4 da = dx_lo[i], db = dx_hi[i];
+            const float2 f0 = __bfloat1622float2(v.v[0]), f1 = __bfloat1622float2(v.v[1]);
+            const float2 f2 = __bfloat1622float2(v.v[2]), f3 = __bfloat1622float2(v.v[3]);
+            s0 = fmaf(da.x, f0.x, fmaf(da.y, f0.y, s0));
+            s1 = fmaf(da.z, f1.x, fmaf(da.w, f1.y, s1));
+            s2 = fmaf(db.x, f2.x, fmaf(db.y, f2.y, s2));
+            s3 = fmaf(db.z, f3.x, fmaf(db.w, f3.y, s3));
+          }
+          s = warp_sum((s0 + s1) + (s2 + s3));
+        }
+        if (lane == 0) sm.u[sub * sm.N4 + n] = s;
+      }
     }
     __syncwarp();
     if (lane == 0) ptx::mbar_arrive(&sm.empty[ring.stage]);
     ring.advance();
   }
   ptx::bar_sync(1, ATT_CONSUMERS);
+  after_dalpha();
   stamp(2);
   // softmax backward, redundantly per warp (see attention_bwd_kernel)
   float duv[ATT_NREG];
@@ -403,7 +472,7 @@ __device__ __forceinline__ void attn_bwd_row(const AttnArgs& a, const AttnPlan& 
       const bool ok = n < a.N;
       m[k] = ok ? mask_img[n] : 0.f;
       sv[k] = ok ? sm.sv(cur)[n] : 0.f;
-      da[k] = ok ? gather_partial(sm.u, sm.N4, a.N, pl.bF, n) : 0.f;
+      da[k] = ok ? gather_partial(sm.u, sm.N4, a.N, pl.bF, n, true) : 0.f;
       sr += sv[k] * m[k];
     }
     const float Rn = warp_sum(sr) + 1e-13f;

@@ -14,7 +14,7 @@
 //   "big" pairs:   S6A  d[x_hat|h1|h_dec_{t-1}] = dG_dec W_dec_x + dG_enc W_enc_x   (N = 128 tiles x splitA; the decoder half is
 //                       accumulated while the latent chain of the step is still running)
 //                  S6B  d h_enc_{t-1} = dG_enc W_enc_hh                               (N = 64 x splitB; not needed before step t-1,
-//                       runs under the attention of step t)
+//                       runs behind the attention of step t, under the query GEMM and the attention-LSTM cell)
 //                  S10  d[h1_{t-1}|h_dec_{t-1}] = dG_att W_att_rec                    (N = 128 x splitX)
 //   "small" pairs: S2   d z = dG_dec W_dec_z                                          (N = 96 x splitZ)
 //                  S4   d h_enc (latent heads) = d[mean|log_var] W_fc                 (N = N4 tiles, K = 2Z)
@@ -22,7 +22,8 @@
 // The pointwise stages (the three LSTM cell backwards, the latent backward) and the attention rows are spread over the
 // compute warps of ALL CTAs. Saved forward state is read in the row-tiled layout the persistent forward kernel wrote.
 #define ATT_TID0 64
-#define ATT_STAGES_N 3
+#define ATT_STAGES_N 2
+#define ATT_STAGE_BYTES_N 32768
 #include "kernels.cuh"
 #include "gemm.cuh"
 #include "prof.cuh"
@@ -106,6 +107,7 @@ struct RbParams {
   int w_policy;
   int sig_mode;
   int att_stages;                  // attention ring stages in use (<= ATT_STAGES)
+  int probe;                       // timing experiments only (SSCVAE_RB_PROBE): 1 = attention consumes the feature chunks without computing, 2 = tiny copies
   int att_prefetch;                // 1: bulk L2 prefetch of this CTA's attention rows ahead of the attention stage
   int stages;
   unsigned long long timeout_ns;
@@ -497,7 +499,9 @@ __device__ void build_jobs(const RbParams& p, int pair, RbJob* jobs, int* njobs)
       RbJob& j = jobs[n++];
       set_tile(j, K_S6B, tile * 64, 64, p.dXEB + (size_t)pt * B * p.Hp, tile * 64, p.Hp, F_DXEB);
       j.nseg = 1;
-      j.seg[0] = make_seg(AM_DGENC, WM_ENCH, k0, k1 - k0, F_DGENC, p.cnt[F_DGENC]);
+      // gated on the END of the step's attention (not on dG_enc): its operand stream would otherwise share the SM's ingest
+      // with the attention's feature stream (measured: first attention row 17 us with S6B underneath, 12 us without)
+      j.seg[0] = make_seg(AM_DGENC, WM_ENCH, k0, k1 - k0, F_DQ, p.cnt[F_DQ]);
     }
     if (i < p.nX * p.splitX) {
       const int tile = i / p.splitX, pt = i % p.splitX;
@@ -543,8 +547,8 @@ recurrent_bwd_kernel(const __grid_constant__ RbParams p) {
   uint8_t* att_raw = smem + RB_STAGES * RB_STAGE_BYTES;
   const AttnArgs a = p.att;
   const int ndx = p.splitA;
-  const AttnSmem asm_ = carve(att_raw, a, true, ndx);
-  uint8_t* tail = att_raw + ((attn_smem_bytes(a, true, ndx) + 127) & ~size_t(127));
+  const AttnSmem asm_ = carve(att_raw, a, true, ndx, 1);
+  uint8_t* tail = att_raw + ((attn_smem_bytes(a, true, ndx, 1) + 127) & ~size_t(127));
   sm.full = reinterpret_cast<uint64_t*>(tail);
   sm.empty = sm.full + RB_STAGES;
   sm.tfull = sm.empty + RB_STAGES;
@@ -664,12 +668,15 @@ recurrent_bwd_kernel(const __grid_constant__ RbParams p) {
       const size_t r = (size_t)t * B + b;
       prefetch_vec(asm_.q(slot), p.q + r * p.A, a.A);
       prefetch_vec(asm_.sv(slot), p.smx + r * a.N, a.N);
+      prefetch_vec(asm_.msk(slot), a.mask + (size_t)b * a.N, a.N);
     };
     auto prefetch_dx = [&](int b, int slot) {
       for (int k = 0; k < ndx; ++k) {
         const float* src = p.dXEA + (size_t)k * B * p.KX;
         float* dst = asm_.dx(slot, k);
-        for (int i = ctid; i < (a.Fp >> 2); i += RB_CTHREADS) ptx::cp_async16(dst + i * 4, src + ((size_t)i * B + b) * 4);
+        // quad i of the row -> two-plane layout of attn_bwd_row
+        for (int i = ctid; i < (a.Fp >> 2); i += RB_CTHREADS)
+          ptx::cp_async16(dst + (i & 1) * (a.Fp >> 1) + (i >> 1) * 4, src + ((size_t)i * B + b) * 4);
       }
     };
     cell_prefetch<2>(p, T - 1, gw, GW, lane);
@@ -745,15 +752,15 @@ recurrent_bwd_kernel(const __grid_constant__ RbParams p) {
           const int b = act[i];
           const size_t r = (size_t)t * B + b;
           const int bn = i + G < nact ? act[i + G] : -1;
-          attn_bwd_row(a, p.plan, asm_, ring, cur, a.mask + (size_t)b * a.N,
-                       [&] { if (bn >= 0) { prefetch_qs(t, bn, cur ^ 1); prefetch_dx(bn, cur ^ 1); ptx::cp_async_commit(); } },
+          attn_bwd_row(a, p.plan, asm_, ring, cur, nullptr,
+                       [&] { if (bn >= 0) { prefetch_qs(t, bn, cur ^ 1); ptx::cp_async_commit(); } },
                        p.dqb + r * p.Ap, p.Ap, p.du + r * a.N,
-                       [&](int k) { RB_STAMP(ctid == 0 && i == cta, k == 0 ? 19 : k == 1 ? 23 : k == 2 ? 25 : k == 3 ? 26 : 27); });
+                       [&] { if (bn >= 0) { prefetch_dx(bn, cur ^ 1); ptx::cp_async_commit(); } },   // single d xhat buffer
+                       [&](int k) { RB_STAMP(ctid == 0 && i == cta, k == 0 ? 19 : k == 1 ? 23 : k == 2 ? 25 : k == 3 ? 26 : 27); }, p.probe);
         }
       }
       RB_STAMP(ctid == 0, 13);
       signal_done(p, F_DQ, ctid);
-      epilogue(K_S6B, s);
       epilogue(K_S8, s);
       RB_STAMP(ctid == 0, 14);
       // ---- attention-LSTM cell: needs S8, S6A of this step, S10 of step t + 1
@@ -765,6 +772,7 @@ recurrent_bwd_kernel(const __grid_constant__ RbParams p) {
       signal_done(p, F_DGATT, ctid);
       cell_prefetch<0>(p, t - 1, gw, GW, lane);
       RB_STAMP(ctid == 0, 17);
+      epilogue(K_S6B, s);
       epilogue(K_S10, s);
       RB_STAMP(ctid == 0, 18);
     }
@@ -780,7 +788,11 @@ recurrent_bwd_kernel(const __grid_constant__ RbParams p) {
         const int* act = p.rows + (size_t)t * p.B;
         for (int i = cta; i < nact; i += G) {
           const int b = act[i];
-          produce_block(asm_, ring, reinterpret_cast<const uint8_t*>(a.feats + (size_t)b * a.N * a.Fp), a.N, a.Fp * 2, p.plan.nF, p.plan.bF, pol);
+          if (p.probe == 2) {                              // same number of chunks, 16 x fewer bytes (what the consumers read is stale)
+            produce_block(asm_, ring, reinterpret_cast<const uint8_t*>(a.feats + (size_t)b * a.N * a.Fp), a.N, a.Fp * 2 / 16, p.plan.nF, p.plan.bF, pol);
+          } else {
+            produce_block(asm_, ring, reinterpret_cast<const uint8_t*>(a.feats + (size_t)b * a.N * a.Fp), a.N, a.Fp * 2, p.plan.nF, p.plan.bF, pol);
+          }
           produce_block(asm_, ring, reinterpret_cast<const uint8_t*>(a.proj + (size_t)b * a.N * a.Ap), a.N, a.Ap * 2, p.plan.nP, p.plan.bP, pol);
         }
       }
@@ -850,7 +862,7 @@ static int rb_encode_w2d(CUtensorMap* out, const bf16* base, int K, int rows, in
 }
 
 static size_t rb_smem_bytes(const AttnArgs& a, int ndx) {
-  return 1024 + (size_t)RB_STAGES * RB_STAGE_BYTES + ((attn_smem_bytes(a, true, ndx) + 127) & ~size_t(127)) +
+  return 1024 + (size_t)RB_STAGES * RB_STAGE_BYTES + ((attn_smem_bytes(a, true, ndx, 1) + 127) & ~size_t(127)) +
          (2 * RB_STAGES + RB_SLOTS) * 8 + 16 + RB_MAX_JOBS * sizeof(RbJob) + 64;
 }
 
@@ -959,6 +971,8 @@ int recurrent_backward(cudaStream_t s, const RecBwdArgs& r) {
   static const int sig_mode = [] { const char* e = getenv("SSCVAE_RB_SIG_MODE"); return e ? atoi(e) : 1; }();
   static const int att_pf = [] { const char* e = getenv("SSCVAE_RB_ATT_PREFETCH"); return e ? atoi(e) : 0; }();
   p.sig_mode = sig_mode; p.att_prefetch = att_pf;
+  static const int probe = [] { const char* e = getenv("SSCVAE_RB_PROBE"); return e ? atoi(e) : 0; }();
+  p.probe = probe;
   static const int att_stages = [] { const char* e = getenv("SSCVAE_RB_ATT_STAGES"); return e ? std::min(ATT_STAGES, std::max(2, atoi(e))) : ATT_STAGES; }();
   p.att_stages = att_stages;
   static const int n_stages = [] { const char* e = getenv("SSCVAE_RB_STAGES"); return e ? std::min(RB_STAGES, std::max(2, atoi(e))) : RB_STAGES; }();

@@ -28,6 +28,8 @@
 // (q / fc tiles never share a pair with LSTM tiles); the launch is cooperative (all CTAs co-resident). Every wait
 // is bounded: on a timeout the kernel raises the abort flag, prints the wait that failed and traps.
 #define ATT_TID0 64
+#define ATT_STAGES_N 2
+#define ATT_STAGE_BYTES_N 32768
 #include "kernels.cuh"
 #include "gemm.cuh"
 #include "prof.cuh"
@@ -703,6 +705,16 @@ recurrent_fwd_kernel(const __grid_constant__ RfParams p) {
       init_lstm_const<2>(p, tile, tmem_base, cw, lane, rank);
     }
     tc_fence_before();
+    // the rows of this CTA are the same at every step (b = cta, cta + G): with at most two of them their box masks stay
+    // in the two mask buffers of the attention for the whole kernel
+    const bool mask_resident = cta + 2 * G >= p.B;
+    if (mask_resident) {
+      for (int k = 0; k < 2; ++k) {
+        const int b = cta + k * G;
+        if (b < p.B && ctid < a.N) asm_.msk(k)[ctid] = a.mask[(size_t)b * a.N + ctid];
+      }
+      ptx::bar_sync(1, RF_CTHREADS);
+    }
     for (int t = 0; t < T; ++t) {
       RF_STAMP(ctid == 0, 0);
       if (role == ROLE_ENC) {
@@ -725,7 +737,7 @@ recurrent_fwd_kernel(const __grid_constant__ RfParams p) {
         int cur = 0;
         for (int b = cta; b < p.B; b += G, cur ^= 1) {
           const size_t r = (size_t)t * p.B + b;
-          attn_fwd_row(a, p.plan, asm_, ring, cur, a.mask + (size_t)b * a.N, b + G < p.B ? q_t + (size_t)(b + G) * p.A : nullptr,
+          attn_fwd_row(a, p.plan, asm_, ring, cur, mask_resident ? nullptr : a.mask + (size_t)b * a.N, b + G < p.B ? q_t + (size_t)(b + G) * p.A : nullptr,
                        p.alpha + r * a.N, p.smx + r * a.N, p.XE + r * p.KX);
         }
         RF_STAMP(ctid == 0, 4);
