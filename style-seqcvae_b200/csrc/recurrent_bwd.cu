@@ -809,22 +809,21 @@ recurrent_bwd_kernel(const __grid_constant__ RbParams p) {
 
 // rows[t*B + i] = i-th batch row (ascending) that still carries gradient at step t, nrows[t] = how many: a row is live at t
 // if any target at a step >= t is unmasked (the loss and KL of masked steps have zero weight, updown_captioner.py:295-323,
-// and nothing flows into a row from later steps once all of them are masked). One block of >= B threads.
+// and nothing flows into a row from later steps once all of them are masked). One block of >= B threads per timestep.
 __global__ void rb_active_rows_kernel(const float* __restrict__ tmask, int T, int B, int* __restrict__ rows, int* __restrict__ nrows) {
   __shared__ int wsum[32];
+  const int t = blockIdx.x;
   const int b = threadIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
   bool live = false;
-  for (int t = T - 1; t >= 0; --t) {
-    if (b < B && tmask[(size_t)t * B + b] != 0.f) live = true;
-    const unsigned m = __ballot_sync(0xffffffffu, live);
-    if (lane == 0) wsum[warp] = __popc(m);
-    __syncthreads();
-    int base = 0, total = 0;
-    for (int w = 0; w < nw; ++w) { if (w < warp) base += wsum[w]; total += wsum[w]; }
-    if (live) rows[(size_t)t * B + base + __popc(m & ((1u << lane) - 1u))] = b;
-    if (threadIdx.x == 0) nrows[t] = total;
-    __syncthreads();
-  }
+  if (b < B)
+    for (int u = t; u < T; ++u) live = live || tmask[(size_t)u * B + b] != 0.f;
+  const unsigned m = __ballot_sync(0xffffffffu, live);
+  if (lane == 0) wsum[warp] = __popc(m);
+  __syncthreads();
+  int base = 0, total = 0;
+  for (int w = 0; w < nw; ++w) { if (w < warp) base += wsum[w]; total += wsum[w]; }
+  if (live) rows[(size_t)t * B + base + __popc(m & ((1u << lane) - 1u))] = b;
+  if (threadIdx.x == 0) nrows[t] = total;
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -1002,7 +1001,7 @@ int recurrent_backward(cudaStream_t s, const RecBwdArgs& r) {
     p.dbg_s = r.T / 2;
   }
   CUDA_TRY(cudaMemsetAsync(r.flags, 0, 64 * sizeof(unsigned int), s));
-  rb_active_rows_kernel<<<1, round_up(r.B, 32), 0, s>>>(r.tmask, r.T, r.B, r.rows, r.rows + (size_t)r.T * r.B);
+  rb_active_rows_kernel<<<r.T, round_up(r.B, 32), 0, s>>>(r.tmask, r.T, r.B, r.rows, r.rows + (size_t)r.T * r.B);
   CUDA_TRY(cudaGetLastError());
   ++g_launch_count;
   cudaLaunchConfig_t cfg = {};
