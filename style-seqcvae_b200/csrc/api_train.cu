@@ -669,7 +669,14 @@ static int train_backward_impl(Handle* h, int B, int N, const char* pk, const vo
     }
     if (Gr(SSCVAE_W_OUT_PROJ_B)) TRY(rowsum_bf16(s, Wb("dlogitsT"), V, TB, TBp, Gr(SSCVAE_W_OUT_PROJ_B), 0));
   }
-  TRY(event(0));
+  // With the persistent BPTT kernel the head group's event is recorded BEHIND the loop: the all-reduce it releases must not
+  // share the GPU with a cooperative kernel whose resident CTAs spin on flags that its not-yet-resident CTAs have to set.
+  // NCCL's CTAs also need to be co-resident with each other, and two such kernels placed at the same time can each hold
+  // the SMs the other still needs (seen at 8 GPUs: every rank stuck behind the first warm-up steps; at 2 GPUs NCCL uses
+  // too few CTAs to interleave with the placement of the 148). The all-reduce of the head bucket then overlaps the
+  // weight-gradient GEMMs like the other buckets.
+  const bool event0_late = pbwd;
+  if (!event0_late) TRY(event(0));
 
   // ---- reverse time loop
   LatentArgs la = {}; la.R = B; la.Z = Z; la.Zp = d.Zp; la.sentiment_vae = d.sv; la.prior_var = d.prior_std * d.prior_std;
@@ -696,6 +703,7 @@ static int train_backward_impl(Handle* h, int B, int N, const char* pk, const vo
     rb.flags = reinterpret_cast<unsigned int*>(ws + tp.find("rb_flags")->off);
     rb.rows = Wi("rb_rows");
     TRY(recurrent_backward(s, rb));
+    TRY(event(0));
   }
   for (int t = T - 1; t >= 0 && !pbwd; --t) {
     const int cur = t & 1, nxt = cur ^ 1;
@@ -771,12 +779,30 @@ static int train_backward_impl(Handle* h, int B, int N, const char* pk, const vo
   }
 
   TRY(set_l2_window(s, nullptr, 0));
-  // ---- weight gradients: one GEMM per weight block over all T*B rows (K = T*B)
+  // ---- weight gradients: one GEMM per weight block over all T*B rows (K = T*B). The GEMMs of one LSTM share the
+  //      transposed gate-gradient operand dGT and are otherwise independent: optionally (see below) they are spread over
+  //      auxiliary streams (StreamFork) so that the partial last wave of one overlaps the first wave of the next.
+  StreamFork& fk = h->fork;
+  // OFF by default (SSCVAE_WGRAD_FORK=1 turns it on): the first GPU run with it on hung in the test suite and in bench.py
+  // (not investigated: no GPU budget left this round); with it off every launch below goes to `s` as before.
+  static const bool want_fork = [] { const char* e = getenv("SSCVAE_WGRAD_FORK"); return e && e[0] == '1'; }();
+  const bool use_fork = want_fork && !g_prof_enabled;  // the per-launch profiler times launches on ONE stream
+  int item = 0;
+  auto next_stream = [&]() { return fk.pick(s, item++); };
   auto wgrad = [&](const bf16* AT, int M, const bf16* BT, int Ncols, int K, int ldk, float* C, int ldc) -> int {
     if (!C) return 0;
     GemmSeg sg = seg(AT, ldk, BT, ldk, K);
     GemmEpi e; e.tag = "gemm.wgrad"; e.C32 = C; e.ldc32 = ldc;
-    return gemm_bf16_tn(s, M, Ncols, 1, &sg, e);
+    return gemm_bf16_tn(next_stream(), M, Ncols, 1, &sg, e);
+  };
+  // b_ih and b_hh get the same gradient (both are added to the gates): one row sum, copied
+  auto bias_pair = [&](const bf16* dGT_, int ib, int ih) -> int {
+    float* g1 = Gr(ib); float* g2 = Gr(ih);
+    if (!g1 && !g2) return 0;
+    cudaStream_t st = next_stream();
+    TRY(rowsum_bf16(st, dGT_, G, TB, TBp, g1 ? g1 : g2, 0));
+    if (g1 && g2) CUDA_TRY(cudaMemcpyAsync(g2, g1, (size_t)G * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    return 0;
   };
   auto any = [&](std::initializer_list<int> ids) { for (int i : ids) if (gv[i]) return true; return false; };
   bf16* dGT = Wb("dGT");
@@ -793,48 +819,53 @@ static int train_backward_impl(Handle* h, int B, int N, const char* pk, const vo
   // group 1: decoder LSTM. W_ih column blocks [xhat | h1 | h_dec | cond | z]; W_hh shares the h_dec operand.
   if (any({SSCVAE_W_DEC_IH, SSCVAE_W_DEC_HH, SSCVAE_W_DEC_BIH, SSCVAE_W_DEC_BHH})) {
     TRY(transpose_bf16(s, Wb("dG_dec"), TB, G, Gp, dGT, TBp));
+    if (use_fork) TRY(fk.fork(s));
+    item = 0;
     float* g = Gr(SSCVAE_W_DEC_IH);
     if (g) {
       TRY(wgrad(dGT, G, xhatT, F, TB, TBp, g, ldD));
       TRY(wgrad(dGT, G, h1T, H, TB, TBp, g + F, ldD));
       TRY(wgrad(dGT, G, hdecpT, H, TB, TBp, g + F + H, ldD));
       TRY(wgrad(dGT, G, Wb("ZBT"), Z, TB, TBp, g + F + 2 * H + c, ldD));
-      if (c && !d.cvar) TRY(rowdot_bf16(s, dGT, G, TB, TBp, sentv, B, g + F + 2 * H, ldD));
+      if (c && !d.cvar) TRY(rowdot_bf16(next_stream(), dGT, G, TB, TBp, sentv, B, g + F + 2 * H, ldD));
       if (d.cvar) TRY(wgrad(dGT, G, condT, c, TB, TBp, g + F + 2 * H, ldD));
     }
     TRY(wgrad(dGT, G, hdecpT, H, TB, TBp, Gr(SSCVAE_W_DEC_HH), H));
-    if (Gr(SSCVAE_W_DEC_BIH)) TRY(rowsum_bf16(s, dGT, G, TB, TBp, Gr(SSCVAE_W_DEC_BIH), 0));
-    if (Gr(SSCVAE_W_DEC_BHH)) TRY(rowsum_bf16(s, dGT, G, TB, TBp, Gr(SSCVAE_W_DEC_BHH), 0));
+    TRY(bias_pair(dGT, SSCVAE_W_DEC_BIH, SSCVAE_W_DEC_BHH));
+    TRY(fk.join(s));
   }
   TRY(event(1));
 
   // group 2: encoder LSTM + latent heads
   if (any({SSCVAE_W_ENC_IH, SSCVAE_W_ENC_HH, SSCVAE_W_ENC_BIH, SSCVAE_W_ENC_BHH})) {
     TRY(transpose_bf16(s, Wb("dG_enc"), TB, G, Gp, dGT, TBp));
+    if (Gr(SSCVAE_W_ENC_HH)) TRY(transpose_bf16(s, Wb("HE"), TB, Hp, Hp, Wb("HETp"), TBp));   // h_enc_{t-1}
+    if (use_fork) TRY(fk.fork(s));
+    item = 0;
     float* g = Gr(SSCVAE_W_ENC_IH);
     if (g) {
       TRY(wgrad(dGT, G, xhatT, F, TB, TBp, g, ldE));
       TRY(wgrad(dGT, G, h1T, H, TB, TBp, g + F, ldE));
       TRY(wgrad(dGT, G, hdecpT, H, TB, TBp, g + F + H, ldE));
-      if (c && !d.cvar) TRY(rowdot_bf16(s, dGT, G, TB, TBp, sentv, B, g + F + 2 * H, ldE));
+      if (c && !d.cvar) TRY(rowdot_bf16(next_stream(), dGT, G, TB, TBp, sentv, B, g + F + 2 * H, ldE));
       if (d.cvar) TRY(wgrad(dGT, G, condT, c, TB, TBp, g + F + 2 * H, ldE));
     }
-    if (Gr(SSCVAE_W_ENC_HH)) {
-      TRY(transpose_bf16(s, Wb("HE"), TB, Hp, Hp, Wb("HETp"), TBp));               // h_enc_{t-1}
-      TRY(wgrad(dGT, G, Wb("HETp"), H, TB, TBp, Gr(SSCVAE_W_ENC_HH), H));
-    }
-    if (Gr(SSCVAE_W_ENC_BIH)) TRY(rowsum_bf16(s, dGT, G, TB, TBp, Gr(SSCVAE_W_ENC_BIH), 0));
-    if (Gr(SSCVAE_W_ENC_BHH)) TRY(rowsum_bf16(s, dGT, G, TB, TBp, Gr(SSCVAE_W_ENC_BHH), 0));
+    TRY(wgrad(dGT, G, Wb("HETp"), H, TB, TBp, Gr(SSCVAE_W_ENC_HH), H));
+    TRY(bias_pair(dGT, SSCVAE_W_ENC_BIH, SSCVAE_W_ENC_BHH));
+    TRY(fk.join(s));
   }
   if (any({SSCVAE_W_FC_MEAN_W, SSCVAE_W_FC_MEAN_B, SSCVAE_W_FC_LOGVAR_W, SSCVAE_W_FC_LOGVAR_B})) {
     TRY(transpose_bf16(s, Wb("dml"), TB, d.Z2p, d.Z2p, Wb("dmlT"), TBp));
     TRY(transpose_bf16(s, Wb("HE") + (size_t)B * Hp, TB, Hp, Hp, Wb("HETc"), TBp));   // h_enc_t
     const bf16* dmT = Wb("dmlT");
     const bf16* dlT = Wb("dmlT") + (size_t)Z * TBp;
+    if (use_fork) TRY(fk.fork(s));
+    item = 0;
     TRY(wgrad(dmT, Z, Wb("HETc"), H, TB, TBp, Gr(SSCVAE_W_FC_MEAN_W), H));
     TRY(wgrad(dlT, Z, Wb("HETc"), H, TB, TBp, Gr(SSCVAE_W_FC_LOGVAR_W), H));
-    if (Gr(SSCVAE_W_FC_MEAN_B)) TRY(rowsum_bf16(s, dmT, Z, TB, TBp, Gr(SSCVAE_W_FC_MEAN_B), 0));
-    if (Gr(SSCVAE_W_FC_LOGVAR_B)) TRY(rowsum_bf16(s, dlT, Z, TB, TBp, Gr(SSCVAE_W_FC_LOGVAR_B), 0));
+    if (Gr(SSCVAE_W_FC_MEAN_B)) TRY(rowsum_bf16(next_stream(), dmT, Z, TB, TBp, Gr(SSCVAE_W_FC_MEAN_B), 0));
+    if (Gr(SSCVAE_W_FC_LOGVAR_B)) TRY(rowsum_bf16(next_stream(), dlT, Z, TB, TBp, Gr(SSCVAE_W_FC_LOGVAR_B), 0));
+    TRY(fk.join(s));
   }
   TRY(event(2));
 
@@ -848,25 +879,30 @@ static int train_backward_impl(Handle* h, int B, int N, const char* pk, const vo
     float* g = Gr(SSCVAE_W_ATT_IH);
     if (g) {
       TRY(transpose_bf16(s, Wb("embb_t"), TB, d.Ep, d.Ep, Wb("embT_t"), TBp));
-      TRY(wgrad(dGT, G, Wb("embT_t"), E, TB, TBp, g, ldA));
       // mean-feature block: the operand is constant over time, so sum the gate gradients over t first
       TRY(timesum_bf16(s, Wb("dG_att"), T, B, G, Gp, Wb("dGsum"), Gp));
       TRY(transpose_bf16(s, Wb("dGsum"), B, G, Gp, Wb("dGsumT"), Bp));
       TRY(transpose_bf16(s, Wb("avgb"), B, Fp, Fp, Wb("avgT"), Bp));
+    }
+    if (use_fork) TRY(fk.fork(s));
+    item = 0;
+    if (g) {
+      TRY(wgrad(dGT, G, Wb("embT_t"), E, TB, TBp, g, ldA));
       TRY(wgrad(Wb("dGsumT"), G, Wb("avgT"), F, B, Bp, g + E, ldA));
       TRY(wgrad(dGT, G, h1pT, H, TB, TBp, g + E + F, ldA));
       TRY(wgrad(dGT, G, hdecp2T, H, TB, TBp, g + E + F + H, ldA));
     }
     TRY(wgrad(dGT, G, h1pT, H, TB, TBp, Gr(SSCVAE_W_ATT_HH), H));
-    if (Gr(SSCVAE_W_ATT_BIH)) TRY(rowsum_bf16(s, dGT, G, TB, TBp, Gr(SSCVAE_W_ATT_BIH), 0));
-    if (Gr(SSCVAE_W_ATT_BHH)) TRY(rowsum_bf16(s, dGT, G, TB, TBp, Gr(SSCVAE_W_ATT_BHH), 0));
+    TRY(bias_pair(dGT, SSCVAE_W_ATT_BIH, SSCVAE_W_ATT_BHH));
     if (need_demb) {  // learned embedding (untied): d emb rows = dG_att W_att_ih[:, :E], scattered by token id
+      cudaStream_t st = next_stream();
       GemmSeg sg = seg(Wb("dG_att"), Gp, Pb("w_att_eT"), Gp, G);
       GemmEpi e; e.tag = "gemm.wgrad"; e.C32 = Wf("dxemb"); e.ldc32 = E;
-      TRY(gemm_bf16_tn(s, TB, E, 1, &sg, e));
-      CUDA_TRY(cudaMemsetAsync(Gr(SSCVAE_W_EMBEDDING), 0, (size_t)V * E * sizeof(float), s));
-      TRY(embed_scatter_add(s, tok, B, d.L, d.pad, Wf("dxemb"), E, E, Gr(SSCVAE_W_EMBEDDING)));
+      TRY(gemm_bf16_tn(st, TB, E, 1, &sg, e));
+      CUDA_TRY(cudaMemsetAsync(Gr(SSCVAE_W_EMBEDDING), 0, (size_t)V * E * sizeof(float), st));
+      TRY(embed_scatter_add(st, tok, B, d.L, d.pad, Wf("dxemb"), E, E, Gr(SSCVAE_W_EMBEDDING)));
     }
+    TRY(fk.join(s));
   }
   TRY(event(3));
 

@@ -23,12 +23,39 @@ __global__ void image_prep_kernel(const TIn* __restrict__ feats, int N, int F, b
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
   const TIn* x = feats + (size_t)b * N * F;
   bf16* xb = featsb + (size_t)b * N * Fp;
+  // 16-byte loads when the rows allow it (F % 4 == 0, 16-byte aligned base: every row then starts on a 16-byte boundary for
+  // fp32 and on an 8-byte boundary for bf16 input); the scalar loop otherwise
+  const bool vec = (F & 3) == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0;
   for (int n = warp; n < N; n += nwarp) {
     float s = 0.f;
-    for (int f = lane; f < Fp; f += 32) {
-      float v = (f < F) ? (float)x[(size_t)n * F + f] : 0.f;
-      s += fabsf(v);
-      xb[(size_t)n * Fp + f] = __float2bfloat16_rn(v);
+    if (vec) {
+      const int nq = F >> 2;
+#pragma unroll 4
+      for (int q = lane; q < (Fp >> 2); q += 32) {
+        float v0 = 0.f, v1 = 0.f, v2 = 0.f, v3 = 0.f;
+        if (q < nq) {
+          if (sizeof(TIn) == 4) {
+            const float4 v = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(x) + (size_t)n * F + 4 * q);
+            v0 = v.x; v1 = v.y; v2 = v.z; v3 = v.w;
+          } else {
+            const uint2 v = *reinterpret_cast<const uint2*>(reinterpret_cast<const bf16*>(x) + (size_t)n * F + 4 * q);
+            v0 = __uint_as_float(v.x << 16); v1 = __uint_as_float(v.x & 0xffff0000u);
+            v2 = __uint_as_float(v.y << 16); v3 = __uint_as_float(v.y & 0xffff0000u);
+          }
+        }
+        s += (fabsf(v0) + fabsf(v1)) + (fabsf(v2) + fabsf(v3));
+        const __nv_bfloat162 lo = __floats2bfloat162_rn(v0, v1), hi = __floats2bfloat162_rn(v2, v3);
+        uint2 o;
+        o.x = *reinterpret_cast<const uint32_t*>(&lo);
+        o.y = *reinterpret_cast<const uint32_t*>(&hi);
+        *reinterpret_cast<uint2*>(xb + (size_t)n * Fp + 4 * q) = o;
+      }
+    } else {
+      for (int f = lane; f < Fp; f += 32) {
+        float v = (f < F) ? (float)x[(size_t)n * F + f] : 0.f;
+        s += fabsf(v);
+        xb[(size_t)n * Fp + f] = __float2bfloat16_rn(v);
+      }
     }
     s = warp_sum(s);
     if (lane == 0) { float m = s > 0.f ? 1.f : 0.f; s_mask[n] = m; mask[(size_t)b * N + n] = m; }
@@ -37,12 +64,23 @@ __global__ void image_prep_kernel(const TIn* __restrict__ feats, int N, int F, b
   float cnt = 0.f;
   for (int n = 0; n < N; ++n) cnt += s_mask[n];
   const float inv = 1.0f / fmaxf(cnt, 1e-8f);
-  for (int f = threadIdx.x; f < Fp; f += blockDim.x) {
-    float s = 0.f;
-    if (f < F)
-      for (int n = 0; n < N; ++n)
-        if (s_mask[n] != 0.f) s += __bfloat162float(xb[(size_t)n * Fp + f]);
-    avgb[(size_t)b * Fp + f] = __float2bfloat16_rn(s * inv);
+  // masked mean over the bf16-rounded values, boxes in ascending order; a thread owns 8 consecutive features (Fp % 64 == 0)
+  for (int f0 = threadIdx.x * 8; f0 < Fp; f0 += blockDim.x * 8) {
+    float acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+    for (int n = 0; n < N; ++n)
+      if (s_mask[n] != 0.f) {
+        const uint4 v = *reinterpret_cast<const uint4*>(xb + (size_t)n * Fp + f0);
+        acc[0] += __uint_as_float(v.x << 16); acc[1] += __uint_as_float(v.x & 0xffff0000u);
+        acc[2] += __uint_as_float(v.y << 16); acc[3] += __uint_as_float(v.y & 0xffff0000u);
+        acc[4] += __uint_as_float(v.z << 16); acc[5] += __uint_as_float(v.z & 0xffff0000u);
+        acc[6] += __uint_as_float(v.w << 16); acc[7] += __uint_as_float(v.w & 0xffff0000u);
+      }
+    bf16x8 o;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) o.v[i] = __floats2bfloat162_rn(f0 + 2 * i < F ? acc[2 * i] * inv : 0.f, f0 + 2 * i + 1 < F ? acc[2 * i + 1] * inv : 0.f);
+    st_bf16x8(avgb + (size_t)b * Fp + f0, o);
   }
 }
 
