@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define SSCVAE_ABI_VERSION 5
+#define SSCVAE_ABI_VERSION 6
 
 #define SSCVAE_ERR_BAD_ARG (-1)
 #define SSCVAE_ERR_WORKSPACE (-2)

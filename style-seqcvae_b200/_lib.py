@@ -115,7 +115,7 @@ def lib():
         fn = getattr(L, name)
         if fn.restype is C.c_int and name not in ("sscvae_abi_version",):
             fn.restype = C.c_int
-    if L.sscvae_abi_version() != 5:
+    if L.sscvae_abi_version() != 6:
         raise ImportError("libsscvae_b200.so ABI version mismatch")
     _lib = L
     return L

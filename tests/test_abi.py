@@ -28,7 +28,7 @@ def test_library_exports_every_declared_symbol():
 
 def test_abi_version_and_error_string():
     L = _lib.lib()
-    assert L.sscvae_abi_version() == 5
+    assert L.sscvae_abi_version() == 6
     h = ctypes.c_void_p()
     bad = _lib.SscvaeDims(64, 600, 32, 24, 16, 100, 20, 3, 0, 1, 0, 1, 1.0, 0.5, 0)   # sentiment_vae is 0, 1 or 2
     rc = L.sscvae_create(ctypes.byref(bad), ctypes.byref(h))
