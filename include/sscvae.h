@@ -265,6 +265,11 @@ int sscvae_set_option(SscvaeHandle* h, const char* name, int value);
  * the two). Replaces nothing in the reference: autograd owns its backward (var_updown/scripts/train.py:172). */
 int sscvae_train_backward_is_persistent(const SscvaeHandle* h, int batch, int num_boxes);
 
+/* Host-only (no device needed): the job map of the persistent BPTT kernel for `pairs` co-resident CTA pairs (74 on a B200),
+ * out12 = {big pairs, small pairs, S6A tiles, S6A K parts, S6B tiles, parts, S10 tiles, parts, d z tiles, parts, S4 / S8 tiles,
+ * their width}; returns 1, or 0 if the shape does not fit (the per-launch path is used). For the CPU tests of the tiling. */
+int sscvae_debug_bptt_tiling(const SscvaeHandle* h, int batch, int num_boxes, int pairs, int32_t* out12);
+
 /* Optional instrumentation (off by default): CUDA events around every kernel launch of the library,
  * aggregated per kernel class. report() synchronises the device and writes a JSON object
  * {"class": {"count", "ms", "flops", "bytes"}} (algorithmic FLOPs / bytes as declared at the call site). */

@@ -38,7 +38,7 @@ GRAD_GROUPS = 5
 
 # every symbol include/sscvae.h declares (tests/test_abi.py checks the library exports each one)
 SYMBOLS = [
-    "sscvae_abi_version", "sscvae_last_error", "sscvae_launch_count", "sscvae_create", "sscvae_destroy", "sscvae_set_option", "sscvae_train_backward_is_persistent",
+    "sscvae_abi_version", "sscvae_last_error", "sscvae_launch_count", "sscvae_create", "sscvae_destroy", "sscvae_set_option", "sscvae_train_backward_is_persistent", "sscvae_debug_bptt_tiling",
     "sscvae_packed_bytes", "sscvae_pack_weights", "sscvae_test_gemm_splitk", "sscvae_sgd_step_multi", "sscvae_train_workspace_bytes", "sscvae_train_forward",
     "sscvae_train_backward", "sscvae_train_region", "sscvae_fsm_pack", "sscvae_fsm_build", "sscvae_select_best_beam", "sscvae_search_first_step",
     "sscvae_search_step", "sscvae_search_scratch_bytes", "sscvae_search_finish",
@@ -109,6 +109,7 @@ def lib():
     L.sscvae_test_gemm.argtypes = [vp, i32, vp, i32, i32, i32, i32, vp, i32, vp, i32, i32, vp]
     L.sscvae_set_option.argtypes = [vp, C.c_char_p, i32]
     L.sscvae_train_backward_is_persistent.argtypes = [vp, i32, i32]
+    L.sscvae_debug_bptt_tiling.argtypes = [vp, i32, i32, i32, C.POINTER(i32)]
     L.sscvae_profile_enable.argtypes = [i32]
     L.sscvae_profile_report.argtypes = [C.c_char_p, sz]
     for name in SYMBOLS:

@@ -954,6 +954,18 @@ int sscvae_train_backward_is_persistent(const SscvaeHandle* hh, int batch, int n
   return h->opt_persistent_bwd && persistent_backward(h->d, batch, num_boxes) ? 1 : 0;
 }
 
+int sscvae_debug_bptt_tiling(const SscvaeHandle* hh, int batch, int num_boxes, int pairs, int32_t* out12) {
+  const Handle* h = reinterpret_cast<const Handle*>(hh);
+  REQUIRE(h && out12 && batch > 0 && num_boxes > 0 && pairs > 0, "bad argument");
+  if (h->d.cvar) return 0;
+  RecBwdArgs rb;
+  fill_rec_bwd_args(h->d, batch, num_boxes, rb);
+  int v[12];
+  if (!recurrent_backward_tiling(rb, pairs, v)) return 0;
+  for (int i = 0; i < 12; ++i) out12[i] = v[i];
+  return 1;
+}
+
 int sscvae_create(const SscvaeDims* dims, SscvaeHandle** out) {
   REQUIRE(out != nullptr, "out is NULL");
   Handle* h = new Handle();

@@ -238,6 +238,7 @@ struct RecBwdArgs {
   unsigned int* flags;                 // >= 256 B of scratch for the dataflow counters
 };
 bool recurrent_backward_supported(const RecBwdArgs& r);
+bool recurrent_backward_tiling(const RecBwdArgs& r, int pairs, int out[12]);   // host only, no device needed
 int recurrent_backward(cudaStream_t s, const RecBwdArgs& r);
 
 extern unsigned long long g_launch_count_pw;   // launches from the non-GEMM kernels

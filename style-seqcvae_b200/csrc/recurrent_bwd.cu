@@ -904,11 +904,22 @@ static bool rb_tiling(const RecBwdArgs& r, int NP, RbTiling& t) {
 }
 
 static bool rb_shape_ok(const RecBwdArgs& r) {
-  if (r.B > 256 || r.B < 1 || (r.H & 3) || (r.Hp & 63) || (r.Fp & 63) || (r.Zp & 63) || (r.Z2p & 63) || (r.Ap & 63) || (r.Gp & 63)) return false;
+  // Z even: the latent stage reads mean / log_var / eps as 8-byte pairs
+  if (r.B > 256 || r.B < 1 || (r.H & 3) || (r.Z & 1) || (r.Hp & 63) || (r.Fp & 63) || (r.Zp & 63) || (r.Z2p & 63) || (r.Ap & 63) || (r.Gp & 63)) return false;
   const AttnArgs& a = r.att;
   if (a.N > 32 * ATT_NREG || a.Fp > 8 * ATT_CONSUMERS * ATT_FV || a.Ap * 2 > ATT_STAGE_BYTES || a.Fp * 2 > ATT_STAGE_BYTES ||
       a.Ap > 2 * ATT_CONSUMERS * ATT_PV || (a.Ap % 8) || (a.Fp % 8))
     return false;
+  return true;
+}
+
+// host-only view of the job map for `pairs` co-resident CTA pairs (tests): nbig, nsmall, nA, splitA, nB, splitB, nX, splitX,
+// nZt, splitZ, n4, N4; false if the shape does not fit
+bool recurrent_backward_tiling(const RecBwdArgs& r, int pairs, int out[12]) {
+  RbTiling t;
+  if (!rb_shape_ok(r) || !rb_tiling(r, pairs, t)) return false;
+  const int v[12] = {t.nbig, t.nsmall, t.nA, t.splitA, t.nB, t.splitB, t.nX, t.splitX, t.nZt, t.splitZ, t.n4, t.N4};
+  for (int i = 0; i < 12; ++i) out[i] = v[i];
   return true;
 }
 
