@@ -280,7 +280,7 @@ def main():
     args = ap.parse_args()
     # a stalled run ends itself with every thread's stack on stderr instead of waiting for the caller's timeout
     import faulthandler
-    faulthandler.dump_traceback_later(int(os.environ.get("SSCVAE_BENCH_WATCHDOG_S", "540")), exit=True)
+    faulthandler.dump_traceback_later(int(os.environ.get("SSCVAE_BENCH_WATCHDOG_S", "420")), exit=True)
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
