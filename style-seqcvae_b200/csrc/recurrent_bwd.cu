@@ -20,7 +20,9 @@
 //                  S4   d h_enc (latent heads) = d[mean|log_var] W_fc                 (N = N4 tiles, K = 2Z)
 //                  S8   d h1 (query) = d q W_q                                        (N = N4 tiles, K = A)
 // The pointwise stages (the three LSTM cell backwards, the latent backward) and the attention rows are spread over the
-// compute warps of ALL CTAs. Saved forward state is read in the row-tiled layout the persistent forward kernel wrote.
+// compute warps of ALL CTAs; the attention walks the per-step list of rows that still carry gradient (rb_active_rows_kernel).
+// The saved gates / cell states are read in the row-tiled layout of the persistent forward kernel or in the row-major
+// layout of the per-launch forward (RbParams::tiled).
 #define ATT_TID0 64
 #define ATT_STAGES_N 2
 #define ATT_STAGE_BYTES_N 32768
